@@ -1,0 +1,77 @@
+/* TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, bench.py cpu_baseline). */
+#include "liftover.h"
+#include <cstdio>
+#include <memory>
+
+using namespace oracle;
+
+struct OracleHandle {
+    HalView view;
+    std::vector<uint64_t> offsets;
+    std::vector<OutLine> lines;
+    Stats stats;
+    std::string err;
+};
+
+extern "C" {
+
+void *oracle_open(const char *path) {
+    std::unique_ptr<OracleHandle> h(new OracleHandle);
+    try {
+        h->view.open(path);
+    } catch (std::exception &e) {
+        fprintf(stderr, "oracle_open: %s\n", e.what());
+        return nullptr;
+    }
+    return h.release();
+}
+void oracle_close(void *hp) { delete (OracleHandle *)hp; }
+int oracle_num_genomes(void *hp) { return (int)((OracleHandle *)hp)->view.genomes.size(); }
+const char *oracle_genome_name(void *hp, int g) { return ((OracleHandle *)hp)->view.genomes[g].name.c_str(); }
+int oracle_genome_id(void *hp, const char *name) { return ((OracleHandle *)hp)->view.genomeId(name); }
+int oracle_genome_parent(void *hp, int g) { return ((OracleHandle *)hp)->view.genomes[g].parent; }
+int64_t oracle_genome_length(void *hp, int g) { return ((OracleHandle *)hp)->view.genomes[g].len; }
+int64_t oracle_genome_num_top(void *hp, int g) { return ((OracleHandle *)hp)->view.genomes[g].numTop; }
+int64_t oracle_genome_num_bottom(void *hp, int g) { return ((OracleHandle *)hp)->view.genomes[g].numBot; }
+int oracle_num_sequences(void *hp, int g) { return (int)((OracleHandle *)hp)->view.genomes[g].seqs.size(); }
+const char *oracle_seq_name(void *hp, int g, int s) { return ((OracleHandle *)hp)->view.genomes[g].seqs[s].name.c_str(); }
+int64_t oracle_seq_start(void *hp, int g, int s) { return ((OracleHandle *)hp)->view.genomes[g].seqs[s].start; }
+int64_t oracle_seq_length(void *hp, int g, int s) { return ((OracleHandle *)hp)->view.genomes[g].seqs[s].length; }
+const char *oracle_newick(void *hp) { return ((OracleHandle *)hp)->view.newick.c_str(); }
+
+/* Lift n intervals given in genome-global inclusive coordinates.  Returns the total number of output
+ * lines (kept inside the handle until the next call); fetch them with oracle_fetch. */
+int64_t oracle_liftover(void *hp, int src, int tgt, int noDupes, int64_t n, const int64_t *gs, const int64_t *ge,
+                        const char *strand) {
+    OracleHandle *h = (OracleHandle *)hp;
+    Plan plan = makePlan(h->view, src, tgt);
+    h->offsets.assign(1, 0);
+    h->lines.clear();
+    h->stats = Stats();
+    for (int64_t i = 0; i < n; i++) {
+        liftInterval(h->view, plan, !noDupes, gs[i], ge[i], strand ? strand[i] : '+', h->lines, &h->stats);
+        h->offsets.push_back(h->lines.size());
+    }
+    return (int64_t)h->lines.size();
+}
+
+void oracle_fetch(void *hp, uint64_t *offsets, int32_t *tgtSeq, int64_t *start, int64_t *end, char *strand,
+                  int64_t *srcStart, char *srcStrand) {
+    OracleHandle *h = (OracleHandle *)hp;
+    for (size_t i = 0; i < h->offsets.size(); i++) offsets[i] = h->offsets[i];
+    for (size_t i = 0; i < h->lines.size(); i++) {
+        const OutLine &o = h->lines[i];
+        tgtSeq[i] = o.tgtSeq; start[i] = o.start; end[i] = o.end; strand[i] = o.strand;
+        srcStart[i] = o.srcStart; srcStrand[i] = o.srcStrand;
+    }
+}
+
+/* stats of the last oracle_liftover call: seeds, visitsTop, visitsBot, visitBytes, searchProbes, rawFrags,
+ * refinedFrags, outLines */
+void oracle_stats(void *hp, uint64_t *out8) {
+    const Stats &s = ((OracleHandle *)hp)->stats;
+    out8[0] = s.seeds; out8[1] = s.visitsTop; out8[2] = s.visitsBot; out8[3] = s.visitBytes;
+    out8[4] = s.searchProbes; out8[5] = s.rawFrags; out8[6] = s.refinedFrags; out8[7] = s.outLines;
+}
+
+} // extern "C"
