@@ -1,0 +1,190 @@
+"""hal_b200 -- B200-native HAL liftover hot path.
+
+The product is the C-ABI shared library ``hal_b200/libhalgpu.so`` (declared in ``include/halgpu.h``,
+built for sm_100a by ``hal_b200/build.py``) plus the C++ host layer / CLIs under ``hal_b200/csrc/host``.
+This module is only the ctypes binding the tests and ``bench.py`` drive it through; there is no CPU
+implementation behind it -- without the CUDA library, or without a GPU, every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhalgpu.so")
+
+HALGPU_NO_DUPES = 1
+HALGPU_NO_SORT = 2
+
+
+class HalGpuError(RuntimeError):
+    pass
+
+
+class _Seq(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("start", C.c_int64), ("length", C.c_int64), ("num_top", C.c_int64),
+                ("num_bottom", C.c_int64)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("n_rec", C.c_size_t), ("offsets", C.c_void_p), ("recs", C.c_void_p),
+                ("on_device", C.c_int), ("kernel_ms", C.c_float), ("launches", C.c_int), ("n_retry", C.c_size_t)]
+
+
+REC_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("src_start", "<i8"), ("tgt_seq", "<i4"),
+                      ("strand", "u1"), ("src_strand", "u1"), ("n_frag", "<u2")])
+assert REC_DTYPE.itemsize == 32
+
+# every symbol include/halgpu.h declares
+ABI_SYMBOLS = [
+    "halgpu_open", "halgpu_close", "halgpu_num_genomes", "halgpu_genome_name", "halgpu_genome_id",
+    "halgpu_genome_parent", "halgpu_genome_num_children", "halgpu_genome_child", "halgpu_genome_length",
+    "halgpu_genome_num_top", "halgpu_genome_num_bottom", "halgpu_newick", "halgpu_sequence_table", "halgpu_mrca",
+    "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
+    "halgpu_free_string", "halgpu_launch_count",
+]
+
+
+def load_library(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise HalGpuError(f"{path} is missing: build it with `python -m hal_b200.build` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.halgpu_open.argtypes = [C.c_char_p, i32, C.POINTER(vp), C.POINTER(C.c_char_p)]
+    L.halgpu_close.argtypes = [vp]
+    L.halgpu_num_genomes.argtypes = [vp]
+    L.halgpu_genome_name.argtypes = [vp, i32]
+    L.halgpu_genome_name.restype = C.c_char_p
+    L.halgpu_genome_id.argtypes = [vp, C.c_char_p]
+    for f in ("halgpu_genome_parent", "halgpu_genome_num_children"):
+        getattr(L, f).argtypes = [vp, i32]
+    L.halgpu_genome_child.argtypes = [vp, i32, i32]
+    for f in ("halgpu_genome_length", "halgpu_genome_num_top", "halgpu_genome_num_bottom"):
+        getattr(L, f).argtypes = [vp, i32]
+        getattr(L, f).restype = i64
+    L.halgpu_newick.argtypes = [vp]
+    L.halgpu_newick.restype = C.c_char_p
+    L.halgpu_sequence_table.argtypes = [vp, i32, C.POINTER(C.POINTER(_Seq)), C.POINTER(C.c_size_t)]
+    L.halgpu_mrca.argtypes = [vp, i32, i32]
+    L.halgpu_staged_bytes.argtypes = [vp]
+    L.halgpu_staged_bytes.restype = C.c_size_t
+    L.halgpu_stream.argtypes = [vp]
+    L.halgpu_stream.restype = vp
+    for f in ("halgpu_liftover", "halgpu_liftover_device"):
+        getattr(L, f).argtypes = [vp, i32, i32, i32, C.c_uint32, C.c_size_t, vp, vp, vp,
+                                  C.POINTER(C.POINTER(_Result)), C.POINTER(C.c_char_p)]
+    L.halgpu_free_result.argtypes = [C.POINTER(_Result)]
+    L.halgpu_free_string.argtypes = [C.c_void_p]
+    L.halgpu_launch_count.restype = C.c_uint64
+    return L
+
+
+def _take_err(L, err):
+    msg = err.value.decode() if err.value else "unknown error"
+    return msg
+
+
+class DeviceResult:
+    """Result of liftover_device: device pointers, freed on close()."""
+
+    def __init__(self, lib, res):
+        self._lib, self._res = lib, res
+        r = res.contents
+        self.n, self.n_rec = r.n, r.n_rec
+        self.offsets_ptr, self.recs_ptr = r.offsets, r.recs
+        self.kernel_ms, self.launches, self.n_retry = r.kernel_ms, r.launches, r.n_retry
+
+    def close(self):
+        if self._res is not None:
+            self._lib.halgpu_free_result(self._res)
+            self._res = None
+
+
+class Alignment:
+    """Read-only alignment staged in the HBM of one GPU (mirrors hal::Alignment's query surface for the path)."""
+
+    def __init__(self, path, device=0, lib_path=None):
+        self.L = load_library(lib_path)
+        h, err = C.c_void_p(), C.c_char_p()
+        # char** out-param: ctypes cannot free a c_char_p for us, keep the raw pointer
+        errp = C.c_void_p()
+        rc = self.L.halgpu_open(path.encode(), device, C.byref(h), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else "halgpu_open failed"
+            if errp.value:
+                self.L.halgpu_free_string(errp)
+            raise HalGpuError(msg)
+        self.h = h
+        self.genomes = [self.L.halgpu_genome_name(h, g).decode() for g in range(self.L.halgpu_num_genomes(h))]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.halgpu_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def genome_id(self, name):
+        return self.L.halgpu_genome_id(self.h, name.encode())
+
+    def genome_length(self, g):
+        return self.L.halgpu_genome_length(self.h, g)
+
+    def sequences(self, g):
+        p, n = C.POINTER(_Seq)(), C.c_size_t()
+        if self.L.halgpu_sequence_table(self.h, g, C.byref(p), C.byref(n)) != 0:
+            raise HalGpuError("bad genome index")
+        return [(p[i].name.decode(), p[i].start, p[i].length) for i in range(n.value)]
+
+    @property
+    def newick(self):
+        return self.L.halgpu_newick(self.h).decode()
+
+    @property
+    def staged_bytes(self):
+        return self.L.halgpu_staged_bytes(self.h)
+
+    @property
+    def stream(self):
+        return self.L.halgpu_stream(self.h)
+
+    def _call(self, fn, src, tgt, flags, n, a, b, s):
+        res, errp = C.POINTER(_Result)(), C.c_void_p()
+        rc = fn(self.h, src, tgt, -1, flags, n, a, b, s, C.byref(res), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else "liftover failed"
+            if errp.value:
+                self.L.halgpu_free_string(errp)
+            raise HalGpuError(msg)
+        return res
+
+    def liftover(self, src, tgt, start, end_incl, strand=None, flags=0):
+        """Host arrays in (forward genome coordinates), numpy arrays out: (offsets[n+1], recs[REC_DTYPE], info)."""
+        start = np.ascontiguousarray(start, dtype=np.int64)
+        end_incl = np.ascontiguousarray(end_incl, dtype=np.int64)
+        st = None if strand is None else np.ascontiguousarray(strand, dtype=np.uint8)
+        n = len(start)
+        res = self._call(self.L.halgpu_liftover, src, tgt, flags, n, start.ctypes.data, end_incl.ctypes.data,
+                         None if st is None else st.ctypes.data)
+        r = res.contents
+        offsets = np.ctypeslib.as_array(C.cast(r.offsets, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        if r.n_rec:
+            buf = (C.c_char * (r.n_rec * 32)).from_address(r.recs)
+            recs = np.frombuffer(buf, dtype=REC_DTYPE).copy()
+        else:
+            recs = np.zeros(0, dtype=REC_DTYPE)
+        info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry)
+        self.L.halgpu_free_result(res)
+        return offsets, recs, info
+
+    def liftover_ptrs(self, src, tgt, n, start_ptr, end_ptr, strand_ptr=None, flags=0, device=False):
+        """Raw-pointer variants (pinned host buffers, or device buffers with device=True)."""
+        fn = self.L.halgpu_liftover_device if device else self.L.halgpu_liftover
+        res = self._call(fn, src, tgt, flags, n, start_ptr, end_ptr, strand_ptr)
+        return DeviceResult(self.L, res)

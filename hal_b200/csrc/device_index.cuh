@@ -1,0 +1,82 @@
+// Device-resident index layout (HBM) and the per-launch parameter blocks.
+//
+// The file's AoS records (top 40 B, bottom 8*(2+nc)+roundup8(nc) B) are re-packed
+// once at staging time into sector-friendly arrays; the file format itself is untouched.
+//   TopRec   32 B  == one DRAM sector: start | parent<<1|reversed | bottomParseIndex | nextParalogyIndex
+//   BotCore  16 B : start | topParseIndex          (what every walk needs from a bottom record)
+//   childEnc  8 B : child<<1|reversed, one array per child slot (a walk only ever follows ONE slot per level,
+//                   so the other slots' columns are never fetched -- AoS bottoms of an 8-child genome are 88 B)
+// Both arrays keep the file's +1 sentinel record so that length(i) = start(i+1) - start(i)
+// (api/mmap_impl/mmapTopSegment.h:78-80).
+#pragma once
+#include <cstdint>
+
+#if defined(HALGPU_SIMT_EMUL)
+#include "simt_emul.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "../../include/halgpu.h"
+
+namespace halgpu {
+
+struct alignas(32) TopRec {
+    int64_t start;
+    int64_t parentEnc; // -1: no parent; else (parentIndex << 1) | parentReversed
+    int64_t botParse;  // bottomParseIndex (-1 for leaves)
+    int64_t nextPara;  // nextParalogyIndex (-1: none)
+};
+
+struct alignas(16) BotCore {
+    int64_t start;
+    int64_t topParse; // topParseIndex (-1 for the root)
+};
+
+// One genome on the src -> mrca -> tgt path.  Entry p describes genome path[p] and the transition p -> p+1.
+struct PathStep {
+    const TopRec *top;
+    const BotCore *bot;
+    const int64_t *child; // down transitions: childEnc column of path[p] for the slot of path[p+1]
+    int64_t numTop, numBot;
+    int32_t up;  // 1: transition p -> p+1 goes to the parent
+    int32_t pad;
+};
+
+struct LiftParams {
+    const PathStep *steps;
+    int32_t P;      // genomes on the path (>= 1)
+    int32_t dupes;  // !--noDupes
+    // seeds come from the source genome's top array if it has one, else its bottom array
+    // (liftover/impl/halBlockLiftover.cpp:24-30)
+    int32_t srcIsTop;
+    int32_t srcShift;
+    int64_t srcN;
+    const uint32_t *srcBucket; // srcBucket[b] = index of the segment containing position b << srcShift
+    int64_t srcNumBuckets;
+    // target genome sequence starts (numSeq + 1 entries, last = genome length)
+    const int64_t *tgtSeqStart;
+    int32_t tgtNumSeq;
+    int32_t pad0;
+    // batch
+    int64_t n;               // work items of this launch
+    const uint32_t *work;    // optional: work[w] = interval id (sorted order or retry subset); NULL: identity
+    const int64_t *gs, *ge;  // genome-global inclusive
+    const uint8_t *strand;   // may be NULL
+    // outputs
+    uint32_t *outCount;      // per interval
+    uint64_t *outOffset;     // per interval: first record in pool
+    uint32_t *status;        // per interval: ST_*
+    halgpu_lift_rec *pool;
+    unsigned long long *poolCursor;
+    uint64_t poolCap;
+    // scratch: lists live in dynamic shared memory unless gscratch != NULL
+    int32_t listCap;   // fragments per list (two lists per warp)
+    int32_t frameCap;  // work-pool frames per warp
+    uint8_t *gscratch;
+    uint64_t gscratchPerWarp;
+};
+
+enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2 };
+
+} // namespace halgpu

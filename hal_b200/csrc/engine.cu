@@ -1,0 +1,304 @@
+#include "engine.hpp"
+#include "liftover_kernel.cuh"
+#include "stage_kernels.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace halgpu {
+namespace rt {
+unsigned long long g_launches = 0;
+}
+
+namespace {
+struct DevBuf { // RAII for per-batch device scratch
+    void *p = nullptr;
+    explicit DevBuf(size_t n) : p(rt::dmalloc(n)) {}
+    ~DevBuf() { rt::dfree(p); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    void *release() { void *q = p; p = nullptr; return q; }
+};
+unsigned gridFor(int64_t n, unsigned block, int sms) {
+    int64_t g = (n + block - 1) / block;
+    const int64_t cap = (int64_t)sms * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+} // namespace
+
+void *Context::alloc(size_t bytes) {
+    void *p = rt::dmalloc(bytes);
+    _owned.push_back(p);
+    _staged += bytes;
+    return p;
+}
+
+Context::Context(const std::string &path, int device) : _file(new HalFile(path)), _device(device) {
+    rt::setDevice(device);
+    _stream = rt::createStream();
+    _sms = rt::smCount();
+    _g.resize(_file->genomes().size());
+    try {
+        for (size_t g = 0; g < _g.size(); ++g) stageGenome((int)g);
+        rt::sync(_stream);
+    } catch (...) {
+        for (void *p : _owned) rt::dfree(p);
+        rt::destroyStream(_stream);
+        throw;
+    }
+}
+
+Context::~Context() {
+    for (auto &kv : _plans) rt::dfree(kv.second.dSteps);
+    for (void *p : _owned) rt::dfree(p);
+    rt::destroyStream(_stream);
+}
+
+void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb) {
+    // bucket width ~ mean segment length, so a lookup lands within a segment or two of the answer
+    shift = 0;
+    while (shift < 40 && (len >> (shift + 1)) >= N) ++shift;
+    nb = (len >> shift) + 1;
+    table = static_cast<uint32_t *>(alloc((size_t)nb * sizeof(uint32_t)));
+    BucketParams bp;
+    bp.arr = arr; bp.bucket = table; bp.N = N; bp.numBuckets = nb; bp.isTop = isTop ? 1 : 0; bp.shift = shift;
+    rt::launch(bucketKernel, gridFor(nb, 256, _sms), 256, 0, _stream, bp);
+}
+
+void Context::stageGenome(int gi) {
+    const GenomeInfo &g = _file->genomes()[gi];
+    GenomeDev &d = _g[gi];
+    if (g.numTop >= (int64_t)0xffffffffll || g.numBottom >= (int64_t)0xffffffffll) {
+        throw HalError("genome " + g.name + " has more than 2^32 segments; not supported by the bucket index");
+    }
+    const int nc = (int)g.children.size();
+    // top records
+    {
+        const size_t rawBytes = (size_t)(g.numTop + 1) * 40;
+        DevBuf raw(rawBytes);
+        rt::h2d(raw.p, g.top, rawBytes, _stream);
+        d.top = static_cast<TopRec *>(alloc((size_t)(g.numTop + 1) * sizeof(TopRec)));
+        PackTopParams pp;
+        pp.raw = raw.as<uint8_t>(); pp.out = d.top; pp.n = g.numTop + 1;
+        rt::launch(packTopKernel, gridFor(pp.n, 256, _sms), 256, 0, _stream, pp);
+        rt::sync(_stream);
+    }
+    // bottom records
+    {
+        const size_t rawBytes = (size_t)(g.numBottom + 1) * g.bottomStride;
+        DevBuf raw(rawBytes);
+        rt::h2d(raw.p, g.bottom, rawBytes, _stream);
+        d.bot = static_cast<BotCore *>(alloc((size_t)(g.numBottom + 1) * sizeof(BotCore)));
+        d.child = static_cast<int64_t *>(alloc(std::max<size_t>(8, (size_t)nc * (size_t)g.numBottom * sizeof(int64_t))));
+        PackBotParams pp;
+        pp.raw = raw.as<uint8_t>(); pp.core = d.bot; pp.child = d.child;
+        pp.n = g.numBottom + 1; pp.numBot = g.numBottom; pp.nc = nc; pp.stride = (int32_t)g.bottomStride;
+        rt::launch(packBotKernel, gridFor(pp.n, 256, _sms), 256, 0, _stream, pp);
+        rt::sync(_stream);
+    }
+    // DNA (packed nibbles, used by the column / MAF path)
+    {
+        const size_t bytes = (size_t)((g.length + 1) / 2);
+        d.dna = static_cast<uint8_t *>(alloc(std::max<size_t>(bytes, 1)));
+        rt::h2d(d.dna, g.dna, bytes, _stream);
+    }
+    // sequence start table (+ sentinel)
+    {
+        std::vector<int64_t> ss;
+        for (const SequenceInfo &s : g.sequences) ss.push_back(s.start);
+        ss.push_back(g.length);
+        d.seqStart = static_cast<int64_t *>(alloc(ss.size() * sizeof(int64_t)));
+        rt::h2d(d.seqStart, ss.data(), ss.size() * sizeof(int64_t), _stream);
+        rt::sync(_stream); // ss goes out of scope
+    }
+    if (g.numTop > 0) buildBucket(d.top, true, g.numTop, g.length, d.topBucket, d.topShift, d.topBuckets);
+    if (g.numBottom > 0) buildBucket(d.bot, false, g.numBottom, g.length, d.botBucket, d.botShift, d.botBuckets);
+}
+
+const Plan &Context::plan(int src, int tgt) {
+    auto key = std::make_pair(src, tgt);
+    auto it = _plans.find(key);
+    if (it != _plans.end()) return it->second;
+    const auto &G = _file->genomes();
+    Plan p;
+    p.src = src; p.tgt = tgt; p.mrca = _file->mrca(src, tgt);
+    if (p.mrca < 0) throw HalError("source and target genomes share no ancestor");
+    for (int g = src; g != p.mrca; g = G[g].parent) p.path.push_back(g);
+    p.path.push_back(p.mrca);
+    p.upSteps = (int)p.path.size() - 1;
+    std::vector<int> down;
+    for (int g = tgt; g != p.mrca; g = G[g].parent) down.push_back(g);
+    std::reverse(down.begin(), down.end());
+    p.path.insert(p.path.end(), down.begin(), down.end());
+    std::vector<PathStep> steps(p.path.size());
+    for (size_t i = 0; i < p.path.size(); ++i) {
+        const int g = p.path[i];
+        PathStep &s = steps[i];
+        s.top = _g[g].top; s.bot = _g[g].bot; s.child = nullptr;
+        s.numTop = G[g].numTop; s.numBot = G[g].numBottom;
+        s.up = (int)i < p.upSteps ? 1 : 0;
+        s.pad = 0;
+        if (!s.up && i + 1 < p.path.size()) {
+            const int c = p.path[i + 1];
+            s.child = _g[g].child + (size_t)G[c].slotInParent * (size_t)G[g].numBottom;
+        }
+    }
+    p.dSteps = static_cast<PathStep *>(rt::dmalloc(steps.size() * sizeof(PathStep)));
+    rt::h2d(p.dSteps, steps.data(), steps.size() * sizeof(PathStep), _stream);
+    rt::sync(_stream);
+    return _plans.emplace(key, p).first->second;
+}
+
+void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
+                       const uint8_t *dStrand, LiftOutput &out) {
+    const auto &G = _file->genomes();
+    if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
+    if (n >= 0xffffffffull) throw HalError("batch too large (>= 2^32 intervals); split it");
+    const Plan &pl = plan(src, tgt);
+    const GenomeInfo &S = G[src];
+    const bool srcIsTop = S.numTop > 0; // liftover/impl/halBlockLiftover.cpp:24-30
+    if (!srcIsTop && S.numBottom == 0) throw HalError("source genome " + S.name + " has no segments");
+    out = LiftOutput();
+    out.n = n;
+    const int launches0 = (int)rt::g_launches;
+
+    DevBuf outCount((n + 1) * sizeof(uint32_t)), outOffset((n + 1) * sizeof(uint64_t)), status((n + 1) * sizeof(uint32_t));
+    rt::dmemset(outCount.p, 0, (n + 1) * sizeof(uint32_t), _stream);
+    rt::dmemset(status.p, 0xff, (n + 1) * sizeof(uint32_t), _stream);
+    DevBuf cursor(2 * sizeof(unsigned long long));
+    rt::dmemset(cursor.p, 0, 2 * sizeof(unsigned long long), _stream);
+
+    // visit the batch in source order so that neighbouring warps walk neighbouring records (L2 reuse)
+    std::unique_ptr<DevBuf> work, keysIn, keysOut, valsIn;
+    const uint32_t *dWork = nullptr;
+    if (!(flags & HALGPU_NO_SORT) && n > 1) {
+        keysIn.reset(new DevBuf(n * 8)); keysOut.reset(new DevBuf(n * 8));
+        valsIn.reset(new DevBuf(n * 4)); work.reset(new DevBuf(n * 4));
+        IotaParams ip;
+        ip.out = valsIn->as<uint32_t>(); ip.keys = keysIn->as<uint64_t>(); ip.gs = dGs; ip.n = (int64_t)n;
+        rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
+        int endBit = 1;
+        while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
+        rt::sortPairsU64U32(keysIn->as<uint64_t>(), keysOut->as<uint64_t>(), valsIn->as<uint32_t>(), work->as<uint32_t>(), n, endBit, _stream);
+        dWork = work->as<uint32_t>();
+        keysIn.reset(); keysOut.reset(); valsIn.reset();
+    }
+
+    uint64_t poolCap = (uint64_t)n + (uint64_t)n / 4 + 4096;
+    std::unique_ptr<DevBuf> pool(new DevBuf(poolCap * sizeof(halgpu_lift_rec)));
+
+    LiftParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.steps = pl.dSteps; P.P = (int32_t)pl.path.size(); P.dupes = (flags & HALGPU_NO_DUPES) ? 0 : 1;
+    P.srcIsTop = srcIsTop ? 1 : 0;
+    P.srcShift = srcIsTop ? _g[src].topShift : _g[src].botShift;
+    P.srcN = srcIsTop ? S.numTop : S.numBottom;
+    P.srcBucket = srcIsTop ? _g[src].topBucket : _g[src].botBucket;
+    P.srcNumBuckets = srcIsTop ? _g[src].topBuckets : _g[src].botBuckets;
+    P.tgtSeqStart = _g[tgt].seqStart; P.tgtNumSeq = (int32_t)G[tgt].sequences.size();
+    P.gs = dGs; P.ge = dGe; P.strand = dStrand;
+    P.outCount = outCount.as<uint32_t>(); P.outOffset = outOffset.as<uint64_t>(); P.status = status.as<uint32_t>();
+    P.pool = pool->as<halgpu_lift_rec>(); P.poolCursor = cursor.as<unsigned long long>(); P.poolCap = poolCap;
+
+    // rung 1: all n intervals, scratch in shared memory
+    const unsigned block = 128, warpsPerBlock = block / 32;
+    {
+        P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
+        P.n = (int64_t)n; P.work = dWork;
+        const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
+        rt::allowSmem(liftoverKernel, smem);
+        rt::Event e0, e1;
+        e0.record(_stream);
+        rt::launch(liftoverKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
+        e1.record(_stream);
+        rt::sync(_stream);
+        out.kernelMs = rt::Event::elapsedMs(e0, e1);
+    }
+
+    // retry ladder: pool growth, then larger per-warp scratch in global memory
+    DevBuf list((n + 1) * sizeof(uint32_t));
+    unsigned long long *dCount = cursor.as<unsigned long long>() + 1;
+    auto collect = [&](uint32_t want, const uint32_t *subset, int64_t cnt) -> uint64_t {
+        rt::dmemset(dCount, 0, sizeof(unsigned long long), _stream);
+        CollectParams cp;
+        cp.status = P.status; cp.list = list.as<uint32_t>(); cp.count = dCount; cp.subset = subset; cp.n = cnt; cp.want = want;
+        rt::launch(collectKernel, gridFor(cnt, 256, _sms), 256, 0, _stream, cp);
+        unsigned long long c = 0;
+        rt::d2h(&c, dCount, sizeof(c), _stream);
+        rt::sync(_stream);
+        return c;
+    };
+    int listCap = 64, frameCap = 32;
+    std::unique_ptr<DevBuf> pending; // ids still to do (copy of list)
+    for (int round = 0; round < 64; ++round) {
+        // (a) intervals that found the output pool full: grow it (old records stay valid) and redo them
+        uint64_t nFull = collect(ST_POOL_FULL, nullptr, (int64_t)n);
+        if (nFull > 0) {
+            unsigned long long used = 0;
+            rt::d2h(&used, P.poolCursor, sizeof(used), _stream);
+            rt::sync(_stream);
+            const uint64_t newCap = std::max<uint64_t>(poolCap * 2, used * 2);
+            std::unique_ptr<DevBuf> np(new DevBuf(newCap * sizeof(halgpu_lift_rec)));
+            rt::d2d(np->p, pool->p, poolCap * sizeof(halgpu_lift_rec), _stream);
+            rt::sync(_stream);
+            pool.swap(np);
+            poolCap = newCap;
+            P.pool = pool->as<halgpu_lift_rec>(); P.poolCap = poolCap;
+            DevBuf ids(nFull * sizeof(uint32_t));
+            rt::d2d(ids.p, list.p, nFull * sizeof(uint32_t), _stream);
+            P.n = (int64_t)nFull; P.work = ids.as<uint32_t>();
+            const bool inSmem = listCap == 64;
+            const uint64_t per = liftScratchBytes(listCap, frameCap);
+            const int64_t warps = std::min<int64_t>((int64_t)nFull, (int64_t)_sms * 8);
+            std::unique_ptr<DevBuf> scratch;
+            P.listCap = listCap; P.frameCap = frameCap;
+            if (inSmem) { P.gscratch = nullptr; P.gscratchPerWarp = 0; }
+            else { scratch.reset(new DevBuf(per * (uint64_t)warps)); P.gscratch = scratch->as<uint8_t>(); P.gscratchPerWarp = per; }
+            const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
+            rt::launch(liftoverKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
+            rt::sync(_stream);
+            continue;
+        }
+        // (b) intervals whose fragment lists outgrew the scratch: next rung
+        uint64_t nOver = collect(ST_SCRATCH_OVERFLOW, nullptr, (int64_t)n);
+        if (nOver == 0) break;
+        if (round == 0 || out.nRetry == 0) out.nRetry = nOver;
+        listCap *= (listCap == 64 ? 64 : 16); // 64 -> 4096 -> 65536 -> 1M
+        frameCap = listCap / 4;
+        if (listCap > (1 << 24)) throw HalError("an interval maps to more than 16M fragments; not supported");
+        const uint64_t per = liftScratchBytes(listCap, frameCap);
+        int64_t warps = std::min<int64_t>((int64_t)nOver, (int64_t)_sms * 8);
+        const uint64_t budget = 8ull << 30; // scratch budget
+        if ((uint64_t)warps * per > budget) warps = std::max<int64_t>(1, (int64_t)(budget / per));
+        DevBuf scratch(per * (uint64_t)warps);
+        DevBuf ids(nOver * sizeof(uint32_t));
+        rt::d2d(ids.p, list.p, nOver * sizeof(uint32_t), _stream);
+        P.n = (int64_t)nOver; P.work = ids.as<uint32_t>();
+        P.listCap = listCap; P.frameCap = frameCap; P.gscratch = scratch.as<uint8_t>(); P.gscratchPerWarp = per;
+        rt::launch(liftoverKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
+        rt::sync(_stream);
+    }
+
+    // CSR assembly in input order
+    DevBuf *csr = new DevBuf((n + 2) * sizeof(uint64_t));
+    std::unique_ptr<DevBuf> csrHold(csr);
+    rt::exclusiveScanU32(P.outCount, csr->as<uint64_t>(), n, _stream);
+    uint64_t total = 0;
+    rt::d2h(&total, csr->as<uint64_t>() + n, sizeof(total), _stream);
+    rt::sync(_stream);
+    DevBuf *recs = new DevBuf(std::max<uint64_t>(total, 1) * sizeof(halgpu_lift_rec));
+    std::unique_ptr<DevBuf> recsHold(recs);
+    GatherParams gp;
+    gp.outCount = P.outCount; gp.outOffset = P.outOffset; gp.csr = csr->as<uint64_t>();
+    gp.pool = pool->as<halgpu_lift_rec>(); gp.recs = recs->as<halgpu_lift_rec>(); gp.n = (int64_t)n;
+    rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
+    rt::sync(_stream);
+    out.offsets = static_cast<uint64_t *>(csrHold->release());
+    out.recs = static_cast<halgpu_lift_rec *>(recsHold->release());
+    out.nRec = total;
+    out.launches = (int)rt::g_launches - launches0;
+}
+
+} // namespace halgpu

@@ -1,0 +1,67 @@
+// Host-side engine behind the C ABI: owns the mapped HAL file, the staged device index, the per-(src,tgt)
+// path plans and the batch pipeline (sort -> map kernel -> retry ladder -> scan -> gather).
+#pragma once
+#include "device_index.cuh"
+#include "halmmap.hpp"
+#include "rt.hpp"
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace halgpu {
+
+struct GenomeDev {
+    TopRec *top = nullptr;     // numTop + 1
+    BotCore *bot = nullptr;    // numBottom + 1
+    int64_t *child = nullptr;  // nc columns x numBottom
+    uint8_t *dna = nullptr;    // (length + 1) / 2
+    int64_t *seqStart = nullptr; // numSeq + 1
+    uint32_t *topBucket = nullptr, *botBucket = nullptr;
+    int topShift = 0, botShift = 0;
+    int64_t topBuckets = 0, botBuckets = 0;
+};
+
+struct Plan {
+    int src = -1, tgt = -1, mrca = -1;
+    std::vector<int> path; // src .. mrca .. tgt
+    int upSteps = 0;
+    PathStep *dSteps = nullptr;
+};
+
+struct LiftOutput { // device-side result of one batch
+    uint64_t *offsets = nullptr; // n + 1
+    halgpu_lift_rec *recs = nullptr;
+    size_t n = 0, nRec = 0, nRetry = 0;
+    float kernelMs = 0;
+    int launches = 0;
+};
+
+class Context {
+  public:
+    Context(const std::string &path, int device);
+    ~Context();
+    const HalFile &file() const { return *_file; }
+    rt::Stream stream() const { return _stream; }
+    size_t stagedBytes() const { return _staged; }
+    int device() const { return _device; }
+    // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
+    void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
+                  const uint8_t *dStrand, LiftOutput &out);
+
+  private:
+    void stageGenome(int g);
+    void buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb);
+    const Plan &plan(int src, int tgt);
+    void *alloc(size_t bytes);
+
+    std::unique_ptr<HalFile> _file;
+    int _device;
+    rt::Stream _stream;
+    std::vector<GenomeDev> _g;
+    std::map<std::pair<int, int>, Plan> _plans;
+    std::vector<void *> _owned;
+    size_t _staged = 0;
+    int _sms = 0;
+};
+
+} // namespace halgpu

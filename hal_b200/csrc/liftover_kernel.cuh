@@ -1,0 +1,606 @@
+// liftover_kernel.cuh -- the per-interval liftover walk, one warp per source interval.
+//
+// Replaces, for one BED interval, the reference call chain
+//   BlockLiftover::liftInterval            liftover/impl/halBlockLiftover.cpp:46-113
+//     SegmentIterator::toSite / toRight    api/impl/halSegmentIterator.cpp:240-299, 208-238      (seeds)
+//     halMapSegment -> mapSource           api/impl/halSegmentMapper.cpp:578-670
+//       mapUp / mapDown / mapSelf          api/impl/halSegmentMapper.cpp:25-80, 128-186, 263-288
+//       insertAndBreakOverlaps             api/impl/halSegmentMapper.cpp:475-520                  (refinement)
+//     BlockMapper::extractSegment          liftover/impl/halBlockMapper.cpp:331-394               (merge)
+//   + stable sort by source start          liftover/impl/halLiftover.cpp:90
+//
+// Phase 1 (map): every lane owns one mapped fragment and advances it one genome per iteration along the
+//   src -> mrca -> tgt path.  Lanes that run dry take the next source segment of the interval (a "seed");
+//   when a fragment fans out (it straddles a parse boundary, or lands on a paralogy ring) the extra piece
+//   is pushed as a 48-byte frame to a per-warp work pool that any idle lane pops -- pushes, pops and
+//   emits are compacted with __ballot_sync/popc, so list order is deterministic.  With collinear data
+//   all 32 lanes stay in lock step on adjacent records: every hop is one coalesced 1 KB read.
+// Phase 2 (reduce): the warp sorts the interval's fragments by target, cuts overlapping target extents
+//   to their common refinement, merges collinear neighbours into output lines and writes 32-byte
+//   records to the output pool (one atomicAdd per interval).
+//
+// The same source compiles for the host under HALGPU_SIMT_EMUL (tests/simt: 32 threads emulate a warp)
+// so that the control flow can be checked against the CPU oracle without a GPU.  That build is a test
+// harness only; the product library contains the sm_100a build alone.
+#pragma once
+#include "device_index.cuh"
+
+namespace halgpu {
+
+#define HG_FULL 0xffffffffu
+
+struct Frag { // 32 B
+    int64_t sLo, tLo, len;
+    int64_t meta; // bit0 sRev, bit1 tRev, bit2 kindTop, bits 3.. : segment index (phase 1) / sequence id (phase 2)
+};
+
+struct Frame { // 48 B
+    int64_t sLo, tLo, len, meta;
+    int64_t aux;  // PARSE: index of the next segment of the other array; RING: first ring member
+    int32_t p;    // path position
+    int32_t type; // 0 PARSE, 1 RING
+};
+
+__device__ __forceinline__ int64_t ldS(const int64_t *p) {
+    return (int64_t)__ldg(reinterpret_cast<const long long *>(p));
+}
+__device__ __forceinline__ TopRec ldTop(const TopRec *p) {
+    const longlong2 *q = reinterpret_cast<const longlong2 *>(p);
+    longlong2 a = __ldg(q), b = __ldg(q + 1);
+    TopRec r;
+    r.start = a.x; r.parentEnc = a.y; r.botParse = b.x; r.nextPara = b.y;
+    return r;
+}
+__device__ __forceinline__ BotCore ldBot(const BotCore *p) {
+    longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(p));
+    BotCore r;
+    r.start = a.x; r.topParse = a.y;
+    return r;
+}
+__device__ __forceinline__ int64_t topStart(const TopRec *t, int64_t i) { return ldS(&t[i].start); }
+__device__ __forceinline__ int64_t botStart(const BotCore *b, int64_t i) { return ldS(&b[i].start); }
+
+// largest i in [i0, N) with start(i) <= pos, given start(i0) <= pos: gallop then bisect
+template <bool TOP>
+__device__ __forceinline__ int64_t searchFrom(const void *arr, int64_t i0, int64_t N, int64_t pos) {
+    auto st = [&](int64_t i) -> int64_t {
+        return TOP ? topStart(static_cast<const TopRec *>(arr), i) : botStart(static_cast<const BotCore *>(arr), i);
+    };
+    int64_t lo = i0, step = 1, hi;
+    while (true) {
+        hi = lo + step;
+        if (hi >= N) { hi = N; break; }
+        if (st(hi) <= pos) { lo = hi; step <<= 1; } else break;
+    }
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (st(mid) <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// the part of a fragment whose target extent is [a,b]  (sub-range rule: replaces the parse-back-and-
+// difference trick of halSegmentMapper.cpp:52-62,157-167 and MappedSegment::slice)
+__device__ __forceinline__ void subRange(int64_t &sLo, int64_t &tLo, int64_t &len, bool sRev, bool tRev, int64_t a,
+                                         int64_t b) {
+    const int64_t u = tRev ? (tLo + len - 1 - b) : (a - tLo);
+    const int64_t m = b - a + 1;
+    sLo = sRev ? (sLo + len - u - m) : (sLo + u);
+    tLo = a;
+    len = m;
+}
+
+__device__ __forceinline__ int lanePrefix(unsigned mask, int lane) { return __popc(mask & ((1u << lane) - 1u)); }
+
+// index of the sequence containing genome position pos (replaces Genome::getSequenceBySite,
+// api/mmap_impl/mmapGenomeSiteMap.cpp:99-113)
+__device__ __forceinline__ int seqOf(const int64_t *seqStart, int nseq, int64_t pos) {
+    int lo = 0, hi = nseq;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (ldS(&seqStart[mid]) <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// key order of MappedSegmentLess (api/impl/halMappedSegment.cpp:36-43): target (lo, hi) then source (lo, hi);
+// hi is implied by len.  Flags break the (impossible in a valid HAL) exact-coordinate tie deterministically.
+__device__ __forceinline__ bool fragLess(const Frag &a, const Frag &b) {
+    if (a.tLo != b.tLo) return a.tLo < b.tLo;
+    if (a.len != b.len) return a.len < b.len;
+    if (a.sLo != b.sLo) return a.sLo < b.sLo;
+    return (a.meta & 3) < (b.meta & 3);
+}
+__device__ __forceinline__ bool fragSameCoords(const Frag &a, const Frag &b) {
+    return a.tLo == b.tLo && a.len == b.len && a.sLo == b.sLo;
+}
+
+// MappedSegment::canMergeRightWith (api/impl/halMappedSegment.cpp:109-161) + the same-sequence test of
+// BlockMapper::extractSegment (liftover/impl/halBlockMapper.cpp:364-371); cut sets handled by the caller
+__device__ __forceinline__ bool canMergeRight(const Frag &p, const Frag &q) {
+    if (((p.meta ^ q.meta) & 3) != 0) return false;      // same target strand, same source strand
+    if ((p.meta >> 3) != (q.meta >> 3)) return false;    // same target sequence
+    if (q.tLo - (p.tLo + p.len - 1) != 1) return false;
+    const bool sRev = p.meta & 1, tRev = (p.meta >> 1) & 1;
+    if (sRev == tRev) return q.sLo - (p.sLo + p.len - 1) == 1;
+    return p.sLo - (q.sLo + q.len - 1) == 1;
+}
+
+// stable rank sort of src[0..m) into dst by fragLess (ties keep list order)
+__device__ __forceinline__ void warpRankSort(const Frag *src, Frag *dst, int m, int lane) {
+    for (int i = lane; i < m; i += 32) {
+        const Frag me = src[i];
+        int r = 0;
+        for (int j = 0; j < m; ++j) {
+            const Frag o = src[j];
+            r += (fragLess(o, me) || (!fragLess(me, o) && j < i)) ? 1 : 0;
+        }
+        dst[r] = me;
+    }
+    __syncwarp();
+}
+
+struct WarpScratch {
+    Frag *listA, *listB;
+    Frame *frames;
+};
+
+__device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
+    const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
+    const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
+    const bool flip = bedStrand == '-';
+    const PathStep *steps = P.steps;
+    const int np = P.P;
+    const int listCap = P.listCap, frameCap = P.frameCap;
+    Frag *listA = ws.listA, *listB = ws.listB;
+    Frame *frames = ws.frames;
+
+    // ---- seeds: first / last source segment overlapping [gs, ge] (toSite + toRight) ----
+    const void *srcArr = P.srcIsTop ? (const void *)steps[0].top : (const void *)steps[0].bot;
+    int64_t mySeg = 0;
+    if (lane < 2) {
+        const int64_t pos = lane == 0 ? gs : ge;
+        const int64_t i0 = (int64_t)__ldg(&P.srcBucket[pos >> P.srcShift]);
+        mySeg = P.srcIsTop ? searchFrom<true>(srcArr, i0, P.srcN, pos) : searchFrom<false>(srcArr, i0, P.srcN, pos);
+    }
+    int64_t nextSeg = __shfl_sync(HG_FULL, mySeg, 0);
+    const int64_t lastSeg = __shfl_sync(HG_FULL, mySeg, 1);
+
+    // ---- phase 1 ----
+    bool valid = false;
+    int64_t sLo = 0, tLo = 0, len = 0, idx = 0, cursor = -1, ringFirst = -1;
+    bool sRev = false, tRev = false, kindTop = false;
+    int p = 0;
+    int listCount = 0, poolCount = 0;
+    bool overflow = false;
+
+    while (true) {
+        // 1. idle lanes take work: pool frames first (LIFO), then fresh seeds
+        const unsigned idle = __ballot_sync(HG_FULL, !valid);
+        if (idle) {
+            const int rank = lanePrefix(idle, lane);
+            const int nIdle = __popc(idle);
+            const int takePool = nIdle < poolCount ? nIdle : poolCount;
+            if (!valid && rank < takePool) {
+                const Frame f = frames[poolCount - 1 - rank];
+                sLo = f.sLo; tLo = f.tLo; len = f.len;
+                sRev = f.meta & 1; tRev = (f.meta >> 1) & 1; kindTop = (f.meta >> 2) & 1; idx = f.meta >> 3;
+                p = f.p;
+                if (f.type == 0) { cursor = f.aux; ringFirst = -1; } else { cursor = -1; ringFirst = f.aux; }
+                valid = true;
+            }
+            poolCount -= takePool;
+            int64_t avail = lastSeg - nextSeg + 1;
+            if (avail < 0) avail = 0;
+            const int want = nIdle - takePool;
+            const int takeSeeds = (int64_t)want < avail ? want : (int)avail;
+            if (!valid && rank >= takePool && rank - takePool < takeSeeds) {
+                const int64_t seg = nextSeg + (rank - takePool);
+                int64_t s0, s1;
+                if (P.srcIsTop) {
+                    s0 = topStart(steps[0].top, seg); s1 = topStart(steps[0].top, seg + 1);
+                } else {
+                    s0 = botStart(steps[0].bot, seg); s1 = botStart(steps[0].bot, seg + 1);
+                }
+                const int64_t a = gs > s0 ? gs : s0, b = ge < s1 - 1 ? ge : s1 - 1;
+                sLo = a; tLo = a; len = b - a + 1;
+                sRev = flip; tRev = flip; kindTop = P.srcIsTop != 0; idx = seg;
+                p = 0; cursor = -1; ringFirst = -1;
+                valid = true;
+            }
+            nextSeg += takeSeeds;
+            __syncwarp();
+        }
+        if (!__any_sync(HG_FULL, valid)) break;
+
+        // 2. paralogy ring: queue the next member (mapSelf, halSegmentMapper.cpp:265-288:
+        //    do { emit(cur); if (hasNext) toNext; } while (cur.hasNext && cur != first))
+        Frame push;
+        bool doPush = false;
+        if (valid && ringFirst >= 0) {
+            const TopRec *top = steps[p].top;
+            const TopRec rm = ldTop(&top[idx]);
+            const int64_t nx = rm.nextPara;
+            if (nx >= 0) {
+                const TopRec rn = ldTop(&top[nx]);
+                if (rn.nextPara >= 0 && nx != ringFirst) {
+                    const int64_t L = topStart(top, idx + 1) - rm.start;
+                    const int64_t off = tLo - rm.start;
+                    const bool fl = ((rn.parentEnc ^ rm.parentEnc) & 1) != 0; // toNextParalogy, halTopSegmentIterator.cpp:99-107
+                    push.sLo = sLo;
+                    push.tLo = fl ? rn.start + L - off - len : rn.start + off;
+                    push.len = len;
+                    push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)((tRev != fl) ? 1 : 0) << 1) | (1ll << 2) | (nx << 3);
+                    push.aux = ringFirst;
+                    push.p = p;
+                    push.type = 1;
+                    doPush = true;
+                }
+            }
+            ringFirst = -1;
+        }
+        {
+            const unsigned pm = __ballot_sync(HG_FULL, doPush);
+            if (pm) {
+                const int slot = poolCount + lanePrefix(pm, lane);
+                if (doPush && slot < frameCap) frames[slot] = push;
+                poolCount += __popc(pm);
+                if (poolCount > frameCap) overflow = true;
+            }
+        }
+
+        // 3. one genome hop; a fragment that straddles a parse boundary leaves its remainder in the pool
+        doPush = false;
+        bool landedDown = false;
+        if (valid && p < np - 1) {
+            const PathStep st = steps[p];
+            const int64_t tHi = tLo + len - 1;
+            if (st.up) {
+                if (!kindTop) { // bottom fragment: cut at the top-segment boundary (toParseUp, halTopSegmentIterator.cpp:55-81)
+                    int64_t t = cursor;
+                    if (t < 0) t = searchFrom<true>(st.top, ldBot(&st.bot[idx]).topParse, st.numTop, tLo);
+                    const int64_t tEnd = topStart(st.top, t + 1) - 1;
+                    if (tEnd < tHi) {
+                        push.sLo = sLo; push.tLo = tLo; push.len = len;
+                        subRange(push.sLo, push.tLo, push.len, sRev, tRev, tEnd + 1, tHi);
+                        push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1) | (idx << 3);
+                        push.aux = t + 1; push.p = p; push.type = 0;
+                        doPush = true;
+                        subRange(sLo, tLo, len, sRev, tRev, tLo, tEnd);
+                    }
+                    kindTop = true; idx = t; cursor = -1;
+                }
+                const TopRec r = ldTop(&st.top[idx]); // toParent, halBottomSegmentIterator.cpp:40-49
+                if (r.parentEnc < 0) {
+                    valid = false;
+                } else {
+                    const int64_t L = topStart(st.top, idx + 1) - r.start;
+                    const int64_t pi = r.parentEnc >> 1;
+                    const bool fl = (r.parentEnc & 1) != 0;
+                    const int64_t ps = botStart(steps[p + 1].bot, pi);
+                    const int64_t off = tLo - r.start;
+                    tLo = fl ? ps + L - off - len : ps + off;
+                    tRev = tRev != fl;
+                    kindTop = false; idx = pi; ++p;
+                }
+            } else {
+                if (kindTop) { // top fragment: cut at the bottom-segment boundary (toParseDown, halBottomSegmentIterator.cpp:51-76)
+                    int64_t b = cursor;
+                    if (b < 0) b = searchFrom<false>(st.bot, ldTop(&st.top[idx]).botParse, st.numBot, tLo);
+                    const int64_t bEnd = botStart(st.bot, b + 1) - 1;
+                    if (bEnd < tHi) {
+                        push.sLo = sLo; push.tLo = tLo; push.len = len;
+                        subRange(push.sLo, push.tLo, push.len, sRev, tRev, bEnd + 1, tHi);
+                        push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1) | (1ll << 2) | (idx << 3);
+                        push.aux = b + 1; push.p = p; push.type = 0;
+                        doPush = true;
+                        subRange(sLo, tLo, len, sRev, tRev, tLo, bEnd);
+                    }
+                    kindTop = false; idx = b; cursor = -1;
+                }
+                const int64_t ce = ldS(&st.child[idx]); // toChild, halTopSegmentIterator.cpp:36-45
+                if (ce < 0) {
+                    valid = false;
+                } else {
+                    const int64_t b0 = botStart(st.bot, idx);
+                    const int64_t L = botStart(st.bot, idx + 1) - b0;
+                    const int64_t ci = ce >> 1;
+                    const bool fl = (ce & 1) != 0;
+                    const int64_t cs = topStart(steps[p + 1].top, ci);
+                    const int64_t off = tLo - b0;
+                    tLo = fl ? cs + L - off - len : cs + off;
+                    tRev = tRev != fl;
+                    kindTop = true; idx = ci; ++p;
+                    landedDown = true;
+                }
+            }
+        }
+        if (landedDown && P.dupes) ringFirst = idx;
+        {
+            const unsigned pm = __ballot_sync(HG_FULL, doPush);
+            if (pm) {
+                const int slot = poolCount + lanePrefix(pm, lane);
+                if (doPush && slot < frameCap) frames[slot] = push;
+                poolCount += __popc(pm);
+                if (poolCount > frameCap) overflow = true;
+            }
+        }
+
+        // 4. fragments that reached the target genome join the interval's result list
+        {
+            const bool doEmit = valid && p == np - 1 && ringFirst < 0;
+            const unsigned em = __ballot_sync(HG_FULL, doEmit);
+            if (em) {
+                const int slot = listCount + lanePrefix(em, lane);
+                if (doEmit) {
+                    if (slot < listCap) {
+                        Frag f;
+                        f.sLo = sLo; f.tLo = tLo; f.len = len;
+                        f.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1);
+                        listA[slot] = f;
+                    }
+                    valid = false;
+                }
+                listCount += __popc(em);
+                if (listCount > listCap) overflow = true;
+            }
+        }
+        __syncwarp();
+        if (overflow) break;
+    }
+
+    if (overflow) {
+        if (lane == 0) { P.status[item] = ST_SCRATCH_OVERFLOW; P.outCount[item] = 0; }
+        return;
+    }
+
+    // ---- phase 2 ----
+    int m = listCount;
+    if (m == 0) {
+        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = 0; P.outOffset[item] = 0; }
+        return;
+    }
+    // target sequence of every fragment (MappedSegment::getSequence)
+    if (P.tgtNumSeq > 1) {
+        for (int i = lane; i < m; i += 32) {
+            listA[i].meta |= (int64_t)seqOf(P.tgtSeqStart, P.tgtNumSeq, listA[i].tLo) << 3;
+        }
+    }
+    __syncwarp();
+    // order of the MappedSegmentSet
+    bool unsorted = false;
+    for (int i = lane; i + 1 < m; i += 32) unsorted |= fragLess(listA[i + 1], listA[i]);
+    Frag *cur = listA, *oth = listB;
+    if (__any_sync(HG_FULL, unsorted)) {
+        warpRankSort(cur, oth, m, lane);
+        Frag *t = cur; cur = oth; oth = t;
+    }
+    // identical-or-disjoint invariant of the set (insertAndBreakOverlaps): violated -> common refinement
+    bool clash = false;
+    for (int i = lane; i + 1 < m; i += 32) {
+        const Frag a = cur[i], b = cur[i + 1];
+        const bool same = a.tLo == b.tLo && a.len == b.len;
+        const bool disjoint = b.tLo > a.tLo + a.len - 1;
+        clash |= !(same || disjoint);
+    }
+    if (__any_sync(HG_FULL, clash)) {
+        // cut every fragment at every other fragment's tLo and tHi+1 that falls strictly inside it
+        int total = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            int pieces = 0;
+            if (i < m) {
+                const Frag f = cur[i];
+                const int64_t hi = f.tLo + f.len - 1;
+                int64_t at = f.tLo;
+                pieces = 1;
+                while (true) { // next breakpoint in (at, hi]
+                    int64_t best = hi + 1;
+                    for (int j = 0; j < m; ++j) {
+                        const int64_t v0 = cur[j].tLo, v1 = v0 + cur[j].len;
+                        if (v0 > at && v0 < best) best = v0;
+                        if (v1 > at && v1 < best) best = v1;
+                    }
+                    if (best > hi) break;
+                    ++pieces;
+                    at = best;
+                }
+            }
+            // exclusive scan of pieces over the 32 lanes
+            int incl = pieces;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(HG_FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int first = total + incl - pieces;
+            total += __shfl_sync(HG_FULL, incl, 31);
+            if (i < m && first + pieces <= listCap) {
+                const Frag f = cur[i];
+                const bool sR = f.meta & 1, tR = (f.meta >> 1) & 1;
+                const int64_t hi = f.tLo + f.len - 1;
+                int64_t at = f.tLo;
+                int k = 0;
+                while (true) {
+                    int64_t best = hi + 1;
+                    for (int j = 0; j < m; ++j) {
+                        const int64_t v0 = cur[j].tLo, v1 = v0 + cur[j].len;
+                        if (v0 > at && v0 < best) best = v0;
+                        if (v1 > at && v1 < best) best = v1;
+                    }
+                    Frag g = f;
+                    subRange(g.sLo, g.tLo, g.len, sR, tR, at, best - 1);
+                    oth[first + k] = g;
+                    ++k;
+                    if (best > hi) break;
+                    at = best;
+                }
+            }
+        }
+        __syncwarp();
+        if (total > listCap) {
+            if (lane == 0) { P.status[item] = ST_SCRATCH_OVERFLOW; P.outCount[item] = 0; }
+            return;
+        }
+        m = total;
+        // sort the pieces, then drop exact duplicates (set semantics: equal keys are one element)
+        warpRankSort(oth, cur, m, lane);
+        int kept = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            const bool keep = i < m && (i == 0 || !fragSameCoords(cur[i - 1], cur[i]));
+            const unsigned km = __ballot_sync(HG_FULL, keep);
+            if (keep) oth[kept + lanePrefix(km, lane)] = cur[i];
+            kept += __popc(km);
+        }
+        __syncwarp();
+        m = kept;
+        Frag *t = cur; cur = oth; oth = t;
+    }
+
+    // ---- merge into output lines (BlockMapper::extractSegment) ----
+    // scratch in the free list: run heads/tails, then (general path only) cut points, flags, classes
+    int32_t *runHead = reinterpret_cast<int32_t *>(oth);
+    int32_t *runTail = runHead + m;
+    bool classes = false;
+    for (int i = lane; i + 1 < m; i += 32) classes |= cur[i].tLo == cur[i + 1].tLo;
+    int nLines = 0;
+    if (!__any_sync(HG_FULL, classes)) {
+        // every equal-target-start class has one member: a run is a maximal chain of mergeable neighbours
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            const bool head = i < m && (i == 0 || !canMergeRight(cur[i - 1], cur[i]));
+            const bool tail = i < m && (i == m - 1 || !canMergeRight(cur[i], cur[i + 1]));
+            const unsigned hm = __ballot_sync(HG_FULL, head);
+            const unsigned tm = __ballot_sync(HG_FULL, tail);
+            if (head) runHead[nLines + lanePrefix(hm, lane)] = i;
+            // a tail closes the run opened by the latest head at or before it
+            if (tail) {
+                const int headsUpToMe = __popc(hm & ((2u << lane) - 1u));
+                runTail[nLines + headsUpToMe - 1] = i;
+            }
+            nLines += __popc(hm);
+        }
+        __syncwarp();
+    } else {
+        // general case, exact sequential restatement by one lane (rare: paralogous source pieces in one interval)
+        if (lane == 0) {
+            int64_t *qcut = reinterpret_cast<int64_t *>(runTail + m);
+            int32_t *v1 = reinterpret_cast<int32_t *>(qcut + m);
+            int32_t *v2 = v1 + m;
+            uint8_t *dead = reinterpret_cast<uint8_t *>(v2 + m);
+            for (int i = 0; i < m; ++i) dead[i] = 0;
+            int nq = 0;
+            for (int x = 0; x < m; ++x) {
+                if (dead[x]) continue;
+                int n1 = 0, n2 = 0, tailIdx = x;
+                v1[n1++] = x;
+                int nx = x + 1;
+                while (nx < m && dead[nx]) ++nx;
+                while (nx < m && cur[nx].tLo == cur[v1[n1 - 1]].tLo) {
+                    v1[n1++] = nx;
+                    ++nx;
+                    while (nx < m && dead[nx]) ++nx;
+                }
+                while (nx < m) {
+                    n2 = 0;
+                    while (nx < m && (n2 == 0 || cur[v2[n2 - 1]].tLo == cur[nx].tLo) && n2 < n1) {
+                        v2[n2++] = nx;
+                        ++nx;
+                        while (nx < m && dead[nx]) ++nx;
+                    }
+                    bool can = n1 == n2;
+                    for (int i = 0; i < n1 && can; ++i) {
+                        const Frag a = cur[v1[i]], b = cur[v2[i]];
+                        bool ok = (b.meta >> 3) == (cur[x].meta >> 3) && canMergeRight(a, b);
+                        if (ok) {
+                            const int64_t cut = a.tLo + a.len - 1;
+                            for (int q = 0; q < nq; ++q) ok &= qcut[q] != cut;
+                        }
+                        can = ok;
+                    }
+                    if (!can) break;
+                    tailIdx = v2[0];
+                    dead[v2[0]] = 1;
+                    for (int i = 0; i < n2; ++i) v1[i] = v2[i];
+                    n1 = n2;
+                }
+                if (n1 > 1) qcut[nq++] = cur[tailIdx].tLo + cur[tailIdx].len - 1;
+                runHead[nLines] = x;
+                runTail[nLines] = tailIdx;
+                ++nLines;
+            }
+        }
+        nLines = __shfl_sync(HG_FULL, nLines, 0);
+        __syncwarp();
+    }
+
+    // ---- emit: stable by source start (Liftover::visitLine, halLiftover.cpp:90) ----
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)nLines);
+    base = __shfl_sync(HG_FULL, base, 0);
+    if (base + (unsigned long long)nLines > P.poolCap) {
+        if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+        return;
+    }
+    for (int r = lane; r < nLines; r += 32) {
+        const Frag h = cur[runHead[r]], t = cur[runTail[r]];
+        const int64_t src = h.sLo < t.sLo ? h.sLo : t.sLo;
+        int rank = 0;
+        for (int j = 0; j < nLines; ++j) {
+            const Frag hj = cur[runHead[j]], tj = cur[runTail[j]];
+            const int64_t sj = hj.sLo < tj.sLo ? hj.sLo : tj.sLo;
+            rank += (sj < src || (sj == src && j < r)) ? 1 : 0;
+        }
+        const int seq = (int)(h.meta >> 3);
+        const int64_t seqStart = P.tgtNumSeq > 1 ? ldS(&P.tgtSeqStart[seq]) : 0;
+        halgpu_lift_rec o;
+        o.start = (h.tLo < t.tLo ? h.tLo : t.tLo) - seqStart;
+        const int64_t hHi = h.tLo + h.len, tHi = t.tLo + t.len;
+        o.end = (hHi > tHi ? hHi : tHi) - seqStart;
+        o.src_start = src;
+        o.tgt_seq = seq;
+        if (bedStrand == '.') {
+            o.strand = '.'; o.src_strand = '.';
+        } else {
+            o.strand = ((h.meta >> 1) & 1) ? '-' : '+';
+            o.src_strand = (h.meta & 1) ? '-' : '+';
+        }
+        const int nf = runTail[r] - runHead[r] + 1;
+        o.n_frag = (uint16_t)(nf > 65535 ? 65535 : nf);
+        P.pool[base + rank] = o;
+    }
+    if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)nLines; P.outOffset[item] = base; }
+}
+
+// bytes of scratch one warp needs for the given capacities
+__host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) {
+    return (uint64_t)listCap * 2u * sizeof(Frag) + (uint64_t)frameCap * sizeof(Frame);
+}
+
+#if !defined(HALGPU_SIMT_EMUL)
+extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
+#endif
+
+__global__ void __launch_bounds__(128) liftoverKernel(const LiftParams P) {
+#if defined(HALGPU_SIMT_EMUL)
+    uint8_t *hg_dyn_smem = simt::dynamicSmem();
+#endif
+    const int lane = threadIdx.x & 31;
+    const int warpInBlock = threadIdx.x >> 5;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const uint64_t per = liftScratchBytes(P.listCap, P.frameCap);
+    const int64_t gwarp = (int64_t)blockIdx.x * warpsPerBlock + warpInBlock;
+    const int64_t nwarps = (int64_t)gridDim.x * warpsPerBlock;
+    uint8_t *basePtr = P.gscratch ? P.gscratch + (uint64_t)gwarp * P.gscratchPerWarp : hg_dyn_smem + (uint64_t)warpInBlock * per;
+    WarpScratch ws;
+    ws.listA = reinterpret_cast<Frag *>(basePtr);
+    ws.listB = ws.listA + P.listCap;
+    ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
+    for (int64_t w = gwarp; w < P.n; w += nwarps) {
+        const uint32_t item = P.work ? __ldg(&P.work[w]) : (uint32_t)w;
+        liftOneInterval(P, ws, item, lane);
+        __syncwarp();
+    }
+}
+
+} // namespace halgpu

@@ -1,0 +1,140 @@
+// Thin runtime layer under the engine: device memory, copies, kernel launch, events, and the two
+// library primitives used for batch plumbing (radix sort of the interval keys, exclusive scan of the
+// per-interval counts).  The product build maps it onto the CUDA runtime + CUB; the tests/simt harness
+// build (HALGPU_SIMT_EMUL) maps it onto host memory and the thread-based warp emulator so that the
+// engine's control flow (plans, retry ladder, CSR assembly) is covered by the CPU-only test tier.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#if defined(HALGPU_SIMT_EMUL)
+#include "simt_emul.h"
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+#include <vector>
+#else
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#include <cuda_runtime.h>
+#endif
+
+namespace halgpu {
+namespace rt {
+
+struct GpuError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+extern unsigned long long g_launches; // kernels launched by this library in this process
+
+#if defined(HALGPU_SIMT_EMUL)
+
+typedef int Stream;
+inline void setDevice(int) {}
+inline Stream createStream() { return 0; }
+inline void destroyStream(Stream) {}
+inline void *dmalloc(size_t n) { void *p = std::calloc(n ? n : 1, 1); if (!p) throw GpuError("out of memory"); return p; }
+inline void dfree(void *p) { std::free(p); }
+inline void *hostAlloc(size_t n) { return std::malloc(n ? n : 1); }
+inline void hostFree(void *p) { std::free(p); }
+inline void h2d(void *d, const void *h, size_t n, Stream) { if (n) std::memcpy(d, h, n); }
+inline void d2h(void *h, const void *d, size_t n, Stream) { if (n) std::memcpy(h, d, n); }
+inline void d2d(void *dst, const void *src, size_t n, Stream) { if (n) std::memcpy(dst, src, n); }
+inline void dmemset(void *d, int v, size_t n, Stream) { if (n) std::memset(d, v, n); }
+inline void sync(Stream) {}
+inline int smCount() { return 2; }
+struct Event {
+    std::chrono::steady_clock::time_point t;
+    void record(Stream) { t = std::chrono::steady_clock::now(); }
+    static float elapsedMs(const Event &a, const Event &b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
+};
+template <class K, class P> inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, Stream, const P &param) {
+    ++g_launches;
+    if (grid > 4) grid = 4; // kernels are grid-stride; keep the emulated thread count small
+    simt::launch(kernel, dim3(grid), dim3(block), smem, param);
+}
+template <class K> inline void allowSmem(K, size_t) {}
+inline void sortPairsU64U32(const uint64_t *keysIn, uint64_t *keysOut, const uint32_t *valsIn, uint32_t *valsOut, size_t n, int, Stream) {
+    std::vector<uint32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keysIn[a] < keysIn[b]; });
+    for (size_t i = 0; i < n; ++i) { keysOut[i] = keysIn[idx[i]]; valsOut[i] = valsIn[idx[i]]; }
+}
+inline void exclusiveScanU32(const uint32_t *in, uint64_t *out, size_t n, Stream) { // writes n+1 entries
+    uint64_t s = 0;
+    for (size_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+    out[n] = s;
+}
+
+#else // ---------------------------------------------------------------- CUDA
+
+typedef cudaStream_t Stream;
+inline void check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw GpuError(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void setDevice(int d) { check(cudaSetDevice(d), "cudaSetDevice"); }
+inline Stream createStream() { Stream s; check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"); return s; }
+inline void destroyStream(Stream s) { cudaStreamDestroy(s); }
+inline void *dmalloc(size_t n) { void *p = nullptr; check(cudaMalloc(&p, n ? n : 1), "cudaMalloc"); return p; }
+inline void dfree(void *p) { if (p) cudaFree(p); }
+inline void *hostAlloc(size_t n) { void *p = nullptr; check(cudaMallocHost(&p, n ? n : 1), "cudaMallocHost"); return p; }
+inline void hostFree(void *p) { if (p) cudaFreeHost(p); }
+inline void h2d(void *d, const void *h, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy"); }
+inline void d2h(void *h, const void *d, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy"); }
+inline void d2d(void *dst, const void *src, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "D2D copy"); }
+inline void dmemset(void *d, int v, size_t n, Stream s) { if (n) check(cudaMemsetAsync(d, v, n, s), "memset"); }
+inline void sync(Stream s) { check(cudaStreamSynchronize(s), "stream synchronize"); }
+inline int smCount() {
+    int dev = 0, n = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "SM count");
+    return n;
+}
+struct Event {
+    cudaEvent_t e = nullptr;
+    Event() { check(cudaEventCreate(&e), "cudaEventCreate"); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+    Event(const Event &) = delete;
+    Event &operator=(const Event &) = delete;
+    void record(Stream s) { check(cudaEventRecord(e, s), "cudaEventRecord"); }
+    static float elapsedMs(const Event &a, const Event &b) { float ms = 0; check(cudaEventElapsedTime(&ms, a.e, b.e), "cudaEventElapsedTime"); return ms; }
+};
+template <class K, class P> inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, Stream s, const P &param) {
+    ++g_launches;
+    kernel<<<grid, block, smem, s>>>(param);
+    check(cudaGetLastError(), "kernel launch");
+}
+template <class K> inline void allowSmem(K kernel, size_t bytes) {
+    check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute(smem)");
+}
+inline void sortPairsU64U32(const uint64_t *keysIn, uint64_t *keysOut, const uint32_t *valsIn, uint32_t *valsOut, size_t n, int endBit, Stream s) {
+    size_t tmpBytes = 0;
+    check(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, 0, endBit, s), "radix sort (size)");
+    void *tmp = dmalloc(tmpBytes);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, 0, endBit, s);
+    g_launches += 1;
+    cudaStreamSynchronize(s);
+    dfree(tmp);
+    check(e, "radix sort");
+}
+struct U32toU64 {
+    __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+inline void exclusiveScanU32(const uint32_t *in, uint64_t *out, size_t n, Stream s) { // writes n+1 entries
+    auto it = thrust::make_transform_iterator(in, U32toU64());
+    size_t tmpBytes = 0;
+    check(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, it, out, (int64_t)(n + 1), s), "scan (size)");
+    void *tmp = dmalloc(tmpBytes);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, it, out, (int64_t)(n + 1), s);
+    g_launches += 1;
+    cudaStreamSynchronize(s);
+    dfree(tmp);
+    check(e, "scan");
+}
+#endif
+
+} // namespace rt
+} // namespace halgpu

@@ -1,0 +1,113 @@
+/*
+ * halgpu.h -- C ABI of the B200-native HAL liftover / column-extraction hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.
+ * Conventions follow the reference's in-tree C precedent, blockViz/inc/halBlockViz.h: functions
+ * return 0 on success / non-zero on error with a malloc'd message in *err (caller frees it with
+ * halgpu_free_string; err may be NULL), results are freed by the caller with halgpu_free_*.
+ * A context is safe for one host thread at a time (the reference objects are single-thread only,
+ * blockViz/impl/halBlockViz.cpp:29-38); it owns one CUDA stream.
+ *
+ * Each entry point names the reference interface it replaces.
+ */
+#ifndef HALGPU_H
+#define HALGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct halgpu_ctx halgpu_ctx;
+
+/* One chromosome / scaffold of a genome (replaces hal::Sequence getName/getStartPosition/
+ * getSequenceLength, api/inc/halSequence.h; backed by MMapSequenceData, mmapSequenceData.h:21-30). */
+typedef struct halgpu_seq {
+    const char *name;  /* owned by the context */
+    int64_t start;     /* first base in forward genome coordinates */
+    int64_t length;
+    int64_t num_top;   /* top / bottom segments of this sequence */
+    int64_t num_bottom;
+} halgpu_seq;
+
+/* One lifted interval == one output BedLine of BlockLiftover::liftInterval
+ * (liftover/impl/halBlockLiftover.cpp:82-105).  32 bytes, one DRAM sector. */
+typedef struct halgpu_lift_rec {
+    int64_t start;       /* target start, relative to its sequence */
+    int64_t end;         /* exclusive */
+    int64_t src_start;   /* BedLine::_srcStart: source start in forward GENOME coordinates */
+    int32_t tgt_seq;     /* index into halgpu_sequence_table(tgtGenome) */
+    uint8_t strand;      /* '+', '-' or '.' */
+    uint8_t src_strand;  /* '+', '-' or '.' */
+    uint16_t n_frag;     /* mapped fragments merged into this line (saturates at 65535) */
+} halgpu_lift_rec;
+
+/* Result of one liftover batch, CSR by input interval, lines of one interval in the reference's
+ * output order (stable by src_start, liftover/impl/halLiftover.cpp:90). */
+typedef struct halgpu_lift_result {
+    size_t n;                 /* number of input intervals */
+    size_t n_rec;             /* total output lines */
+    uint64_t *offsets;        /* n+1 entries */
+    halgpu_lift_rec *recs;    /* n_rec entries */
+    int on_device;            /* 1: offsets/recs are device pointers (halgpu_liftover_device) */
+    /* measurement: device time of the mapping kernel(s) of this batch and launch count */
+    float kernel_ms;
+    int launches;
+    size_t n_retry;           /* intervals that needed the large-scratch re-launch */
+} halgpu_lift_result;
+
+enum {
+    HALGPU_NO_DUPES = 1u,     /* halLiftover --noDupes (liftover/impl/halLiftoverMain.cpp:24) */
+    HALGPU_NO_SORT = 2u       /* do not reorder the batch by source position inside the call */
+};
+
+/* ---- open / stage (replaces openHalAlignment + MMapAlignment ctor, api/impl/halAlignmentInstance.cpp:133,
+ *      api/mmap_impl/mmapAlignment.cpp:10-19,74-80): mmap the HAL-MMAP file, parse it and stage the
+ *      segment index arrays and packed DNA into the HBM of `device` once. ---- */
+int halgpu_open(const char *mmap_hal_path, int device, halgpu_ctx **out, char **err);
+void halgpu_close(halgpu_ctx *ctx);
+
+/* ---- read-only object model (replaces Alignment::getNumGenomes/getRootName/getParentName/getChildNames/
+ *      getNewickTree, api/inc/halAlignment.h, and Genome::getSequence*/
+int halgpu_num_genomes(const halgpu_ctx *ctx);
+const char *halgpu_genome_name(const halgpu_ctx *ctx, int genome);
+int halgpu_genome_id(const halgpu_ctx *ctx, const char *name); /* -1 if absent (openGenome == NULL) */
+int halgpu_genome_parent(const halgpu_ctx *ctx, int genome);   /* -1 for the root */
+int halgpu_genome_num_children(const halgpu_ctx *ctx, int genome);
+int halgpu_genome_child(const halgpu_ctx *ctx, int genome, int slot);
+int64_t halgpu_genome_length(const halgpu_ctx *ctx, int genome);
+int64_t halgpu_genome_num_top(const halgpu_ctx *ctx, int genome);
+int64_t halgpu_genome_num_bottom(const halgpu_ctx *ctx, int genome);
+const char *halgpu_newick(const halgpu_ctx *ctx);
+int halgpu_sequence_table(const halgpu_ctx *ctx, int genome, const halgpu_seq **out, size_t *n);
+int halgpu_mrca(const halgpu_ctx *ctx, int genome_a, int genome_b); /* getLowestCommonAncestor, halCommon.cpp:123 */
+size_t halgpu_staged_bytes(const halgpu_ctx *ctx);                  /* bytes resident in HBM */
+void *halgpu_stream(const halgpu_ctx *ctx);                         /* the cudaStream_t all work runs on */
+
+/* ---- liftover (replaces halMapSegment + BlockMapper::extractSegment as driven by
+ *      BlockLiftover::liftInterval, liftover/impl/halBlockLiftover.cpp:46-113).
+ *      Inputs are forward GENOME coordinates: src_start = bed.start + seq.start,
+ *      src_end_incl = bed.end - 1 + seq.start (halBlockLiftover.cpp:48-49); strand may be NULL ('+').
+ *      coalescence_limit must be -1 (== MRCA, the CLI default).  Host buffers in, host result out;
+ *      the host<->device copies are part of the call. ---- */
+int halgpu_liftover(halgpu_ctx *ctx, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
+                    size_t n, const int64_t *src_start, const int64_t *src_end_incl, const uint8_t *strand,
+                    halgpu_lift_result **out, char **err);
+
+/* Same, with the three input arrays already resident in device memory of the context's GPU and the
+ * result left in device memory (result->on_device == 1). */
+int halgpu_liftover_device(halgpu_ctx *ctx, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
+                           size_t n, const int64_t *d_src_start, const int64_t *d_src_end_incl,
+                           const uint8_t *d_strand, halgpu_lift_result **out, char **err);
+
+void halgpu_free_result(halgpu_lift_result *res);
+void halgpu_free_string(char *s);
+
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t halgpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
