@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- liftover throughput of the B200 hot path on BASELINE.json's configs[1].
+
+Workload (config.workload = "C2"): halRandGen-shaped 16-genome 4-level tree
+(((L0,L1)A0,(L2,L3)A1)B0,((L4,L5)A2,(L6)A3)B1,(L7)B2)R, 1,562,500 x 32 bp segments = 50 Mbp per genome
+(written by hal_b200/bin/halSynth, branch length 0 == what halRandGen produces), 10 M BED3 intervals on L0_seq,
+length U[50,2000], lifted L0 -> L7 (3 hops up, 2 down).  One "step" = one pass over the whole batch.
+
+  value : input intervals / s, inputs resident in HBM, device-timed (CUDA events on the library's stream)
+  e2e   : the same through halgpu_liftover with pinned HOST buffers (H2D of the batch + D2H of the result inside)
+  roofline : algorithmic bytes (visit counts from the CPU oracle on a sample) / mapping-kernel time
+  cpu_baseline / --impl reference : the reference's own halLiftover (oracle/_ref, built from /root/reference) on
+             all host cores over a bounded sample of the same batch (the reference has no threads: one process per core)
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torch.distributed.run (one rank per GPU).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NEWICK = "(((L0,L1)A0,(L2,L3)A1)B0,((L4,L5)A2,(L6)A3)B1,(L7)B2)R;"
+SRC, TGT = "L0", "L7"
+SEG_LEN = 32
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_intervals(n, genome_len, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    ln = rng.integers(50, 2001, n)
+    gs = rng.integers(0, genome_len - 2 * SEG_LEN - ln)  # stay clear of the unaligned tail segment
+    return gs.astype(np.int64), (gs + ln - 1).astype(np.int64)
+
+
+def hal_path(segs):
+    d = os.environ.get("HALB200_BENCH_DIR", os.path.join(tempfile.gettempdir(), "hal_b200_bench"))
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, f"c2_{segs}x{SEG_LEN}.hal")
+
+
+def ensure_hal(segs):
+    from hal_b200 import build
+    build.build()
+    p = hal_path(segs)
+    if not os.path.exists(p):
+        t = time.time()
+        subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", NEWICK, "--segs", str(segs),
+                               "--segLen", str(SEG_LEN), "--branch", "0", "--seed", "7", p + ".tmp"])
+        os.replace(p + ".tmp", p)
+        log(f"[bench] wrote {p} ({os.path.getsize(p) / 1e9:.2f} GB) in {time.time() - t:.1f}s")
+    return p
+
+
+class ClockSampler:
+    def __init__(self, gpu):
+        self.rows, self.gpu, self.proc = [], gpu, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def algorithmic_bytes_per_interval(hal, gs, ge, n_src_segs, sample=20000):
+    """24 B input + 8*ceil(log2(N+1)) search + sum of visited record bytes (+8 B successor start each)
+    + 40 B per output line; visit counts from the instrumented CPU oracle on a sample of the batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from pyoracle import Oracle
+    o = Oracle(hal)
+    r = o.liftover(o.genome_id(SRC), o.genome_id(TGT), gs[:sample], ge[:sample])
+    s = r["stats"]
+    m = min(sample, len(gs))
+    per = 24 + 8 * math.ceil(math.log2(n_src_segs + 1)) + s["visitBytes"] / m + 40 * s["outLines"] / m
+    o.close()
+    return per, s
+
+
+def reference_throughput(hal, gs, ge, seq_name, sample, cores):
+    """Times oracle/_ref/halLiftover (the reference's own CLI, parse + map + print) as `cores` independent processes
+    over a `cores`-way split of the first `sample` intervals; falls back to the single-threaded oracle port."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "halLiftover")
+    sample = min(sample, len(gs))
+    if os.path.exists(ref):
+        d = tempfile.mkdtemp(prefix="halb200_ref_")
+        per = (sample + cores - 1) // cores
+        files = []
+        for c in range(cores):
+            lo, hi = c * per, min(sample, (c + 1) * per)
+            if lo >= hi:
+                break
+            p = os.path.join(d, f"in{c}.bed")
+            with open(p, "w") as f:
+                f.write("".join(f"{seq_name}\t{gs[i]}\t{ge[i] + 1}\n" for i in range(lo, hi)))
+            files.append(p)
+        subprocess.run(["cat", hal], stdout=subprocess.DEVNULL)  # pre-fault the page cache
+        t = time.time()
+        procs = [subprocess.Popen([ref, hal, SRC, p, TGT, p + ".out"]) for p in files]
+        rc = [p.wait() for p in procs]
+        dt = time.time() - t
+        assert all(r == 0 for r in rc), "reference halLiftover failed"
+        lines = sum(sum(1 for _ in open(p + ".out")) for p in files)
+        return dict(value=sample / dt, kind="reference", cores=len(files), seconds=dt, lines=lines,
+                    sample=f"first {sample} intervals of the batch, {len(files)} processes of oracle/_ref/halLiftover (BED3 in, BED3 out)")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from pyoracle import Oracle
+    o = Oracle(hal)
+    sample = min(sample, 200000)
+    t = time.time()
+    o.liftover(o.genome_id(SRC), o.genome_id(TGT), gs[:sample], ge[:sample])
+    dt = time.time() - t
+    return dict(value=sample / dt, kind="port", cores=1, seconds=dt,
+                sample=f"first {sample} intervals of the batch, oracle/liboracle.so restatement, 1 thread")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--intervals", type=int, default=10_000_000)
+    ap.add_argument("--segs", type=int, default=1_562_500)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="intervals in the CPU sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    genome_len = args.segs * SEG_LEN
+    cores = os.cpu_count() or 1
+    config = {"workload": "C2: halRandGen-shaped 16-genome 4-level tree, %d x %d bp segments (%.0f Mbp/genome), "
+                          "%d BED3 intervals U[50,2000] bp on L0_seq, L0->L7 (3 up, 2 down), dupes on"
+                          % (args.segs, SEG_LEN, genome_len / 1e6, args.intervals),
+              "intervals_per_gpu": args.intervals, "parallelism": f"index replicated, intervals sharded x{world}",
+              "l2": "staged index (~1.7 GB) and the 10M-interval batch are far larger than the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        hal = ensure_hal(args.segs)
+        gs, ge = make_intervals(args.intervals, genome_len, 2)
+        sample = args.cpu_sample or max(2000, int(3000 * cores * 4))  # ~4 s per step on all cores
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
+            if i >= args.warmup:
+                vals.append(r)
+        dt = sum(v["seconds"] for v in vals) / len(vals)
+        v = sample / dt
+        print(json.dumps({"impl": "reference", "metric": "liftover_intervals_per_sec", "value": v, "unit": "intervals/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "intervals/s", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"],
+                                           "sample": vals[-1]["sample"]},
+                          "e2e": {"value": v, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import hal_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if rank == 0:
+        hal = ensure_hal(args.segs)
+    if dist:
+        dist.barrier()
+    hal = hal_path(args.segs)
+
+    t0 = time.time()
+    a = hal_b200.Alignment(hal, device=local)
+    stage_s = time.time() - t0
+    src, tgt = a.genome_id(SRC), a.genome_id(TGT)
+    n = args.intervals
+    gs, ge = make_intervals(n, genome_len, 2 + rank)  # every rank lifts its own shard of the (conceptual) N*n batch
+    d_gs = torch.from_numpy(gs).cuda()
+    d_ge = torch.from_numpy(ge).cuda()
+    h_gs = torch.from_numpy(gs).pin_memory()
+    h_ge = torch.from_numpy(ge).pin_memory()
+    stream = torch.cuda.ExternalStream(a.stream)
+    torch.cuda.synchronize()
+
+    class _Arr:  # expose a raw device pointer to torch
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def step_resident(gather):
+        res = a.liftover_ptrs(src, tgt, n, d_gs.data_ptr(), d_ge.data_ptr(), None, 0, device=True)
+        if gather and dist:
+            # one all-gather of the output interval buffer (records padded to the max count over ranks)
+            cnt = torch.tensor([res.n_rec], device="cuda", dtype=torch.int64)
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+            mx = int(max(int(c) for c in cnts))
+            mine = torch.zeros(mx * 32, dtype=torch.uint8, device="cuda")
+            if res.n_rec:
+                mine[: res.n_rec * 32] = torch.as_tensor(_Arr(res.recs_ptr, res.n_rec * 32), device="cuda")
+            allr = torch.empty(world * mx * 32, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allr, mine)
+        out = (res.n_rec, res.kernel_ms, res.launches, res.n_retry)
+        res.close()
+        return out
+
+    def step_e2e():
+        res = a.liftover_ptrs(src, tgt, n, h_gs.data_ptr(), h_ge.data_ptr(), None, 0, device=False)
+        out = (res.n_rec, res.kernel_ms)
+        res.close()
+        return out
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        nrec, *_ = step_resident(True)
+    barrier()
+    l0 = a.L.halgpu_launch_count()
+    kms = []
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            nrec, k, launches, nretry = step_resident(True)
+            kms.append(k)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        dev_ms = e0.elapsed_time(e1)
+    launches_total = a.L.halgpu_launch_count() - l0
+    # e2e through the host-buffer ABI call
+    for _ in range(max(1, args.warmup - 1)):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - w0) / args.steps
+
+    ms_step = max(dev_ms, 0.0) / args.steps
+    if dist:
+        t = torch.tensor([ms_step, e2e_s, float(np.mean(kms))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_s, kmean = (float(x) for x in t)
+    else:
+        kmean = float(np.mean(kms))
+    if rank != 0:
+        a.close()
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    value = world * n / (ms_step / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    per_interval, ostats = algorithmic_bytes_per_interval(hal, gs, ge, args.segs)
+    achieved = per_interval * n / (kmean / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("liftoverKernel_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": "liftover_intervals_per_sec", "value": value, "unit": "intervals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic", "config": config,
+        "e2e": {"value": world * n / e2e_s, "unit": "intervals/s", "h2d_bytes_per_step": int(n * 16),
+                "d2h_bytes_per_step": int((n + 1) * 8 + nrec * 32)},
+        "gpu_launches": int(launches_total),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "liftoverKernel", "kernel_ms": kmean,
+                     "algorithmic_bytes_per_interval": per_interval,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"},
+        "detail": {"output_lines_per_step": int(nrec), "retry_intervals": int(nretry), "wall_s_per_step": wall / args.steps,
+                   "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step,
+                   "oracle_sample_stats": ostats},
+    }
+    if not args.no_cpu_baseline:
+        sample = args.cpu_sample or max(2000, int(3000 * cores * 5))
+        r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "intervals/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+    a.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""Build the product artefacts in-tree (they travel to the GPU box with the snapshot):
+
+  hal_b200/libhalgpu.so   C-ABI library, CUDA kernels compiled for sm_100a (nvcc cross-compiles without a GPU)
+  hal_b200/bin/halSynth   synthetic HAL-MMAP writer (host C++)
+
+Run: python -m hal_b200.build
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libhalgpu.so")
+BIN = os.path.join(HERE, "bin")
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-Wno-deprecated-declarations", "-shared"]
+LIB_SOURCES = ["capi.cu", "engine.cu", "halmmap.cpp"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _all_sources():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files]
+    out.append(os.path.join(os.path.dirname(HERE), "include", "halgpu.h"))
+    return out
+
+
+def build(force=False, verbose=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    srcs = _all_sources()
+    os.makedirs(BIN, exist_ok=True)
+    if force or _newer(LIB, srcs):
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+              [os.path.join(CSRC, s) for s in LIB_SOURCES]
+        subprocess.check_call(cmd)
+    synth = os.path.join(BIN, "halSynth")
+    if force or _newer(synth, [os.path.join(CSRC, "host", "halsynth.cpp")]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", synth, os.path.join(CSRC, "host", "halsynth.cpp")])
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,58 @@
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_cases():
+    return json.load(open(os.path.join(GOLDEN, "cases", "index.json")))
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    """Builds oracle/liboracle.so (the CPU restatement) on demand."""
+    import pyoracle
+    if not os.path.exists(pyoracle.LIB):
+        pyoracle.build()
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    """hal_b200/libhalgpu.so (built for sm_100a; nvcc cross-compiles without a GPU)."""
+    from hal_b200 import build
+    return build.build()
+
+
+@pytest.fixture(scope="session")
+def emul_lib():
+    """tests/simt/libhalgpu_emul.so: the SAME kernel/engine sources compiled for the host warp emulator."""
+    out = os.path.join(ROOT, "tests", "simt", "libhalgpu_emul.so")
+    csrc = os.path.join(ROOT, "hal_b200", "csrc")
+    srcs = [os.path.join(csrc, f) for f in ("capi.cu", "engine.cu", "halmmap.cpp")]
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if os.path.isfile(os.path.join(csrc, f))] + \
+           [os.path.join(ROOT, "tests", "simt", "simt_emul.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        cmd = ["g++", "-std=c++17", "-O2", "-DHALGPU_SIMT_EMUL", "-I" + os.path.join(ROOT, "tests", "simt"), "-I" + csrc,
+               "-fPIC", "-shared", "-pthread"]
+        for s in srcs:
+            cmd += ["-x", "c++", s]
+        subprocess.check_call(cmd + ["-o", out])
+    return out
+
+
+def ref_bin(name):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
+    return p if os.path.exists(p) else None

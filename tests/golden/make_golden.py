@@ -1,0 +1,101 @@
+"""Regenerates tests/golden/ (run in the build container, where /root/reference and oracle/_ref exist).
+
+  *.hal                     fixture alignments:
+      randgenSmallSeed0.hal   `halRandGen --preset small --seed 0 --testRand --format mmap` (the file behind the
+                              reference's CLI goldens, liftover/Makefile:32-63, maf/Makefile:38-54)
+      refBedLiftoverTest.hal  the hand-built 5-genome alignment of liftover/tests/halLiftoverTests.cpp:15-252,
+                              written by the reference's own test executable (ORACLE_KEEP_FIXTURE)
+      varlen8.hal             oracle/gen/halTreeGen --mode varlen: 8 genomes, 4 sequences each, variable segment
+                              lengths, inversions, duplications, insertions
+  ref_liftover/             verbatim copies of the reference's golden INPUT/EXPECTED data files
+                              (liftover/tests/input/*, liftover/tests/expected/*) for randgenSmallSeed0.hal
+  cases/<name>.in.bed, .out.bed   random or hand-written BED inputs and the output of oracle/_ref/halLiftover
+  cases/index.json          [{name, hal, src, tgt, args}]
+"""
+import json
+import os
+import random
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from pyoracle import Oracle  # noqa: E402
+
+
+def run(*a, env=None):
+    subprocess.check_call(list(a), env=env)
+
+
+def main():
+    os.makedirs(os.path.join(HERE, "cases"), exist_ok=True)
+    small = os.path.join(HERE, "randgenSmallSeed0.hal")
+    run(REF + "/halRandGen", "--preset", "small", "--seed", "0", "--testRand", "--format", "mmap", "--mmapFileSize", "1", small)
+    tmp = "/tmp/golden_fix"
+    shutil.rmtree(tmp, ignore_errors=True)
+    os.makedirs(tmp)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/halLiftoverTests"])
+    run(REF + "/halLiftoverTests", env=dict(os.environ, ORACLE_KEEP_FIXTURE=tmp))
+    shutil.copy(os.path.join(tmp, "15BedLiftoverTest.hal"), os.path.join(HERE, "refBedLiftoverTest.hal"))
+    varlen = os.path.join(HERE, "varlen8.hal")
+    run(REF + "/halTreeGen", "--mode", "varlen", "--newick", "((L0,L1)A0,(L2,(L3)A2)A1)R;", "--segs", "1500", "--minLen", "3",
+        "--maxLen", "40", "--seqs", "4", "--seed", "11", "--pDup", "0.15", "--pInv", "0.25", varlen)
+    for f in (small, os.path.join(HERE, "refBedLiftoverTest.hal"), varlen):
+        run(REF + "/halValidate", f)
+
+    cases = []
+
+    def add(name, hal, src, tgt, bed, args=()):
+        inp = os.path.join(HERE, "cases", name + ".in.bed")
+        out = os.path.join(HERE, "cases", name + ".out.bed")
+        open(inp, "w").write(bed)
+        run(REF + "/halLiftover", *args, os.path.join(HERE, hal), src, inp, tgt, out)
+        cases.append(dict(name=name, hal=hal, src=src, tgt=tgt, args=list(args)))
+
+    # the BED inputs of BedLiftoverTest::testOneBranchLifts / testMultiBranchLifts (BED6 parts)
+    t = "refBedLiftoverTest.hal"
+    add("ref_child1_root", t, "child1", "root", "Sequence\t0\t20\tPARALOGY1REV\t0\t+\nSequence\t60\t80\tREV\t0\t+\n"
+        "Sequence\t20\t40\tINSERTION\t0\t+\nSequence\t80\t100\tPARALOGY2\t0\t+\n")
+    add("ref_leaf1_root", t, "leaf1", "root", "Sequence\t0\t5\tNORMALREV\t0\t+\nSequence\t10\t30\tOVERLAP\t0\t+\n"
+        "Sequence\t50\t70\tOVERLAPINSERTION\t0\t+\nSequence\t70\t100\tOVERLAPINSERTION2\t0\t+\n")
+    add("ref_root_child1", t, "root", "child1", "Sequence\t0\t10\tPARALOGY\t0\t+\nSequence\t30\t50\tOVERLAPINSERTION\t0\t+\n")
+    add("ref_leaf2_leaf3", t, "leaf2", "leaf3", "Sequence\t30\t35\tREV\t0\t+\nSequence\t40\t60\tOVERLAP\t0\t+\n")
+    add("ref_root_leaf2", t, "root", "leaf2", "Sequence\t0\t20\tBLOCK_A\t0\t+\nSequence\t30\t50\tBLOCK_B\t0\t+\n")
+    # every genome pair of the hand-built fixture, every 7-base window, both strands
+    o = Oracle(os.path.join(HERE, t))
+    for s in o.genomes:
+        for d in o.genomes:
+            ln = o.genome_length(o.genome_id(s))
+            bed = "".join(f"Sequence\t{a}\t{min(a + 7, ln)}\tw{a}\t0\t{'+-'[a % 2]}\n" for a in range(0, ln - 1, 3))
+            add(f"ref_all_{s}_{d}", t, s, d, bed)
+            add(f"ref_all_nodupes_{s}_{d}", t, s, d, bed, ("--noDupes",))
+
+    def rand_bed(hal, src, n, maxlen, seed, strands="+-."):
+        o = Oracle(os.path.join(HERE, hal))
+        seqs = o.sequences(o.genome_id(src))
+        rng = random.Random(seed)
+        lines = []
+        for i in range(n):
+            nm, st, ln = rng.choice(seqs)
+            L = rng.randint(1, min(maxlen, ln))
+            a = rng.randint(0, ln - L)
+            lines.append(f"{nm}\t{a}\t{a + L}\tn{i}\t{rng.randint(0, 999)}\t{rng.choice(strands)}")
+        return "\n".join(lines) + "\n"
+
+    v = "varlen8.hal"
+    for i, (s, d, args) in enumerate([("L0", "L3", ()), ("L3", "L1", ()), ("L0", "L3", ("--noDupes",)), ("R", "L3", ()),
+                                      ("R", "A2", ()), ("A0", "R", ()), ("A1", "L3", ()), ("A0", "L2", ()), ("A1", "A1", ()),
+                                      ("L2", "A1", ()), ("L1", "L0", ())]):
+        add(f"varlen_{s}_{d}{'_nodupes' if args else ''}", v, s, d, rand_bed(v, s, 400, 300, 100 + i), args)
+    s = "randgenSmallSeed0.hal"
+    for i, (a, b) in enumerate([("Genome_0", "Genome_2"), ("Genome_3", "Genome_2"), ("Genome_2", "Genome_3"), ("Genome_1", "Genome_0")]):
+        add(f"small_{a}_{b}", s, a, b, rand_bed(s, a, 300, 900, 200 + i))
+    json.dump(cases, open(os.path.join(HERE, "cases", "index.json"), "w"), indent=1)
+    print(len(cases), "cases written")
+
+
+if __name__ == "__main__":
+    main()

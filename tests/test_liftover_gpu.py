@@ -1,0 +1,114 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden fixtures."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from helpers import assert_same_as_oracle, random_intervals, bed_to_batch, batch_to_bed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hal_b200
+    return hal_b200
+
+
+@pytest.mark.parametrize("hal,src,tgt,n,maxlen,flags", [
+    ("varlen8.hal", "L0", "L3", 20000, 400, 0),
+    ("varlen8.hal", "L3", "L1", 20000, 300, 1),
+    ("varlen8.hal", "R", "L3", 5000, 2000, 0),
+    ("varlen8.hal", "R", "A2", 5000, 2000, 0),
+    ("varlen8.hal", "A0", "R", 10000, 500, 0),
+    ("varlen8.hal", "A0", "L2", 10000, 500, 0),
+    ("varlen8.hal", "A1", "L3", 10000, 500, 0),
+    ("varlen8.hal", "A1", "A1", 3000, 500, 0),
+    ("varlen8.hal", "L2", "A1", 10000, 500, 0),
+    ("randgenSmallSeed0.hal", "Genome_0", "Genome_2", 5000, 900, 0),
+    ("randgenSmallSeed0.hal", "Genome_3", "Genome_2", 5000, 900, 0),
+    ("refBedLiftoverTest.hal", "leaf3", "leaf1", 2000, 60, 0),
+    ("refBedLiftoverTest.hal", "root", "leaf2", 2000, 100, 0),
+])
+def test_cuda_equals_oracle(hb, oracle_lib, hal, src, tgt, n, maxlen, flags):
+    path = os.path.join(GOLDEN, hal)
+    o = oracle_lib.Oracle(path)
+    with hb.Alignment(path) as a:
+        s, t = a.genome_id(src), a.genome_id(tgt)
+        gs, ge, st = random_intervals(a.genome_length(s), n, maxlen, seed=n + len(src))
+        off, recs, info = a.liftover(s, t, gs, ge, st, flags)
+        assert_same_as_oracle(off, recs, o.liftover(s, t, gs, ge, st, no_dupes=bool(flags & 1)))
+        assert info["launches"] > 0
+        off2, recs2, _ = a.liftover(s, t, gs, ge, st, flags | hb.HALGPU_NO_SORT)
+        assert np.array_equal(off, off2) and np.array_equal(recs, recs2)
+
+
+def test_cuda_golden_text(hb, golden_cases):
+    opened = {}
+    try:
+        for c in golden_cases:
+            a = opened.get(c["hal"]) or opened.setdefault(c["hal"], hb.Alignment(os.path.join(GOLDEN, c["hal"])))
+            bed = open(os.path.join(GOLDEN, "cases", c["name"] + ".in.bed")).read()
+            exp = open(os.path.join(GOLDEN, "cases", c["name"] + ".out.bed")).read()
+            s, t = a.genome_id(c["src"]), a.genome_id(c["tgt"])
+            rows, gs, ge, st = bed_to_batch(a.sequences(s), bed)
+            off, recs, _ = a.liftover(s, t, gs, ge, st, 1 if "--noDupes" in c["args"] else 0)
+            assert batch_to_bed(rows, a.sequences(t), off, recs) == exp, c["name"]
+    finally:
+        for a in opened.values():
+            a.close()
+
+
+def test_cuda_reference_repo_golden_bed3(hb):
+    with hb.Alignment(os.path.join(GOLDEN, "randgenSmallSeed0.hal")) as a:
+        s, t = a.genome_id("Genome_0"), a.genome_id("Genome_2")
+        bed = open(os.path.join(GOLDEN, "ref_liftover", "test1.bed3")).read()
+        exp = open(os.path.join(GOLDEN, "ref_liftover", "halLiftoverBed3Test.bed")).read()
+        rows, gs, ge, st = bed_to_batch(a.sequences(s), bed)
+        off, recs, _ = a.liftover(s, t, gs, ge, st)
+        assert batch_to_bed(rows, a.sequences(t), off, recs) == exp
+
+
+def test_cuda_edge_cases(hb, oracle_lib):
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    with hb.Alignment(path) as a:
+        s, t = a.genome_id("L0"), a.genome_id("L3")
+        L = a.genome_length(s)
+        # empty batch
+        off, recs, _ = a.liftover(s, t, [], [])
+        assert list(off) == [0] and len(recs) == 0
+        # single base at both ends, whole genome in one interval (deep fan-out -> retry ladder)
+        gs = np.array([0, L - 1, 0, 0], np.int64)
+        ge = np.array([0, L - 1, L - 1, min(L - 1, 4999)], np.int64)
+        st = np.frombuffer(b"+-+.", np.uint8)
+        off, recs, info = a.liftover(s, t, gs, ge, st)
+        assert_same_as_oracle(off, recs, o.liftover(s, t, gs, ge, st))
+        assert info["n_retry"] >= 1
+        # out-of-range is an error, not a crash
+        with pytest.raises(hb.HalGpuError):
+            a.liftover(s, t, [0], [L])
+        with pytest.raises(hb.HalGpuError):
+            a.liftover(99, t, [0], [1])
+
+
+def test_cuda_synthetic_faithful_properties(hb, tmp_path):
+    """halRandGen-faithful shape at a size the oracle cannot cover quickly: every leaf->leaf interval that avoids
+    the unaligned last segment maps to exactly itself (identity alignment), so the result is checkable in closed form."""
+    from hal_b200 import build
+    build.build()
+    hal = str(tmp_path / "synth.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick",
+                           "(((L0,L1)A0,(L2,L3)A1)B0,((L4,L5)A2,(L6)A3)B1,(L7)B2)R;", "--segs", "200000", "--segLen", "32", hal])
+    with hb.Alignment(hal) as a:
+        s, t = a.genome_id("L0"), a.genome_id("L7")
+        n = 1_000_000
+        L = a.genome_length(s) - 64  # the last two segments are unaligned by construction
+        gs, ge, st = random_intervals(L, n, 2000, seed=5, strands=b"+")
+        off, recs, info = a.liftover(s, t, gs, ge, st)
+        assert np.array_equal(off, np.arange(n + 1, dtype=np.uint64))
+        assert np.array_equal(recs["start"], gs) and np.array_equal(recs["end"], ge + 1)
+        assert np.array_equal(recs["src_start"], gs) and (recs["strand"] == ord("+")).all()
+        assert info["n_retry"] == 0
