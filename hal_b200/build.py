@@ -1,6 +1,7 @@
 """Build the product artefacts in-tree (they travel to the GPU box with the snapshot):
 
   hal_b200/libhalgpu.so   C-ABI library, CUDA kernels compiled for sm_100a (nvcc cross-compiles without a GPU)
+  hal_b200/bin/halLiftover  the reference CLI's GPU build (host C++ over the C ABI)
   hal_b200/bin/halSynth   synthetic HAL-MMAP writer (host C++)
 
 Run: python -m hal_b200.build
@@ -46,6 +47,11 @@ def build(force=False, verbose=False):
     synth = os.path.join(BIN, "halSynth")
     if force or _newer(synth, [os.path.join(CSRC, "host", "halsynth.cpp")]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", synth, os.path.join(CSRC, "host", "halsynth.cpp")])
+    host = os.path.join(CSRC, "host")
+    cli = os.path.join(BIN, "halLiftover")
+    cli_srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp")]
+    if force or _newer(cli, cli_srcs + [os.path.join(host, "gpu_liftover.hpp"), os.path.join(host, "bed.hpp"), LIB]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", cli] + cli_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     return LIB
 
 

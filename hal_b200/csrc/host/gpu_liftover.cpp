@@ -1,0 +1,207 @@
+#include "gpu_liftover.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <istream>
+#include <list>
+#include <map>
+#include <ostream>
+#include <stdexcept>
+#include <vector>
+
+namespace halgpu {
+
+namespace {
+
+struct PendingLine {
+    BedLine bed;          // the parsed input line (a full copy: sticky fields already resolved)
+    size_t firstInterval; // first element of the batch arrays that belongs to this line
+    size_t numIntervals;  // 1 for BED<=9, one per non-empty block for BED12
+};
+
+// Liftover::compatible (liftover/impl/halLiftover.cpp:169-195)
+bool compatible(const BedLine &tgtBed, const BedLine &newBlock, char inputStrand) {
+    if (tgtBed.strand != newBlock.strand) return false;
+    if (tgtBed.srcStart == newBlock.srcStart) return false;
+    const BedBlock &tb = tgtBed.blocks.back();
+    int64_t delta;
+    if (tgtBed.strand != inputStrand) delta = tb.start - newBlock.end;
+    else delta = newBlock.start - (tb.start + tb.length);
+    if (delta < 0) return false;
+    return tgtBed.chrName == newBlock.chrName;
+}
+
+} // namespace
+
+void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, std::ostream *out, int bedType,
+                               bool traverseDupes, bool outPSL, bool outPSLWithName, int coalescenceLimit) {
+    if (_ctx == nullptr || in == nullptr || out == nullptr) throw std::runtime_error("GpuBlockLiftover::convert: null argument");
+    if (outPSL || outPSLWithName) {
+        throw std::runtime_error("PSL output is not implemented in the GPU liftover yet (SURVEY.md 8(f) row 2)");
+    }
+    const halgpu_seq *sseq = nullptr, *tseq = nullptr;
+    size_t ns = 0, nt = 0;
+    if (halgpu_sequence_table(_ctx, srcGenome, &sseq, &ns) != 0 || halgpu_sequence_table(_ctx, tgtGenome, &tseq, &nt) != 0) {
+        throw std::runtime_error("genome index out of range");
+    }
+    std::map<std::string, size_t> seqByName;
+    for (size_t i = 0; i < ns; ++i) seqByName[sseq[i].name] = i;
+    const std::string srcName = halgpu_genome_name(_ctx, srcGenome);
+    _missed.clear();
+    linesIn = intervalsLifted = linesOut = 0;
+    gpuSeconds = 0;
+
+    if (in->bad()) throw std::runtime_error("Error reading bed input stream");
+    BedLine cur; // persists across lines like BedScanner::_bedLine
+    std::string lineBuf, outBuf;
+    size_t lineNumber = 0;
+    bool eof = false;
+    auto skipWs = [&]() {
+        while (in->good() && std::isspace((unsigned char)in->peek())) in->get();
+    };
+    skipWs();
+    while (!eof) {
+        std::vector<PendingLine> pending;
+        std::vector<int64_t> gs, ge;
+        std::vector<uint8_t> st;
+        // ---- read one batch (Liftover::visitLine up to the liftInterval call) ----
+        while (pending.size() < batchLines) {
+            if (!in->good()) { eof = true; break; }
+            ++lineNumber;
+            std::getline(*in, lineBuf);
+            try {
+                cur.parse(lineBuf, bedType);
+            } catch (std::exception &e) {
+                throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(lineNumber));
+            }
+            skipWs();
+            ++linesIn;
+            auto it = seqByName.find(cur.chrName);
+            if (it == seqByName.end()) {
+                if (_missed.insert(cur.chrName).second) {
+                    std::cerr << "Unable to find sequence " << cur.chrName << " in genome " << srcName << std::endl;
+                }
+                continue;
+            }
+            const halgpu_seq &sq = sseq[it->second];
+            if (cur.end > sq.length) {
+                std::cerr << "Skipping interval with endpoint " << cur.end << "because sequence " << cur.chrName << " has length "
+                          << sq.length << std::endl;
+                continue;
+            }
+            if (cur.bedType > 9 && cur.blocks.empty()) {
+                std::cerr << "Skipping input line with 0 blocks" << std::endl;
+                continue;
+            }
+            PendingLine p;
+            p.firstInterval = gs.size();
+            if (cur.bedType <= 9) {
+                gs.push_back(cur.start + sq.start);
+                ge.push_back(cur.end - 1 + sq.start);
+                st.push_back((uint8_t)cur.strand);
+            } else { // liftBlockIntervals (halLiftover.cpp:296-310): blocks in ascending start order
+                std::sort(cur.blocks.begin(), cur.blocks.end(), [](const BedBlock &a, const BedBlock &b) { return a.start < b.start; });
+                for (const BedBlock &b : cur.blocks) {
+                    const int64_t s0 = b.start + cur.start, e0 = s0 + b.length;
+                    if (e0 > s0) {
+                        gs.push_back(s0 + sq.start);
+                        ge.push_back(e0 - 1 + sq.start);
+                        st.push_back((uint8_t)cur.strand);
+                    }
+                }
+            }
+            p.numIntervals = gs.size() - p.firstInterval;
+            p.bed = cur;
+            pending.push_back(std::move(p));
+        }
+        if (pending.empty()) continue;
+
+        // ---- one GPU call for the whole batch ----
+        halgpu_lift_result *res = nullptr;
+        char *err = nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit, traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES,
+                                       gs.size(), gs.data(), ge.data(), st.data(), &res, &err);
+        gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != 0) {
+            std::string m = err ? err : "halgpu_liftover failed";
+            halgpu_free_string(err);
+            throw std::runtime_error(m);
+        }
+        intervalsLifted += gs.size();
+
+        // ---- per-line post-processing and output ----
+        outBuf.clear();
+        std::vector<BedLine> mapped;
+        std::list<BedLine> outLines;
+        for (const PendingLine &p : pending) {
+            const BedLine &src = p.bed;
+            mapped.clear();
+            for (size_t k = 0; k < p.numIntervals; ++k) {
+                const size_t iv = p.firstInterval + k;
+                for (uint64_t r = res->offsets[iv]; r < res->offsets[iv + 1]; ++r) {
+                    const halgpu_lift_rec &rec = res->recs[r];
+                    mapped.push_back(src); // outBedLine = _bedLine (halBlockLiftover.cpp:84-86)
+                    BedLine &o = mapped.back();
+                    o.blocks.clear();
+                    o.chrName = tseq[rec.tgt_seq].name;
+                    o.start = rec.start;
+                    o.end = rec.end;
+                    o.strand = (char)rec.strand;
+                    o.srcStart = rec.src_start;
+                    o.srcStrand = (char)rec.src_strand;
+                }
+            }
+            outLines.clear();
+            if (src.bedType <= 9) { // writeBlocksAsIntervals
+                outLines.assign(mapped.begin(), mapped.end());
+            } else if (!mapped.empty()) { // assignBlocksToIntervals (halLiftover.cpp:108-167), BED output
+                std::stable_sort(mapped.begin(), mapped.end(), [](const BedLine &a, const BedLine &b) { return a.srcStart < b.srcStart; });
+                for (const BedLine &blk : mapped) {
+                    if (outLines.empty() || !compatible(outLines.back(), blk, src.strand)) {
+                        outLines.push_back(blk);
+                    }
+                    BedLine &t = outLines.back();
+                    t.start = std::min(t.start, blk.start);
+                    t.end = std::max(t.end, blk.end);
+                    BedBlock b;
+                    b.start = blk.start; // absolute for now
+                    b.length = blk.end - blk.start;
+                    t.blocks.push_back(b);
+                }
+                for (BedLine &t : outLines) {
+                    for (BedBlock &b : t.blocks) b.start -= t.start;
+                    if (t.blocks.size() > 1) { // flipBlocks: ascending in the output
+                        const int64_t delta = t.blocks[1].start - (t.blocks[0].start + t.blocks[0].length);
+                        if (delta < 0) std::reverse(t.blocks.begin(), t.blocks.end());
+                    }
+                }
+            }
+            // cleanResults (halLiftover.cpp:313-355)
+            if (src.bedType > 6) {
+                for (auto it = outLines.begin(); it != outLines.end();) {
+                    if (src.thickStart != 0 || src.thickEnd != 0) {
+                        it->thickStart = it->start;
+                        it->thickEnd = it->end;
+                    }
+                    if (src.bedType > 9 && it->blocks.empty()) it = outLines.erase(it);
+                    else ++it;
+                }
+            }
+            outLines.sort([](const BedLine &a, const BedLine &b) { return a.srcStart < b.srcStart; }); // stable
+            for (const BedLine &l : outLines) {
+                l.append(outBuf);
+                ++linesOut;
+            }
+            if (outBuf.size() > (8u << 20)) {
+                out->write(outBuf.data(), (std::streamsize)outBuf.size());
+                outBuf.clear();
+            }
+        }
+        out->write(outBuf.data(), (std::streamsize)outBuf.size());
+        halgpu_free_result(res);
+    }
+}
+
+} // namespace halgpu

@@ -53,6 +53,19 @@ def emul_lib():
     return out
 
 
+@pytest.fixture(scope="session")
+def emul_cli(emul_lib):
+    """The halLiftover CLI (hal_b200/csrc/host) linked against the emulated library."""
+    out = os.path.join(ROOT, "tests", "simt", "halLiftover_emul")
+    host = os.path.join(ROOT, "hal_b200", "csrc", "host")
+    srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp")]
+    deps = srcs + [os.path.join(host, "gpu_liftover.hpp"), os.path.join(host, "bed.hpp"), emul_lib]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs +
+                              ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    return out
+
+
 def ref_bin(name):
     p = os.path.join(ROOT, "oracle", "_ref", name)
     return p if os.path.exists(p) else None

@@ -93,6 +93,40 @@ def main():
     s = "randgenSmallSeed0.hal"
     for i, (a, b) in enumerate([("Genome_0", "Genome_2"), ("Genome_3", "Genome_2"), ("Genome_2", "Genome_3"), ("Genome_1", "Genome_0")]):
         add(f"small_{a}_{b}", s, a, b, rand_bed(s, a, 300, 900, 200 + i))
+    # BED12: the unit test's case3 (halLiftoverTests.cpp:339-345) and random multi-block lines
+    add("ref_bed12_leaf3_leaf1", t, "leaf3", "leaf1",
+        "Sequence\t0\t10\tSEGMENT_0\t0\t+\t0\t10\t128,0,0\t1\t10\t0,\n"
+        "Sequence\t10\t30\tSEGMENT_1\t0\t+\t10\t30\t128,0,0\t1\t20\t0,\n"
+        "Sequence\t30\t45\tSEGMENT_2\t0\t+\t30\t45\t128,0,0\t1\t15\t0,\n"
+        "Sequence\t45\t65\tSEGMENT_3\t0\t+\t45\t65\t128,0,0\t1\t20\t0,\n"
+        "Sequence\t65\t75\tSEGMENT_4\t0\t+\t65\t75\t128,0,0\t1\t10\t0,\n"
+        "Sequence\t75\t100\tSEGMENT_5\t0\t+\t75\t100\t128,0,0\t1\t25\t0,\n")
+
+    def rand_bed12(hal, src, n, seed):
+        o = Oracle(os.path.join(HERE, hal))
+        seqs = o.sequences(o.genome_id(src))
+        rng = random.Random(seed)
+        lines = []
+        for i in range(n):
+            nm, st, ln = rng.choice(seqs)
+            span = rng.randint(30, min(1500, ln))
+            a = rng.randint(0, ln - span)
+            nb = rng.randint(1, 6)
+            cuts = sorted(rng.sample(range(1, span), min(2 * nb - 1, span - 1)))
+            pts = [0] + cuts + [span]
+            blocks = [(pts[k], pts[k + 1] - pts[k]) for k in range(0, len(pts) - 1, 2)]
+            rng.shuffle(blocks) if rng.random() < 0.2 else None
+            thick = (a, a + span) if rng.random() < 0.5 else (0, 0)
+            lines.append("\t".join([nm, str(a), str(a + span), f"g{i}", str(rng.randint(0, 1000)), rng.choice("+-"), str(thick[0]),
+                                    str(thick[1]), rng.choice(["0", "255,0,0", "1,2,3"]), str(len(blocks)),
+                                    ",".join(str(b[1]) for b in blocks) + ",", ",".join(str(b[0]) for b in blocks) + ","]
+                                   + (["extraA", "extraB"] if rng.random() < 0.3 else [])))
+        return "\n".join(lines) + "\n"
+
+    add("varlen_bed12_L0_L3", v, "L0", "L3", rand_bed12(v, "L0", 300, 301))
+    add("varlen_bed12_R_L1", v, "R", "L1", rand_bed12(v, "R", 200, 302))
+    add("varlen_bed12_L3_A0_nodupes", v, "L3", "A0", rand_bed12(v, "L3", 200, 303), ("--noDupes",))
+    add("small_bed12", s, "Genome_0", "Genome_2", rand_bed12(s, "Genome_0", 200, 304))
     json.dump(cases, open(os.path.join(HERE, "cases", "index.json"), "w"), indent=1)
     print(len(cases), "cases written")
 

@@ -1,0 +1,61 @@
+"""halLiftover CLI (host C++ mirror of hal::Liftover::convert + BedLine) -- byte-for-byte against the
+reference CLI's outputs.  CPU tier: linked against the emulated library; GPU tier: the real binary."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+REF_GOLDENS = [("test1.bed3", "halLiftoverBed3Test.bed", []), ("test1.bed12", "halLiftoverBed12Test.bed", []),
+               ("test1.bed12+2", "halLiftoverBed12ExtraTest.bed", []), ("test1.bed4+2", "halLiftoverBed4ExtraTest.bed", ["--bedType", "4"])]
+
+
+def run_cli(cli, args, hal, src, inp, tgt, out):
+    return subprocess.run([cli] + args + [hal, src, inp, tgt, out], capture_output=True, text=True)
+
+
+def check_all(cli, golden_cases, tmp_path, pick):
+    out = str(tmp_path / "o.bed")
+    # liftover/Makefile:32-63 -- the reference's CLI tests
+    for inp, exp, args in REF_GOLDENS:
+        r = run_cli(cli, args, os.path.join(GOLDEN, "randgenSmallSeed0.hal"), "Genome_0", os.path.join(GOLDEN, "ref_liftover", inp), "Genome_2", out)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == open(os.path.join(GOLDEN, "ref_liftover", exp)).read(), exp
+    for c in golden_cases:
+        if not pick(c):
+            continue
+        r = run_cli(cli, c["args"], os.path.join(GOLDEN, c["hal"]), c["src"], os.path.join(GOLDEN, "cases", c["name"] + ".in.bed"), c["tgt"], out)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == open(os.path.join(GOLDEN, "cases", c["name"] + ".out.bed")).read(), c["name"]
+
+
+def test_cli_emulated_matches_reference_outputs(emul_cli, golden_cases, tmp_path):
+    check_all(emul_cli, golden_cases, tmp_path, lambda c: "bed12" in c["name"] or c["name"].startswith("ref_") and "_all_" not in c["name"])
+
+
+def test_cli_errors(emul_cli, tmp_path):
+    hal = os.path.join(GOLDEN, "randgenSmallSeed0.hal")
+    bed = tmp_path / "i.bed"
+    out = str(tmp_path / "o.bed")
+    bed.write_text("Genome_0_seq\t10\t5\n")
+    r = run_cli(emul_cli, [], hal, "Genome_0", str(bed), "Genome_2", out)
+    assert r.returncode == 1 and "Error zero or negative length BED range" in r.stderr and "in input bed line 1" in r.stderr
+    bed.write_text("Genome_0_seq\t1\t5\nnope\t1\t5\nnope\t2\t9\nGenome_0_seq\t1\t999999999\n")
+    r = run_cli(emul_cli, [], hal, "Genome_0", str(bed), "Genome_2", out)
+    assert r.returncode == 0
+    assert r.stderr.count("Unable to find sequence nope in genome Genome_0") == 1
+    assert "Skipping interval with endpoint 999999999" in r.stderr
+    r = run_cli(emul_cli, [], hal, "Genome_X", str(bed), "Genome_2", out)
+    assert r.returncode == 1 and "srcGenome, Genome_X, not found in alignment" in r.stderr
+    r = run_cli(emul_cli, [], str(tmp_path / "missing.hal"), "Genome_0", str(bed), "Genome_2", out)
+    assert r.returncode == 1 and "can't open HAL file" in r.stderr
+    r = run_cli(emul_cli, ["--bedType", "2"], hal, "Genome_0", str(bed), "Genome_2", out)
+    assert r.returncode == 1 and "--bedType must be between 3 and 12" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_cuda_matches_reference_outputs(golden_cases, tmp_path):
+    from hal_b200 import build
+    build.build()
+    check_all(os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), golden_cases, tmp_path, lambda c: True)
