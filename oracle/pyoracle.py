@@ -49,6 +49,9 @@ def _lib():
     L.oracle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.oracle_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     L.oracle_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.oracle_depth.restype = C.c_int64
+    L.oracle_depth.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -92,6 +95,29 @@ class Oracle:
         r["stats"] = dict(zip(("seeds", "visitsTop", "visitsBot", "visitBytes", "searchProbes", "rawFrags",
                                "refinedFrags", "outLines"), (int(x) for x in s)))
         return r
+
+    def depth(self, ref, first, last, step=1, targets=(), count_dupes=False, no_ancestors=False, no_dupes=False):
+        """halAlignmentDepth values for genome positions first..last (inclusive).  Returns (int32 array, visits)."""
+        n = (last - first) // step + 1
+        out = np.zeros(n, np.int32)
+        t = np.ascontiguousarray(list(targets), dtype=np.int32)
+        vis = C.c_uint64(0)
+        got = self.L.oracle_depth(self.h, ref, first, last, step, t.ctypes.data if len(t) else None, len(t), int(count_dupes),
+                                  int(no_ancestors), int(no_dupes), out.ctypes.data, C.byref(vis))
+        assert got == n
+        return out, vis.value
+
+    def depth_wig(self, ref_name, **kw):
+        """Text of `halAlignmentDepth <hal> <ref>` (whole genome; alignmentDepth/halAlignmentDepth.cpp:215-346)."""
+        g = self.genome_id(ref_name)
+        step = kw.get("step", 1)
+        out = []
+        for (name, start, length) in self.sequences(g):
+            if length == 0:
+                continue
+            d, _ = self.depth(g, start, start + length - 1, **kw)
+            out.append(f"fixedStep chrom={name} start=1 step={step}\n" + "".join(f"{x}\n" for x in d))
+        return "".join(out)
 
     def liftover_bed(self, src_name, tgt_name, bed_text, no_dupes=False):
         """BED3..BED9 text in -> text out, formatted as halLiftover would (no BED12 regrouping / PSL)."""

@@ -1,4 +1,5 @@
 /* TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, bench.py cpu_baseline). */
+#include "columns.h"
 #include "liftover.h"
 #include <cstdio>
 #include <memory>
@@ -72,6 +73,24 @@ void oracle_stats(void *hp, uint64_t *out8) {
     const Stats &s = ((OracleHandle *)hp)->stats;
     out8[0] = s.seeds; out8[1] = s.visitsTop; out8[2] = s.visitsBot; out8[3] = s.visitBytes;
     out8[4] = s.searchProbes; out8[5] = s.rawFrags; out8[6] = s.refinedFrags; out8[7] = s.outLines;
+}
+
+/* halAlignmentDepth per-base values for reference positions first..last (genome coordinates, inclusive) every `step`.
+ * targets: genome ids (nt == 0: all).  Returns the number of values written; visits (optional) receives the landing count. */
+int64_t oracle_depth(void *hp, int ref, int64_t first, int64_t last, int64_t step, const int *targets, int nt, int countDupes,
+                     int noAncestors, int noDupes, int32_t *out, uint64_t *visits) {
+    OracleHandle *h = (OracleHandle *)hp;
+    std::vector<int> t(targets, targets + nt);
+    ColumnOpts o = makeColumnOpts(h->view, ref, t, noDupes != 0, noAncestors != 0, false);
+    std::vector<ColRow> rows;
+    int64_t n = 0;
+    uint64_t vis = 0;
+    for (int64_t p = first; p <= last; p += step) {
+        column(h->view, ref, p, o, rows, &vis);
+        out[n++] = (int32_t)depthOf(h->view, rows, countDupes != 0);
+    }
+    if (visits) *visits = vis;
+    return n;
 }
 
 } // extern "C"
