@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(HERE, "libhalgpu.so")
 
 HALGPU_NO_DUPES = 1
 HALGPU_NO_SORT = 2
+HALGPU_COUNT_DUPES = 1
+HALGPU_NO_ANCESTORS = 2
+HALGPU_COL_NO_DUPES = 4
 
 
 class HalGpuError(RuntimeError):
@@ -41,7 +44,7 @@ ABI_SYMBOLS = [
     "halgpu_genome_parent", "halgpu_genome_num_children", "halgpu_genome_child", "halgpu_genome_length",
     "halgpu_genome_num_top", "halgpu_genome_num_bottom", "halgpu_newick", "halgpu_sequence_table", "halgpu_mrca",
     "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
-    "halgpu_free_string", "halgpu_launch_count",
+    "halgpu_free_string", "halgpu_launch_count", "halgpu_columns_depth", "halgpu_columns_depth_device",
 ]
 
 
@@ -75,6 +78,9 @@ def load_library(path=None):
     for f in ("halgpu_liftover", "halgpu_liftover_device"):
         getattr(L, f).argtypes = [vp, i32, i32, i32, C.c_uint32, C.c_size_t, vp, vp, vp,
                                   C.POINTER(C.POINTER(_Result)), C.POINTER(C.c_char_p)]
+    for f in ("halgpu_columns_depth", "halgpu_columns_depth_device"):
+        getattr(L, f).argtypes = [vp, i32, i64, i64, i64, vp, C.c_size_t, C.c_uint32, vp, C.POINTER(C.c_float),
+                                  C.POINTER(C.c_char_p)]
     L.halgpu_free_result.argtypes = [C.POINTER(_Result)]
     L.halgpu_free_string.argtypes = [C.c_void_p]
     L.halgpu_launch_count.restype = C.c_uint64
@@ -182,6 +188,23 @@ class Alignment:
         info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry)
         self.L.halgpu_free_result(res)
         return offsets, recs, info
+
+    def depth(self, ref, first, last, step=1, targets=(), flags=0, out_ptr=None):
+        """halAlignmentDepth values for genome positions first..last (inclusive).  Returns (int32 array, kernel_ms);
+        with out_ptr (a device pointer) the values stay on the GPU and None is returned in their place."""
+        n = (last - first) // step + 1
+        t = np.ascontiguousarray(list(targets), dtype=np.int32)
+        ms, errp = C.c_float(0), C.c_void_p()
+        out = None if out_ptr is not None else np.zeros(n, np.int32)
+        fn = self.L.halgpu_columns_depth_device if out_ptr is not None else self.L.halgpu_columns_depth
+        rc = fn(self.h, ref, first, last, step, t.ctypes.data if len(t) else None, len(t), flags,
+                out_ptr if out_ptr is not None else out.ctypes.data, C.byref(ms), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else "depth failed"
+            if errp.value:
+                self.L.halgpu_free_string(errp)
+            raise HalGpuError(msg)
+        return out, ms.value
 
     def liftover_ptrs(self, src, tgt, n, start_ptr, end_ptr, strand_ptr=None, flags=0, device=False):
         """Raw-pointer variants (pinned host buffers, or device buffers with device=True)."""

@@ -52,6 +52,10 @@ def build(force=False, verbose=False):
     cli_srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp")]
     if force or _newer(cli, cli_srcs + [os.path.join(host, "gpu_liftover.hpp"), os.path.join(host, "bed.hpp"), LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", cli] + cli_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
+    dep = os.path.join(BIN, "halAlignmentDepth")
+    dep_src = os.path.join(host, "halAlignmentDepthMain.cpp")
+    if force or _newer(dep, [dep_src, LIB]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", dep, dep_src, "-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     return LIB
 
 

@@ -123,7 +123,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                 throw HalError("interval " + std::to_string(i) + " is outside genome " + S->name);
             }
         }
-        void *dS = rt::dmalloc(n * 8), *dE = rt::dmalloc(n * 8), *dT = strand ? rt::dmalloc(n) : nullptr;
+        void *dS = rt::dmallocAsync(n * 8, s), *dE = rt::dmallocAsync(n * 8, s), *dT = strand ? rt::dmallocAsync(n, s) : nullptr;
         halgpu_lift_result *dev = nullptr;
         char *e2 = nullptr;
         rt::h2d(dS, start, n * 8, s);
@@ -131,7 +131,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         if (strand) rt::h2d(dT, strand, n, s);
         int rc = halgpu_liftover_device(ctx, src, tgt, coalescenceLimit, flags, n, (const int64_t *)dS, (const int64_t *)dE,
                                         (const uint8_t *)dT, &dev, &e2);
-        rt::dfree(dS); rt::dfree(dE); rt::dfree(dT);
+        rt::dfreeAsync(dS, s); rt::dfreeAsync(dE, s); rt::dfreeAsync(dT, s);
         if (rc != 0) {
             std::string m = e2 ? e2 : "liftover failed";
             std::free(e2);
@@ -147,6 +147,40 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         rt::sync(s);
         halgpu_free_result(dev);
         *out = r;
+    });
+}
+
+int halgpu_columns_depth_device(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, int64_t step, const int *targets,
+                                size_t nt, uint32_t flags, int32_t *dOut, float *kernelMs, char **err) {
+    if (ctx == nullptr || dOut == nullptr || (nt > 0 && targets == nullptr)) return fail(err, "halgpu_columns_depth: null argument");
+    return guarded(err, [&] {
+        rt::setDevice(ctx->impl->device());
+        std::vector<int> t(targets, targets + nt);
+        ctx->impl->depth(ref, first, last, step, t, flags, dOut, kernelMs);
+    });
+}
+
+int halgpu_columns_depth(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, int64_t step, const int *targets, size_t nt,
+                         uint32_t flags, int32_t *out, float *kernelMs, char **err) {
+    if (ctx == nullptr || out == nullptr) return fail(err, "halgpu_columns_depth: null argument");
+    if (step < 1 || last < first) return fail(err, "halgpu_columns_depth: empty or malformed range");
+    return guarded(err, [&] {
+        rt::setDevice(ctx->impl->device());
+        rt::Stream s = ctx->impl->stream();
+        const size_t n = (size_t)((last - first) / step + 1);
+        int32_t *d = static_cast<int32_t *>(rt::dmallocAsync(n * sizeof(int32_t), s));
+        char *e2 = nullptr;
+        const int rc = halgpu_columns_depth_device(ctx, ref, first, last, step, targets, nt, flags, d, kernelMs, &e2);
+        if (rc == 0) {
+            rt::d2h(out, d, n * sizeof(int32_t), s);
+            rt::sync(s);
+        }
+        rt::dfreeAsync(d, s);
+        if (rc != 0) {
+            std::string m = e2 ? e2 : "depth failed";
+            std::free(e2);
+            throw HalError(m);
+        }
     });
 }
 

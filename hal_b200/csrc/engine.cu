@@ -1,19 +1,71 @@
 #include "engine.hpp"
+#include "columns_kernel.cuh"
 #include "liftover_kernel.cuh"
 #include "stage_kernels.cuh"
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 namespace halgpu {
 namespace rt {
 unsigned long long g_launches = 0;
+#if !defined(HALGPU_SIMT_EMUL)
+namespace {
+struct PinnedCache {
+    std::mutex m;
+    std::multimap<size_t, void *> idle;
+    std::map<void *, size_t> sizeOf;
+    size_t idleBytes = 0;
+};
+PinnedCache &pinned() {
+    static PinnedCache *c = new PinnedCache; // leaked on purpose: outlives the CUDA context teardown order
+    return *c;
+}
+} // namespace
+void *hostAlloc(size_t n) {
+    n = std::max<size_t>(n, 1);
+    PinnedCache &c = pinned();
+    {
+        std::lock_guard<std::mutex> g(c.m);
+        auto it = c.idle.lower_bound(n);
+        if (it != c.idle.end() && it->first <= 2 * n + (1u << 20)) {
+            void *p = it->second;
+            c.idleBytes -= it->first;
+            c.idle.erase(it);
+            return p;
+        }
+    }
+    const size_t cap = n + n / 8;
+    void *p = nullptr;
+    check(cudaMallocHost(&p, cap), "cudaMallocHost");
+    std::lock_guard<std::mutex> g(c.m);
+    c.sizeOf[p] = cap;
+    return p;
+}
+void hostFree(void *p) {
+    if (p == nullptr) return;
+    PinnedCache &c = pinned();
+    std::lock_guard<std::mutex> g(c.m);
+    auto it = c.sizeOf.find(p);
+    if (it == c.sizeOf.end()) { cudaFreeHost(p); return; }
+    if (c.idleBytes + it->second > (8ull << 30)) { // keep at most 8 GB parked
+        c.sizeOf.erase(it);
+        cudaFreeHost(p);
+        return;
+    }
+    c.idle.emplace(it->second, p);
+    c.idleBytes += it->second;
+}
+#endif
 }
 
 namespace {
-struct DevBuf { // RAII for per-batch device scratch
+struct DevBuf { // RAII for per-batch device scratch (stream-ordered)
     void *p = nullptr;
-    explicit DevBuf(size_t n) : p(rt::dmalloc(n)) {}
-    ~DevBuf() { rt::dfree(p); }
+    rt::Stream s;
+    static rt::Stream &current() { static thread_local rt::Stream cur{}; return cur; }
+    explicit DevBuf(size_t n) : p(rt::dmallocAsync(n, current())), s(current()) {}
+    ~DevBuf() { rt::dfreeAsync(p, s); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     template <class T> T *as() const { return static_cast<T *>(p); }
@@ -37,6 +89,7 @@ void *Context::alloc(size_t bytes) {
 
 Context::Context(const std::string &path, int device) : _file(new HalFile(path)), _device(device) {
     rt::setDevice(device);
+    rt::retainPool(device);
     _stream = rt::createStream();
     _sms = rt::smCount();
     _g.resize(_file->genomes().size());
@@ -68,6 +121,7 @@ void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, u
 }
 
 void Context::stageGenome(int gi) {
+    DevBuf::current() = _stream;
     const GenomeInfo &g = _file->genomes()[gi];
     GenomeDev &d = _g[gi];
     if (g.numTop >= (int64_t)0xffffffffll || g.numBottom >= (int64_t)0xffffffffll) {
@@ -113,6 +167,13 @@ void Context::stageGenome(int gi) {
         rt::h2d(d.seqStart, ss.data(), ss.size() * sizeof(int64_t), _stream);
         rt::sync(_stream); // ss goes out of scope
     }
+    {
+        std::vector<int32_t> kids(g.children.begin(), g.children.end());
+        kids.push_back(-1);
+        d.childGenome = static_cast<int32_t *>(alloc(kids.size() * sizeof(int32_t)));
+        rt::h2d(d.childGenome, kids.data(), kids.size() * sizeof(int32_t), _stream);
+        rt::sync(_stream);
+    }
     if (g.numTop > 0) buildBucket(d.top, true, g.numTop, g.length, d.topBucket, d.topShift, d.topBuckets);
     if (g.numBottom > 0) buildBucket(d.bot, false, g.numBottom, g.length, d.botBucket, d.botShift, d.botBuckets);
 }
@@ -151,6 +212,57 @@ const Plan &Context::plan(int src, int tgt) {
     return _plans.emplace(key, p).first->second;
 }
 
+void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
+                    int32_t *dOut, float *kernelMs) {
+    const auto &G = _file->genomes();
+    const int ng = (int)G.size();
+    if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
+    if (ng > 256) throw HalError("alignment depth supports at most 256 genomes");
+    if (step < 1 || first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
+    DevBuf::current() = _stream;
+    // scope = spanning tree of targets + reference (api/impl/halColumnIterator.cpp:47-51); rows reported for targets only
+    std::vector<char> inScope(ng, targets.empty() ? 1 : 0), isTarget(ng, targets.empty() ? 1 : 0);
+    if (!targets.empty()) {
+        std::vector<int> all(targets);
+        all.push_back(ref);
+        int m = all[0];
+        for (int t : all) {
+            if (t < 0 || t >= ng) throw HalError("target genome index out of range");
+            isTarget[t] = 1;
+            m = _file->mrca(m, t);
+        }
+        for (int t : all)
+            for (int g = t;; g = G[g].parent) { inScope[g] = 1; if (g == m) break; }
+    }
+    std::vector<GenomeTab> tab(ng);
+    for (int g = 0; g < ng; ++g) {
+        GenomeTab &t = tab[g];
+        std::memset(&t, 0, sizeof(t));
+        t.top = _g[g].top; t.bot = _g[g].bot; t.child = _g[g].child; t.childGenome = _g[g].childGenome;
+        t.topBucket = _g[g].topBucket; t.botBucket = _g[g].botBucket;
+        t.numTop = G[g].numTop; t.numBot = G[g].numBottom;
+        t.nc = (int32_t)G[g].children.size(); t.parent = G[g].parent; t.slot = G[g].slotInParent;
+        t.topShift = _g[g].topShift; t.botShift = _g[g].botShift;
+        t.inScope = (uint8_t)inScope[g]; t.isTarget = (uint8_t)isTarget[g];
+    }
+    DevBuf dTab(tab.size() * sizeof(GenomeTab)), dErr(sizeof(uint32_t));
+    rt::h2d(dTab.p, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
+    rt::dmemset(dErr.p, 0, sizeof(uint32_t), _stream);
+    DepthParams P;
+    P.genomes = dTab.as<GenomeTab>(); P.numGenomes = ng; P.ref = ref;
+    P.first = first; P.step = step; P.n = (last - first) / step + 1;
+    P.flags = flags; P.depth = dOut; P.error = dErr.as<uint32_t>();
+    rt::Event e0, e1;
+    e0.record(_stream);
+    rt::launch(depthKernel, gridFor(P.n, 128, _sms), 128, 0, _stream, P);
+    e1.record(_stream);
+    uint32_t err = 0;
+    rt::d2h(&err, dErr.p, sizeof(err), _stream);
+    rt::sync(_stream);
+    if (kernelMs) *kernelMs = rt::Event::elapsedMs(e0, e1);
+    if (err) throw HalError("column walk exceeded its stack (more than " + std::to_string(HG_WALK_STACK) + " pending branches)");
+}
+
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
                        const uint8_t *dStrand, LiftOutput &out) {
     const auto &G = _file->genomes();
@@ -162,6 +274,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     if (!srcIsTop && S.numBottom == 0) throw HalError("source genome " + S.name + " has no segments");
     out = LiftOutput();
     out.n = n;
+    DevBuf::current() = _stream;
     const int launches0 = (int)rt::g_launches;
 
     DevBuf outCount((n + 1) * sizeof(uint32_t)), outOffset((n + 1) * sizeof(uint64_t)), status((n + 1) * sizeof(uint32_t));

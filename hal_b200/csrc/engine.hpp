@@ -16,6 +16,7 @@ struct GenomeDev {
     int64_t *child = nullptr;  // nc columns x numBottom
     uint8_t *dna = nullptr;    // (length + 1) / 2
     int64_t *seqStart = nullptr; // numSeq + 1
+    int32_t *childGenome = nullptr; // nc entries
     uint32_t *topBucket = nullptr, *botBucket = nullptr;
     int topShift = 0, botShift = 0;
     int64_t topBuckets = 0, botBuckets = 0;
@@ -47,6 +48,10 @@ class Context {
     // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
                   const uint8_t *dStrand, LiftOutput &out);
+
+    // per-base alignment depth of reference positions first, first+step, ... <= last (device output, n = count)
+    void depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
+               int32_t *dOut, float *kernelMs);
 
   private:
     void stageGenome(int g);

@@ -38,6 +38,8 @@ inline Stream createStream() { return 0; }
 inline void destroyStream(Stream) {}
 inline void *dmalloc(size_t n) { void *p = std::calloc(n ? n : 1, 1); if (!p) throw GpuError("out of memory"); return p; }
 inline void dfree(void *p) { std::free(p); }
+inline void *dmallocAsync(size_t n, Stream) { return dmalloc(n); }
+inline void dfreeAsync(void *p, Stream) { dfree(p); }
 inline void *hostAlloc(size_t n) { return std::malloc(n ? n : 1); }
 inline void hostFree(void *p) { std::free(p); }
 inline void h2d(void *d, const void *h, size_t n, Stream) { if (n) std::memcpy(d, h, n); }
@@ -46,6 +48,7 @@ inline void d2d(void *dst, const void *src, size_t n, Stream) { if (n) std::memc
 inline void dmemset(void *d, int v, size_t n, Stream) { if (n) std::memset(d, v, n); }
 inline void sync(Stream) {}
 inline int smCount() { return 2; }
+inline void retainPool(int) {}
 struct Event {
     std::chrono::steady_clock::time_point t;
     void record(Stream) { t = std::chrono::steady_clock::now(); }
@@ -80,8 +83,12 @@ inline Stream createStream() { Stream s; check(cudaStreamCreateWithFlags(&s, cud
 inline void destroyStream(Stream s) { cudaStreamDestroy(s); }
 inline void *dmalloc(size_t n) { void *p = nullptr; check(cudaMalloc(&p, n ? n : 1), "cudaMalloc"); return p; }
 inline void dfree(void *p) { if (p) cudaFree(p); }
-inline void *hostAlloc(size_t n) { void *p = nullptr; check(cudaMallocHost(&p, n ? n : 1), "cudaMallocHost"); return p; }
-inline void hostFree(void *p) { if (p) cudaFreeHost(p); }
+// per-batch scratch: stream-ordered pool allocations (no device-wide synchronisation, memory is retained by the pool)
+inline void *dmallocAsync(size_t n, Stream s) { void *p = nullptr; check(cudaMallocAsync(&p, n ? n : 1, s), "cudaMallocAsync"); return p; }
+inline void dfreeAsync(void *p, Stream s) { if (p) cudaFreeAsync(p, s); }
+// pinned host buffers for results are recycled: cudaMallocHost of a few hundred MB costs ~100 ms
+void *hostAlloc(size_t n);
+void hostFree(void *p);
 inline void h2d(void *d, const void *h, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy"); }
 inline void d2h(void *h, const void *d, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy"); }
 inline void d2d(void *dst, const void *src, size_t n, Stream s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "D2D copy"); }
@@ -92,6 +99,12 @@ inline int smCount() {
     check(cudaGetDevice(&dev), "cudaGetDevice");
     check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "SM count");
     return n;
+}
+inline void retainPool(int device) { // keep freed stream-ordered memory in the pool across synchronisations
+    cudaMemPool_t pool;
+    check(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
+    uint64_t keep = ~0ull;
+    check(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
 }
 struct Event {
     cudaEvent_t e = nullptr;
@@ -113,11 +126,10 @@ template <class K> inline void allowSmem(K kernel, size_t bytes) {
 inline void sortPairsU64U32(const uint64_t *keysIn, uint64_t *keysOut, const uint32_t *valsIn, uint32_t *valsOut, size_t n, int endBit, Stream s) {
     size_t tmpBytes = 0;
     check(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, 0, endBit, s), "radix sort (size)");
-    void *tmp = dmalloc(tmpBytes);
+    void *tmp = dmallocAsync(tmpBytes, s);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, 0, endBit, s);
     g_launches += 1;
-    cudaStreamSynchronize(s);
-    dfree(tmp);
+    dfreeAsync(tmp, s);
     check(e, "radix sort");
 }
 struct U32toU64 {
@@ -127,11 +139,10 @@ inline void exclusiveScanU32(const uint32_t *in, uint64_t *out, size_t n, Stream
     auto it = thrust::make_transform_iterator(in, U32toU64());
     size_t tmpBytes = 0;
     check(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, it, out, (int64_t)(n + 1), s), "scan (size)");
-    void *tmp = dmalloc(tmpBytes);
+    void *tmp = dmallocAsync(tmpBytes, s);
     cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, it, out, (int64_t)(n + 1), s);
     g_launches += 1;
-    cudaStreamSynchronize(s);
-    dfree(tmp);
+    dfreeAsync(tmp, s);
     check(e, "scan");
 }
 #endif

@@ -101,6 +101,24 @@ int halgpu_liftover_device(halgpu_ctx *ctx, int src_genome, int tgt_genome, int 
                            size_t n, const int64_t *d_src_start, const int64_t *d_src_end_incl,
                            const uint8_t *d_strand, halgpu_lift_result **out, char **err);
 
+/* ---- alignment depth (replaces the ColumnIterator sweep of halAlignmentDepth::printSequence,
+ *      alignmentDepth/halAlignmentDepth.cpp:215-308, for one contiguous reference range).
+ *      Positions first, first+step, ... <= last are forward GENOME coordinates of ref_genome; depth_out receives
+ *      one int32 per position: (#distinct genomes with >= 1 aligned base) - 1, or (#aligned bases) - 1 with
+ *      HALGPU_COUNT_DUPES (:262-280).  targets (n_targets == 0: all genomes) restricts the genomes counted and
+ *      the traversal to their spanning tree (api/impl/halColumnIterator.cpp:47-51, 802-803). ---- */
+enum {
+    HALGPU_COUNT_DUPES = 1u,   /* halAlignmentDepth --countDupes */
+    HALGPU_NO_ANCESTORS = 2u,  /* --noAncestors */
+    HALGPU_COL_NO_DUPES = 4u   /* ColumnIterator noDupes */
+};
+int halgpu_columns_depth(halgpu_ctx *ctx, int ref_genome, int64_t first, int64_t last, int64_t step, const int *targets,
+                         size_t n_targets, uint32_t flags, int32_t *depth_out, float *kernel_ms, char **err);
+/* same with depth_out in device memory */
+int halgpu_columns_depth_device(halgpu_ctx *ctx, int ref_genome, int64_t first, int64_t last, int64_t step,
+                                const int *targets, size_t n_targets, uint32_t flags, int32_t *d_depth_out,
+                                float *kernel_ms, char **err);
+
 void halgpu_free_result(halgpu_lift_result *res);
 void halgpu_free_string(char *s);
 

@@ -66,6 +66,16 @@ def emul_cli(emul_lib):
     return out
 
 
+@pytest.fixture(scope="session")
+def emul_depth_cli(emul_lib):
+    out = os.path.join(ROOT, "tests", "simt", "halAlignmentDepth_emul")
+    src = os.path.join(ROOT, "hal_b200", "csrc", "host", "halAlignmentDepthMain.cpp")
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in (src, emul_lib)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out, src, "-L" + os.path.dirname(emul_lib), "-lhalgpu_emul",
+                               "-Wl,-rpath,$ORIGIN", "-pthread"])
+    return out
+
+
 def ref_bin(name):
     p = os.path.join(ROOT, "oracle", "_ref", name)
     return p if os.path.exists(p) else None

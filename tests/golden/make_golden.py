@@ -127,6 +127,26 @@ def main():
     add("varlen_bed12_R_L1", v, "R", "L1", rand_bed12(v, "R", 200, 302))
     add("varlen_bed12_L3_A0_nodupes", v, "L3", "A0", rand_bed12(v, "L3", 200, 303), ("--noDupes",))
     add("small_bed12", s, "Genome_0", "Genome_2", rand_bed12(s, "Genome_0", 200, 304))
+    # halAlignmentDepth wiggles (no in-tree pin in the reference: alignmentDepth/Makefile:19) -> oracle/_ref outputs
+    dcases = []
+    def addd(name, hal, ref, args):
+        out = os.path.join(HERE, "cases", name + ".wig")
+        with open(out, "w") as f:
+            subprocess.check_call([REF + "/halAlignmentDepth", os.path.join(HERE, hal), ref] + list(args), stdout=f)
+        dcases.append(dict(name=name, hal=hal, ref=ref, args=list(args)))
+    addd("depth_varlen_L0", v, "L0", [])
+    addd("depth_varlen_L3_dupes", v, "L3", ["--countDupes"])
+    addd("depth_varlen_L1_noanc", v, "L1", ["--noAncestors"])
+    addd("depth_varlen_A1", v, "A1", [])
+    addd("depth_varlen_R_dupes", v, "R", ["--countDupes"])
+    addd("depth_varlen_L2_targets", v, "L2", ["--targetGenomes", "L0,A1"])
+    addd("depth_varlen_L0_rootA0", v, "L0", ["--rootGenome", "A0"])
+    addd("depth_varlen_L0_window", v, "L0", ["--start", "9000", "--length", "7000"])
+    addd("depth_varlen_L0_seq", v, "L0", ["--refSequence", "L0_s2", "--start", "100", "--length", "999"])
+    addd("depth_varlen_L0_step", v, "L0", ["--refSequence", "L0_s1", "--start", "10", "--length", "3003", "--step", "7"])
+    addd("depth_small_G2", s, "Genome_2", [])
+    addd("depth_ref_leaf3", t, "leaf3", ["--countDupes"])
+    json.dump(dcases, open(os.path.join(HERE, "cases", "depth_index.json"), "w"), indent=1)
     json.dump(cases, open(os.path.join(HERE, "cases", "index.json"), "w"), indent=1)
     print(len(cases), "cases written")
 

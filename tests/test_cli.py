@@ -59,3 +59,25 @@ def test_cli_cuda_matches_reference_outputs(golden_cases, tmp_path):
     from hal_b200 import build
     build.build()
     check_all(os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), golden_cases, tmp_path, lambda c: True)
+
+
+def check_depth(cli, tmp_path):
+    import json
+    for c in json.load(open(os.path.join(GOLDEN, "cases", "depth_index.json"))):
+        out = str(tmp_path / "d.wig")
+        r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"]), c["ref"], "--outWiggle", out] + c["args"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == open(os.path.join(GOLDEN, "cases", c["name"] + ".wig")).read(), c["name"]
+
+
+def test_depth_cli_emulated_matches_reference_outputs(emul_depth_cli, tmp_path):
+    check_depth(emul_depth_cli, tmp_path)
+    r = subprocess.run([emul_depth_cli, os.path.join(GOLDEN, "varlen8.hal"), "A0", "--noAncestors"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--noAncestors cannot be used when reference genome (A0) is ancetral" in r.stderr
+
+
+@pytest.mark.gpu
+def test_depth_cli_cuda_matches_reference_outputs(tmp_path):
+    from hal_b200 import build
+    build.build()
+    check_depth(os.path.join(ROOT, "hal_b200", "bin", "halAlignmentDepth"), tmp_path)
