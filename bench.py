@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--segs", type=int, default=1_562_500)
     ap.add_argument("--cpu-sample", type=int, default=0, help="intervals in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-depth", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +179,7 @@ def main():
             return
         hal = ensure_hal(args.segs)
         gs, ge = make_intervals(args.intervals, genome_len, 2)
-        sample = args.cpu_sample or max(2000, int(3000 * cores * 4))  # ~4 s per step on all cores
+        sample = args.cpu_sample or min(1_000_000, max(2000, cores * 3000))
         vals = []
         for i in range(args.warmup + args.steps):
             r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
@@ -232,16 +233,11 @@ def main():
     def step_resident(gather):
         res = a.liftover_ptrs(src, tgt, n, d_gs.data_ptr(), d_ge.data_ptr(), None, 0, device=True)
         if gather and dist:
-            # one all-gather of the output interval buffer (records padded to the max count over ranks)
-            cnt = torch.tensor([res.n_rec], device="cuda", dtype=torch.int64)
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            mx = int(max(int(c) for c in cnts))
-            mine = torch.zeros(mx * 32, dtype=torch.uint8, device="cuda")
-            if res.n_rec:
-                mine[: res.n_rec * 32] = torch.as_tensor(_Arr(res.recs_ptr, res.n_rec * 32), device="cuda")
-            allr = torch.empty(world * mx * 32, dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(allr, mine)
+            # one all-gather of the output interval buffer over NCCL (hal_b200/parallel.py)
+            from hal_b200 import parallel
+            offs = torch.as_tensor(_Arr(res.offsets_ptr, (n + 1) * 8), device="cuda").view(torch.int64)
+            recs = torch.as_tensor(_Arr(res.recs_ptr, max(res.n_rec, 1) * 32), device="cuda")[: res.n_rec * 32]
+            parallel.all_gather_records(offs[1:] - offs[:-1], recs)
         out = (res.n_rec, res.kernel_ms, res.launches, res.n_retry)
         res.close()
         return out
@@ -328,8 +324,32 @@ def main():
                    "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step,
                    "oracle_sample_stats": ostats},
     }
+    # secondary (BASELINE.json configs[4] shape on one GPU): halAlignmentDepth column sweep, ref = leaf L0, all targets
+    if world == 1 and not args.no_depth:
+        d_out = torch.empty(genome_len, dtype=torch.int32, device="cuda")
+        dk = []
+        for i in range(2 + 3):
+            _, ms = a.depth(src, 0, genome_len - 1, 1, (), 0, out_ptr=d_out.data_ptr())
+            if i >= 2:
+                dk.append(ms)
+        torch.cuda.synchronize()
+        dms = float(np.mean(dk))
+        line["secondary"] = {"metric": "alignment_depth_columns_per_sec", "value": genome_len / (dms / 1e3), "unit": "columns/s",
+                             "kernel_ms": dms, "columns": genome_len, "rows_per_column": 16,
+                             "check": {"depth15_fraction": float((d_out == 15).float().mean())}}
+        if not args.no_cpu_baseline:
+            ref = os.path.join(ROOT, "oracle", "_ref", "halAlignmentDepth")
+            if os.path.exists(ref):
+                win = 100000
+                t0 = time.time()
+                procs = [subprocess.Popen([ref, hal, SRC, "--start", str(c * win), "--length", str(win)], stdout=subprocess.DEVNULL)
+                         for c in range(cores)]
+                assert all(p.wait() == 0 for p in procs)
+                dt = time.time() - t0
+                line["secondary"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
+                                                     "sample": f"{cores} processes of oracle/_ref/halAlignmentDepth, {win} columns each"}
     if not args.no_cpu_baseline:
-        sample = args.cpu_sample or max(2000, int(3000 * cores * 5))
+        sample = args.cpu_sample or min(2_000_000, max(2000, cores * 6000))
         r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
         line["cpu_baseline"] = {"value": r["value"], "unit": "intervals/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     print(json.dumps(line), flush=True)
