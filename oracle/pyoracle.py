@@ -49,6 +49,9 @@ def _lib():
     L.oracle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.oracle_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     L.oracle_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.oracle_hal2maf.restype = C.c_void_p
+    L.oracle_hal2maf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int64, C.c_void_p]
     L.oracle_depth.restype = C.c_int64
     L.oracle_depth.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p]
@@ -118,6 +121,22 @@ class Oracle:
             d, _ = self.depth(g, start, start + length - 1, **kw)
             out.append(f"fixedStep chrom={name} start=1 step={step}\n" + "".join(f"{x}\n" for x in d))
         return "".join(out)
+
+    def hal2maf(self, ref_name, ref_seq=None, start=0, length=0, targets=(), no_dupes=False, no_ancestors=False,
+                only_orthologs=False, only_sequence_names=False, keep_empty_ref_blocks=False, max_block_len=0):
+        """MAF text of `hal2maf --refGenome ref [--refSequence s --start a --length n] ...` (bytes)."""
+        g = self.genome_id(ref_name)
+        si = -1
+        if ref_seq is not None:
+            si = [n for (n, _, _) in self.sequences(g)].index(ref_seq)
+        t = np.ascontiguousarray([self.genome_id(x) for x in targets], dtype=np.int32)
+        n = C.c_uint64(0)
+        p = self.L.oracle_hal2maf(self.h, g, si, start, length, t.ctypes.data if len(t) else None, len(t), int(no_dupes),
+                                  int(no_ancestors), int(only_orthologs), int(only_sequence_names), int(keep_empty_ref_blocks),
+                                  max_block_len, C.byref(n))
+        if not p:
+            raise RuntimeError("oracle_hal2maf failed")
+        return C.string_at(p, n.value)
 
     def liftover_bed(self, src_name, tgt_name, bed_text, no_dupes=False):
         """BED3..BED9 text in -> text out, formatted as halLiftover would (no BED12 regrouping / PSL)."""

@@ -1,6 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, bench.py cpu_baseline). */
 #include "columns.h"
 #include "liftover.h"
+#include "maf.h"
 #include <cstdio>
 #include <memory>
 
@@ -12,6 +13,7 @@ struct OracleHandle {
     std::vector<OutLine> lines;
     Stats stats;
     std::string err;
+    std::string maf;
 };
 
 extern "C" {
@@ -91,6 +93,29 @@ int64_t oracle_depth(void *hp, int ref, int64_t first, int64_t last, int64_t ste
     }
     if (visits) *visits = vis;
     return n;
+}
+
+/* hal2maf text for one reference genome (default flags + noDupes/noAncestors/onlyOrthologs/targets).  Returns a pointer to
+ * the text kept inside the handle until the next call; *len receives its length.  NULL on error. */
+const char *oracle_hal2maf(void *hp, int ref, int refSeq, int64_t start, int64_t length, const int *targets, int nt, int noDupes,
+                           int noAncestors, int onlyOrthologs, int onlySequenceNames, int keepEmptyRefBlocks, int64_t maxBlockLen,
+                           uint64_t *len) {
+    OracleHandle *h = (OracleHandle *)hp;
+    try {
+        MafOpts o;
+        std::vector<int> t(targets, targets + nt);
+        o.col = makeColumnOpts(h->view, ref, t, noDupes != 0, noAncestors != 0, onlyOrthologs != 0);
+        o.fullNames = !onlySequenceNames;
+        o.keepEmptyRefBlocks = keepEmptyRefBlocks != 0;
+        if (maxBlockLen > 0) o.maxBlockLen = maxBlockLen;
+        h->maf.clear();
+        hal2maf(h->view, ref, refSeq, start, length, o, h->maf);
+    } catch (std::exception &e) {
+        fprintf(stderr, "oracle_hal2maf: %s\n", e.what());
+        return nullptr;
+    }
+    *len = h->maf.size();
+    return h->maf.c_str();
 }
 
 } // extern "C"
