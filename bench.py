@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="intervals in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-depth", action="store_true")
+    ap.add_argument("--no-maf", action="store_true")
+    ap.add_argument("--maf-columns", type=int, default=50_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -348,6 +350,33 @@ def main():
                 dt = time.time() - t0
                 line["secondary"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
                                                      "sample": f"{cores} processes of oracle/_ref/halAlignmentDepth, {win} columns each"}
+    # secondary (BASELINE.json configs[2]): hal2maf block extraction, ref = root, through the product CLI (GPU column
+    # runs + host block state machine + text), whole genome, output to a file on the box
+    if world == 1 and not args.no_maf:
+        cli = os.path.join(ROOT, "hal_b200", "bin", "hal2maf")
+        mcols = min(genome_len, args.maf_columns)
+        outp = os.path.join(os.path.dirname(hal), "bench_out.maf")
+        if os.path.exists(outp):
+            os.remove(outp)
+        t0 = time.time()
+        subprocess.check_call([cli, hal, outp, "--refGenome", "R", "--refSequence", "R_seq", "--start", "0", "--length", str(mcols)])
+        dt = time.time() - t0
+        msize = os.path.getsize(outp)
+        line["secondary_maf"] = {"metric": "hal2maf_columns_per_sec", "value": mcols / dt, "unit": "columns/s", "seconds": dt,
+                                 "columns": mcols, "maf_bytes": msize, "includes": "open+stage (%.2f s), GPU column runs, host blocker, text, file write" % stage_s}
+        if not args.no_cpu_baseline:
+            ref = os.path.join(ROOT, "oracle", "_ref", "hal2maf")
+            if os.path.exists(ref):
+                win = 40000
+                d = tempfile.mkdtemp(prefix="halb200_maf_")
+                t0 = time.time()
+                procs = [subprocess.Popen([ref, hal, os.path.join(d, f"o{c}.maf"), "--refGenome", "R", "--refSequence", "R_seq", "--start",
+                                           str(c * win), "--length", str(win)]) for c in range(cores)]
+                assert all(p.wait() == 0 for p in procs)
+                dt = time.time() - t0
+                line["secondary_maf"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
+                                                         "sample": f"{cores} processes of oracle/_ref/hal2maf, {win}-column windows (hal2mafMP style)"}
+        os.remove(outp)
     if not args.no_cpu_baseline:
         sample = args.cpu_sample or min(2_000_000, max(2000, cores * 6000))
         r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)

@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "halgpu_genome_num_top", "halgpu_genome_num_bottom", "halgpu_newick", "halgpu_sequence_table", "halgpu_mrca",
     "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
     "halgpu_free_string", "halgpu_launch_count", "halgpu_columns_depth", "halgpu_columns_depth_device",
+    "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna",
 ]
 
 

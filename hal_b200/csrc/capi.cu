@@ -184,6 +184,38 @@ int halgpu_columns_depth(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, 
     });
 }
 
+int halgpu_column_runs(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, const int *targets, size_t nt, uint32_t flags,
+                       halgpu_col_runs **out, char **err) {
+    if (ctx == nullptr || out == nullptr || (nt > 0 && targets == nullptr)) return fail(err, "halgpu_column_runs: null argument");
+    *out = nullptr;
+    static_assert(sizeof(halgpu_col_row) == sizeof(ColRowRec), "row record layout");
+    return guarded(err, [&] {
+        rt::setDevice(ctx->impl->device());
+        std::vector<int> t(targets, targets + nt);
+        halgpu_col_runs *r = static_cast<halgpu_col_runs *>(std::calloc(1, sizeof(halgpu_col_runs)));
+        try {
+            ctx->impl->columnRuns(ref, first, last, t, flags, *r);
+        } catch (...) {
+            halgpu_free_col_runs(r);
+            throw;
+        }
+        *out = r;
+    });
+}
+
+void halgpu_free_col_runs(halgpu_col_runs *r) {
+    if (r == nullptr) return;
+    rt::hostFree(r->run_col);
+    rt::hostFree(r->row_offset);
+    rt::hostFree(r->rows);
+    std::free(r);
+}
+
+const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int g) {
+    const GenomeInfo *i = genome(ctx, g);
+    return i ? i->dna : nullptr;
+}
+
 void halgpu_free_result(halgpu_lift_result *r) {
     if (r == nullptr) return;
     if (r->on_device) {

@@ -17,17 +17,6 @@
 
 namespace halgpu {
 
-struct GenomeTab { // one per genome, device resident
-    const TopRec *top;
-    const BotCore *bot;
-    const int64_t *child;       // nc columns of numBot entries
-    const int32_t *childGenome; // nc entries
-    const uint32_t *topBucket, *botBucket;
-    int64_t numTop, numBot;
-    int32_t nc, parent, slot, topShift, botShift;
-    uint8_t inScope, isTarget, pad[2];
-};
-
 enum : uint32_t { COL_COUNT_DUPES = 1u, COL_NO_ANCESTORS = 2u, COL_NO_DUPES = 4u, COL_ONLY_ORTHOLOGS = 8u };
 
 struct DepthParams {
@@ -179,6 +168,128 @@ __global__ void __launch_bounds__(128) depthKernel(const DepthParams P) {
             }
         }
         P.depth[i] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column runs: the ColumnIterator sweep (toRight per base) compressed to maximal runs of consecutive reference
+// columns whose rows are the same sequences/strands advancing collinearly -- what MafBlock::canAppendColumn
+// (maf/impl/halMafBlock.cpp:401-450) needs to know.  Rows of a column are kept in ColumnMap order: by
+// (genome name, sequence index), discovery order within a sequence (api/inc/halColumnIterator.h:45-54).
+// ---------------------------------------------------------------------------------------------------------
+#define HG_MAX_ROWS 128
+
+struct ColSigParams {
+    const GenomeTab *genomes;
+    int32_t ref;
+    uint32_t flags;
+    int64_t first, n;
+    uint64_t *sigA, *sigB; // n entries each: 128-bit signature of the column's normalised rows
+    uint32_t *nrows;       // n entries
+    uint32_t *error;
+};
+
+struct ColEmitParams {
+    const GenomeTab *genomes;
+    int32_t ref;
+    uint32_t flags;
+    int64_t first, n;         // n = number of runs
+    const int64_t *runCol;    // per run: column index (relative to first)
+    const uint64_t *runRowOff; // per run: first row
+    ColRowRec *rows;
+    uint32_t *error;
+};
+
+__device__ __forceinline__ uint64_t hgMix(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+// walk column p and leave its rows sorted in ColumnMap order; returns the row count or -1 on overflow
+__device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkItem *stack, ColRowRec *rows,
+                                            uint64_t *keys) {
+    int n = 0;
+    bool over = false;
+    const bool ok = walkColumn(G, ref, p, flags, stack, [&](int g, int64_t pos, bool rev) {
+        if (n >= HG_MAX_ROWS) { over = true; return; }
+        const GenomeTab &T = G[g];
+        const int sq = T.numSeq > 1 ? seqOf(T.seqStart, T.numSeq, pos) : 0;
+        ColRowRec r;
+        r.pos = pos; r.seq = sq; r.genome = (int16_t)g; r.rev = rev ? 1 : 0; r.pad = 0;
+        const uint64_t key = ((uint64_t)(uint32_t)T.nameRank << 32) | (uint32_t)sq;
+        int j = n; // stable insertion: after every row with key <= this key
+        while (j > 0 && keys[j - 1] > key) { rows[j] = rows[j - 1]; keys[j] = keys[j - 1]; --j; }
+        rows[j] = r; keys[j] = key;
+        ++n;
+    });
+    return (ok && !over) ? n : -1;
+}
+
+__global__ void __launch_bounds__(128) colSigKernel(const ColSigParams P) {
+    WalkItem stack[HG_WALK_STACK];
+    ColRowRec rows[HG_MAX_ROWS];
+    uint64_t keys[HG_MAX_ROWS];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys);
+        if (n < 0) { *P.error = 1u; P.nrows[i] = 0; P.sigA[i] = 0; P.sigB[i] = 0; continue; }
+        uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)n, b = 0xd1b54a32d192ed03ull + (uint64_t)n;
+        for (int k = 0; k < n; ++k) {
+            const ColRowRec r = rows[k];
+            const uint64_t norm = (uint64_t)(r.rev ? r.pos + i : r.pos - i); // constant along a collinear run
+            const uint64_t id = keys[k] * 2 + r.rev;
+            a = hgMix(a ^ norm) + hgMix(id + 0x632be59bd9b4e019ull * (uint64_t)(k + 1));
+            b = hgMix(b + id) ^ hgMix(norm * 0x9fb21c651e98df25ull + (uint64_t)k);
+        }
+        P.sigA[i] = a; P.sigB[i] = b; P.nrows[i] = (uint32_t)n;
+    }
+}
+
+struct RunFlagParams {
+    const uint64_t *sigA, *sigB;
+    const uint32_t *nrows;
+    uint32_t *isStart, *startRows; // n + 1 entries each (last = 0) for the scans
+    int64_t n;
+};
+__global__ void runFlagKernel(const RunFlagParams P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= P.n; i += stride) {
+        uint32_t s = 0;
+        if (i < P.n) s = (i == 0 || P.sigA[i] != P.sigA[i - 1] || P.sigB[i] != P.sigB[i - 1] || P.nrows[i] != P.nrows[i - 1]) ? 1u : 0u;
+        P.isStart[i] = s;
+        P.startRows[i] = s ? P.nrows[i] : 0u;
+    }
+}
+
+struct RunScatterParams {
+    const uint32_t *isStart;
+    const uint64_t *runIndex, *rowOffset;
+    int64_t *runCol;     // nRuns + 1 (sentinel = n)
+    uint64_t *runRowOff; // nRuns + 1 (sentinel = total rows)
+    int64_t n;
+};
+__global__ void runScatterKernel(const RunScatterParams P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= P.n; i += stride) {
+        if (i == P.n || P.isStart[i]) {
+            P.runCol[P.runIndex[i]] = i;
+            P.runRowOff[P.runIndex[i]] = P.rowOffset[i];
+        }
+    }
+}
+
+// one thread per run: re-walk the run's first column and store its rows
+__global__ void __launch_bounds__(128) colEmitKernel(const ColEmitParams P) {
+    WalkItem stack[HG_WALK_STACK];
+    ColRowRec rows[HG_MAX_ROWS];
+    uint64_t keys[HG_MAX_ROWS];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += stride) {
+        const int64_t i = P.runCol[r];
+        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys);
+        if (n < 0) { *P.error = 1u; continue; }
+        const uint64_t off = P.runRowOff[r];
+        for (int k = 0; k < n; ++k) P.rows[off + k] = rows[k];
     }
 }
 

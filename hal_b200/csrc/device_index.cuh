@@ -77,6 +77,30 @@ struct LiftParams {
     uint64_t gscratchPerWarp;
 };
 
+struct GenomeTab { // one per genome, device resident
+    const TopRec *top;
+    const BotCore *bot;
+    const int64_t *child;       // nc columns of numBot entries
+    const int32_t *childGenome; // nc entries
+    const uint32_t *topBucket, *botBucket;
+    int64_t numTop, numBot;
+    int32_t nc, parent, slot, topShift, botShift;
+    uint8_t inScope, isTarget, pad[2];
+    const int64_t *seqStart; // numSeq + 1 entries
+    int32_t numSeq;
+    int32_t nameRank;        // rank of the genome name in byte order (ColumnIterator::SequenceLess, halColumnIterator.h:45-50)
+};
+
+
+struct ColRowRec { // 16 B
+    int64_t pos;    // forward genome coordinate
+    int32_t seq;    // sequence index within the genome
+    int16_t genome;
+    uint8_t rev;
+    uint8_t pad;
+};
+
+
 enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2 };
 
 } // namespace halgpu

@@ -212,14 +212,9 @@ const Plan &Context::plan(int src, int tgt) {
     return _plans.emplace(key, p).first->second;
 }
 
-void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
-                    int32_t *dOut, float *kernelMs) {
+void Context::buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab) {
     const auto &G = _file->genomes();
     const int ng = (int)G.size();
-    if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
-    if (ng > 256) throw HalError("alignment depth supports at most 256 genomes");
-    if (step < 1 || first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
-    DevBuf::current() = _stream;
     // scope = spanning tree of targets + reference (api/impl/halColumnIterator.cpp:47-51); rows reported for targets only
     std::vector<char> inScope(ng, targets.empty() ? 1 : 0), isTarget(ng, targets.empty() ? 1 : 0);
     if (!targets.empty()) {
@@ -234,7 +229,12 @@ void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const st
         for (int t : all)
             for (int g = t;; g = G[g].parent) { inScope[g] = 1; if (g == m) break; }
     }
-    std::vector<GenomeTab> tab(ng);
+    std::vector<int> order(ng);
+    for (int g = 0; g < ng; ++g) order[g] = g;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return G[a].name < G[b].name; });
+    std::vector<int> rank(ng);
+    for (int i = 0; i < ng; ++i) rank[order[i]] = i;
+    tab.resize(ng);
     for (int g = 0; g < ng; ++g) {
         GenomeTab &t = tab[g];
         std::memset(&t, 0, sizeof(t));
@@ -244,7 +244,76 @@ void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const st
         t.nc = (int32_t)G[g].children.size(); t.parent = G[g].parent; t.slot = G[g].slotInParent;
         t.topShift = _g[g].topShift; t.botShift = _g[g].botShift;
         t.inScope = (uint8_t)inScope[g]; t.isTarget = (uint8_t)isTarget[g];
+        t.seqStart = _g[g].seqStart; t.numSeq = (int32_t)G[g].sequences.size(); t.nameRank = rank[g];
     }
+}
+
+void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out) {
+    const auto &G = _file->genomes();
+    const int ng = (int)G.size();
+    if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
+    if (ng > 32767) throw HalError("too many genomes for the column row record");
+    if (first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
+    DevBuf::current() = _stream;
+    std::vector<GenomeTab> tab;
+    buildGenomeTab(ref, targets, tab);
+    const int64_t n = last - first + 1;
+    DevBuf dTab(tab.size() * sizeof(GenomeTab)), dErr(sizeof(uint32_t));
+    rt::h2d(dTab.p, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
+    rt::dmemset(dErr.p, 0, sizeof(uint32_t), _stream);
+    DevBuf sigA(n * 8), sigB(n * 8), nrows((n + 1) * 4), isStart((n + 1) * 4), startRows((n + 1) * 4), runIndex((n + 2) * 8), rowOffset((n + 2) * 8);
+    rt::Event e0, e1, e2, e3;
+    ColSigParams sp;
+    sp.genomes = dTab.as<GenomeTab>(); sp.ref = ref; sp.flags = flags; sp.first = first; sp.n = n;
+    sp.sigA = sigA.as<uint64_t>(); sp.sigB = sigB.as<uint64_t>(); sp.nrows = nrows.as<uint32_t>(); sp.error = dErr.as<uint32_t>();
+    e0.record(_stream);
+    rt::launch(colSigKernel, gridFor(n, 128, _sms), 128, 0, _stream, sp);
+    e1.record(_stream);
+    RunFlagParams fp;
+    fp.sigA = sp.sigA; fp.sigB = sp.sigB; fp.nrows = sp.nrows; fp.isStart = isStart.as<uint32_t>(); fp.startRows = startRows.as<uint32_t>(); fp.n = n;
+    rt::launch(runFlagKernel, gridFor(n + 1, 256, _sms), 256, 0, _stream, fp);
+    rt::exclusiveScanU32(fp.isStart, runIndex.as<uint64_t>(), (size_t)n, _stream);
+    rt::exclusiveScanU32(fp.startRows, rowOffset.as<uint64_t>(), (size_t)n, _stream);
+    uint64_t totals[2] = {0, 0};
+    rt::d2h(&totals[0], runIndex.as<uint64_t>() + n, 8, _stream);
+    rt::d2h(&totals[1], rowOffset.as<uint64_t>() + n, 8, _stream);
+    uint32_t err = 0;
+    rt::d2h(&err, dErr.p, sizeof(err), _stream);
+    rt::sync(_stream);
+    if (err) throw HalError("column walk exceeded its stack or " + std::to_string(HG_MAX_ROWS) + " rows per column");
+    const uint64_t nRuns = totals[0], nRows = totals[1];
+    DevBuf runCol((nRuns + 1) * 8), runRowOff((nRuns + 1) * 8), rows(std::max<uint64_t>(nRows, 1) * sizeof(ColRowRec));
+    RunScatterParams rp;
+    rp.isStart = fp.isStart; rp.runIndex = runIndex.as<uint64_t>(); rp.rowOffset = rowOffset.as<uint64_t>();
+    rp.runCol = runCol.as<int64_t>(); rp.runRowOff = runRowOff.as<uint64_t>(); rp.n = n;
+    rt::launch(runScatterKernel, gridFor(n + 1, 256, _sms), 256, 0, _stream, rp);
+    ColEmitParams ep;
+    ep.genomes = sp.genomes; ep.ref = ref; ep.flags = flags; ep.first = first; ep.n = (int64_t)nRuns;
+    ep.runCol = rp.runCol; ep.runRowOff = rp.runRowOff; ep.rows = rows.as<ColRowRec>(); ep.error = sp.error;
+    e2.record(_stream);
+    rt::launch(colEmitKernel, gridFor((int64_t)nRuns, 128, _sms), 128, 0, _stream, ep);
+    e3.record(_stream);
+    out.n_cols = (size_t)n; out.n_runs = (size_t)nRuns; out.n_rows = (size_t)nRows;
+    out.run_col = static_cast<int64_t *>(rt::hostAlloc((nRuns + 1) * 8));
+    out.row_offset = static_cast<uint64_t *>(rt::hostAlloc((nRuns + 1) * 8));
+    out.rows = static_cast<halgpu_col_row *>(rt::hostAlloc(std::max<uint64_t>(nRows, 1) * sizeof(halgpu_col_row)));
+    rt::d2h(out.run_col, runCol.p, (nRuns + 1) * 8, _stream);
+    rt::d2h(out.row_offset, runRowOff.p, (nRuns + 1) * 8, _stream);
+    rt::d2h(out.rows, rows.p, nRows * sizeof(halgpu_col_row), _stream);
+    rt::sync(_stream);
+    out.kernel_ms = rt::Event::elapsedMs(e0, e1) + rt::Event::elapsedMs(e2, e3);
+}
+
+void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
+                    int32_t *dOut, float *kernelMs) {
+    const auto &G = _file->genomes();
+    const int ng = (int)G.size();
+    if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
+    if (ng > 256) throw HalError("alignment depth supports at most 256 genomes");
+    if (step < 1 || first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
+    DevBuf::current() = _stream;
+    std::vector<GenomeTab> tab;
+    buildGenomeTab(ref, targets, tab);
     DevBuf dTab(tab.size() * sizeof(GenomeTab)), dErr(sizeof(uint32_t));
     rt::h2d(dTab.p, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
     rt::dmemset(dErr.p, 0, sizeof(uint32_t), _stream);

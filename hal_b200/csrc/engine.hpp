@@ -53,7 +53,11 @@ class Context {
     void depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
                int32_t *dOut, float *kernelMs);
 
+    // column runs of reference positions first..last; host (pinned) output owned by the caller
+    void columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out);
+
   private:
+    void buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab);
     void stageGenome(int g);
     void buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb);
     const Plan &plan(int src, int tgt);

@@ -1,0 +1,152 @@
+// hal2maf -- GPU build of the reference CLI (maf/impl/hal2maf.cpp): same arguments, options, MAF text and
+// messages for the ColumnIterator flags the GPU column walk implements (unique=false, maxRefGap=0).
+// Not implemented (rejected with an error): --maxRefGap > 0, --unique, --global, --printTree, --refTargets.
+#include "maf_export.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace std;
+
+static void usage(ostream &os, const char *prog) {
+    os << prog << " v-b200: Convert hal database to maf on a B200 GPU.\n\nUSAGE:\n" << prog << " [Options] <halFile> <mafFile>\n\n"
+       << "OPTIONS:\n--refGenome <name>, --refSequence <name>, --start <n>, --length <n>, --rootGenome <name>, --targetGenomes <a,b,..>,\n"
+       << "--noDupes, --noAncestors, --onlySequenceNames, --onlyOrthologs, --keepEmptyRefBlocks, --append, --maxBlockLen <n>,\n"
+       << "--device <n>, --help\n";
+}
+
+static void subTree(halgpu_ctx *ctx, int g, vector<int> &out) { // getGenomesInSubTree (api/impl/halCommon.cpp:189-195)
+    out.push_back(g);
+    for (int k = 0; k < halgpu_genome_num_children(ctx, g); ++k) subTree(ctx, halgpu_genome_child(ctx, g, k), out);
+}
+
+static string fixString(const string &s) { // maf/impl/hal2maf.cpp:94-101
+    if (s == "\"\"") {
+        cerr << "WARNING missing string arguments should be specified as empty strings, not the obsolete '\"\"'" << endl;
+        return "";
+    }
+    return s;
+}
+
+int main(int argc, char **argv) {
+    string halPath, mafPath, refGenomeName, rootGenomeName, targetGenomes, refSequenceName;
+    int64_t start = 0, maxBlockLen = 1000;
+    uint64_t length = 0;
+    bool noDupes = false, noAncestors = false, onlySequenceNames = false, append = false, onlyOrthologs = false, keepEmptyRefBlocks = false;
+    int device = 0;
+    vector<string> pos;
+    try {
+        for (int i = 1; i < argc; ++i) {
+            string a = argv[i];
+            auto val = [&]() -> string { if (i + 1 >= argc) throw runtime_error("Option " + a + " requires a value"); return argv[++i]; };
+            if (a == "--refGenome") refGenomeName = fixString(val());
+            else if (a == "--refSequence") refSequenceName = fixString(val());
+            else if (a == "--start") start = strtoll(val().c_str(), nullptr, 10);
+            else if (a == "--length") length = strtoull(val().c_str(), nullptr, 10);
+            else if (a == "--rootGenome") rootGenomeName = fixString(val());
+            else if (a == "--targetGenomes") targetGenomes = fixString(val());
+            else if (a == "--maxBlockLen") maxBlockLen = strtoll(val().c_str(), nullptr, 10);
+            else if (a == "--device") device = atoi(val().c_str());
+            else if (a == "--noDupes") noDupes = true;
+            else if (a == "--noAncestors") noAncestors = true;
+            else if (a == "--onlySequenceNames") onlySequenceNames = true;
+            else if (a == "--append") append = true;
+            else if (a == "--onlyOrthologs") onlyOrthologs = true;
+            else if (a == "--keepEmptyRefBlocks") keepEmptyRefBlocks = true;
+            else if (a == "--help") { usage(cerr, argv[0]); return 1; }
+            else if (a == "--maxRefGap") { if (atoll(val().c_str()) != 0) throw runtime_error("--maxRefGap > 0 is not implemented in the GPU build"); }
+            else if (a == "--unique" || a == "--global" || a == "--printTree") throw runtime_error(a + " is not implemented in the GPU build");
+            else if (a == "--refTargets") { if (!fixString(val()).empty()) throw runtime_error("--refTargets is not implemented in the GPU build"); }
+            else if (a == "--format" || a == "--cacheMDC" || a == "--cacheRDC" || a == "--cacheBytes" || a == "--cacheW0" ||
+                     a == "--mmapFileSize" || a == "--mmapSizeIncrease" || a == "--udcCacheDir") val();
+            else if (a == "--inMemory") {}
+            else if (a.rfind("--", 0) == 0) throw runtime_error("Unrecognized option: " + a);
+            else pos.push_back(a);
+        }
+        if (pos.size() != 2) throw runtime_error(pos.size() < 2 ? "Too few (required positional) arguments" : "Too many (required positional) arguments");
+        halPath = pos[0];
+        mafPath = pos[1];
+        if (rootGenomeName != "" && targetGenomes != "") throw runtime_error("--rootGenome and --targetGenomes options are mutually exclusive");
+        if (refSequenceName == "" && (start != 0 || length != 0)) throw runtime_error("--start and --length require --refSequence");
+    } catch (exception &e) {
+        cerr << e.what() << endl;
+        usage(cerr, argv[0]);
+        return 1;
+    }
+    halgpu_ctx *ctx = nullptr;
+    int rc = 0;
+    try {
+        char *err = nullptr;
+        if (halgpu_open(halPath.c_str(), device, &ctx, &err) != 0) {
+            string m = err ? err : "cannot open";
+            halgpu_free_string(err);
+            throw runtime_error(m);
+        }
+        int rootId = -1;
+        for (int g = 0; g < halgpu_num_genomes(ctx); ++g) if (halgpu_genome_parent(ctx, g) < 0) rootId = g;
+        vector<int> targets;
+        if (rootGenomeName != "") {
+            const int r = halgpu_genome_id(ctx, rootGenomeName.c_str());
+            if (r < 0) throw runtime_error("Root genome " + rootGenomeName + ", not found in alignment");
+            if (r != rootId) subTree(ctx, r, targets);
+        }
+        if (targetGenomes != "") {
+            size_t b = 0;
+            while (b <= targetGenomes.size()) {
+                size_t e = targetGenomes.find(',', b);
+                if (e == string::npos) e = targetGenomes.size();
+                if (e > b) {
+                    const string name = targetGenomes.substr(b, e - b);
+                    const int t = halgpu_genome_id(ctx, name.c_str());
+                    if (t < 0) throw runtime_error("Target genome, " + name + ", not found in alignment");
+                    targets.push_back(t);
+                }
+                b = e + 1;
+            }
+        }
+        int ref = rootId;
+        if (refGenomeName != "") {
+            ref = halgpu_genome_id(ctx, refGenomeName.c_str());
+            if (ref < 0) throw runtime_error("Reference genome, " + refGenomeName + ", not found in alignment");
+        }
+        if (noAncestors && halgpu_genome_num_children(ctx, ref) != 0) {
+            throw runtime_error(string("Since the reference genome to be used for the MAF is ancestral (") + halgpu_genome_name(ctx, ref) +
+                                "), the --noAncestors option is invalid.  The --refGenome option can be used to specify a different reference.");
+        }
+        const halgpu_seq *seqs = nullptr;
+        size_t nseq = 0;
+        halgpu_sequence_table(ctx, ref, &seqs, &nseq);
+        int refSeq = -1;
+        if (refSequenceName != "") {
+            for (size_t i = 0; i < nseq; ++i) if (refSequenceName == seqs[i].name) refSeq = (int)i;
+            if (refSeq < 0) {
+                throw runtime_error("Reference sequence, " + refSequenceName + ", not found in reference genome, " + halgpu_genome_name(ctx, ref));
+            }
+        }
+        ofstream mafFile;
+        if (mafPath != "stdout") {
+            mafFile.open(mafPath, append ? ios_base::out | ios_base::app : ios_base::out);
+            if (!mafFile) throw runtime_error("Error opening " + mafPath);
+        }
+        ostream &maf = mafPath != "stdout" ? mafFile : cout;
+        halgpu::GpuMafExport ex(ctx);
+        ex.setNoDupes(noDupes); ex.setNoAncestors(noAncestors); ex.setUcscNames(!onlySequenceNames); ex.setAppend(append);
+        ex.setMaxBlockLength(maxBlockLen); ex.setOnlyOrthologs(onlyOrthologs); ex.setKeepEmptyRefBlocks(keepEmptyRefBlocks);
+        if (refSeq >= 0) {
+            ex.convertSequence(maf, ref, refSeq, start, length, targets);
+        } else {
+            for (size_t i = 0; i < nseq; ++i) ex.convertSequence(maf, ref, (int)i, start, length, targets);
+        }
+        maf.flush();
+        if (mafPath != "stdout" && mafFile.tellp() == (streampos)0) std::remove(mafPath.c_str()); // hal2maf.cpp:206-215
+    } catch (exception &e) {
+        cerr << "hal exception caught: " << e.what() << endl;
+        rc = 1;
+    }
+    halgpu_close(ctx);
+    return rc;
+}

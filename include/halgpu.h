@@ -119,6 +119,39 @@ int halgpu_columns_depth_device(halgpu_ctx *ctx, int ref_genome, int64_t first, 
                                 const int *targets, size_t n_targets, uint32_t flags, int32_t *d_depth_out,
                                 float *kernel_ms, char **err);
 
+/* ---- column runs (replaces the ColumnIterator sweep consumed by MafExport::convertSequence,
+ *      maf/impl/halMafExport.cpp:46-81: seq->getColumnIterator(...) + toRight() per base, default flags
+ *      unique=false, maxRefGap=0).  The reference columns first..last (forward GENOME coordinates, one
+ *      reference sequence) are returned as maximal runs of consecutive columns whose rows are the same
+ *      sequences and strands advancing collinearly: run r covers columns run_col[r] .. run_col[r+1]-1
+ *      (relative to `first`); its FIRST column's rows are rows[row_offset[r] .. row_offset[r+1]) in ColumnMap
+ *      order (genome name, sequence index, discovery order -- api/inc/halColumnIterator.h:45-54); in column
+ *      run_col[r]+j every row sits at pos + j (forward strand) or pos - j (rev). ---- */
+typedef struct halgpu_col_row {
+    int64_t pos;     /* forward genome coordinate in its genome */
+    int32_t seq;     /* index into halgpu_sequence_table(genome) */
+    int16_t genome;
+    uint8_t rev;     /* DnaIterator::getReversed() */
+    uint8_t pad;
+} halgpu_col_row;
+
+typedef struct halgpu_col_runs {
+    size_t n_cols, n_runs, n_rows;
+    int64_t *run_col;       /* n_runs + 1 entries, run_col[n_runs] == n_cols */
+    uint64_t *row_offset;   /* n_runs + 1 entries */
+    halgpu_col_row *rows;   /* n_rows entries */
+    float kernel_ms;        /* device time of the column-walk kernels */
+} halgpu_col_runs;
+
+enum { HALGPU_ONLY_ORTHOLOGS = 8u }; /* hal2maf --onlyOrthologs; also HALGPU_NO_ANCESTORS, HALGPU_COL_NO_DUPES */
+
+int halgpu_column_runs(halgpu_ctx *ctx, int ref_genome, int64_t first, int64_t last, const int *targets, size_t n_targets,
+                       uint32_t flags, halgpu_col_runs **out, char **err);
+void halgpu_free_col_runs(halgpu_col_runs *runs);
+/* packed DNA of a genome as staged (host pointer into the mapped file, 2 bases per byte, even index = high nibble;
+ * replaces Genome::getDnaIterator for bulk text emission, api/inc/halDnaIterator.h:131-138) */
+const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int genome);
+
 void halgpu_free_result(halgpu_lift_result *res);
 void halgpu_free_string(char *s);
 

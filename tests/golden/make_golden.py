@@ -146,6 +146,29 @@ def main():
     addd("depth_varlen_L0_step", v, "L0", ["--refSequence", "L0_s1", "--start", "10", "--length", "3003", "--step", "7"])
     addd("depth_small_G2", s, "Genome_2", [])
     addd("depth_ref_leaf3", t, "leaf3", ["--countDupes"])
+    # hal2maf (maf/Makefile:38-54 style): windows keep the fixtures small; the tiny hand-built file is exported whole
+    mcases = []
+    def addm(name, hal, args):
+        out = os.path.join(HERE, "cases", name + ".maf")
+        if os.path.exists(out):
+            os.remove(out)
+        subprocess.check_call([REF + "/hal2maf", os.path.join(HERE, hal), out] + list(args))
+        mcases.append(dict(name=name, hal=hal, args=list(args)))
+    addm("maf_small_default", s, [])
+    addm("maf_small_seqpart", s, ["--refGenome", "Genome_2", "--refSequence", "Genome_2_seq", "--start", "1000", "--length", "2000"])
+    addm("maf_ref_root", t, [])
+    addm("maf_ref_leaf3", t, ["--refGenome", "leaf3"])
+    addm("maf_ref_child1_nodupes", t, ["--refGenome", "child1", "--noDupes"])
+    for ref, sq in (("R", "R_s1"), ("L0", "L0_s2"), ("A1", "A1_s0"), ("L3", "L3_s3")):
+        addm(f"maf_varlen_{ref}_win", v, ["--refGenome", ref, "--refSequence", sq, "--start", "200", "--length", "2500"])
+    addm("maf_varlen_L0_nodupes", v, ["--refGenome", "L0", "--refSequence", "L0_s3", "--start", "0", "--length", "2500", "--noDupes"])
+    addm("maf_varlen_L0_noanc", v, ["--refGenome", "L0", "--refSequence", "L0_s1", "--start", "100", "--length", "2500", "--noAncestors"])
+    addm("maf_varlen_L1_orth", v, ["--refGenome", "L1", "--refSequence", "L1_s1", "--start", "100", "--length", "2500", "--onlyOrthologs"])
+    addm("maf_varlen_L2_targets", v, ["--refGenome", "L2", "--refSequence", "L2_s0", "--length", "2500", "--targetGenomes", "L0,A1"])
+    addm("maf_varlen_L2_root", v, ["--refGenome", "L2", "--refSequence", "L2_s2", "--length", "2500", "--rootGenome", "A1"])
+    addm("maf_varlen_L3_names_len7", v, ["--refGenome", "L3", "--refSequence", "L3_s0", "--length", "1500", "--onlySequenceNames", "--maxBlockLen", "7"])
+    addm("maf_varlen_A0_keepempty", v, ["--refGenome", "A0", "--refSequence", "A0_s2", "--length", "2500", "--keepEmptyRefBlocks"])
+    json.dump(mcases, open(os.path.join(HERE, "cases", "maf_index.json"), "w"), indent=1)
     json.dump(dcases, open(os.path.join(HERE, "cases", "depth_index.json"), "w"), indent=1)
     json.dump(cases, open(os.path.join(HERE, "cases", "index.json"), "w"), indent=1)
     print(len(cases), "cases written")

@@ -5,7 +5,7 @@ import subprocess
 
 import pytest
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, ref_bin
 
 REF_GOLDENS = [("test1.bed3", "halLiftoverBed3Test.bed", []), ("test1.bed12", "halLiftoverBed12Test.bed", []),
                ("test1.bed12+2", "halLiftoverBed12ExtraTest.bed", []), ("test1.bed4+2", "halLiftoverBed4ExtraTest.bed", ["--bedType", "4"])]
@@ -81,3 +81,48 @@ def test_depth_cli_cuda_matches_reference_outputs(tmp_path):
     from hal_b200 import build
     build.build()
     check_depth(os.path.join(ROOT, "hal_b200", "bin", "halAlignmentDepth"), tmp_path)
+
+
+def check_maf(cli, tmp_path, whole_genome_hal=None):
+    import json
+    for c in json.load(open(os.path.join(GOLDEN, "cases", "maf_index.json"))):
+        out = str(tmp_path / "o.maf")
+        if os.path.exists(out):
+            os.remove(out)
+        r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"]), out] + c["args"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == open(os.path.join(GOLDEN, "cases", c["name"] + ".maf"), "rb").read(), c["name"]
+
+
+def test_maf_cli_emulated_matches_reference_outputs(emul_maf_cli, tmp_path):
+    check_maf(emul_maf_cli, tmp_path)
+    r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--noAncestors"], capture_output=True, text=True)
+    assert r.returncode == 1 and "the --noAncestors option is invalid" in r.stderr
+    r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--unique"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not implemented in the GPU build" in r.stderr
+
+
+@pytest.mark.skipif(ref_bin("hal2maf") is None, reason="oracle/_ref not built")
+def test_maf_cli_emulated_whole_genome_live(emul_maf_cli, tmp_path):
+    """multi-sequence whole-genome export: 4 convertSequence calls sharing one MafBlock"""
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    for args in (["--refGenome", "L1"], ["--refGenome", "A2", "--maxBlockLen", "50"]):
+        a, b = str(tmp_path / "a.maf"), str(tmp_path / "b.maf")
+        subprocess.check_call([ref_bin("hal2maf"), hal, a] + args)
+        subprocess.check_call([emul_maf_cli, hal, b] + args)
+        assert open(a, "rb").read() == open(b, "rb").read(), args
+
+
+@pytest.mark.gpu
+def test_maf_cli_cuda_matches_reference_outputs(tmp_path):
+    from hal_b200 import build
+    build.build()
+    cli = os.path.join(ROOT, "hal_b200", "bin", "hal2maf")
+    check_maf(cli, tmp_path)
+    if ref_bin("hal2maf"):
+        hal = os.path.join(GOLDEN, "varlen8.hal")
+        for args in (["--refGenome", "L1"], ["--refGenome", "R"], ["--refGenome", "A2", "--maxBlockLen", "50"], ["--refGenome", "L3", "--noDupes"]):
+            a, b = str(tmp_path / "a.maf"), str(tmp_path / "b.maf")
+            subprocess.check_call([ref_bin("hal2maf"), hal, a] + args)
+            subprocess.check_call([cli, hal, b] + args)
+            assert open(a, "rb").read() == open(b, "rb").read(), args
