@@ -581,7 +581,7 @@ __host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) 
 extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
 #endif
 
-__global__ void __launch_bounds__(128) liftoverKernel(const LiftParams P) {
+__global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
 #if defined(HALGPU_SIMT_EMUL)
     uint8_t *hg_dyn_smem = simt::dynamicSmem();
 #endif
