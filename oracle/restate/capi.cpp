@@ -2,6 +2,7 @@
 #include "columns.h"
 #include "liftover.h"
 #include "maf.h"
+#include <algorithm>
 #include <cstdio>
 #include <memory>
 
@@ -116,6 +117,49 @@ const char *oracle_hal2maf(void *hp, int ref, int refSeq, int64_t start, int64_t
     }
     *len = h->maf.size();
     return h->maf.c_str();
+}
+
+/* ColumnLiftover::liftInterval restated (liftover/impl/halColumnLiftover.cpp:21-92) for one interval [gs,ge] of src:
+ * union of the target-genome bases of every column, split by (sequence, strand), merged into maximal runs.  With
+ * unique=true the reference skips columns whose reference base was already seen as a paralog of an earlier column; the
+ * union over all columns is the same set.  Output (kept in the handle): one line per run, forward-strand runs first, each
+ * group by sequence index then by position (the reference orders sequences by POINTER value, so compare after sorting).
+ * Returns the number of lines; fetch with oracle_fetch (srcStart = -1, srcStrand as strand). */
+int64_t oracle_column_liftover(void *hp, int src, int tgt, int noDupes, int64_t gs, int64_t ge, char strand) {
+    OracleHandle *h = (OracleHandle *)hp;
+    ColumnOpts o = makeColumnOpts(h->view, src, std::vector<int>{tgt}, noDupes != 0, false, false);
+    std::vector<ColRow> rows;
+    std::vector<std::pair<int64_t, int>> hits[2]; /* (pos, seq) per strand */
+    const GenomeView &T = h->view.genomes[tgt];
+    for (int64_t p = gs; p <= ge; ++p) {
+        column(h->view, src, p, o, rows);
+        for (const ColRow &r : rows) {
+            if (r.genome != tgt) continue;
+            bool rev = r.rev != (strand == '-'); /* reverseStrand iterator flips every row */
+            hits[rev ? 1 : 0].push_back(std::make_pair(r.pos, T.seqOf(r.pos)));
+        }
+    }
+    h->offsets.assign(1, 0);
+    h->lines.clear();
+    for (int s = 0; s < 2; ++s) {
+        auto &v = hits[s];
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        for (size_t i = 0; i < v.size();) {
+            size_t j = i + 1;
+            while (j < v.size() && v[j].first == v[j - 1].first + 1 && v[j].second == v[i].second) ++j;
+            OutLine l;
+            l.tgtSeq = v[i].second;
+            l.start = v[i].first - T.seqs[l.tgtSeq].start;
+            l.end = v[j - 1].first + 1 - T.seqs[l.tgtSeq].start;
+            l.strand = strand == '.' ? '.' : (s ? '-' : '+');
+            l.srcStart = -1; l.srcStrand = l.strand; l.nFrag = 1;
+            h->lines.push_back(l);
+            i = j;
+        }
+    }
+    h->offsets.push_back(h->lines.size());
+    return (int64_t)h->lines.size();
 }
 
 } // extern "C"
