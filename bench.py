@@ -263,11 +263,14 @@ def main():
     with ClockSampler(local) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
-        e0.record(stream)
+        # Every step ends with the library synchronising its own stream on the host, and the N>1 all-gather runs on
+        # torch's stream: events on torch's current stream bracket all of it (device clock, includes in-step gaps).
+        cur = torch.cuda.current_stream()
+        e0.record(cur)
         for _ in range(args.steps):
             nrec, k, launches, nretry = step_resident(True)
             kms.append(k)
-        e1.record(stream)
+        e1.record(cur)
         barrier()
         wall = time.perf_counter() - w0
         dev_ms = e0.elapsed_time(e1)

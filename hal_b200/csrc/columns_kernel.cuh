@@ -38,10 +38,45 @@ struct WalkItem { // 32 B
 };
 
 #define HG_WALK_STACK 96
+#define HG_WALK_SMEM 12 // stack slots kept in shared memory per thread; deeper pushes spill to the local array
+
+// Per-thread LIFO of pending walk branches.  The first HG_WALK_SMEM slots live in shared memory, laid out
+// [slot][thread] so a warp's accesses are conflict-free; a local-memory array catches the (rare) deeper stacks.
+// (A purely local stack cost 15.8 GB of DRAM writes per 50 M columns: profiles/r01_depthKernel_ncu.txt.)
+struct WalkStack {
+    int64_t (*sPos)[128];
+    uint32_t (*sA)[128], (*sB)[128], (*sMeta)[128];
+    WalkItem *spill;
+    int tid;
+    __device__ __forceinline__ void put(int sp, const WalkItem &w) {
+        if (sp < HG_WALK_SMEM) {
+            sPos[sp][tid] = w.pos; sA[sp][tid] = (uint32_t)w.a; sB[sp][tid] = (uint32_t)w.b;
+            sMeta[sp][tid] = (uint32_t)w.g | ((uint32_t)w.type << 16) | ((uint32_t)w.rev << 19) | ((uint32_t)w.k << 20);
+        } else {
+            spill[sp - HG_WALK_SMEM] = w;
+        }
+    }
+    __device__ __forceinline__ WalkItem get(int sp) const {
+        if (sp < HG_WALK_SMEM) {
+            WalkItem w;
+            const uint32_t m = sMeta[sp][tid];
+            w.pos = sPos[sp][tid]; w.a = sA[sp][tid]; w.b = sB[sp][tid];
+            w.g = (int32_t)(m & 0xffffu); w.type = (uint8_t)((m >> 16) & 7u); w.rev = (uint8_t)((m >> 19) & 1u); w.k = (uint16_t)(m >> 20);
+            return w;
+        }
+        return spill[sp - HG_WALK_SMEM];
+    }
+};
+#define HG_WALK_STACK_DECL                                                                                       \
+    __shared__ int64_t hgPos[HG_WALK_SMEM][128];                                                                   \
+    __shared__ uint32_t hgA[HG_WALK_SMEM][128], hgB[HG_WALK_SMEM][128], hgMeta[HG_WALK_SMEM][128];                 \
+    WalkItem hgSpill[HG_WALK_STACK - HG_WALK_SMEM];                                                                \
+    WalkStack stack;                                                                                               \
+    stack.sPos = hgPos; stack.sA = hgA; stack.sB = hgB; stack.sMeta = hgMeta; stack.spill = hgSpill; stack.tid = (int)threadIdx.x;
 
 // Visitor: void emit(int g, int64_t pos, bool rev) for rows that pass the colMapInsert filters.
 template <class Emit>
-__device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkItem *stack, Emit &&emit) {
+__device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, Emit &&emit) {
     const bool noDupes = (flags & COL_NO_DUPES) != 0, noAnc = (flags & COL_NO_ANCESTORS) != 0,
                onlyOrtho = (flags & COL_ONLY_ORTHOLOGS) != 0;
     int sp = 0;
@@ -50,7 +85,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
         if (sp >= HG_WALK_STACK) { ok = false; return; }
         WalkItem w;
         w.a = a; w.b = b; w.pos = pos; w.g = g; w.type = type; w.rev = rev ? 1 : 0; w.k = (uint16_t)k;
-        stack[sp++] = w;
+        stack.put(sp++, w);
     };
     auto report = [&](int g, int64_t pos, bool rev) {
         const GenomeTab &T = G[g];
@@ -70,7 +105,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
         for (int k = R.nc - 1; k >= 0; --k) push(W_CHILD, ref, b, 0, p, false, k);
     }
     while (sp > 0 && ok) {
-        const WalkItem w = stack[--sp];
+        const WalkItem w = stack.get(--sp);
         const GenomeTab T = G[w.g];
         const bool rev = w.rev != 0;
         switch (w.type) {
@@ -147,7 +182,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
 }
 
 __global__ void __launch_bounds__(128) depthKernel(const DepthParams P) {
-    WalkItem stack[HG_WALK_STACK];
+    HG_WALK_STACK_DECL
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
         uint64_t seen[4] = {0, 0, 0, 0}; // distinct genomes (<= 256, checked on the host)
@@ -206,7 +241,7 @@ __device__ __forceinline__ uint64_t hgMix(uint64_t x) {
 }
 
 // walk column p and leave its rows sorted in ColumnMap order; returns the row count or -1 on overflow
-__device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkItem *stack, ColRowRec *rows,
+__device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, ColRowRec *rows,
                                             uint64_t *keys) {
     int n = 0;
     bool over = false;
@@ -225,22 +260,26 @@ __device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t
     return (ok && !over) ? n : -1;
 }
 
+// Signature of a column = 128-bit hash of its rows IN DISCOVERY ORDER, each normalised by the column offset, so
+// that it is constant along a collinear run.  (Equal discovery order implies equal ColumnMap order; the converse
+// can only split a run, which the host state machine handles.)  Nothing but the walk stack is stored.
 __global__ void __launch_bounds__(128) colSigKernel(const ColSigParams P) {
-    WalkItem stack[HG_WALK_STACK];
-    ColRowRec rows[HG_MAX_ROWS];
-    uint64_t keys[HG_MAX_ROWS];
+    HG_WALK_STACK_DECL
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys);
-        if (n < 0) { *P.error = 1u; P.nrows[i] = 0; P.sigA[i] = 0; P.sigB[i] = 0; continue; }
-        uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)n, b = 0xd1b54a32d192ed03ull + (uint64_t)n;
-        for (int k = 0; k < n; ++k) {
-            const ColRowRec r = rows[k];
-            const uint64_t norm = (uint64_t)(r.rev ? r.pos + i : r.pos - i); // constant along a collinear run
-            const uint64_t id = keys[k] * 2 + r.rev;
-            a = hgMix(a ^ norm) + hgMix(id + 0x632be59bd9b4e019ull * (uint64_t)(k + 1));
-            b = hgMix(b + id) ^ hgMix(norm * 0x9fb21c651e98df25ull + (uint64_t)k);
-        }
+        uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xd1b54a32d192ed03ull;
+        int n = 0;
+        const GenomeTab *G = P.genomes;
+        const bool ok = walkColumn(G, P.ref, P.first + i, P.flags, stack, [&](int g, int64_t pos, bool rev) {
+            const GenomeTab &T = G[g];
+            const int sq = T.numSeq > 1 ? seqOf(T.seqStart, T.numSeq, pos) : 0;
+            const uint64_t norm = (uint64_t)(rev ? pos + i : pos - i);
+            const uint64_t id = ((((uint64_t)(uint32_t)g << 32) | (uint32_t)sq) << 1) | (rev ? 1u : 0u);
+            a = hgMix(a ^ norm) + hgMix(id + 0x632be59bd9b4e019ull * (uint64_t)(n + 1));
+            b = hgMix(b + id) ^ hgMix(norm * 0x9fb21c651e98df25ull + (uint64_t)n);
+            ++n;
+        });
+        if (!ok || n > HG_MAX_ROWS) { *P.error = 1u; P.nrows[i] = 0; P.sigA[i] = 0; P.sigB[i] = 0; continue; }
         P.sigA[i] = a; P.sigB[i] = b; P.nrows[i] = (uint32_t)n;
     }
 }
@@ -280,7 +319,7 @@ __global__ void runScatterKernel(const RunScatterParams P) {
 
 // one thread per run: re-walk the run's first column and store its rows
 __global__ void __launch_bounds__(128) colEmitKernel(const ColEmitParams P) {
-    WalkItem stack[HG_WALK_STACK];
+    HG_WALK_STACK_DECL
     ColRowRec rows[HG_MAX_ROWS];
     uint64_t keys[HG_MAX_ROWS];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

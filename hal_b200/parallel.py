@@ -21,25 +21,36 @@ def shard_bounds(n, world):
 
 
 def all_gather_records(counts_per_interval, recs_u8):
-    """counts_per_interval: int64 tensor (this rank's shard, lines per interval); recs_u8: uint8 tensor of
-    len(sum(counts)) * 32 bytes.  Returns (offsets int64 [N+1] for the WHOLE batch in input order, recs uint8) on every rank."""
+    """counts_per_interval: integer tensor (this rank's shard, lines per interval); recs_u8: uint8 tensor of
+    sum(counts) * 32 bytes.  Returns (offsets int64 [N+1] for the WHOLE batch in input order, recs uint8) on every rank.
+    One small all-gather of the shard sizes, one of the counts, one of the records; equal-sized shards (the weak-scaling
+    bench, and any batch of one-line-per-interval lifts) are gathered straight into the result without padding."""
     world = dist.get_world_size()
     dev = recs_u8.device
-    meta = torch.tensor([counts_per_interval.numel(), recs_u8.numel() // REC_BYTES], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    max_iv = int(max(int(m[0]) for m in metas))
-    max_rec = int(max(int(m[1]) for m in metas))
-    cpad = torch.zeros(max_iv, dtype=torch.int64, device=dev)
-    cpad[: counts_per_interval.numel()] = counts_per_interval
-    rpad = torch.zeros(max_rec * REC_BYTES, dtype=torch.uint8, device=dev)
-    rpad[: recs_u8.numel()] = recs_u8
-    call = torch.empty(world * max_iv, dtype=torch.int64, device=dev)
+    counts = counts_per_interval.to(torch.int32)
+    n_iv, n_rec = counts.numel(), recs_u8.numel() // REC_BYTES
+    meta = torch.tensor([n_iv, n_rec], dtype=torch.int64, device=dev)
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta)
+    metas = metas.view(world, 2).tolist()
+    max_iv = max(m[0] for m in metas)
+    max_rec = max(m[1] for m in metas)
+    uniform = all(m[0] == max_iv and m[1] == max_rec for m in metas)
+    call = torch.empty(world * max_iv, dtype=torch.int32, device=dev)
     rall = torch.empty(world * max_rec * REC_BYTES, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(call, cpad)
-    dist.all_gather_into_tensor(rall, rpad)
-    counts = torch.cat([call[r * max_iv: r * max_iv + int(metas[r][0])] for r in range(world)])
-    recs = torch.cat([rall[r * max_rec * REC_BYTES: (r * max_rec + int(metas[r][1])) * REC_BYTES] for r in range(world)])
-    offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
-    offsets[1:] = torch.cumsum(counts, 0)
+    if uniform:
+        dist.all_gather_into_tensor(call, counts)
+        dist.all_gather_into_tensor(rall, recs_u8)
+        all_counts, recs = call, rall
+    else:
+        cpad = torch.zeros(max_iv, dtype=torch.int32, device=dev)
+        cpad[:n_iv] = counts
+        rpad = torch.zeros(max_rec * REC_BYTES, dtype=torch.uint8, device=dev)
+        rpad[: recs_u8.numel()] = recs_u8
+        dist.all_gather_into_tensor(call, cpad)
+        dist.all_gather_into_tensor(rall, rpad)
+        all_counts = torch.cat([call[r * max_iv: r * max_iv + metas[r][0]] for r in range(world)])
+        recs = torch.cat([rall[r * max_rec * REC_BYTES: (r * max_rec + metas[r][1]) * REC_BYTES] for r in range(world)])
+    offsets = torch.zeros(all_counts.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(all_counts, 0, dtype=torch.int64, out=offsets[1:])
     return offsets, recs

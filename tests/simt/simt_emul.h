@@ -18,6 +18,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
+#define __shared__ static /* blocks run one at a time in the emulator, so one static copy == per-block shared memory */
 
 struct dim3 {
     unsigned x, y, z;
@@ -63,11 +64,9 @@ template <class T> inline T fromBits(uint64_t b) {
 inline void warpBarrier() { pthread_barrier_wait(&ctx().warp->bar); }
 
 template <class K, class P> void launch(K kernel, dim3 grid, dim3 block, size_t smemBytes, const P &param) {
-    // all blocks run concurrently (grid sizes used in tests are tiny)
     const unsigned nb = grid.x, nt = block.x, nw = (nt + 31) / 32;
     std::vector<Block> blocks(nb);
     std::vector<std::vector<uint8_t>> smems(nb);
-    std::vector<std::thread> threads;
     for (unsigned b = 0; b < nb; ++b) {
         smems[b].assign(smemBytes + 64, 0);
         blocks[b].smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smems[b].data()) + 63) & ~uintptr_t(63));
@@ -78,7 +77,8 @@ template <class K, class P> void launch(K kernel, dim3 grid, dim3 block, size_t 
             pthread_barrier_init(&blocks[b].warps[w].bar, nullptr, lanes);
         }
     }
-    for (unsigned b = 0; b < nb; ++b) {
+    for (unsigned b = 0; b < nb; ++b) { // one block at a time (see __shared__)
+        std::vector<std::thread> threads;
         for (unsigned t = 0; t < nt; ++t) {
             threads.emplace_back([&, b, t]() {
                 ThreadCtx &c = ctx();
@@ -89,8 +89,8 @@ template <class K, class P> void launch(K kernel, dim3 grid, dim3 block, size_t 
                 kernel(param);
             });
         }
+        for (auto &th : threads) th.join();
     }
-    for (auto &th : threads) th.join();
 }
 } // namespace simt
 
