@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libhalgpu.so")
 
 HALGPU_NO_DUPES = 1
 HALGPU_NO_SORT = 2
+HALGPU_PSL = 4
 HALGPU_COUNT_DUPES = 1
 HALGPU_NO_ANCESTORS = 2
 HALGPU_COL_NO_DUPES = 4
@@ -31,7 +32,8 @@ class _Seq(C.Structure):
 
 class _Result(C.Structure):
     _fields_ = [("n", C.c_size_t), ("n_rec", C.c_size_t), ("offsets", C.c_void_p), ("recs", C.c_void_p),
-                ("on_device", C.c_int), ("kernel_ms", C.c_float), ("launches", C.c_int), ("n_retry", C.c_size_t)]
+                ("on_device", C.c_int), ("kernel_ms", C.c_float), ("launches", C.c_int), ("n_retry", C.c_size_t),
+                ("psl", C.c_void_p)]
 
 
 REC_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("src_start", "<i8"), ("tgt_seq", "<i4"),
@@ -187,6 +189,8 @@ class Alignment:
         else:
             recs = np.zeros(0, dtype=REC_DTYPE)
         info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry)
+        if r.psl and r.n_rec:
+            info["psl"] = np.ctypeslib.as_array(C.cast(r.psl, C.POINTER(C.c_uint32)), shape=(r.n_rec, 4)).copy()
         self.L.halgpu_free_result(res)
         return offsets, recs, info
 

@@ -100,7 +100,7 @@ int halgpu_liftover_device(halgpu_ctx *ctx, int src, int tgt, int coalescenceLim
         ctx->impl->liftover(src, tgt, flags, n, dStart, dEnd, dStrand, lo);
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = n; r->n_rec = lo.nRec; r->offsets = lo.offsets; r->recs = lo.recs; r->on_device = 1;
-        r->kernel_ms = lo.kernelMs; r->launches = lo.launches; r->n_retry = lo.nRetry;
+        r->kernel_ms = lo.kernelMs; r->launches = lo.launches; r->n_retry = lo.nRetry; r->psl = lo.psl;
         *out = r;
     });
 }
@@ -144,6 +144,10 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         r->recs = static_cast<halgpu_lift_rec *>(rt::hostAlloc(std::max<size_t>(dev->n_rec, 1) * sizeof(halgpu_lift_rec)));
         rt::d2h(r->offsets, dev->offsets, (n + 1) * sizeof(uint64_t), s);
         rt::d2h(r->recs, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), s);
+        if (dev->psl != nullptr) {
+            r->psl = static_cast<uint32_t *>(rt::hostAlloc(std::max<size_t>(dev->n_rec, 1) * 16));
+            rt::d2h(r->psl, dev->psl, dev->n_rec * 16, s);
+        }
         rt::sync(s);
         halgpu_free_result(dev);
         *out = r;
@@ -221,9 +225,11 @@ void halgpu_free_result(halgpu_lift_result *r) {
     if (r->on_device) {
         rt::dfree(r->offsets);
         rt::dfree(r->recs);
+        rt::dfree(r->psl);
     } else {
         rt::hostFree(r->offsets);
         rt::hostFree(r->recs);
+        rt::hostFree(r->psl);
     }
     std::free(r);
 }

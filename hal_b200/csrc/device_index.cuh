@@ -68,6 +68,8 @@ struct LiftParams {
     uint64_t *outOffset;     // per interval: first record in pool
     uint32_t *status;        // per interval: ST_*
     halgpu_lift_rec *pool;
+    uint32_t *pslPool;        // optional (HALGPU_PSL): 4 counters per pool record (matches, misMatches, repMatches, nCount), zeroed
+    const uint8_t *srcDna, *tgtDna; // packed nibbles of the source / target genome (PSL only)
     unsigned long long *poolCursor;
     uint64_t poolCap;
     // scratch: lists live in dynamic shared memory unless gscratch != NULL

@@ -370,6 +370,12 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
     uint64_t poolCap = (uint64_t)n + (uint64_t)n / 4 + 4096;
     std::unique_ptr<DevBuf> pool(new DevBuf(poolCap * sizeof(halgpu_lift_rec)));
+    const bool wantPsl = (flags & HALGPU_PSL) != 0;
+    std::unique_ptr<DevBuf> pslPool;
+    if (wantPsl) {
+        pslPool.reset(new DevBuf(poolCap * 16));
+        rt::dmemset(pslPool->p, 0, poolCap * 16, _stream);
+    }
 
     LiftParams P;
     std::memset(&P, 0, sizeof(P));
@@ -383,6 +389,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     P.gs = dGs; P.ge = dGe; P.strand = dStrand;
     P.outCount = outCount.as<uint32_t>(); P.outOffset = outOffset.as<uint64_t>(); P.status = status.as<uint32_t>();
     P.pool = pool->as<halgpu_lift_rec>(); P.poolCursor = cursor.as<unsigned long long>(); P.poolCap = poolCap;
+    P.pslPool = wantPsl ? pslPool->as<uint32_t>() : nullptr;
+    P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
 
     // rung 1: all n intervals, scratch in shared memory
     const unsigned block = 128, warpsPerBlock = block / 32;
@@ -426,6 +434,14 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             rt::d2d(np->p, pool->p, poolCap * sizeof(halgpu_lift_rec), _stream);
             rt::sync(_stream);
             pool.swap(np);
+            if (wantPsl) { // counters of the records already written move along; the new tail starts at zero
+                std::unique_ptr<DevBuf> nq(new DevBuf(newCap * 16));
+                rt::dmemset(nq->p, 0, newCap * 16, _stream);
+                rt::d2d(nq->p, pslPool->p, poolCap * 16, _stream);
+                rt::sync(_stream);
+                pslPool.swap(nq);
+                P.pslPool = pslPool->as<uint32_t>();
+            }
             poolCap = newCap;
             P.pool = pool->as<halgpu_lift_rec>(); P.poolCap = poolCap;
             DevBuf ids(nFull * sizeof(uint32_t));
@@ -472,13 +488,17 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     rt::sync(_stream);
     DevBuf *recs = new DevBuf(std::max<uint64_t>(total, 1) * sizeof(halgpu_lift_rec));
     std::unique_ptr<DevBuf> recsHold(recs);
+    std::unique_ptr<DevBuf> pslHold;
+    if (wantPsl) pslHold.reset(new DevBuf(std::max<uint64_t>(total, 1) * 16));
     GatherParams gp;
+    gp.pslPool = P.pslPool; gp.psl = wantPsl ? pslHold->as<uint32_t>() : nullptr;
     gp.outCount = P.outCount; gp.outOffset = P.outOffset; gp.csr = csr->as<uint64_t>();
     gp.pool = pool->as<halgpu_lift_rec>(); gp.recs = recs->as<halgpu_lift_rec>(); gp.n = (int64_t)n;
     rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
     rt::sync(_stream);
     out.offsets = static_cast<uint64_t *>(csrHold->release());
     out.recs = static_cast<halgpu_lift_rec *>(recsHold->release());
+    out.psl = wantPsl ? static_cast<uint32_t *>(pslHold->release()) : nullptr;
     out.nRec = total;
     out.launches = (int)rt::g_launches - launches0;
 }

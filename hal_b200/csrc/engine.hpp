@@ -32,6 +32,7 @@ struct Plan {
 struct LiftOutput { // device-side result of one batch
     uint64_t *offsets = nullptr; // n + 1
     halgpu_lift_rec *recs = nullptr;
+    uint32_t *psl = nullptr;     // 4 per record when HALGPU_PSL
     size_t n = 0, nRec = 0, nRetry = 0;
     float kernelMs = 0;
     int launches = 0;

@@ -120,4 +120,69 @@ void BedLine::append(std::string &out) const {
     out += '\n';
 }
 
+void BedLine::expandToBed12() {
+    if (bedType <= 3) name = "";
+    if (bedType <= 4) score = 0;
+    if (bedType <= 5) strand = '+';
+    if (bedType <= 6) thickStart = start;
+    if (bedType <= 7) thickEnd = end;
+    if (bedType <= 8) itemR = itemG = itemB = 0;
+    if (bedType <= 9) {
+        blocks.resize(1);
+        blocks[0].start = 0;
+        blocks[0].length = end - start;
+    }
+    bedType = 12;
+}
+
+bool BedLine::validatePSL() const {
+    if (psl.size() != 1 || blocks.empty()) return false;
+    const PslInfo &p = psl[0];
+    if (blocks.size() != p.qBlockStarts.size()) return false;
+    uint64_t tot = 0;
+    for (const BedBlock &b : blocks) tot += (uint64_t)b.length;
+    if (tot != p.matches + p.misMatches + p.repMatches + p.nCount) return false;
+    if (tot + p.qBaseInsert != p.qEnd - (uint64_t)srcStart) return false;
+    if (tot + p.tBaseInsert != (uint64_t)(end - start)) return false;
+    if (strand != '-') {
+        if (blocks[0].start != 0 || blocks.back().start + blocks.back().length + start != end) return false;
+    } else {
+        if (blocks.back().start != 0 || blocks[0].start + blocks[0].length + start != end) return false;
+    }
+    if (p.qStrand != '-') {
+        if (p.qBlockStarts[0] != srcStart || (uint64_t)(p.qBlockStarts.back() + blocks.back().length) != p.qEnd) return false;
+    } else {
+        if (p.qBlockStarts.back() != srcStart || (uint64_t)(p.qBlockStarts[0] + blocks[0].length) != p.qEnd) return false;
+    }
+    return true;
+}
+
+void BedLine::appendPSL(std::string &out, bool prefixWithName) const {
+    if (!validatePSL()) throw std::runtime_error("Internal error: PSL does not validate");
+    const PslInfo &p = psl[0];
+    auto num = [&](uint64_t v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); out.append(b, r.ptr); };
+    auto snum = [&](int64_t v) { putInt(out, v); };
+    if (prefixWithName) { out += name; out += '\t'; }
+    num(p.matches); out += '\t'; num(p.misMatches); out += '\t'; num(p.repMatches); out += '\t'; num(p.nCount); out += '\t';
+    num(p.qNumInsert); out += '\t'; num(p.qBaseInsert); out += '\t'; num(p.tNumInsert); out += '\t'; num(p.tBaseInsert); out += '\t';
+    out += p.qStrand; out += strand; out += '\t';
+    out += p.qSeqName; out += '\t'; num(p.qSeqSize); out += '\t'; snum(srcStart - (int64_t)p.qChromOffset); out += '\t';
+    num(p.qEnd - p.qChromOffset); out += '\t'; out += chrName; out += '\t'; num(p.tSeqSize); out += '\t'; snum(start); out += '\t';
+    snum(end); out += '\t'; num(blocks.size()); out += '\t';
+    for (const BedBlock &b : blocks) { snum(b.length); out += ','; }
+    out += '\t';
+    for (size_t i = 0; i < p.qBlockStarts.size(); ++i) {
+        int64_t st = p.qBlockStarts[i] - (int64_t)p.qChromOffset;
+        if (p.qStrand == '-') st = (int64_t)p.qSeqSize - st - blocks[i].length;
+        snum(st); out += ',';
+    }
+    out += '\t';
+    for (const BedBlock &b : blocks) {
+        int64_t st = b.start + start;
+        if (strand == '-') st = (int64_t)p.tSeqSize - st - b.length;
+        snum(st); out += ',';
+    }
+    out += '\n';
+}
+
 } // namespace halgpu

@@ -13,6 +13,14 @@ struct BedBlock {
     int64_t start = 0, length = 0;
 };
 
+struct PslInfo { // liftover/inc/halBedLine.h:31-48
+    uint64_t matches = 0, misMatches = 0, repMatches = 0, nCount = 0, qNumInsert = 0, qBaseInsert = 0, tNumInsert = 0, tBaseInsert = 0;
+    std::string qSeqName;
+    uint64_t qSeqSize = 0, qEnd = 0, qChromOffset = 0, tSeqSize = 0;
+    char qStrand = '+';
+    std::vector<int64_t> qBlockStarts; // absolute (genome) coordinates
+};
+
 struct BedLine {
     std::string chrName, name;
     int64_t start = -1, end = -1, score = 0, thickStart = 0, thickEnd = 0, itemR = 0, itemG = 0, itemB = 0;
@@ -27,6 +35,10 @@ struct BedLine {
     // Throws std::runtime_error with the reference's messages on malformed input.
     void parse(const std::string &line, int forcedBedType);
     void append(std::string &out) const; // BedLine::write
+    std::vector<PslInfo> psl;            // 0 or 1 element, as in the reference
+    void expandToBed12();                // BedLine::expandToBed12 (halBedLine.cpp:153-182)
+    bool validatePSL() const;            // BedLine::validatePSL (:251-334)
+    void appendPSL(std::string &out, bool prefixWithName) const; // BedLine::writePSL (:206-249)
 };
 
 std::vector<std::string> chopString(const std::string &s, char sep); // hal::chopString (api/impl/halCommon.cpp:28-43)

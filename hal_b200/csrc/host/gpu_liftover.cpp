@@ -37,9 +37,7 @@ bool compatible(const BedLine &tgtBed, const BedLine &newBlock, char inputStrand
 void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, std::ostream *out, int bedType,
                                bool traverseDupes, bool outPSL, bool outPSLWithName, int coalescenceLimit) {
     if (_ctx == nullptr || in == nullptr || out == nullptr) throw std::runtime_error("GpuBlockLiftover::convert: null argument");
-    if (outPSL || outPSLWithName) {
-        throw std::runtime_error("PSL output is not implemented in the GPU liftover yet (SURVEY.md 8(f) row 2)");
-    }
+    if (outPSLWithName) outPSL = true;
     const halgpu_seq *sseq = nullptr, *tseq = nullptr;
     size_t ns = 0, nt = 0;
     if (halgpu_sequence_table(_ctx, srcGenome, &sseq, &ns) != 0 || halgpu_sequence_table(_ctx, tgtGenome, &tseq, &nt) != 0) {
@@ -77,6 +75,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
             }
             skipWs();
             ++linesIn;
+            if (outPSL && cur.bedType < 12) cur.expandToBed12(); // forcing to BED12 makes PSL code simpler (halLiftover.cpp:47-50)
             auto it = seqByName.find(cur.chrName);
             if (it == seqByName.end()) {
                 if (_missed.insert(cur.chrName).second) {
@@ -121,7 +120,8 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         halgpu_lift_result *res = nullptr;
         char *err = nullptr;
         auto t0 = std::chrono::steady_clock::now();
-        const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit, traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES,
+        const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit,
+                                       (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u),
                                        gs.size(), gs.data(), ge.data(), st.data(), &res, &err);
         gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rc != 0) {
@@ -151,6 +151,19 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                     o.strand = (char)rec.strand;
                     o.srcStart = rec.src_start;
                     o.srcStrand = (char)rec.src_strand;
+                    if (outPSL) { // BlockLiftover::readPSLInfo (halBlockLiftover.cpp:115-162); base counts come from the GPU
+                        const halgpu_seq &ssq = sseq[seqByName[src.chrName]];
+                        o.psl.assign(1, PslInfo());
+                        PslInfo &ps = o.psl[0];
+                        ps.matches = res->psl[4 * r]; ps.misMatches = res->psl[4 * r + 1];
+                        ps.repMatches = res->psl[4 * r + 2]; ps.nCount = res->psl[4 * r + 3];
+                        ps.qSeqName = ssq.name;
+                        ps.qSeqSize = (uint64_t)ssq.length;
+                        ps.qStrand = src.strand == '-' ? '-' : '+'; // the source is reversed iff the BED strand is '-' (:50,64-70)
+                        ps.qChromOffset = (uint64_t)ssq.start;
+                        ps.qEnd = (uint64_t)(o.srcStart + (o.end - o.start));
+                        ps.tSeqSize = (uint64_t)tseq[rec.tgt_seq].length;
+                    }
                 }
             }
             outLines.clear();
@@ -158,10 +171,16 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                 outLines.assign(mapped.begin(), mapped.end());
             } else if (!mapped.empty()) { // assignBlocksToIntervals (halLiftover.cpp:108-167), BED output
                 std::stable_sort(mapped.begin(), mapped.end(), [](const BedLine &a, const BedLine &b) { return a.srcStart < b.srcStart; });
-                for (const BedLine &blk : mapped) {
-                    if (outLines.empty() || !compatible(outLines.back(), blk, src.strand)) {
+                int64_t prevSrcBlockEnd = -1;
+                for (size_t bi = 0; bi < mapped.size(); ++bi) {
+                    const BedLine &blk = mapped[bi];
+                    const int64_t srcBlockEnd = blk.srcStart + (blk.end - blk.start);
+                    const bool dupe = blk.srcStart < prevSrcBlockEnd || (bi + 1 < mapped.size() && mapped[bi + 1].srcStart < srcBlockEnd);
+                    // filter dupes in psl but let them be on single bed line
+                    if (outLines.empty() || (outPSL && dupe) || !compatible(outLines.back(), blk, src.strand)) {
                         outLines.push_back(blk);
                     }
+                    prevSrcBlockEnd = srcBlockEnd;
                     BedLine &t = outLines.back();
                     t.start = std::min(t.start, blk.start);
                     t.end = std::max(t.end, blk.end);
@@ -169,12 +188,40 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                     b.start = blk.start; // absolute for now
                     b.length = blk.end - blk.start;
                     t.blocks.push_back(b);
+                    if (outPSL) {
+                        PslInfo &tp = t.psl[0];
+                        tp.qBlockStarts.push_back(blk.srcStart);
+                        if (t.blocks.size() > 1) { // the first block's counts came with the copy
+                            tp.matches += blk.psl[0].matches; tp.misMatches += blk.psl[0].misMatches;
+                            tp.repMatches += blk.psl[0].repMatches; tp.nCount += blk.psl[0].nCount;
+                        }
+                    }
                 }
                 for (BedLine &t : outLines) {
                     for (BedBlock &b : t.blocks) b.start -= t.start;
-                    if (t.blocks.size() > 1) { // flipBlocks: ascending in the output
+                    if (t.blocks.size() > 1) { // flipBlocks (halLiftover.cpp:197-234)
                         const int64_t delta = t.blocks[1].start - (t.blocks[0].start + t.blocks[0].length);
-                        if (delta < 0) std::reverse(t.blocks.begin(), t.blocks.end());
+                        const bool mustFlip = !outPSL ? delta < 0 : ((t.strand == '-' && delta >= 0) || (t.strand != '-' && delta < 0));
+                        if (mustFlip) {
+                            std::reverse(t.blocks.begin(), t.blocks.end());
+                            if (outPSL) std::reverse(t.psl[0].qBlockStarts.begin(), t.psl[0].qBlockStarts.end());
+                        }
+                    }
+                    if (outPSL) { // computePSLInserts (halLiftover.cpp:236-290)
+                        PslInfo &ps = t.psl[0];
+                        ps.qNumInsert = ps.qBaseInsert = ps.tNumInsert = ps.tBaseInsert = 0;
+                        for (size_t i = 1; i < t.blocks.size(); ++i) {
+                            const BedBlock *cur = &t.blocks[i], *prev = &t.blocks[i - 1];
+                            const BedBlock *tc = cur, *tp = prev;
+                            if (t.strand == '-') std::swap(tc, tp);
+                            const int64_t tgap = tc->start - (tp->start + tp->length);
+                            if (tgap > 0) { ++ps.tNumInsert; ps.tBaseInsert += (uint64_t)tgap; }
+                            int64_t qc = ps.qBlockStarts[i], qp = ps.qBlockStarts[i - 1];
+                            const BedBlock *qpb = prev;
+                            if (ps.qStrand == '-') { std::swap(qc, qp); qpb = cur; }
+                            const int64_t qgap = qc >= qp + qpb->length ? qc - (qp + qpb->length) : 0; // duplicated blocks can overlap
+                            if (qgap > 0) { ++ps.qNumInsert; ps.qBaseInsert += (uint64_t)qgap; }
+                        }
                     }
                 }
             }
@@ -185,13 +232,22 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                         it->thickStart = it->start;
                         it->thickEnd = it->end;
                     }
-                    if (src.bedType > 9 && it->blocks.empty()) it = outLines.erase(it);
-                    else ++it;
+                    if (src.bedType > 9 && it->blocks.empty()) { it = outLines.erase(it); continue; }
+                    if (src.bedType > 9 && outPSL) { // halLiftover.cpp:336-346
+                        PslInfo &ps = it->psl[0];
+                        it->srcStart = INT64_MAX;
+                        ps.qEnd = 0;
+                        for (size_t j = 0; j < ps.qBlockStarts.size(); ++j) {
+                            it->srcStart = std::min(it->srcStart, ps.qBlockStarts[j]);
+                            ps.qEnd = std::max<uint64_t>(ps.qEnd, (uint64_t)(ps.qBlockStarts[j] + it->blocks[j].length));
+                        }
+                    }
+                    ++it;
                 }
             }
             outLines.sort([](const BedLine &a, const BedLine &b) { return a.srcStart < b.srcStart; }); // stable
             for (const BedLine &l : outLines) {
-                l.append(outBuf);
+                if (outPSL) l.appendPSL(outBuf, outPSLWithName); else l.append(outBuf);
                 ++linesOut;
             }
             if (outBuf.size() > (8u << 20)) {

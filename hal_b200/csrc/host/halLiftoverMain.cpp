@@ -25,7 +25,8 @@ static void usage(ostream &os, const char *prog) {
        << "--coalescenceLimit <value>: coalescence limit genome (only the MRCA, the default, is supported) [default = \"\"]\n"
        << "--device <value>:     CUDA device index [default = 0]\n--help:               display this help page [default = 0]\n"
        << "--noDupes:            do not map between duplications in graph. [default = 0]\n"
-       << "--outPSL / --outPSLWithName: not implemented in the GPU build\n";
+       << "--outPSL:             write output in PSL instead of bed format [default = 0]\n"
+       << "--outPSLWithName:     write output as input BED name followed by PSL line instead of bed format [default = 0]\n";
 }
 
 int main(int argc, char **argv) {

@@ -459,8 +459,14 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
 
     // ---- merge into output lines (BlockMapper::extractSegment) ----
     // scratch in the free list: run heads/tails, then (general path only) cut points, flags, classes
+    // layout (<= 32 bytes per fragment): runHead 4m | runTail 4m | qcut 8m | v1 4m | v2 4m | dead m | runOf 4m
     int32_t *runHead = reinterpret_cast<int32_t *>(oth);
     int32_t *runTail = runHead + m;
+    int64_t *qcut = reinterpret_cast<int64_t *>(runTail + m);
+    int32_t *v1 = reinterpret_cast<int32_t *>(qcut + m);
+    int32_t *v2 = v1 + m;
+    uint8_t *dead = reinterpret_cast<uint8_t *>(v2 + m);
+    int32_t *runOf = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(oth) + (((size_t)25 * (size_t)m + 3) & ~(size_t)3));
     bool classes = false;
     for (int i = lane; i + 1 < m; i += 32) classes |= cur[i].tLo == cur[i + 1].tLo;
     int nLines = 0;
@@ -474,25 +480,21 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
             const unsigned tm = __ballot_sync(HG_FULL, tail);
             if (head) runHead[nLines + lanePrefix(hm, lane)] = i;
             // a tail closes the run opened by the latest head at or before it
-            if (tail) {
-                const int headsUpToMe = __popc(hm & ((2u << lane) - 1u));
-                runTail[nLines + headsUpToMe - 1] = i;
-            }
+            const int headsUpToMe = __popc(hm & ((2u << lane) - 1u));
+            if (tail) runTail[nLines + headsUpToMe - 1] = i;
+            if (i < m) runOf[i] = nLines + headsUpToMe - 1;
             nLines += __popc(hm);
         }
         __syncwarp();
     } else {
         // general case, exact sequential restatement by one lane (rare: paralogous source pieces in one interval)
         if (lane == 0) {
-            int64_t *qcut = reinterpret_cast<int64_t *>(runTail + m);
-            int32_t *v1 = reinterpret_cast<int32_t *>(qcut + m);
-            int32_t *v2 = v1 + m;
-            uint8_t *dead = reinterpret_cast<uint8_t *>(v2 + m);
             for (int i = 0; i < m; ++i) dead[i] = 0;
             int nq = 0;
             for (int x = 0; x < m; ++x) {
                 if (dead[x]) continue;
                 int n1 = 0, n2 = 0, tailIdx = x;
+                runOf[x] = nLines;
                 v1[n1++] = x;
                 int nx = x + 1;
                 while (nx < m && dead[nx]) ++nx;
@@ -521,6 +523,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                     if (!can) break;
                     tailIdx = v2[0];
                     dead[v2[0]] = 1;
+                    runOf[v2[0]] = nLines;
                     for (int i = 0; i < n2; ++i) v1[i] = v2[i];
                     n1 = n2;
                 }
@@ -568,6 +571,34 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         const int nf = runTail[r] - runHead[r] + 1;
         o.n_frag = (uint16_t)(nf > 65535 ? 65535 : nf);
         P.pool[base + rank] = o;
+        if (P.pslPool) v2[r] = rank; // v1/v2 are free after the merge scan; qcut/v1 may alias runOf's neighbours, v2 does not
+    }
+    if (P.pslPool) {
+        // PSL base counts of every line (BlockLiftover::readPSLInfo, liftover/impl/halBlockLiftover.cpp:115-162):
+        // walk each fragment's source and target strings in traversal order (reverse complement when reversed) and
+        // classify every base pair: equal & upper-case -> match, equal & lower-case (masked) -> repMatch,
+        // different with target n/N -> nCount, else mismatch.  Codes: bit 3 = upper case, low bits a,c,g,t,n = 0..4.
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const Frag f = cur[i];
+            const bool sR = f.meta & 1, tR = (f.meta >> 1) & 1;
+            unsigned cnt[4] = {0u, 0u, 0u, 0u};
+            for (int64_t j = 0; j < f.len; ++j) {
+                const int64_t sp = sR ? f.sLo + f.len - 1 - j : f.sLo + j;
+                const int64_t tp = tR ? f.tLo + f.len - 1 - j : f.tLo + j;
+                unsigned sc = P.srcDna[sp >> 1], tc = P.tgtDna[tp >> 1];
+                sc = (sp & 1) ? (sc & 0xFu) : (sc >> 4);
+                tc = (tp & 1) ? (tc & 0xFu) : (tc >> 4);
+                if (sR && (sc & 7u) < 4u) sc = (sc & 8u) | (3u - (sc & 7u));
+                if (tR && (tc & 7u) < 4u) tc = (tc & 8u) | (3u - (tc & 7u));
+                if (sc == tc) cnt[(sc & 8u) ? 0 : 2]++;
+                else if ((tc & 7u) == 4u) cnt[3]++;
+                else cnt[1]++;
+            }
+            unsigned *dst = P.pslPool + 4ull * (base + (unsigned long long)v2[runOf[i]]);
+            for (int c = 0; c < 4; ++c)
+                if (cnt[c]) atomicAdd(dst + c, cnt[c]);
+        }
     }
     if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)nLines; P.outOffset[item] = base; }
 }

@@ -113,6 +113,8 @@ struct GatherParams {
     const uint64_t *csr;
     const halgpu_lift_rec *pool;
     halgpu_lift_rec *recs;
+    const uint32_t *pslPool; // optional
+    uint32_t *psl;
     int64_t n;
 };
 __global__ void gatherKernel(const GatherParams p) {
@@ -121,6 +123,8 @@ __global__ void gatherKernel(const GatherParams p) {
         const uint32_t c = p.outCount[i];
         const uint64_t from = p.outOffset[i], to = p.csr[i];
         for (uint32_t k = 0; k < c; ++k) p.recs[to + k] = p.pool[from + k];
+        if (p.pslPool)
+            for (uint32_t k = 0; k < 4 * c; ++k) p.psl[4 * to + k] = p.pslPool[4 * from + k];
     }
 }
 

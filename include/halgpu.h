@@ -55,11 +55,15 @@ typedef struct halgpu_lift_result {
     float kernel_ms;
     int launches;
     size_t n_retry;           /* intervals that needed the large-scratch re-launch */
+    /* HALGPU_PSL only (else NULL): per output line the four PSL base counts of BlockLiftover::readPSLInfo
+     * (liftover/impl/halBlockLiftover.cpp:115-162): matches, misMatches, repMatches, nCount -- 4 x uint32 per record */
+    uint32_t *psl;
 } halgpu_lift_result;
 
 enum {
     HALGPU_NO_DUPES = 1u,     /* halLiftover --noDupes (liftover/impl/halLiftoverMain.cpp:24) */
-    HALGPU_NO_SORT = 2u       /* do not reorder the batch by source position inside the call */
+    HALGPU_NO_SORT = 2u,      /* do not reorder the batch by source position inside the call */
+    HALGPU_PSL = 4u           /* also compare source and target DNA of every mapped fragment (halLiftover --outPSL) */
 };
 
 /* ---- open / stage (replaces openHalAlignment + MMapAlignment ctor, api/impl/halAlignmentInstance.cpp:133,

@@ -93,6 +93,21 @@ def main():
     s = "randgenSmallSeed0.hal"
     for i, (a, b) in enumerate([("Genome_0", "Genome_2"), ("Genome_3", "Genome_2"), ("Genome_2", "Genome_3"), ("Genome_1", "Genome_0")]):
         add(f"small_{a}_{b}", s, a, b, rand_bed(s, a, 300, 900, 200 + i))
+    # PSL (liftover/Makefile halLiftoverPsl*Test + BedLiftoverTest case3 PSL expectations, halLiftoverTests.cpp:358-373)
+    def addp(name, hal, src, tgt, bed, args):
+        inp = os.path.join(HERE, "cases", name + ".in.bed")
+        out = os.path.join(HERE, "cases", name + ".out.bed")
+        open(inp, "w").write(bed)
+        run("timeout", "120", REF + "/halLiftover", *args, os.path.join(HERE, hal), src, inp, tgt, out)
+        cases.append(dict(name=name, hal=hal, src=src, tgt=tgt, args=list(args)))
+    case3 = ("Sequence\t0\t10\tSEGMENT_0\t0\t+\t0\t10\t128,0,0\t1\t10\t0,\n"
+             "Sequence\t10\t30\tSEGMENT_1\t0\t+\t10\t30\t128,0,0\t1\t20\t0,\n"
+             "Sequence\t30\t45\tSEGMENT_2\t0\t+\t30\t45\t128,0,0\t1\t15\t0,\n"
+             "Sequence\t45\t65\tSEGMENT_3\t0\t+\t45\t65\t128,0,0\t1\t20\t0,\n"
+             "Sequence\t65\t75\tSEGMENT_4\t0\t+\t65\t75\t128,0,0\t1\t10\t0,\n"
+             "Sequence\t75\t100\tSEGMENT_5\t0\t+\t75\t100\t128,0,0\t1\t25\t0,\n")
+    addp("psl_ref_leaf3_leaf1", t, "leaf3", "leaf1", case3, ("--outPSL",))
+    addp("psl_ref_leaf3_leaf1_name", t, "leaf3", "leaf1", case3, ("--outPSLWithName",))
     # BED12: the unit test's case3 (halLiftoverTests.cpp:339-345) and random multi-block lines
     add("ref_bed12_leaf3_leaf1", t, "leaf3", "leaf1",
         "Sequence\t0\t10\tSEGMENT_0\t0\t+\t0\t10\t128,0,0\t1\t10\t0,\n"
@@ -170,6 +185,11 @@ def main():
     addm("maf_varlen_A0_keepempty", v, ["--refGenome", "A0", "--refSequence", "A0_s2", "--length", "2500", "--keepEmptyRefBlocks"])
     json.dump(mcases, open(os.path.join(HERE, "cases", "maf_index.json"), "w"), indent=1)
     json.dump(dcases, open(os.path.join(HERE, "cases", "depth_index.json"), "w"), indent=1)
+    addp("psl_varlen_L0_L3", v, "L0", "L3", rand_bed(v, "L0", 300, 300, 401, "+-"), ("--outPSL",))
+    addp("psl_varlen_L3_L1_name", v, "L3", "L1", rand_bed(v, "L3", 300, 300, 402, "+-"), ("--outPSLWithName",))
+    addp("psl_varlen_R_L2_bed12", v, "R", "L2", rand_bed12(v, "R", 200, 403), ("--outPSL",))
+    addp("psl_varlen_L1_A1_bed12_nodupes", v, "L1", "A1", rand_bed12(v, "L1", 200, 404), ("--outPSL", "--noDupes"))
+    addp("psl_small_G3_G2", s, "Genome_3", "Genome_2", rand_bed(s, "Genome_3", 200, 900, 405, "+-"), ("--outPSL",))
     json.dump(cases, open(os.path.join(HERE, "cases", "index.json"), "w"), indent=1)
     print(len(cases), "cases written")
 

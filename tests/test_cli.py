@@ -7,7 +7,8 @@ import pytest
 
 from conftest import GOLDEN, ROOT, ref_bin
 
-REF_GOLDENS = [("test1.bed3", "halLiftoverBed3Test.bed", []), ("test1.bed12", "halLiftoverBed12Test.bed", []),
+REF_GOLDENS = [("test1.bed3", "halLiftoverPsl3Test.psl", ["--outPSL"]), ("test1.bed12", "halLiftoverPsl12Test.psl", ["--outPSL"]),
+               ("test1.bed3", "halLiftoverBed3Test.bed", []), ("test1.bed12", "halLiftoverBed12Test.bed", []),
                ("test1.bed12+2", "halLiftoverBed12ExtraTest.bed", []), ("test1.bed4+2", "halLiftoverBed4ExtraTest.bed", ["--bedType", "4"])]
 
 
@@ -31,7 +32,8 @@ def check_all(cli, golden_cases, tmp_path, pick):
 
 
 def test_cli_emulated_matches_reference_outputs(emul_cli, golden_cases, tmp_path):
-    check_all(emul_cli, golden_cases, tmp_path, lambda c: "bed12" in c["name"] or c["name"].startswith("ref_") and "_all_" not in c["name"])
+    check_all(emul_cli, golden_cases, tmp_path,
+              lambda c: "bed12" in c["name"] or c["name"].startswith("psl_") or c["name"].startswith("ref_") and "_all_" not in c["name"])
 
 
 def test_cli_errors(emul_cli, tmp_path):

@@ -40,7 +40,7 @@ def test_emulated_kernel_reference_golden_text(emul_lib, golden_cases):
     import hal_b200
     path = os.path.join(GOLDEN, "refBedLiftoverTest.hal")
     a = hal_b200.Alignment(path, lib_path=emul_lib)
-    for c in [c for c in golden_cases if c["name"].startswith("ref_") and "_all_" not in c["name"] and "bed12" not in c["name"]]:
+    for c in [c for c in golden_cases if c["name"].startswith("ref_") and "_all_" not in c["name"] and "bed12" not in c["name"] and not c["name"].startswith("psl_")]:
         bed = open(os.path.join(GOLDEN, "cases", c["name"] + ".in.bed")).read()
         exp = open(os.path.join(GOLDEN, "cases", c["name"] + ".out.bed")).read()
         s, t = a.genome_id(c["src"]), a.genome_id(c["tgt"])

@@ -49,7 +49,7 @@ def test_cuda_golden_text(hb, golden_cases):
     opened = {}
     try:
         for c in golden_cases:
-            if "bed12" in c["name"]:
+            if "bed12" in c["name"] or c["name"].startswith("psl_"):
                 continue  # BED12 regrouping is host C++ (tests/test_cli.py)
             a = opened.get(c["hal"]) or opened.setdefault(c["hal"], hb.Alignment(os.path.join(GOLDEN, c["hal"])))
             bed = open(os.path.join(GOLDEN, "cases", c["name"] + ".in.bed")).read()
