@@ -306,16 +306,22 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                     const int64_t L = botStart(st.bot, idx + 1) - b0;
                     const int64_t ci = ce >> 1;
                     const bool fl = (ce & 1) != 0;
-                    const int64_t cs = topStart(steps[p + 1].top, ci);
+                    int64_t cs;
+                    if (P.dupes) { // one 32-byte read gives the landing start AND tells whether a paralogy ring hangs here
+                        const TopRec rc = ldTop(&steps[p + 1].top[ci]);
+                        cs = rc.start;
+                        landedDown = rc.nextPara >= 0;
+                    } else {
+                        cs = topStart(steps[p + 1].top, ci);
+                    }
                     const int64_t off = tLo - b0;
                     tLo = fl ? cs + L - off - len : cs + off;
                     tRev = tRev != fl;
                     kindTop = true; idx = ci; ++p;
-                    landedDown = true;
                 }
             }
         }
-        if (landedDown && P.dupes) ringFirst = idx;
+        if (landedDown) ringFirst = idx; // mapSelf: only a top with a next paralog starts a ring walk
         {
             const unsigned pm = __ballot_sync(HG_FULL, doPush);
             if (pm) {
@@ -367,22 +373,32 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         }
     }
     __syncwarp();
-    // order of the MappedSegmentSet
-    bool unsorted = false;
-    for (int i = lane; i + 1 < m; i += 32) unsorted |= fragLess(listA[i + 1], listA[i]);
+    // one pass over neighbouring pairs: order of the MappedSegmentSet, its "identical or disjoint" invariant
+    // (insertAndBreakOverlaps) and whether any equal-target-start class has more than one member
+    bool unsorted = false, clash = false, classes = false, split = false;
+    for (int i = lane; i + 1 < m; i += 32) {
+        const Frag a = listA[i], b = listA[i + 1];
+        unsorted |= fragLess(b, a);
+        const bool same = a.tLo == b.tLo && a.len == b.len;
+        clash |= !(same || b.tLo > a.tLo + a.len - 1);
+        classes |= a.tLo == b.tLo;
+        split |= !canMergeRight(a, b);
+    }
+    // collinear interval (the common case): already in set order, no overlaps, every neighbour merges -> one line
+    const bool single = !__any_sync(HG_FULL, unsorted || clash || classes || split);
     Frag *cur = listA, *oth = listB;
     if (__any_sync(HG_FULL, unsorted)) {
         warpRankSort(cur, oth, m, lane);
         Frag *t = cur; cur = oth; oth = t;
+        clash = false; classes = false;
+        for (int i = lane; i + 1 < m; i += 32) {
+            const Frag a = cur[i], b = cur[i + 1];
+            const bool same = a.tLo == b.tLo && a.len == b.len;
+            clash |= !(same || b.tLo > a.tLo + a.len - 1);
+            classes |= a.tLo == b.tLo;
+        }
     }
-    // identical-or-disjoint invariant of the set (insertAndBreakOverlaps): violated -> common refinement
-    bool clash = false;
-    for (int i = lane; i + 1 < m; i += 32) {
-        const Frag a = cur[i], b = cur[i + 1];
-        const bool same = a.tLo == b.tLo && a.len == b.len;
-        const bool disjoint = b.tLo > a.tLo + a.len - 1;
-        clash |= !(same || disjoint);
-    }
+    bool refined = false;
     if (__any_sync(HG_FULL, clash)) {
         // cut every fragment at every other fragment's tLo and tHi+1 that falls strictly inside it
         int total = 0;
@@ -455,6 +471,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         __syncwarp();
         m = kept;
         Frag *t = cur; cur = oth; oth = t;
+        refined = true;
     }
 
     // ---- merge into output lines (BlockMapper::extractSegment) ----
@@ -467,17 +484,28 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     int32_t *v2 = v1 + m;
     uint8_t *dead = reinterpret_cast<uint8_t *>(v2 + m);
     int32_t *runOf = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(oth) + (((size_t)25 * (size_t)m + 3) & ~(size_t)3));
-    bool classes = false;
-    for (int i = lane; i + 1 < m; i += 32) classes |= cur[i].tLo == cur[i + 1].tLo;
+    if (refined) { // the refinement changed the list: recompute
+        classes = false;
+        for (int i = lane; i + 1 < m; i += 32) classes |= cur[i].tLo == cur[i + 1].tLo;
+    }
     int nLines = 0;
-    if (!__any_sync(HG_FULL, classes)) {
+    if (single) {
+        if (lane == 0) { runHead[0] = 0; runTail[0] = m - 1; }
+        if (P.pslPool) for (int i = lane; i < m; i += 32) runOf[i] = 0;
+        nLines = 1;
+        __syncwarp();
+    } else if (!__any_sync(HG_FULL, classes)) {
         // every equal-target-start class has one member: a run is a maximal chain of mergeable neighbours
+        bool prevMerges = false; // does the last fragment of the previous 32 merge into this chunk's first?
         for (int base = 0; base < m; base += 32) {
             const int i = base + lane;
-            const bool head = i < m && (i == 0 || !canMergeRight(cur[i - 1], cur[i]));
-            const bool tail = i < m && (i == m - 1 || !canMergeRight(cur[i], cur[i + 1]));
+            const bool mr = i + 1 < m && canMergeRight(cur[i], cur[i + 1]);
+            const unsigned mm = __ballot_sync(HG_FULL, mr);
+            const bool mergesFromLeft = lane == 0 ? prevMerges : ((mm >> (lane - 1)) & 1u) != 0;
+            const bool head = i < m && !mergesFromLeft;
+            const bool tail = i < m && !mr;
+            prevMerges = (mm >> 31) != 0;
             const unsigned hm = __ballot_sync(HG_FULL, head);
-            const unsigned tm = __ballot_sync(HG_FULL, tail);
             if (head) runHead[nLines + lanePrefix(hm, lane)] = i;
             // a tail closes the run opened by the latest head at or before it
             const int headsUpToMe = __popc(hm & ((2u << lane) - 1u));
