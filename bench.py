@@ -151,6 +151,9 @@ def reference_throughput(hal, gs, ge, seq_name, sample, cores):
 
 
 def main():
+    # stdout carries exactly one JSON line: anything native libraries print there (NCCL's version banner ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -189,13 +192,13 @@ def main():
                 vals.append(r)
         dt = sum(v["seconds"] for v in vals) / len(vals)
         v = sample / dt
-        print(json.dumps({"impl": "reference", "metric": "liftover_intervals_per_sec", "value": v, "unit": "intervals/s",
+        print(file=real_stdout, flush=True, *[json.dumps({"impl": "reference", "metric": "liftover_intervals_per_sec", "value": v, "unit": "intervals/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
                           "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "intervals/s", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"],
                                            "sample": vals[-1]["sample"]},
-                          "e2e": {"value": v, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
         return
 
     import numpy as np
@@ -384,7 +387,7 @@ def main():
         sample = args.cpu_sample or min(2_000_000, max(2000, cores * 6000))
         r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
         line["cpu_baseline"] = {"value": r["value"], "unit": "intervals/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     a.close()
     if dist:
         dist.barrier()
