@@ -115,41 +115,90 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
     return guarded(err, [&] {
         rt::setDevice(ctx->impl->device());
         rt::Stream s = ctx->impl->stream();
-        // bounds check against the source genome (the CLI layer reports per-line errors; this is the last line of defence)
-        const GenomeInfo *S = genome(ctx, src);
-        if (S == nullptr || genome(ctx, tgt) == nullptr) throw HalError("genome index out of range");
-        for (size_t i = 0; i < n; ++i) {
-            if (start[i] < 0 || endIncl[i] < start[i] || endIncl[i] >= S->length) {
-                throw HalError("interval " + std::to_string(i) + " is outside genome " + S->name);
-            }
+        (void)s;
+        if (genome(ctx, src) == nullptr || genome(ctx, tgt) == nullptr) throw HalError("genome index out of range");
+        // (interval bounds are validated by the kernel itself: an out-of-range interval makes the call fail)
+        // Pipeline: the batch is cut into chunks; while chunk k is being lifted on the engine's stream, chunk k+1's inputs
+        // travel host->device and chunk k-1's records travel device->host on the copy stream.
+        rt::Stream cs = ctx->impl->copyStream();
+        size_t nChunks = n >= (4u << 20) ? 8 : (n >= (1u << 20) ? 4 : 1);
+        if (const char *forced = std::getenv("HALGPU_HOST_CHUNKS")) { // test hook
+            const long f = std::atol(forced);
+            if (f >= 1 && (size_t)f <= std::max<size_t>(n, 1)) nChunks = (size_t)f;
         }
-        void *dS = rt::dmallocAsync(n * 8, s), *dE = rt::dmallocAsync(n * 8, s), *dT = strand ? rt::dmallocAsync(n, s) : nullptr;
-        halgpu_lift_result *dev = nullptr;
-        char *e2 = nullptr;
-        rt::h2d(dS, start, n * 8, s);
-        rt::h2d(dE, endIncl, n * 8, s);
-        if (strand) rt::h2d(dT, strand, n, s);
-        int rc = halgpu_liftover_device(ctx, src, tgt, coalescenceLimit, flags, n, (const int64_t *)dS, (const int64_t *)dE,
-                                        (const uint8_t *)dT, &dev, &e2);
-        rt::dfreeAsync(dS, s); rt::dfreeAsync(dE, s); rt::dfreeAsync(dT, s);
-        if (rc != 0) {
-            std::string m = e2 ? e2 : "liftover failed";
-            std::free(e2);
-            throw HalError(m);
-        }
+        std::vector<size_t> lo(nChunks + 1);
+        for (size_t k = 0; k <= nChunks; ++k) lo[k] = n * k / nChunks;
+        void *dS = rt::dmallocAsync(n * 8, cs), *dE = rt::dmallocAsync(n * 8, cs), *dT = strand ? rt::dmallocAsync(n, cs) : nullptr;
+        std::vector<rt::Event> inReady(nChunks);
+        auto upload = [&](size_t k) {
+            const size_t a = lo[k], c = lo[k + 1] - lo[k];
+            rt::h2d((int64_t *)dS + a, start + a, c * 8, cs);
+            rt::h2d((int64_t *)dE + a, endIncl + a, c * 8, cs);
+            if (strand) rt::h2d((uint8_t *)dT + a, strand + a, c, cs);
+            inReady[k].record(cs);
+        };
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
-        *r = *dev;
-        r->on_device = 0;
-        r->offsets = static_cast<uint64_t *>(rt::hostAlloc((n + 1) * sizeof(uint64_t)));
-        r->recs = static_cast<halgpu_lift_rec *>(rt::hostAlloc(std::max<size_t>(dev->n_rec, 1) * sizeof(halgpu_lift_rec)));
-        rt::d2h(r->offsets, dev->offsets, (n + 1) * sizeof(uint64_t), s);
-        rt::d2h(r->recs, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), s);
-        if (dev->psl != nullptr) {
-            r->psl = static_cast<uint32_t *>(rt::hostAlloc(std::max<size_t>(dev->n_rec, 1) * 16));
-            rt::d2h(r->psl, dev->psl, dev->n_rec * 16, s);
+        std::vector<halgpu_lift_result *> parts;
+        size_t recCap = n + n / 4 + 4096, nRec = 0;
+        const bool wantPsl = (flags & HALGPU_PSL) != 0;
+        try {
+            r->n = n;
+            r->offsets = static_cast<uint64_t *>(rt::hostAlloc((n + 1) * sizeof(uint64_t)));
+            r->recs = static_cast<halgpu_lift_rec *>(rt::hostAlloc(recCap * sizeof(halgpu_lift_rec)));
+            if (wantPsl) r->psl = static_cast<uint32_t *>(rt::hostAlloc(recCap * 16));
+            std::vector<uint64_t> base(nChunks + 1, 0);
+            upload(0);
+            for (size_t k = 0; k < nChunks; ++k) {
+                if (k + 1 < nChunks) upload(k + 1);
+                inReady[k].wait(s); // the engine's stream waits for this chunk's inputs only
+                const size_t a = lo[k], c = lo[k + 1] - lo[k];
+                halgpu_lift_result *dev = nullptr;
+                char *e2 = nullptr;
+                const int rc = halgpu_liftover_device(ctx, src, tgt, coalescenceLimit, flags, c, (const int64_t *)dS + a, (const int64_t *)dE + a,
+                                                      strand ? (const uint8_t *)dT + a : nullptr, &dev, &e2);
+                if (rc != 0) {
+                    std::string m = e2 ? e2 : "liftover failed";
+                    std::free(e2);
+                    throw HalError(m);
+                }
+                parts.push_back(dev);
+                if (nRec + dev->n_rec > recCap) { // grow the pinned result (rare: more than 1.25 lines per interval)
+                    rt::sync(cs);
+                    const size_t newCap = std::max(recCap * 2, nRec + dev->n_rec + (n - lo[k + 1]) * 2);
+                    halgpu_lift_rec *nr = static_cast<halgpu_lift_rec *>(rt::hostAlloc(newCap * sizeof(halgpu_lift_rec)));
+                    std::memcpy(nr, r->recs, nRec * sizeof(halgpu_lift_rec));
+                    rt::hostFree(r->recs);
+                    r->recs = nr;
+                    if (wantPsl) {
+                        uint32_t *np = static_cast<uint32_t *>(rt::hostAlloc(newCap * 16));
+                        std::memcpy(np, r->psl, nRec * 16);
+                        rt::hostFree(r->psl);
+                        r->psl = np;
+                    }
+                    recCap = newCap;
+                }
+                // halgpu_liftover_device returns with the engine's stream idle, so the copy stream may read the result now
+                rt::d2h(r->offsets + a, dev->offsets, (c + (k + 1 == nChunks ? 1 : 0)) * sizeof(uint64_t), cs);
+                rt::d2h(r->recs + nRec, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), cs);
+                if (wantPsl) rt::d2h(r->psl + 4 * nRec, dev->psl, dev->n_rec * 16, cs);
+                base[k] = nRec;
+                nRec += dev->n_rec;
+                r->kernel_ms += dev->kernel_ms; r->launches += dev->launches; r->n_retry += dev->n_retry;
+            }
+            rt::sync(cs);
+            for (size_t k = 1; k < nChunks; ++k) // chunk-local CSR offsets -> batch offsets
+                for (size_t i = lo[k]; i < lo[k + 1]; ++i) r->offsets[i] += base[k];
+            if (nChunks > 1) r->offsets[n] += base[nChunks - 1];
+            r->n_rec = nRec;
+        } catch (...) {
+            rt::sync(cs);
+            for (halgpu_lift_result *d : parts) halgpu_free_result(d);
+            rt::dfreeAsync(dS, cs); rt::dfreeAsync(dE, cs); rt::dfreeAsync(dT, cs);
+            halgpu_free_result(r);
+            throw;
         }
-        rt::sync(s);
-        halgpu_free_result(dev);
+        for (halgpu_lift_result *d : parts) halgpu_free_result(d);
+        rt::dfreeAsync(dS, cs); rt::dfreeAsync(dE, cs); rt::dfreeAsync(dT, cs);
         *out = r;
     });
 }

@@ -52,6 +52,7 @@ struct LiftParams {
     int32_t srcIsTop;
     int32_t srcShift;
     int64_t srcN;
+    int64_t srcLen;            // length of the source genome (inputs are validated on the device)
     const uint32_t *srcBucket; // srcBucket[b] = index of the segment containing position b << srcShift
     int64_t srcNumBuckets;
     // target genome sequence starts (numSeq + 1 entries, last = genome length)
@@ -103,6 +104,6 @@ struct ColRowRec { // 16 B
 };
 
 
-enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2 };
+enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2, ST_BAD_INPUT = 3 };
 
 } // namespace halgpu

@@ -91,6 +91,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     rt::setDevice(device);
     rt::retainPool(device);
     _stream = rt::createStream();
+    _copy = rt::createStream();
     _sms = rt::smCount();
     _g.resize(_file->genomes().size());
     try {
@@ -99,6 +100,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     } catch (...) {
         for (void *p : _owned) rt::dfree(p);
         rt::destroyStream(_stream);
+        rt::destroyStream(_copy);
         throw;
     }
 }
@@ -107,6 +109,7 @@ Context::~Context() {
     for (auto &kv : _plans) rt::dfree(kv.second.dSteps);
     for (void *p : _owned) rt::dfree(p);
     rt::destroyStream(_stream);
+    rt::destroyStream(_copy);
 }
 
 void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb) {
@@ -349,8 +352,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     DevBuf outCount((n + 1) * sizeof(uint32_t)), outOffset((n + 1) * sizeof(uint64_t)), status((n + 1) * sizeof(uint32_t));
     rt::dmemset(outCount.p, 0, (n + 1) * sizeof(uint32_t), _stream);
     rt::dmemset(status.p, 0xff, (n + 1) * sizeof(uint32_t), _stream);
-    DevBuf cursor(2 * sizeof(unsigned long long));
-    rt::dmemset(cursor.p, 0, 2 * sizeof(unsigned long long), _stream);
+    DevBuf cursor(8 * sizeof(unsigned long long)); // [0] pool cursor, [1] list count, [4..7] per-status counts
+    rt::dmemset(cursor.p, 0, 8 * sizeof(unsigned long long), _stream);
 
     // visit the batch in source order so that neighbouring warps walk neighbouring records (L2 reuse)
     std::unique_ptr<DevBuf> work, keysIn, keysOut, valsIn;
@@ -383,6 +386,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     P.srcIsTop = srcIsTop ? 1 : 0;
     P.srcShift = srcIsTop ? _g[src].topShift : _g[src].botShift;
     P.srcN = srcIsTop ? S.numTop : S.numBottom;
+    P.srcLen = S.length;
     P.srcBucket = srcIsTop ? _g[src].topBucket : _g[src].botBucket;
     P.srcNumBuckets = srcIsTop ? _g[src].topBuckets : _g[src].botBuckets;
     P.tgtSeqStart = _g[tgt].seqStart; P.tgtNumSeq = (int32_t)G[tgt].sequences.size();
@@ -421,10 +425,24 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         return c;
     };
     int listCap = 64, frameCap = 32;
-    std::unique_ptr<DevBuf> pending; // ids still to do (copy of list)
     for (int round = 0; round < 64; ++round) {
+        // one pass over the statuses; in the common case (everything ST_OK) this is the only check
+        unsigned long long counts[4] = {0, 0, 0, 0};
+        {
+            unsigned long long *dCounts = cursor.as<unsigned long long>() + 4;
+            rt::dmemset(dCounts, 0, 4 * sizeof(unsigned long long), _stream);
+            StatusCountParams sp;
+            sp.status = P.status; sp.counts = dCounts; sp.n = (int64_t)n;
+            rt::launch(statusCountKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, sp);
+            rt::d2h(counts, dCounts, sizeof(counts), _stream);
+            rt::sync(_stream);
+        }
+        if (counts[ST_BAD_INPUT] > 0) {
+            throw HalError(std::to_string(counts[ST_BAD_INPUT]) + " interval(s) lie outside genome " + S.name + " (length " + std::to_string(S.length) + ")");
+        }
+        if (counts[ST_POOL_FULL] == 0 && counts[ST_SCRATCH_OVERFLOW] == 0) break;
         // (a) intervals that found the output pool full: grow it (old records stay valid) and redo them
-        uint64_t nFull = collect(ST_POOL_FULL, nullptr, (int64_t)n);
+        uint64_t nFull = counts[ST_POOL_FULL] ? collect(ST_POOL_FULL, nullptr, (int64_t)n) : 0;
         if (nFull > 0) {
             unsigned long long used = 0;
             rt::d2h(&used, P.poolCursor, sizeof(used), _stream);
@@ -462,7 +480,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // (b) intervals whose fragment lists outgrew the scratch: next rung
         uint64_t nOver = collect(ST_SCRATCH_OVERFLOW, nullptr, (int64_t)n);
         if (nOver == 0) break;
-        if (round == 0 || out.nRetry == 0) out.nRetry = nOver;
+        if (out.nRetry == 0) out.nRetry = nOver;
         listCap *= (listCap == 64 ? 64 : 16); // 64 -> 4096 -> 65536 -> 1M
         frameCap = listCap / 4;
         if (listCap > (1 << 24)) throw HalError("an interval maps to more than 16M fragments; not supported");

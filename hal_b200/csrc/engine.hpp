@@ -44,6 +44,7 @@ class Context {
     ~Context();
     const HalFile &file() const { return *_file; }
     rt::Stream stream() const { return _stream; }
+    rt::Stream copyStream() const { return _copy; } // host<->device traffic of the pipelined host-buffer entry point
     size_t stagedBytes() const { return _staged; }
     int device() const { return _device; }
     // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
@@ -66,7 +67,7 @@ class Context {
 
     std::unique_ptr<HalFile> _file;
     int _device;
-    rt::Stream _stream;
+    rt::Stream _stream, _copy;
     std::vector<GenomeDev> _g;
     std::map<std::pair<int, int>, Plan> _plans;
     std::vector<void *> _owned;

@@ -149,6 +149,10 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';
+    if (gs < 0 || ge < gs || ge >= P.srcLen) { // reported by the engine as an error; nothing is read for this item
+        if (lane == 0) { P.status[item] = ST_BAD_INPUT; P.outCount[item] = 0; }
+        return;
+    }
     const PathStep *steps = P.steps;
     const int np = P.P;
     const int listCap = P.listCap, frameCap = P.frameCap;

@@ -106,6 +106,23 @@ __global__ void collectKernel(const CollectParams p) {
     }
 }
 
+// how many intervals ended in each state (one pass; the id lists are only built when a retry is needed)
+struct StatusCountParams {
+    const uint32_t *status;
+    unsigned long long *counts; // 4 entries, indexed by ST_*
+    int64_t n;
+};
+__global__ void statusCountKernel(const StatusCountParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    unsigned local[4] = {0u, 0u, 0u, 0u};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const uint32_t s = p.status[i];
+        if (s < 4u) local[s]++;
+    }
+    for (int k = 1; k < 4; ++k)
+        if (local[k]) atomicAdd(p.counts + k, (unsigned long long)local[k]);
+}
+
 // pool (allocation order) -> CSR (input order)
 struct GatherParams {
     const uint32_t *outCount;

@@ -75,3 +75,20 @@ def test_emulated_depth_equals_oracle(emul_lib, oracle_lib, hal, ref, flags, tar
     got3, _ = a.depth(g, 7, last, 3, t, flags)
     assert np.array_equal(got3, exp[7::3])
     a.close()
+
+
+def test_emulated_host_pipeline_chunks(emul_lib, oracle_lib, monkeypatch):
+    """halgpu_liftover cuts big host batches into chunks (copy/compute overlap); forced here on a small batch."""
+    import hal_b200
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    monkeypatch.setenv("HALGPU_HOST_CHUNKS", "3")
+    a = hal_b200.Alignment(path, lib_path=emul_lib)
+    s, t = a.genome_id("L0"), a.genome_id("L3")
+    gs, ge, st = random_intervals(a.genome_length(s), 100, 300, seed=3)
+    off, recs, info = a.liftover(s, t, gs, ge, st, hal_b200.HALGPU_PSL)
+    assert_same_as_oracle(off, recs, o.liftover(s, t, gs, ge, st))
+    monkeypatch.delenv("HALGPU_HOST_CHUNKS")
+    off1, recs1, info1 = a.liftover(s, t, gs, ge, st, hal_b200.HALGPU_PSL)
+    assert np.array_equal(off, off1) and np.array_equal(recs, recs1) and np.array_equal(info["psl"], info1["psl"])
+    a.close()

@@ -151,3 +151,26 @@ def test_cuda_depth_synthetic_properties(hb, tmp_path):
         assert (d[: L - 64] == 15).all() and (d[L - 32:] == 0).all()
         d2, _ = a.depth(g, 0, L - 1, flags=hb.HALGPU_NO_ANCESTORS)
         assert (d2[: L - 64] == 7).all()
+
+
+def _tree(depth, prefix):
+    return prefix if depth == 0 else "(" + _tree(depth - 1, prefix + "a") + "," + _tree(depth - 1, prefix + "b") + ")" + prefix
+
+
+def test_cuda_deep_tree_equals_oracle(hb, oracle_lib, tmp_path):
+    """63 genomes, 6 levels (BASELINE configs[3] shape, scaled down), halRandGen-style events (transpositions ->
+    paralogy rings, inversions, insertions): leaf -> far leaf is 5 hops up + 5 down; compare with the oracle."""
+    hal = str(tmp_path / "t63.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", _tree(5, "N") + ";", "--segs", "20000",
+                           "--segLen", "24", "--branch", "0.08", "--seed", "5", hal])
+    o = oracle_lib.Oracle(hal)
+    with hb.Alignment(hal) as a:
+        for src, tgt, n in (("Naaaaa", "Nbbbbb", 20000), ("Nababa", "Nabbbb", 20000), ("N", "Nbabab", 5000), ("Nbbbba", "N", 5000)):
+            s, t = a.genome_id(src), a.genome_id(tgt)
+            gs, ge, st = random_intervals(a.genome_length(s), n, 600, seed=n + len(src))
+            off, recs, info = a.liftover(s, t, gs, ge, st)
+            assert_same_as_oracle(off, recs, o.liftover(s, t, gs, ge, st))
+        g = a.genome_id("Nabab")
+        d, _ = a.depth(g, 0, 99999)
+        e, _ = o.depth(g, 0, 99999)
+        assert np.array_equal(d, e)
