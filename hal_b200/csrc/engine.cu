@@ -3,6 +3,9 @@
 #include "liftover_kernel.cuh"
 #include "stage_kernels.cuh"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -335,8 +338,25 @@ void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const st
     if (err) throw HalError("column walk exceeded its stack (more than " + std::to_string(HG_WALK_STACK) + " pending branches)");
 }
 
+namespace {
+struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch (diagnostics only)
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string log;
+    PhaseTimer() : on(std::getenv("HALGPU_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        log += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::milli>(t - t0).count()) + "ms ";
+        t0 = t;
+    }
+    ~PhaseTimer() { if (on) fprintf(stderr, "[halgpu timing] %s\n", log.c_str()); }
+};
+} // namespace
+
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
                        const uint8_t *dStrand, LiftOutput &out) {
+    PhaseTimer pt;
     const auto &G = _file->genomes();
     if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
     if (n >= 0xffffffffull) throw HalError("batch too large (>= 2^32 intervals); split it");
@@ -355,6 +375,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     DevBuf cursor(8 * sizeof(unsigned long long)); // [0] pool cursor, [1] list count, [4..7] per-status counts
     rt::dmemset(cursor.p, 0, 8 * sizeof(unsigned long long), _stream);
 
+    pt.mark("alloc0");
     // visit the batch in source order so that neighbouring warps walk neighbouring records (L2 reuse)
     std::unique_ptr<DevBuf> work, keysIn, keysOut, valsIn;
     const uint32_t *dWork = nullptr;
@@ -371,6 +392,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         keysIn.reset(); keysOut.reset(); valsIn.reset();
     }
 
+    if (pt.on) rt::sync(_stream);
+    pt.mark("sort");
     uint64_t poolCap = (uint64_t)n + (uint64_t)n / 4 + 4096;
     std::unique_ptr<DevBuf> pool(new DevBuf(poolCap * sizeof(halgpu_lift_rec)));
     const bool wantPsl = (flags & HALGPU_PSL) != 0;
@@ -410,6 +433,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         rt::sync(_stream);
         out.kernelMs = rt::Event::elapsedMs(e0, e1);
     }
+    pt.mark("kernel");
 
     // retry ladder: pool growth, then larger per-warp scratch in global memory
     DevBuf list((n + 1) * sizeof(uint32_t));
@@ -497,6 +521,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         rt::sync(_stream);
     }
 
+    pt.mark("status");
     // CSR assembly in input order
     DevBuf *csr = new DevBuf((n + 2) * sizeof(uint64_t));
     std::unique_ptr<DevBuf> csrHold(csr);
@@ -504,6 +529,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     uint64_t total = 0;
     rt::d2h(&total, csr->as<uint64_t>() + n, sizeof(total), _stream);
     rt::sync(_stream);
+    pt.mark("scan");
     DevBuf *recs = new DevBuf(std::max<uint64_t>(total, 1) * sizeof(halgpu_lift_rec));
     std::unique_ptr<DevBuf> recsHold(recs);
     std::unique_ptr<DevBuf> pslHold;
@@ -514,6 +540,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     gp.pool = pool->as<halgpu_lift_rec>(); gp.recs = recs->as<halgpu_lift_rec>(); gp.n = (int64_t)n;
     rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
     rt::sync(_stream);
+    pt.mark("gather");
     out.offsets = static_cast<uint64_t *>(csrHold->release());
     out.recs = static_cast<halgpu_lift_rec *>(recsHold->release());
     out.psl = wantPsl ? static_cast<uint32_t *>(pslHold->release()) : nullptr;
