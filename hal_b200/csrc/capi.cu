@@ -86,9 +86,17 @@ int halgpu_mrca(const halgpu_ctx *ctx, int a, int b) {
 size_t halgpu_staged_bytes(const halgpu_ctx *ctx) { return ctx ? ctx->impl->stagedBytes() : 0; }
 void *halgpu_stream(const halgpu_ctx *ctx) { return ctx ? (void *)(uintptr_t)ctx->impl->stream() : nullptr; }
 
+static int liftDeviceWithBase(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uint32_t flags, size_t n, const int64_t *dStart,
+                              const int64_t *dEnd, const uint8_t *dStrand, uint64_t offsetBase, halgpu_lift_result **out, char **err);
+
 int halgpu_liftover_device(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uint32_t flags, size_t n,
                            const int64_t *dStart, const int64_t *dEnd, const uint8_t *dStrand,
                            halgpu_lift_result **out, char **err) {
+    return liftDeviceWithBase(ctx, src, tgt, coalescenceLimit, flags, n, dStart, dEnd, dStrand, 0, out, err);
+}
+
+static int liftDeviceWithBase(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uint32_t flags, size_t n, const int64_t *dStart,
+                              const int64_t *dEnd, const uint8_t *dStrand, uint64_t offsetBase, halgpu_lift_result **out, char **err) {
     if (ctx == nullptr || out == nullptr) return fail(err, "halgpu_liftover: null argument");
     *out = nullptr;
     if (coalescenceLimit != -1 && coalescenceLimit != halgpu_mrca(ctx, src, tgt)) {
@@ -97,7 +105,7 @@ int halgpu_liftover_device(halgpu_ctx *ctx, int src, int tgt, int coalescenceLim
     return guarded(err, [&] {
         rt::setDevice(ctx->impl->device());
         LiftOutput lo;
-        ctx->impl->liftover(src, tgt, flags, n, dStart, dEnd, dStrand, lo);
+        ctx->impl->liftover(src, tgt, flags, n, dStart, dEnd, dStrand, lo, offsetBase);
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = n; r->n_rec = lo.nRec; r->offsets = lo.offsets; r->recs = lo.recs; r->on_device = 1;
         r->kernel_ms = lo.kernelMs; r->launches = lo.launches; r->n_retry = lo.nRetry; r->psl = lo.psl;
@@ -146,7 +154,6 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
             r->offsets = static_cast<uint64_t *>(rt::hostAlloc((n + 1) * sizeof(uint64_t)));
             r->recs = static_cast<halgpu_lift_rec *>(rt::hostAlloc(recCap * sizeof(halgpu_lift_rec)));
             if (wantPsl) r->psl = static_cast<uint32_t *>(rt::hostAlloc(recCap * 16));
-            std::vector<uint64_t> base(nChunks + 1, 0);
             upload(0);
             for (size_t k = 0; k < nChunks; ++k) {
                 if (k + 1 < nChunks) upload(k + 1);
@@ -154,8 +161,8 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                 const size_t a = lo[k], c = lo[k + 1] - lo[k];
                 halgpu_lift_result *dev = nullptr;
                 char *e2 = nullptr;
-                const int rc = halgpu_liftover_device(ctx, src, tgt, coalescenceLimit, flags, c, (const int64_t *)dS + a, (const int64_t *)dE + a,
-                                                      strand ? (const uint8_t *)dT + a : nullptr, &dev, &e2);
+                const int rc = liftDeviceWithBase(ctx, src, tgt, coalescenceLimit, flags, c, (const int64_t *)dS + a, (const int64_t *)dE + a,
+                                                  strand ? (const uint8_t *)dT + a : nullptr, nRec, &dev, &e2);
                 if (rc != 0) {
                     std::string m = e2 ? e2 : "liftover failed";
                     std::free(e2);
@@ -181,15 +188,11 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                 rt::d2h(r->offsets + a, dev->offsets, (c + (k + 1 == nChunks ? 1 : 0)) * sizeof(uint64_t), cs);
                 rt::d2h(r->recs + nRec, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), cs);
                 if (wantPsl) rt::d2h(r->psl + 4 * nRec, dev->psl, dev->n_rec * 16, cs);
-                base[k] = nRec;
                 nRec += dev->n_rec;
                 r->kernel_ms += dev->kernel_ms; r->launches += dev->launches; r->n_retry += dev->n_retry;
             }
             rt::sync(cs);
-            for (size_t k = 1; k < nChunks; ++k) // chunk-local CSR offsets -> batch offsets
-                for (size_t i = lo[k]; i < lo[k + 1]; ++i) r->offsets[i] += base[k];
-            if (nChunks > 1) r->offsets[n] += base[nChunks - 1];
-            r->n_rec = nRec;
+            r->n_rec = nRec; // (offsets already carry each chunk's base: added on the device)
         } catch (...) {
             rt::sync(cs);
             for (halgpu_lift_result *d : parts) halgpu_free_result(d);

@@ -355,7 +355,7 @@ struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch
 } // namespace
 
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                       const uint8_t *dStrand, LiftOutput &out) {
+                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase) {
     PhaseTimer pt;
     const auto &G = _file->genomes();
     if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
@@ -539,6 +539,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     gp.outCount = P.outCount; gp.outOffset = P.outOffset; gp.csr = csr->as<uint64_t>();
     gp.pool = pool->as<halgpu_lift_rec>(); gp.recs = recs->as<halgpu_lift_rec>(); gp.n = (int64_t)n;
     rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
+    if (offsetBase != 0) {
+        AddBaseParams ab;
+        ab.v = csr->as<uint64_t>(); ab.n = (int64_t)n + 1; ab.base = offsetBase;
+        rt::launch(addBaseKernel, gridFor((int64_t)n + 1, 256, _sms), 256, 0, _stream, ab);
+    }
     rt::sync(_stream);
     pt.mark("gather");
     out.offsets = static_cast<uint64_t *>(csrHold->release());

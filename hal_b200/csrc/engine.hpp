@@ -48,8 +48,9 @@ class Context {
     size_t stagedBytes() const { return _staged; }
     int device() const { return _device; }
     // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
+    // offsetBase is added to every CSR offset (the pipelined host entry point lifts a batch chunk by chunk)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                  const uint8_t *dStrand, LiftOutput &out);
+                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0);
 
     // per-base alignment depth of reference positions first, first+step, ... <= last (device output, n = count)
     void depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,

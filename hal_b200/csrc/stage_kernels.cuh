@@ -123,6 +123,16 @@ __global__ void statusCountKernel(const StatusCountParams p) {
         if (local[k]) atomicAdd(p.counts + k, (unsigned long long)local[k]);
 }
 
+struct AddBaseParams {
+    uint64_t *v;
+    int64_t n;
+    uint64_t base;
+};
+__global__ void addBaseKernel(const AddBaseParams p) { // chunk-local CSR offsets -> offsets of the whole batch
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) p.v[i] += p.base;
+}
+
 // pool (allocation order) -> CSR (input order)
 struct GatherParams {
     const uint32_t *outCount;
