@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libhalgpu.so")
 HALGPU_NO_DUPES = 1
 HALGPU_NO_SORT = 2
 HALGPU_PSL = 4
+HALGPU_COLUMN_LIFTOVER = 8
 HALGPU_COUNT_DUPES = 1
 HALGPU_NO_ANCESTORS = 2
 HALGPU_COL_NO_DUPES = 4

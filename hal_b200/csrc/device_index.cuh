@@ -37,7 +37,8 @@ struct alignas(16) BotCore {
 struct PathStep {
     const TopRec *top;
     const BotCore *bot;
-    const int64_t *child; // down transitions: childEnc column of path[p] for the slot of path[p+1]
+    const int64_t *child; // down transitions: childEnc column of path[p] for the slot of path[p+1];
+                          // up transitions: childEnc column of path[p+1] (the parent) for the slot of path[p]
     int64_t numTop, numBot;
     int32_t up;  // 1: transition p -> p+1 goes to the parent
     int32_t pad;
@@ -47,6 +48,8 @@ struct LiftParams {
     const PathStep *steps;
     int32_t P;      // genomes on the path (>= 1)
     int32_t dupes;  // !--noDupes
+    int32_t columnMerge;     // HALGPU_COLUMN_LIFTOVER: phase 2 of hal::ColumnLiftover instead of BlockLiftover's
+    int32_t upCanonicalOnly; // ... whose noDupes mode lets only canonical paralogs map up
     // seeds come from the source genome's top array if it has one, else its bottom array
     // (liftover/impl/halBlockLiftover.cpp:24-30)
     int32_t srcIsTop;

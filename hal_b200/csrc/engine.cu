@@ -210,6 +210,9 @@ const Plan &Context::plan(int src, int tgt) {
         if (!s.up && i + 1 < p.path.size()) {
             const int c = p.path[i + 1];
             s.child = _g[g].child + (size_t)G[c].slotInParent * (size_t)G[g].numBottom;
+        } else if (s.up) { // the parent's column for this genome's slot: canonical-paralog test
+            const int par = p.path[i + 1];
+            s.child = _g[par].child + (size_t)G[g].slotInParent * (size_t)G[par].numBottom;
         }
     }
     p.dSteps = static_cast<PathStep *>(rt::dmalloc(steps.size() * sizeof(PathStep)));
@@ -406,6 +409,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     LiftParams P;
     std::memset(&P, 0, sizeof(P));
     P.steps = pl.dSteps; P.P = (int32_t)pl.path.size(); P.dupes = (flags & HALGPU_NO_DUPES) ? 0 : 1;
+    P.columnMerge = (flags & HALGPU_COLUMN_LIFTOVER) ? 1 : 0;
+    P.upCanonicalOnly = (P.columnMerge && !P.dupes) ? 1 : 0;
     P.srcIsTop = srcIsTop ? 1 : 0;
     P.srcShift = srcIsTop ? _g[src].topShift : _g[src].botShift;
     P.srcN = srcIsTop ? S.numTop : S.numBottom;

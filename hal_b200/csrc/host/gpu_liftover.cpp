@@ -38,6 +38,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                                bool traverseDupes, bool outPSL, bool outPSLWithName, int coalescenceLimit) {
     if (_ctx == nullptr || in == nullptr || out == nullptr) throw std::runtime_error("GpuBlockLiftover::convert: null argument");
     if (outPSLWithName) outPSL = true;
+    if (columnLiftover && outPSL) throw std::runtime_error("PSL output needs BlockLiftover (ColumnLiftover has no source coordinates)");
     const halgpu_seq *sseq = nullptr, *tseq = nullptr;
     size_t ns = 0, nt = 0;
     if (halgpu_sequence_table(_ctx, srcGenome, &sseq, &ns) != 0 || halgpu_sequence_table(_ctx, tgtGenome, &tseq, &nt) != 0) {
@@ -121,7 +122,8 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         char *err = nullptr;
         auto t0 = std::chrono::steady_clock::now();
         const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit,
-                                       (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u),
+                                       (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u) |
+                                           (columnLiftover ? (uint32_t)HALGPU_COLUMN_LIFTOVER : 0u),
                                        gs.size(), gs.data(), ge.data(), st.data(), &res, &err);
         gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rc != 0) {

@@ -22,6 +22,9 @@ class GpuBlockLiftover {
     void convert(int srcGenome, std::istream *inBed, int tgtGenome, std::ostream *outBed, int bedType = 0,
                  bool traverseDupes = true, bool outPSL = false, bool outPSLWithName = false, int coalescenceLimit = -1);
     size_t batchLines = 1u << 20; // BED lines per GPU call
+    // lift with hal::ColumnLiftover::liftInterval semantics (liftover/inc/halColumnLiftover.h:19-26) instead of
+    // BlockLiftover's: the reference compiles that class into libHalLiftover but no CLI instantiates it
+    bool columnLiftover = false;
     // totals of the last convert()
     size_t linesIn = 0, intervalsLifted = 0, linesOut = 0;
     double gpuSeconds = 0;

@@ -25,6 +25,7 @@ static void usage(ostream &os, const char *prog) {
        << "--coalescenceLimit <value>: coalescence limit genome (only the MRCA, the default, is supported) [default = \"\"]\n"
        << "--device <value>:     CUDA device index [default = 0]\n--help:               display this help page [default = 0]\n"
        << "--noDupes:            do not map between duplications in graph. [default = 0]\n"
+       << "--columnLiftover:     (extension) use hal::ColumnLiftover instead of hal::BlockLiftover [default = 0]\n"
        << "--outPSL:             write output in PSL instead of bed format [default = 0]\n"
        << "--outPSLWithName:     write output as input BED name followed by PSL line instead of bed format [default = 0]\n";
 }
@@ -33,7 +34,7 @@ int main(int argc, char **argv) {
     vector<string> pos;
     map<string, string> opt;
     map<string, bool> flag = {{"noDupes", false}, {"append", false}, {"outPSL", false}, {"outPSLWithName", false}, {"help", false},
-                              {"inMemory", false}, {"udcVerbose", false}};
+                              {"inMemory", false}, {"udcVerbose", false}, {"columnLiftover", false}};
     const vector<string> valued = {"coalescenceLimit", "bedType", "device", "format", "cacheMDC", "cacheRDC", "cacheBytes", "cacheW0",
                                    "chunk", "deflate", "mmapFileSize", "mmapSizeIncrease", "udcCacheDir"};
     try {
@@ -101,6 +102,7 @@ int main(int argc, char **argv) {
             if (!tgtBed) throw runtime_error("Error opening tgtBed, " + pos[4]);
         }
         halgpu::GpuBlockLiftover lift(ctx);
+        lift.columnLiftover = flag["columnLiftover"];
         lift.convert(src, in, tgt, out, bedType, !flag["noDupes"], outPSL, outPSLWithName, coal);
         out->flush();
     } catch (exception &e) {

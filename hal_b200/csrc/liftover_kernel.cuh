@@ -277,6 +277,8 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                 const TopRec r = ldTop(&st.top[idx]); // toParent, halBottomSegmentIterator.cpp:40-49
                 if (r.parentEnc < 0) {
                     valid = false;
+                } else if (P.upCanonicalOnly && (ldS(&st.child[r.parentEnc >> 1]) >> 1) != idx) {
+                    valid = false; // ColumnIterator noDupes: only the canonical paralog goes up (halColumnIterator.cpp:559-560)
                 } else {
                     const int64_t L = topStart(st.top, idx + 1) - r.start;
                     const int64_t pi = r.parentEnc >> 1;
@@ -377,6 +379,67 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         }
     }
     __syncwarp();
+    if (P.columnMerge) {
+        // ColumnLiftover::liftInterval (liftover/impl/halColumnLiftover.cpp:21-92): the target bases homologous to the
+        // interval, per (sequence, strand), as maximal position runs -- forward-strand runs first, then reverse.  That set
+        // is the union of the mapped fragments' target extents, so: order by (strand, sequence, start) and sweep.
+        Frag *src = listA, *dst = listB;
+        for (int i = lane; i < m; i += 32) {
+            const Frag me = src[i];
+            const int64_t kme = ((me.meta >> 1) & 1) << 40 | (me.meta >> 3);
+            int r = 0;
+            for (int j = 0; j < m; ++j) {
+                const Frag o = src[j];
+                const int64_t ko = ((o.meta >> 1) & 1) << 40 | (o.meta >> 3);
+                const bool less = ko != kme ? ko < kme : (o.tLo != me.tLo ? o.tLo < me.tLo : (o.len != me.len ? o.len < me.len : j < i));
+                r += less ? 1 : 0;
+            }
+            dst[r] = me;
+        }
+        __syncwarp();
+        int nl = 0;
+        if (lane == 0) { // sweep; line k is kept in src[k]: tLo = start, len = length, sLo = fragments merged
+            int64_t key = -1, lo = 0, hi = -1, cnt = 0;
+            for (int i = 0; i < m; ++i) {
+                const Frag f = dst[i];
+                const int64_t k = ((f.meta >> 1) & 1) << 40 | (f.meta >> 3);
+                if (cnt > 0 && k == key && f.tLo <= hi + 1) {
+                    const int64_t e = f.tLo + f.len - 1;
+                    if (e > hi) hi = e;
+                    ++cnt;
+                } else {
+                    if (cnt > 0) { Frag l; l.tLo = lo; l.len = hi - lo + 1; l.sLo = cnt; l.meta = key; src[nl++] = l; }
+                    key = k; lo = f.tLo; hi = f.tLo + f.len - 1; cnt = 1;
+                }
+            }
+            if (cnt > 0) { Frag l; l.tLo = lo; l.len = hi - lo + 1; l.sLo = cnt; l.meta = key; src[nl++] = l; }
+        }
+        nl = __shfl_sync(HG_FULL, nl, 0);
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)nl);
+        base = __shfl_sync(HG_FULL, base, 0);
+        if (base + (unsigned long long)nl > P.poolCap) {
+            if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+            return;
+        }
+        for (int r = lane; r < nl; r += 32) {
+            const Frag l = src[r];
+            const int seq = (int)(l.meta & 0xffffffffffll);
+            const int64_t seqStart = P.tgtNumSeq > 1 ? ldS(&P.tgtSeqStart[seq]) : 0;
+            halgpu_lift_rec o;
+            o.start = l.tLo - seqStart;
+            o.end = l.tLo + l.len - seqStart;
+            o.src_start = -1; // "not available from posMap" (halColumnLiftover.cpp:70)
+            o.tgt_seq = seq;
+            o.strand = bedStrand == '.' ? '.' : ((l.meta >> 40) & 1 ? '-' : '+');
+            o.src_strand = o.strand;
+            o.n_frag = (uint16_t)(l.sLo > 65535 ? 65535 : l.sLo);
+            P.pool[base + r] = o;
+        }
+        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)nl; P.outOffset[item] = base; }
+        return;
+    }
     // one pass over neighbouring pairs: order of the MappedSegmentSet, its "identical or disjoint" invariant
     // (insertAndBreakOverlaps) and whether any equal-target-start class has more than one member
     bool unsorted = false, clash = false, classes = false, split = false;

@@ -63,7 +63,11 @@ typedef struct halgpu_lift_result {
 enum {
     HALGPU_NO_DUPES = 1u,     /* halLiftover --noDupes (liftover/impl/halLiftoverMain.cpp:24) */
     HALGPU_NO_SORT = 2u,      /* do not reorder the batch by source position inside the call */
-    HALGPU_PSL = 4u           /* also compare source and target DNA of every mapped fragment (halLiftover --outPSL) */
+    HALGPU_PSL = 4u,          /* also compare source and target DNA of every mapped fragment (halLiftover --outPSL) */
+    HALGPU_COLUMN_LIFTOVER = 8u /* hal::ColumnLiftover::liftInterval semantics (liftover/impl/halColumnLiftover.cpp:21-92)
+                                 * instead of BlockLiftover's: per target sequence and strand the maximal runs of target
+                                 * bases homologous to the interval, forward runs first; src_start = -1; with
+                                 * HALGPU_NO_DUPES only canonical paralogs are followed upward (ColumnIterator noDupes) */
 };
 
 /* ---- open / stage (replaces openHalAlignment + MMapAlignment ctor, api/impl/halAlignmentInstance.cpp:133,

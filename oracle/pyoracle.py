@@ -52,6 +52,8 @@ def _lib():
     L.oracle_hal2maf.restype = C.c_void_p
     L.oracle_hal2maf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.oracle_column_liftover.restype = C.c_int64
+    L.oracle_column_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_char]
     L.oracle_depth.restype = C.c_int64
     L.oracle_depth.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p]
@@ -121,6 +123,15 @@ class Oracle:
             d, _ = self.depth(g, start, start + length - 1, **kw)
             out.append(f"fixedStep chrom={name} start=1 step={step}\n" + "".join(f"{x}\n" for x in d))
         return "".join(out)
+
+    def column_liftover(self, src, tgt, gs, ge, strand="+", no_dupes=False):
+        """hal::ColumnLiftover::liftInterval for ONE interval: list of (tgtSeq, start, end, strand), forward-strand runs first,
+        each group by (sequence index, start).  The reference orders sequences by pointer value: compare after sorting."""
+        k = self.L.oracle_column_liftover(self.h, src, tgt, int(no_dupes), gs, ge, strand.encode())
+        r = dict(offsets=np.zeros(2, np.uint64), tgtSeq=np.zeros(k, np.int32), start=np.zeros(k, np.int64), end=np.zeros(k, np.int64),
+                 strand=np.zeros(k, np.uint8), srcStart=np.zeros(k, np.int64), srcStrand=np.zeros(k, np.uint8))
+        self.L.oracle_fetch(self.h, *[r[x].ctypes.data for x in ("offsets", "tgtSeq", "start", "end", "strand", "srcStart", "srcStrand")])
+        return [(int(r["tgtSeq"][j]), int(r["start"][j]), int(r["end"][j]), chr(r["strand"][j])) for j in range(k)]
 
     def hal2maf(self, ref_name, ref_seq=None, start=0, length=0, targets=(), no_dupes=False, no_ancestors=False,
                 only_orthologs=False, only_sequence_names=False, keep_empty_ref_blocks=False, max_block_len=0):

@@ -92,3 +92,21 @@ def test_emulated_host_pipeline_chunks(emul_lib, oracle_lib, monkeypatch):
     off1, recs1, info1 = a.liftover(s, t, gs, ge, st, hal_b200.HALGPU_PSL)
     assert np.array_equal(off, off1) and np.array_equal(recs, recs1) and np.array_equal(info["psl"], info1["psl"])
     a.close()
+
+
+@pytest.mark.parametrize("src,tgt,flags", [("L0", "L3", 8), ("L3", "L1", 9), ("R", "L2", 8), ("A0", "R", 8), ("L1", "L1", 8), ("A1", "L0", 9)])
+def test_emulated_column_liftover_equals_oracle(emul_lib, oracle_lib, src, tgt, flags):
+    """HALGPU_COLUMN_LIFTOVER (hal::ColumnLiftover semantics, SURVEY.md 8(a) row A11) against the oracle's column walk"""
+    import hal_b200
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    a = hal_b200.Alignment(path, lib_path=emul_lib)
+    s, t = a.genome_id(src), a.genome_id(tgt)
+    gs, ge, st = random_intervals(a.genome_length(s), 60, 250, seed=len(src) + flags)
+    off, recs, _ = a.liftover(s, t, gs, ge, st, flags)
+    for i in range(len(gs)):
+        got = [(int(r["tgt_seq"]), int(r["start"]), int(r["end"]), chr(r["strand"])) for r in recs[off[i]:off[i + 1]]]
+        exp = o.column_liftover(s, t, int(gs[i]), int(ge[i]), chr(st[i]), no_dupes=bool(flags & 1))
+        assert got == exp, (i, gs[i], ge[i], chr(st[i]))
+        assert (recs[off[i]:off[i + 1]]["src_start"] == -1).all()
+    a.close()

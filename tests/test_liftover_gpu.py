@@ -174,3 +174,44 @@ def test_cuda_deep_tree_equals_oracle(hb, oracle_lib, tmp_path):
         d, _ = a.depth(g, 0, 99999)
         e, _ = o.depth(g, 0, 99999)
         assert np.array_equal(d, e)
+
+
+@pytest.mark.parametrize("src,tgt,flags", [("L0", "L3", 8), ("L3", "L1", 9), ("R", "L2", 8), ("A0", "R", 8), ("L1", "L1", 8), ("A1", "L0", 9)])
+def test_cuda_column_liftover_equals_oracle(hb, oracle_lib, src, tgt, flags):
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    with hb.Alignment(path) as a:
+        s, t = a.genome_id(src), a.genome_id(tgt)
+        gs, ge, st = random_intervals(a.genome_length(s), 400, 250, seed=len(src) + flags)
+        off, recs, _ = a.liftover(s, t, gs, ge, st, flags)
+        for i in range(len(gs)):
+            got = [(int(r["tgt_seq"]), int(r["start"]), int(r["end"]), chr(r["strand"])) for r in recs[off[i]:off[i + 1]]]
+            assert got == o.column_liftover(s, t, int(gs[i]), int(ge[i]), chr(st[i]), no_dupes=bool(flags & 1)), i
+
+
+def test_cuda_column_liftover_cli_vs_reference_class(tmp_path):
+    """the reference's ColumnLiftover (driven by oracle/gen/halColumnLiftoverCli.cpp) on pairs where it terminates;
+    it orders target sequences by pointer value, so lines are compared after sorting (north_star: bit-exact after sort)"""
+    import random
+    from conftest import ref_bin
+    drv = ref_bin("halColumnLiftoverCli")
+    if drv is None:
+        pytest.skip("oracle/_ref not built")
+    cli = os.path.join(ROOT, "hal_b200", "bin", "halLiftover")
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    import hal_b200
+    with hal_b200.Alignment(hal) as a:
+        for src, tgt, extra in (("L0", "L3", []), ("L3", "L1", ["--noDupes"]), ("R", "L2", [])):
+            seqs = a.sequences(a.genome_id(src))
+            rng = random.Random(len(src) + len(extra))
+            lines = []
+            for i in range(300):
+                nm, st, ln = rng.choice(seqs)
+                l = rng.randint(1, min(200, ln))
+                x = rng.randint(0, ln - l)
+                lines.append(f"{nm}\\t{x}\\t{x + l}\\tn{i}\\t0\\t{rng.choice('+-.')}")
+            bed = tmp_path / "in.bed"
+            bed.write_text("\\n".join(lines) + "\\n")
+            subprocess.check_call(["timeout", "120", drv, hal, src, str(bed), tgt, str(tmp_path / "ref.bed")] + extra)
+            subprocess.check_call([cli, "--columnLiftover"] + extra + [hal, src, str(bed), tgt, str(tmp_path / "got.bed")])
+            assert sorted(open(tmp_path / "ref.bed").read().splitlines()) == sorted(open(tmp_path / "got.bed").read().splitlines()), (src, tgt)
