@@ -209,9 +209,9 @@ def test_cuda_column_liftover_cli_vs_reference_class(tmp_path):
                 nm, st, ln = rng.choice(seqs)
                 l = rng.randint(1, min(200, ln))
                 x = rng.randint(0, ln - l)
-                lines.append(f"{nm}\\t{x}\\t{x + l}\\tn{i}\\t0\\t{rng.choice('+-.')}")
+                lines.append(f"{nm}\t{x}\t{x + l}\tn{i}\t0\t{rng.choice('+-.')}")
             bed = tmp_path / "in.bed"
-            bed.write_text("\\n".join(lines) + "\\n")
+            bed.write_text("\n".join(lines) + "\n")
             subprocess.check_call(["timeout", "120", drv, hal, src, str(bed), tgt, str(tmp_path / "ref.bed")] + extra)
             subprocess.check_call([cli, "--columnLiftover"] + extra + [hal, src, str(bed), tgt, str(tmp_path / "got.bed")])
             assert sorted(open(tmp_path / "ref.bed").read().splitlines()) == sorted(open(tmp_path / "got.bed").read().splitlines()), (src, tgt)
