@@ -64,15 +64,20 @@ def ensure_hal(segs):
 
 
 class ClockSampler:
-    def __init__(self, gpu):
-        self.rows, self.gpu, self.proc = [], gpu, None
+    """nvidia-smi clock / throttle-reason samples during the timed region.  Only rank 0 samples (its own GPU): eight
+    pollers hitting the driver at 10 Hz stalled every rank's CUDA calls and tripled the 8-GPU step time."""
+
+    def __init__(self, gpu, enabled=True):
+        self.rows, self.gpu, self.proc, self.enabled = [], gpu, None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -263,7 +268,7 @@ def main():
     barrier()
     l0 = a.L.halgpu_launch_count()
     kms = []
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         # Every step ends with the library synchronising its own stream on the host, and the N>1 all-gather runs on
