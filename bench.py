@@ -265,10 +265,12 @@ def main():
 
     for _ in range(args.warmup):
         nrec, *_ = step_resident(True)
-    barrier()
-    l0 = a.L.halgpu_launch_count()
     kms = []
     with ClockSampler(local, enabled=(rank == 0)) as clocks:
+        # the sampler is started BEFORE the barrier: spawning nvidia-smi takes rank 0 ~0.1 s, and ranks that entered the
+        # timed loop earlier would sit in the first all-gather waiting for it (their event time is what MAX-over-ranks reports)
+        barrier()
+        l0 = a.L.halgpu_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         # Every step ends with the library synchronising its own stream on the host, and the N>1 all-gather runs on
