@@ -155,6 +155,42 @@ def reference_throughput(hal, gs, ge, seq_name, sample, cores):
                 sample=f"first {sample} intervals of the batch, oracle/liboracle.so restatement, 1 thread")
 
 
+def write_bed3(path, seq_name, gs, ge):
+    try:
+        import pyarrow as pa
+        import pyarrow.csv as pacsv
+        t = pa.table({"c": pa.array([seq_name] * len(gs)), "s": pa.array(gs), "e": pa.array(ge + 1)})
+        pacsv.write_csv(t, path, pacsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+    except ImportError:
+        with open(path, "w") as f:
+            for lo in range(0, len(gs), 1 << 20):
+                f.write("".join(f"{seq_name}\t{s}\t{e + 1}\n" for s, e in zip(gs[lo:lo + (1 << 20)].tolist(), ge[lo:lo + (1 << 20)].tolist())))
+
+
+def cli_throughput(hal, gs, ge, seq_name):
+    """hal_b200/bin/halLiftover on the whole batch written as a BED3 file (same arguments the reference CLI takes)."""
+    d = tempfile.mkdtemp(prefix="halb200_cli_")
+    inp, outp = os.path.join(d, "in.bed"), os.path.join(d, "out.bed")
+    write_bed3(inp, seq_name, gs, ge)
+    cli = os.path.join(ROOT, "hal_b200", "bin", "halLiftover")
+    best = None
+    for _ in range(2):  # the second run has the input file and the binary in the page cache
+        t0 = time.time()
+        r = subprocess.run([cli, hal, SRC, inp, TGT, outp], env=dict(os.environ, HALGPU_TIMING="1"), capture_output=True, text=True)
+        dt = time.time() - t0
+        assert r.returncode == 0, r.stderr
+        if best is None or dt < best[0]:
+            best = (dt, [l for l in r.stderr.splitlines() if l.startswith("[halLiftover]")])
+    out_bytes = os.path.getsize(outp)
+    res = {"metric": "halLiftover_cli_lines_per_sec", "value": len(gs) / best[0], "unit": "BED lines/s", "seconds": best[0],
+           "lines": len(gs), "in_bytes": os.path.getsize(inp), "out_bytes": out_bytes, "breakdown": best[1][0] if best[1] else None,
+           "includes": "process start, CUDA context, open+stage, tokenise, halgpu_liftover (host buffers), format, file write"}
+    os.remove(inp)
+    os.remove(outp)
+    os.rmdir(d)
+    return res
+
+
 def main():
     # stdout carries exactly one JSON line: anything native libraries print there (NCCL's version banner ...) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -171,6 +207,7 @@ def main():
     ap.add_argument("--no-depth", action="store_true")
     ap.add_argument("--no-maf", action="store_true")
     ap.add_argument("--maf-columns", type=int, default=50_000_000)
+    ap.add_argument("--no-cli", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -390,12 +427,19 @@ def main():
                 line["secondary_maf"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
                                                          "sample": f"{cores} processes of oracle/_ref/hal2maf, {win}-column windows (hal2mafMP style)"}
         os.remove(outp)
+    # secondary: the whole halLiftover CLI (text I/O at GPU rate) on the same batch as a BED3 file:
+    # process start + CUDA context + open/stage + multi-threaded tokeniser + halgpu_liftover + multi-threaded printer + file write
+    if world == 1 and not args.no_cli:
+        a.close()
+        a = None
+        line["secondary_cli"] = cli_throughput(hal, gs, ge, SRC + "_seq")
     if not args.no_cpu_baseline:
         sample = args.cpu_sample or min(2_000_000, max(2000, cores * 6000))
         r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)
         line["cpu_baseline"] = {"value": r["value"], "unit": "intervals/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     print(json.dumps(line), file=real_stdout, flush=True)
-    a.close()
+    if a is not None:
+        a.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -49,9 +49,10 @@ def build(force=False, verbose=False):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", synth, os.path.join(CSRC, "host", "halsynth.cpp")])
     host = os.path.join(CSRC, "host")
     cli = os.path.join(BIN, "halLiftover")
-    cli_srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp")]
-    if force or _newer(cli, cli_srcs + [os.path.join(host, "gpu_liftover.hpp"), os.path.join(host, "bed.hpp"), LIB]):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", cli] + cli_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
+    cli_srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp", "bed_fast.cpp")]
+    if force or _newer(cli, cli_srcs + [os.path.join(host, f) for f in ("gpu_liftover.hpp", "bed.hpp", "bed_fast.hpp")] + [LIB]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", cli] + cli_srcs +
+                              ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     dep = os.path.join(BIN, "halAlignmentDepth")
     dep_src = os.path.join(host, "halAlignmentDepthMain.cpp")
     if force or _newer(dep, [dep_src, LIB]):

@@ -288,6 +288,15 @@ void halgpu_free_result(halgpu_lift_result *r) {
 
 void halgpu_free_string(char *s) { std::free(s); }
 
+void *halgpu_host_alloc(size_t bytes) {
+    try {
+        return rt::hostAlloc(bytes);
+    } catch (...) {
+        return nullptr;
+    }
+}
+void halgpu_host_free(void *p) { rt::hostFree(p); }
+
 uint64_t halgpu_launch_count(void) { return rt::g_launches; }
 
 } // extern "C"

@@ -1,5 +1,10 @@
 #include "gpu_liftover.hpp"
+#include "bed_fast.hpp"
 #include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <memory>
+#include <thread>
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -32,7 +37,48 @@ bool compatible(const BedLine &tgtBed, const BedLine &newBlock, char inputStrand
     return tgtBed.chrName == newBlock.chrName;
 }
 
+// Hands the input stream out in blocks of whole lines: about `target` bytes, extended to the end of the line the
+// cut falls into.  The final block may lack a trailing newline (as the final line of a BED file may).
+class BlockReader {
+  public:
+    BlockReader(std::istream &in, size_t target) : _in(in), _target(std::max<size_t>(target, 1)) {}
+    bool next(const char *&p, size_t &n) {
+        if (!_in.good()) return false;
+        if (_cap < _target) {
+            _buf.reset(new char[_target]); // uninitialised on purpose: pages are touched only as far as the input reaches
+            _cap = _target;
+        }
+        _in.read(_buf.get(), (std::streamsize)_target);
+        size_t got = (size_t)_in.gcount();
+        if (got == _target && _in.good() && _buf[got - 1] != '\n') {
+            std::string tail;
+            std::getline(_in, tail); // consumes the newline; it only separated lines
+            if (got + tail.size() > _cap) {
+                std::unique_ptr<char[]> bigger(new char[got + tail.size()]);
+                std::memcpy(bigger.get(), _buf.get(), got);
+                _buf = std::move(bigger);
+                _cap = got + tail.size();
+            }
+            std::memcpy(_buf.get() + got, tail.data(), tail.size());
+            got += tail.size();
+        }
+        p = _buf.get();
+        n = got;
+        return got > 0;
+    }
+
+  private:
+    std::istream &_in;
+    size_t _target, _cap = 0;
+    std::unique_ptr<char[]> _buf;
+};
+
 } // namespace
+
+unsigned GpuBlockLiftover::defaultTextThreads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 32u));
+}
 
 void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, std::ostream *out, int bedType,
                                bool traverseDupes, bool outPSL, bool outPSLWithName, int coalescenceLimit) {
@@ -48,27 +94,94 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
     for (size_t i = 0; i < ns; ++i) seqByName[sseq[i].name] = i;
     const std::string srcName = halgpu_genome_name(_ctx, srcGenome);
     _missed.clear();
-    linesIn = intervalsLifted = linesOut = 0;
-    gpuSeconds = 0;
+    linesIn = intervalsLifted = linesOut = fastLines = 0;
+    gpuSeconds = textSeconds = writeSeconds = parseSeconds = 0;
 
     if (in->bad()) throw std::runtime_error("Error reading bed input stream");
     BedLine cur; // persists across lines like BedScanner::_bedLine
     std::string lineBuf, outBuf;
     size_t lineNumber = 0;
-    bool eof = false;
-    auto skipWs = [&]() {
-        while (in->good() && std::isspace((unsigned char)in->peek())) in->get();
+    unsigned threads = textThreads;
+    if (const char *tt = std::getenv("HALGPU_TEXT_THREADS")) threads = (unsigned)std::max(0L, std::atol(tt));
+    FastBedBlock fast(sseq, ns, tseq, nt);
+    std::vector<TextBuf> fastText;
+    size_t blockTarget = blockBytes;
+    if (const char *bb = std::getenv("HALGPU_BLOCK_BYTES")) blockTarget = (size_t)std::max(1L, std::atol(bb)); // test hook
+    BlockReader reader(*in, blockTarget);
+    const char *block = nullptr;
+    size_t blockLen = 0;
+    const uint32_t liftFlags = (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u) |
+                               (columnLiftover ? (uint32_t)HALGPU_COLUMN_LIFTOVER : 0u);
+    auto lift = [&](size_t n, const int64_t *gs, const int64_t *ge, const uint8_t *st) {
+        halgpu_lift_result *res = nullptr;
+        char *err = nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit, liftFlags, n, gs, ge, st, &res, &err);
+        gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != 0) {
+            std::string m = err ? err : "halgpu_liftover failed";
+            halgpu_free_string(err);
+            throw std::runtime_error(m);
+        }
+        intervalsLifted += n;
+        return res;
     };
-    skipWs();
-    while (!eof) {
+    while (reader.next(block, blockLen)) {
+        // ---- fast path: the whole block tokenised and formatted by `threads` threads (bed_fast.hpp) ----
+        if (threads > 0 && !outPSL) {
+            auto t0 = std::chrono::steady_clock::now();
+            const bool ok = fast.parseBlock(block, blockLen, bedType, cur, threads);
+            textSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            parseSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (ok) {
+                for (const FastEvent &ev : fast.events()) { // Liftover::visitLine's messages (halLiftover.cpp:53-69), in input order
+                    if (ev.kind == FastEvent::MISSING_SEQUENCE) {
+                        if (_missed.insert(ev.chrName).second) {
+                            std::cerr << "Unable to find sequence " << ev.chrName << " in genome " << srcName << std::endl;
+                        }
+                    } else {
+                        std::cerr << "Skipping interval with endpoint " << ev.end << "because sequence " << ev.chrName << " has length "
+                                  << ev.seqLength << std::endl;
+                    }
+                }
+                lineNumber += fast.linesSeen();
+                linesIn += fast.linesSeen();
+                fastLines += fast.linesSeen();
+                if (fast.numIntervals() > 0) {
+                    halgpu_lift_result *res = lift(fast.numIntervals(), fast.starts(), fast.endsIncl(), fast.strands());
+                    t0 = std::chrono::steady_clock::now();
+                    linesOut += fast.formatBlock(block, res, threads, fastText);
+                    textSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    halgpu_free_result(res);
+                    t0 = std::chrono::steady_clock::now();
+                    for (const TextBuf &s : fastText) out->write(s.data(), (std::streamsize)s.size());
+                    writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                }
+                uint64_t lo = 0;
+                uint32_t ll = 0;
+                if (fast.lastLine(lo, ll)) { // carry the scanner's sticky BedLine on for a later serial block
+                    lineBuf.assign(block + lo, ll);
+                    cur.parse(lineBuf, bedType);
+                }
+                continue;
+            }
+        }
+        // ---- serial path over the block: BedLine::parse per line, every BED flavour, the reference's messages ----
+        const char *p = block, *const blockEnd = block + blockLen;
+        auto skipWs = [&]() {
+            while (p < blockEnd && std::isspace((unsigned char)*p)) ++p;
+        };
+        skipWs();
+        while (p < blockEnd) {
         std::vector<PendingLine> pending;
         std::vector<int64_t> gs, ge;
         std::vector<uint8_t> st;
         // ---- read one batch (Liftover::visitLine up to the liftInterval call) ----
-        while (pending.size() < batchLines) {
-            if (!in->good()) { eof = true; break; }
+        while (pending.size() < batchLines && p < blockEnd) {
             ++lineNumber;
-            std::getline(*in, lineBuf);
+            const char *nl = static_cast<const char *>(std::memchr(p, '\n', (size_t)(blockEnd - p)));
+            lineBuf.assign(p, nl ? nl : blockEnd);
+            p = nl ? nl + 1 : blockEnd;
             try {
                 cur.parse(lineBuf, bedType);
             } catch (std::exception &e) {
@@ -118,20 +231,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         if (pending.empty()) continue;
 
         // ---- one GPU call for the whole batch ----
-        halgpu_lift_result *res = nullptr;
-        char *err = nullptr;
-        auto t0 = std::chrono::steady_clock::now();
-        const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit,
-                                       (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u) |
-                                           (columnLiftover ? (uint32_t)HALGPU_COLUMN_LIFTOVER : 0u),
-                                       gs.size(), gs.data(), ge.data(), st.data(), &res, &err);
-        gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (rc != 0) {
-            std::string m = err ? err : "halgpu_liftover failed";
-            halgpu_free_string(err);
-            throw std::runtime_error(m);
-        }
-        intervalsLifted += gs.size();
+        halgpu_lift_result *res = lift(gs.size(), gs.data(), ge.data(), st.data());
 
         // ---- per-line post-processing and output ----
         outBuf.clear();
@@ -259,6 +359,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         }
         out->write(outBuf.data(), (std::streamsize)outBuf.size());
         halgpu_free_result(res);
+        } // batches of the block
     }
 }
 

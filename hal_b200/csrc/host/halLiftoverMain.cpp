@@ -105,6 +105,11 @@ int main(int argc, char **argv) {
         lift.columnLiftover = flag["columnLiftover"];
         lift.convert(src, in, tgt, out, bedType, !flag["noDupes"], outPSL, outPSLWithName, coal);
         out->flush();
+        if (getenv("HALGPU_TIMING")) {
+            cerr << "[halLiftover] lines in " << lift.linesIn << " (" << lift.fastLines << " on the multi-threaded text path), intervals "
+                 << lift.intervalsLifted << ", lines out " << lift.linesOut << "; text " << lift.textSeconds << " s (parse " << lift.parseSeconds << "), halgpu_liftover "
+                 << lift.gpuSeconds << " s, write " << lift.writeSeconds << " s, " << lift.textThreads << " text threads" << endl;
+        }
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;
         rc = 1;

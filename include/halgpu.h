@@ -163,6 +163,12 @@ const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int genome);
 void halgpu_free_result(halgpu_lift_result *res);
 void halgpu_free_string(char *s);
 
+/* page-locked host staging buffers for the input arrays of halgpu_liftover (the copies then run at full PCIe rate and
+ * overlap the kernel); returns NULL on failure.  Buffers are recycled by the library; free with halgpu_host_free.
+ * (The reference has no counterpart: its BedScanner hands one line at a time to liftInterval, halBedScanner.cpp:40-61.) */
+void *halgpu_host_alloc(size_t bytes);
+void halgpu_host_free(void *p);
+
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t halgpu_launch_count(void);
 

@@ -58,8 +58,8 @@ def emul_cli(emul_lib):
     """The halLiftover CLI (hal_b200/csrc/host) linked against the emulated library."""
     out = os.path.join(ROOT, "tests", "simt", "halLiftover_emul")
     host = os.path.join(ROOT, "hal_b200", "csrc", "host")
-    srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp")]
-    deps = srcs + [os.path.join(host, "gpu_liftover.hpp"), os.path.join(host, "bed.hpp"), emul_lib]
+    srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp", "bed_fast.cpp")]
+    deps = srcs + [os.path.join(host, f) for f in ("gpu_liftover.hpp", "bed.hpp", "bed_fast.hpp")] + [emul_lib]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs +
                               ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
