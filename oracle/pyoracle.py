@@ -54,6 +54,10 @@ def _lib():
                                  C.c_int, C.c_int, C.c_int64, C.c_void_p]
     L.oracle_column_liftover.restype = C.c_int64
     L.oracle_column_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_char]
+    L.oracle_wiggle_liftover.restype = C.c_void_p
+    L.oracle_wiggle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p]
+    L.oracle_last_error.restype = C.c_char_p
+    L.oracle_last_error.argtypes = [C.c_void_p]
     L.oracle_depth.restype = C.c_int64
     L.oracle_depth.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p]
@@ -148,6 +152,15 @@ class Oracle:
         if not p:
             raise RuntimeError("oracle_hal2maf failed")
         return C.string_at(p, n.value)
+
+    def wiggle_liftover(self, src_name, tgt_name, wig_text, no_dupes=False, preload_text=None):
+        """Output text of halWiggleLiftover (str); raises RuntimeError carrying the reference's exception message."""
+        n = C.c_uint64(0)
+        p = self.L.oracle_wiggle_liftover(self.h, self.genome_id(src_name), self.genome_id(tgt_name), int(no_dupes), wig_text.encode(),
+                                          None if preload_text is None else preload_text.encode(), C.byref(n))
+        if not p:
+            raise RuntimeError(self.L.oracle_last_error(self.h).decode())
+        return C.string_at(p, n.value).decode()
 
     def liftover_bed(self, src_name, tgt_name, bed_text, no_dupes=False):
         """BED3..BED9 text in -> text out, formatted as halLiftover would (no BED12 regrouping / PSL)."""

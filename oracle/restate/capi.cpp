@@ -2,6 +2,7 @@
 #include "columns.h"
 #include "liftover.h"
 #include "maf.h"
+#include "wiggle.h"
 #include <algorithm>
 #include <cstdio>
 #include <memory>
@@ -161,5 +162,21 @@ int64_t oracle_column_liftover(void *hp, int src, int tgt, int noDupes, int64_t 
     h->offsets.push_back(h->lines.size());
     return (int64_t)h->lines.size();
 }
+
+/* halWiggleLiftover text -> text (oracle/restate/wiggle.cpp).  Returns the output text (kept in the handle) and its length,
+ * or NULL with the reference's exception message in the handle (oracle_last_error). */
+const char *oracle_wiggle_liftover(void *hp, int src, int tgt, int noDupes, const char *inText, const char *preloadText, uint64_t *len) {
+    OracleHandle *h = (OracleHandle *)hp;
+    try {
+        std::string pre = preloadText ? preloadText : "";
+        h->maf = wiggleLiftover(h->view, src, tgt, !noDupes, inText, preloadText ? &pre : nullptr);
+    } catch (std::exception &e) {
+        h->err = e.what();
+        return nullptr;
+    }
+    *len = h->maf.size();
+    return h->maf.c_str();
+}
+const char *oracle_last_error(void *hp) { return ((OracleHandle *)hp)->err.c_str(); }
 
 } // extern "C"

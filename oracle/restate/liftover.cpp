@@ -167,7 +167,7 @@ inline bool lessTargetThenSource(const Frag &a, const Frag &b) {
 } // namespace
 
 void liftInterval(const HalView &v, const Plan &plan, bool dupes, int64_t gs, int64_t ge, char strand,
-                  std::vector<OutLine> &out, Stats *stats, std::vector<Frag> *fragsOut) {
+                  std::vector<OutLine> &out, Stats *stats, std::vector<Frag> *fragsOut, std::vector<size_t> *runSizesOut) {
     Ctx c{v, stats};
     const GenomeView &S = v.genomes[plan.src];
     const GenomeView &T = v.genomes[plan.tgt];
@@ -284,6 +284,7 @@ void liftInterval(const HalView &v, const Plan &plan, bool dupes, int64_t gs, in
         o.nFrag = (int32_t)run.size();
         lines.push_back(o);
         if (fragsOut) for (size_t r : run) fragsOut->push_back(ref[r]);
+        if (runSizesOut) runSizesOut->push_back(run.size());
     }
     std::stable_sort(lines.begin(), lines.end(), [](const OutLine &a, const OutLine &b) { return a.srcStart < b.srcStart; });
     if (stats) stats->outLines += lines.size();

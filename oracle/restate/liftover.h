@@ -38,9 +38,12 @@ Plan makePlan(const HalView &v, int src, int tgt);
 
 /* Lift one interval [gs,ge] (genome-global inclusive) with BED strand ('+','-','.').
  * Appends the reference-ordered output lines (stable by srcStart) to out; optionally the
- * fragments of each line to fragsOut (run order). */
+ * fragments of each line to fragsOut (run order).
+ * runSizesOut (optional) receives, per extracted run in extraction order (BEFORE the stable sort of the lines), the
+ * number of fragments it contributed to fragsOut. */
 void liftInterval(const HalView &v, const Plan &plan, bool dupes, int64_t gs, int64_t ge, char strand,
-                  std::vector<OutLine> &out, Stats *stats, std::vector<Frag> *fragsOut = nullptr);
+                  std::vector<OutLine> &out, Stats *stats, std::vector<Frag> *fragsOut = nullptr,
+                  std::vector<size_t> *runSizesOut = nullptr);
 
 } // namespace oracle
 #endif
