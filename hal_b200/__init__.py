@@ -37,6 +37,11 @@ class _Result(C.Structure):
                 ("psl", C.c_void_p)]
 
 
+class _WigResult(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("pos", C.c_void_p), ("val", C.c_void_p), ("kernel_ms", C.c_float), ("launches", C.c_int),
+                ("n_retry", C.c_size_t)]
+
+
 REC_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("src_start", "<i8"), ("tgt_seq", "<i4"),
                       ("strand", "u1"), ("src_strand", "u1"), ("n_frag", "<u2")])
 assert REC_DTYPE.itemsize == 32
@@ -48,7 +53,8 @@ ABI_SYMBOLS = [
     "halgpu_genome_num_top", "halgpu_genome_num_bottom", "halgpu_newick", "halgpu_sequence_table", "halgpu_mrca",
     "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
     "halgpu_free_string", "halgpu_launch_count", "halgpu_columns_depth", "halgpu_columns_depth_device",
-    "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna",
+    "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna", "halgpu_host_alloc", "halgpu_host_free",
+    "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
 ]
 
 
@@ -85,6 +91,12 @@ def load_library(path=None):
     for f in ("halgpu_columns_depth", "halgpu_columns_depth_device"):
         getattr(L, f).argtypes = [vp, i32, i64, i64, i64, vp, C.c_size_t, C.c_uint32, vp, C.POINTER(C.c_float),
                                   C.POINTER(C.c_char_p)]
+    L.halgpu_wiggle_liftover.argtypes = [vp, i32, i32, C.c_uint32, C.c_size_t, vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp,
+                                         C.POINTER(C.POINTER(_WigResult)), C.POINTER(C.c_char_p)]
+    L.halgpu_free_wig_result.argtypes = [C.POINTER(_WigResult)]
+    L.halgpu_host_alloc.argtypes = [C.c_size_t]
+    L.halgpu_host_alloc.restype = vp
+    L.halgpu_host_free.argtypes = [vp]
     L.halgpu_free_result.argtypes = [C.POINTER(_Result)]
     L.halgpu_free_string.argtypes = [C.c_void_p]
     L.halgpu_launch_count.restype = C.c_uint64
@@ -211,6 +223,31 @@ class Alignment:
                 self.L.halgpu_free_string(errp)
             raise HalGpuError(msg)
         return out, ms.value
+
+    def wiggle_liftover(self, src, tgt, run_first, run_last_incl, val_offset, vals, flags=0, preload_pos=(), preload_val=()):
+        """halgpu_wiggle_liftover: runs of source bases with values in, (positions, values, info) of the target bases out."""
+        f = np.ascontiguousarray(run_first, dtype=np.int64)
+        l = np.ascontiguousarray(run_last_incl, dtype=np.int64)
+        o = np.ascontiguousarray(val_offset, dtype=np.int64)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        pp = np.ascontiguousarray(preload_pos, dtype=np.int64)
+        pv = np.ascontiguousarray(preload_val, dtype=np.float64)
+        res, errp = C.POINTER(_WigResult)(), C.c_void_p()
+        rc = self.L.halgpu_wiggle_liftover(self.h, src, tgt, flags, len(f), f.ctypes.data, l.ctypes.data, o.ctypes.data, v.ctypes.data,
+                                           len(v), len(pp), pp.ctypes.data if len(pp) else None, pv.ctypes.data if len(pp) else None,
+                                           C.byref(res), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else "wiggle liftover failed"
+            if errp.value:
+                self.L.halgpu_free_string(errp)
+            raise HalGpuError(msg)
+        r = res.contents
+        n = r.n
+        pos = np.ctypeslib.as_array(C.cast(r.pos, C.POINTER(C.c_int64)), shape=(max(n, 1),))[:n].copy()
+        val = np.ctypeslib.as_array(C.cast(r.val, C.POINTER(C.c_double)), shape=(max(n, 1),))[:n].copy()
+        info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry)
+        self.L.halgpu_free_wig_result(res)
+        return pos, val, info
 
     def liftover_ptrs(self, src, tgt, n, start_ptr, end_ptr, strand_ptr=None, flags=0, device=False):
         """Raw-pointer variants (pinned host buffers, or device buffers with device=True)."""

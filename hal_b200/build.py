@@ -2,6 +2,7 @@
 
   hal_b200/libhalgpu.so   C-ABI library, CUDA kernels compiled for sm_100a (nvcc cross-compiles without a GPU)
   hal_b200/bin/halLiftover  the reference CLI's GPU build (host C++ over the C ABI)
+  hal_b200/bin/halWiggleLiftover, halAlignmentDepth, hal2maf   likewise
   hal_b200/bin/halSynth   synthetic HAL-MMAP writer (host C++)
 
 Run: python -m hal_b200.build
@@ -53,6 +54,10 @@ def build(force=False, verbose=False):
     if force or _newer(cli, cli_srcs + [os.path.join(host, f) for f in ("gpu_liftover.hpp", "bed.hpp", "bed_fast.hpp")] + [LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", cli] + cli_srcs +
                               ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
+    wig = os.path.join(BIN, "halWiggleLiftover")
+    wig_srcs = [os.path.join(host, f) for f in ("halWiggleLiftoverMain.cpp", "wiggle_liftover.cpp")]
+    if force or _newer(wig, wig_srcs + [os.path.join(host, "wiggle_liftover.hpp"), LIB]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", wig] + wig_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     dep = os.path.join(BIN, "halAlignmentDepth")
     dep_src = os.path.join(host, "halAlignmentDepthMain.cpp")
     if force or _newer(dep, [dep_src, LIB]):

@@ -259,6 +259,31 @@ int halgpu_column_runs(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, co
     });
 }
 
+int halgpu_wiggle_liftover(halgpu_ctx *ctx, int src, int tgt, uint32_t flags, size_t nRuns, const int64_t *first, const int64_t *last,
+                           const int64_t *valOff, const double *vals, size_t nVals, size_t nPre, const int64_t *prePos,
+                           const double *preVal, halgpu_wig_result **out, char **err) {
+    if (ctx == nullptr || out == nullptr || (nRuns > 0 && (first == nullptr || last == nullptr || valOff == nullptr || vals == nullptr)) ||
+        (nPre > 0 && (prePos == nullptr || preVal == nullptr))) {
+        return fail(err, "halgpu_wiggle_liftover: null argument");
+    }
+    *out = nullptr;
+    return guarded(err, [&] {
+        rt::setDevice(ctx->impl->device());
+        WigOutput wo;
+        ctx->impl->wiggle(src, tgt, flags, nRuns, first, last, valOff, vals, nVals, nPre, prePos, preVal, wo);
+        halgpu_wig_result *r = static_cast<halgpu_wig_result *>(std::calloc(1, sizeof(halgpu_wig_result)));
+        r->n = wo.n; r->pos = wo.pos; r->val = wo.val; r->kernel_ms = wo.kernelMs; r->launches = wo.launches; r->n_retry = wo.nRetry;
+        *out = r;
+    });
+}
+
+void halgpu_free_wig_result(halgpu_wig_result *r) {
+    if (r == nullptr) return;
+    rt::hostFree(r->pos);
+    rt::hostFree(r->val);
+    std::free(r);
+}
+
 void halgpu_free_col_runs(halgpu_col_runs *r) {
     if (r == nullptr) return;
     rt::hostFree(r->run_col);
@@ -270,6 +295,16 @@ void halgpu_free_col_runs(halgpu_col_runs *r) {
 const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int g) {
     const GenomeInfo *i = genome(ctx, g);
     return i ? i->dna : nullptr;
+}
+
+const void *halgpu_genome_top_segments(const halgpu_ctx *ctx, int g) {
+    const GenomeInfo *i = genome(ctx, g);
+    return i ? i->top : nullptr;
+}
+const void *halgpu_genome_bottom_segments(const halgpu_ctx *ctx, int g, size_t *stride) {
+    const GenomeInfo *i = genome(ctx, g);
+    if (i && stride) *stride = i->bottomStride;
+    return i ? i->bottom : nullptr;
 }
 
 void halgpu_free_result(halgpu_lift_result *r) {

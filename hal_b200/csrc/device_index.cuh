@@ -76,6 +76,11 @@ struct LiftParams {
     const uint8_t *srcDna, *tgtDna; // packed nibbles of the source / target genome (PSL only)
     unsigned long long *poolCursor;
     uint64_t poolCap;
+    // wiggle mode (halgpu_wiggle_liftover): no result lists; every mapped fragment scatters the source values of its
+    // bases into wigKeys[target base] with atomicMax as soon as it reaches the target genome
+    unsigned long long *wigKeys; // NULL: normal liftover.  One order-preserving key per target base (wigKey below)
+    const int64_t *wigValOff;    // per interval: >= 0 index of its first per-base value in wigVals; < 0: ~index of its single value
+    const double *wigVals;
     // scratch: lists live in dynamic shared memory unless gscratch != NULL
     int32_t listCap;   // fragments per list (two lists per warp)
     int32_t frameCap;  // work-pool frames per warp
@@ -106,6 +111,13 @@ struct ColRowRec { // 16 B
     uint8_t pad;
 };
 
+
+// Wiggle values are kept as keys whose unsigned order is the order of the doubles (sign bit flipped for v >= 0, all bits
+// for v < 0).  WIG_UNSET (== the key of -0.0) marks a base nothing was written to; WiggleLiftover::mapFragments takes
+// max(value, WiggleTiles::get()) where get() is 0.0 until the base is set (liftover/impl/halWiggleLiftover.cpp:150-153,
+// liftover/inc/halWiggleTiles.h:96-107), so the first write to an unset base stores max(v, +0.0).
+static const unsigned long long WIG_UNSET = 0x7fffffffffffffffull;
+static const unsigned long long WIG_ZERO = 0x8000000000000000ull;
 
 enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2, ST_BAD_INPUT = 3 };
 

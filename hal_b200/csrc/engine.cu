@@ -2,6 +2,7 @@
 #include "columns_kernel.cuh"
 #include "liftover_kernel.cuh"
 #include "stage_kernels.cuh"
+#include "wiggle_kernels.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -358,7 +359,7 @@ struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch
 } // namespace
 
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase) {
+                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig) {
     PhaseTimer pt;
     const auto &G = _file->genomes();
     if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
@@ -397,7 +398,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
     if (pt.on) rt::sync(_stream);
     pt.mark("sort");
-    uint64_t poolCap = (uint64_t)n + (uint64_t)n / 4 + 4096;
+    uint64_t poolCap = wig ? 1 : (uint64_t)n + (uint64_t)n / 4 + 4096; // (the wiggle mode emits no records)
     std::unique_ptr<DevBuf> pool(new DevBuf(poolCap * sizeof(halgpu_lift_rec)));
     const bool wantPsl = (flags & HALGPU_PSL) != 0;
     std::unique_ptr<DevBuf> pslPool;
@@ -423,6 +424,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     P.pool = pool->as<halgpu_lift_rec>(); P.poolCursor = cursor.as<unsigned long long>(); P.poolCap = poolCap;
     P.pslPool = wantPsl ? pslPool->as<uint32_t>() : nullptr;
     P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
+    if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
     // rung 1: all n intervals, scratch in shared memory
     const unsigned block = 128, warpsPerBlock = block / 32;
@@ -430,10 +432,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
         P.n = (int64_t)n; P.work = dWork;
         const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
-        rt::allowSmem(liftoverKernel, smem);
+        rt::allowSmem(liftoverKernel<false>, smem);
+        rt::allowSmem(liftoverKernel<true>, smem);
         rt::Event e0, e1;
         e0.record(_stream);
-        rt::launch(liftoverKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
+        rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
         e1.record(_stream);
         rt::sync(_stream);
         out.kernelMs = rt::Event::elapsedMs(e0, e1);
@@ -502,7 +505,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             if (inSmem) { P.gscratch = nullptr; P.gscratchPerWarp = 0; }
             else { scratch.reset(new DevBuf(per * (uint64_t)warps)); P.gscratch = scratch->as<uint8_t>(); P.gscratchPerWarp = per; }
             const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
-            rt::launch(liftoverKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
+            rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
             rt::sync(_stream);
             continue;
         }
@@ -522,11 +525,15 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         rt::d2d(ids.p, list.p, nOver * sizeof(uint32_t), _stream);
         P.n = (int64_t)nOver; P.work = ids.as<uint32_t>();
         P.listCap = listCap; P.frameCap = frameCap; P.gscratch = scratch.as<uint8_t>(); P.gscratchPerWarp = per;
-        rt::launch(liftoverKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
+        rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
         rt::sync(_stream);
     }
 
     pt.mark("status");
+    if (wig) { // values went straight into wig->keys; there is no record list to assemble
+        out.launches = (int)rt::g_launches - launches0;
+        return;
+    }
     // CSR assembly in input order
     DevBuf *csr = new DevBuf((n + 2) * sizeof(uint64_t));
     std::unique_ptr<DevBuf> csrHold(csr);
@@ -555,6 +562,73 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     out.recs = static_cast<halgpu_lift_rec *>(recsHold->release());
     out.psl = wantPsl ? static_cast<uint32_t *>(pslHold->release()) : nullptr;
     out.nRec = total;
+    out.launches = (int)rt::g_launches - launches0;
+}
+
+void Context::wiggle(int src, int tgt, uint32_t flags, size_t nRuns, const int64_t *first, const int64_t *last, const int64_t *valOff,
+                     const double *vals, size_t nVals, size_t nPre, const int64_t *prePos, const double *preVal, WigOutput &out) {
+    const auto &G = _file->genomes();
+    if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
+    const int64_t tgtLen = G[tgt].length;
+    for (size_t i = 0; i < nRuns; ++i) { // every value index the kernel will form must exist
+        if (last[i] < first[i]) throw HalError("wiggle run " + std::to_string(i) + " is empty or reversed");
+        const bool ok = valOff[i] >= 0 ? (uint64_t)valOff[i] + (uint64_t)(last[i] - first[i]) < nVals : (uint64_t)(~valOff[i]) < nVals;
+        if (!ok) throw HalError("wiggle run " + std::to_string(i) + " refers to values outside the value array");
+    }
+    for (size_t i = 0; i < nPre; ++i) {
+        if (prePos[i] < 0 || prePos[i] >= tgtLen) throw HalError("preloaded wiggle position outside genome " + G[tgt].name);
+    }
+    out = WigOutput();
+    DevBuf::current() = _stream;
+    const int launches0 = (int)rt::g_launches;
+    DevBuf keys((size_t)std::max<int64_t>(tgtLen, 1) * 8);
+    {
+        WigFillParams fp;
+        fp.keys = keys.as<unsigned long long>(); fp.n = tgtLen;
+        rt::launch(wigFillKernel, gridFor(tgtLen, 256, _sms), 256, 0, _stream, fp);
+    }
+    if (nPre > 0) {
+        DevBuf dp(nPre * 8), dv(nPre * 8);
+        rt::h2d(dp.p, prePos, nPre * 8, _stream);
+        rt::h2d(dv.p, preVal, nPre * 8, _stream);
+        WigPreloadParams pp;
+        pp.keys = keys.as<unsigned long long>(); pp.pos = dp.as<int64_t>(); pp.val = dv.as<double>(); pp.n = (int64_t)nPre; pp.genomeLen = tgtLen;
+        rt::launch(wigPreloadKernel, gridFor((int64_t)nPre, 256, _sms), 256, 0, _stream, pp);
+        rt::sync(_stream);
+    }
+    if (nRuns > 0) {
+        DevBuf dF(nRuns * 8), dL(nRuns * 8), dO(nRuns * 8), dV(std::max<size_t>(nVals, 1) * 8);
+        rt::h2d(dF.p, first, nRuns * 8, _stream);
+        rt::h2d(dL.p, last, nRuns * 8, _stream);
+        rt::h2d(dO.p, valOff, nRuns * 8, _stream);
+        rt::h2d(dV.p, vals, nVals * 8, _stream);
+        WigScatter ws;
+        ws.keys = keys.as<unsigned long long>(); ws.valOff = dO.as<int64_t>(); ws.vals = dV.as<double>();
+        LiftOutput lo;
+        liftover(src, tgt, flags & HALGPU_NO_DUPES, nRuns, dF.as<int64_t>(), dL.as<int64_t>(), nullptr, lo, 0, &ws);
+        out.kernelMs = lo.kernelMs;
+        out.nRetry = lo.nRetry;
+        DevBuf::current() = _stream;
+    }
+    // read-out: ascending positions of the bases that hold a value, then their values
+    DevBuf flag((size_t)std::max<int64_t>(tgtLen, 1)), pos((size_t)std::max<int64_t>(tgtLen, 1) * 8), cnt(sizeof(unsigned long long));
+    WigFlagParams fl;
+    fl.keys = keys.as<unsigned long long>(); fl.flag = flag.as<uint8_t>(); fl.n = tgtLen;
+    rt::launch(wigFlagKernel, gridFor(tgtLen, 256, _sms), 256, 0, _stream, fl);
+    rt::selectFlagged(flag.as<uint8_t>(), pos.as<int64_t>(), cnt.as<unsigned long long>(), (size_t)tgtLen, _stream);
+    unsigned long long nSet = 0;
+    rt::d2h(&nSet, cnt.p, sizeof(nSet), _stream);
+    rt::sync(_stream);
+    DevBuf val(std::max<size_t>((size_t)nSet, 1) * 8);
+    WigGatherParams gp;
+    gp.keys = keys.as<unsigned long long>(); gp.pos = pos.as<int64_t>(); gp.val = val.as<double>(); gp.n = (int64_t)nSet;
+    rt::launch(wigGatherKernel, gridFor((int64_t)nSet, 256, _sms), 256, 0, _stream, gp);
+    out.pos = static_cast<int64_t *>(rt::hostAlloc(std::max<size_t>((size_t)nSet, 1) * 8));
+    out.val = static_cast<double *>(rt::hostAlloc(std::max<size_t>((size_t)nSet, 1) * 8));
+    rt::d2h(out.pos, pos.p, (size_t)nSet * 8, _stream);
+    rt::d2h(out.val, val.p, (size_t)nSet * 8, _stream);
+    rt::sync(_stream);
+    out.n = (size_t)nSet;
     out.launches = (int)rt::g_launches - launches0;
 }
 

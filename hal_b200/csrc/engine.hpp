@@ -38,6 +38,20 @@ struct LiftOutput { // device-side result of one batch
     int launches = 0;
 };
 
+struct WigScatter { // wiggle mode of the mapping kernel (device pointers)
+    unsigned long long *keys; // one key per base of the target genome
+    const int64_t *valOff;    // per interval
+    const double *vals;
+};
+
+struct WigOutput { // bases of the target genome that hold a value, ascending (pinned host memory, rt::hostFree)
+    int64_t *pos = nullptr;
+    double *val = nullptr;
+    size_t n = 0, nRetry = 0;
+    float kernelMs = 0;
+    int launches = 0;
+};
+
 class Context {
   public:
     Context(const std::string &path, int device);
@@ -50,7 +64,12 @@ class Context {
     // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
     // offsetBase is added to every CSR offset (the pipelined host entry point lifts a batch chunk by chunk)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0);
+                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr);
+
+    // wiggle liftover of nRuns source ranges [first, last] (genome coordinates) carrying per-base values (valOff >= 0) or
+    // one value (valOff < 0: ~index), onto the target genome preloaded with nPre (position, value) pairs; host in, host out
+    void wiggle(int src, int tgt, uint32_t flags, size_t nRuns, const int64_t *first, const int64_t *last, const int64_t *valOff,
+                const double *vals, size_t nVals, size_t nPre, const int64_t *prePos, const double *preVal, WigOutput &out);
 
     // per-base alignment depth of reference positions first, first+step, ... <= last (device output, n = count)
     void depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,

@@ -90,6 +90,24 @@ __device__ __forceinline__ void subRange(int64_t &sLo, int64_t &tLo, int64_t &le
     len = m;
 }
 
+__device__ __forceinline__ unsigned long long wigKey(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double wigUnkey(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+// value = max(v, what the base holds); an unset base holds +0.0 (see WIG_UNSET)
+__device__ __forceinline__ void wigRaise(unsigned long long *p, double v) {
+    const unsigned long long k = wigKey(v);
+    if (k > WIG_UNSET) {
+        atomicMax(p, k);
+    } else if (atomicMax(p, k) == WIG_UNSET) {
+        atomicMax(p, WIG_ZERO);
+    }
+}
+
 __device__ __forceinline__ int lanePrefix(unsigned mask, int lane) { return __popc(mask & ((1u << lane) - 1u)); }
 
 // index of the sequence containing genome position pos (replaces Genome::getSequenceBySite,
@@ -145,6 +163,8 @@ struct WarpScratch {
     Frame *frames;
 };
 
+// WIG: the wiggle mode is a separate instantiation so that the BED path's register allocation is untouched by it
+template <bool WIG>
 __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
@@ -342,7 +362,27 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         {
             const bool doEmit = valid && p == np - 1 && ringFirst < 0;
             const unsigned em = __ballot_sync(HG_FULL, doEmit);
-            if (em) {
+            if (WIG && em) {
+                // WiggleLiftover::mapFragments (liftover/impl/halWiggleLiftover.cpp:134-158): the warp takes the arrived
+                // fragments one at a time and writes max(value of the source base, current) to every target base -- 32
+                // consecutive bases per step, so the value reads and the atomics are coalesced.  max is idempotent and
+                // commutative: duplicates, the set order and the merge step of the BED path do not matter here.
+                const int64_t vo = ldS(&P.wigValOff[item]);
+                unsigned rem = em;
+                while (rem) {
+                    const int from = __ffs((int)rem) - 1;
+                    rem &= rem - 1;
+                    const int64_t fs = __shfl_sync(HG_FULL, sLo, from), ft = __shfl_sync(HG_FULL, tLo, from);
+                    const int64_t fl = __shfl_sync(HG_FULL, len, from);
+                    const int fr = __shfl_sync(HG_FULL, (int)tRev, from);
+                    for (int64_t k = lane; k < fl; k += 32) {
+                        const int64_t u = fr ? fl - 1 - k : k; // offset of target base ft + k along the (forward) source piece
+                        const double v = vo >= 0 ? P.wigVals[vo + (fs + u - gs)] : P.wigVals[~vo];
+                        wigRaise(&P.wigKeys[ft + k], v);
+                    }
+                }
+                if (doEmit) valid = false;
+            } else if (em) {
                 const int slot = listCount + lanePrefix(em, lane);
                 if (doEmit) {
                     if (slot < listCap) {
@@ -707,6 +747,7 @@ __host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) 
 extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
 #endif
 
+template <bool WIG>
 __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
 #if defined(HALGPU_SIMT_EMUL)
     uint8_t *hg_dyn_smem = simt::dynamicSmem();
@@ -724,7 +765,7 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
     ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
     for (int64_t w = gwarp; w < P.n; w += nwarps) {
         const uint32_t item = P.work ? __ldg(&P.work[w]) : (uint32_t)w;
-        liftOneInterval(P, ws, item, lane);
+        liftOneInterval<WIG>(P, ws, item, lane);
         __syncwarp();
     }
 }

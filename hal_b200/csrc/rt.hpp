@@ -72,6 +72,12 @@ inline void exclusiveScanU32(const uint32_t *in, uint64_t *out, size_t n, Stream
     for (size_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
     out[n] = s;
 }
+// positions i in [0, n) with flag[i] != 0, ascending; *dCount receives how many (out must hold n entries)
+inline void selectFlagged(const uint8_t *flag, int64_t *out, unsigned long long *dCount, size_t n, Stream) {
+    unsigned long long c = 0;
+    for (size_t i = 0; i < n; ++i) if (flag[i]) out[c++] = (int64_t)i;
+    *dCount = c;
+}
 
 #else // ---------------------------------------------------------------- CUDA
 
@@ -146,6 +152,17 @@ inline void exclusiveScanU32(const uint32_t *in, uint64_t *out, size_t n, Stream
     g_launches += 1;
     dfreeAsync(tmp, s);
     check(e, "scan");
+}
+// positions i in [0, n) with flag[i] != 0, ascending; *dCount receives how many (out must hold n entries)
+inline void selectFlagged(const uint8_t *flag, int64_t *out, unsigned long long *dCount, size_t n, Stream s) {
+    cub::CountingInputIterator<int64_t> it(0);
+    size_t tmpBytes = 0;
+    check(cub::DeviceSelect::Flagged(nullptr, tmpBytes, it, flag, out, dCount, (int64_t)n, s), "select (size)");
+    void *tmp = dmallocAsync(tmpBytes, s);
+    cudaError_t e = cub::DeviceSelect::Flagged(tmp, tmpBytes, it, flag, out, dCount, (int64_t)n, s);
+    g_launches += 1;
+    dfreeAsync(tmp, s);
+    check(e, "select");
 }
 #endif
 

@@ -159,6 +159,37 @@ void halgpu_free_col_runs(halgpu_col_runs *runs);
 /* packed DNA of a genome as staged (host pointer into the mapped file, 2 bases per byte, even index = high nibble;
  * replaces Genome::getDnaIterator for bulk text emission, api/inc/halDnaIterator.h:131-138) */
 const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int genome);
+/* raw segment arrays of a genome (host pointers into the mapped file; num + 1 records, the last one a sentinel whose
+ * start is the genome length): top records are 40 B (api/mmap_impl/mmapTopSegmentData.h:40-44), bottom records
+ * *stride B (mmapBottomSegmentData.h:35-52); the first int64 of every record is its start position.  Replaces
+ * Genome::getTopSegmentIterator / getBottomSegmentIterator for host code that only needs segment boundaries. */
+const void *halgpu_genome_top_segments(const halgpu_ctx *ctx, int genome);
+const void *halgpu_genome_bottom_segments(const halgpu_ctx *ctx, int genome, size_t *stride);
+
+/* ---- wiggle liftover (replaces the mapping core of hal::WiggleLiftover -- mapSegment / mapFragments and the
+ *      WiggleTiles<double> accumulator, liftover/impl/halWiggleLiftover.cpp:98-158, liftover/inc/halWiggleTiles.h; the
+ *      --append preload of WiggleLoader::visitLine, halWiggleLoader.cpp:37-48).
+ *      Input: n_runs source ranges [run_first, run_last_incl] in forward GENOME coordinates of src_genome.  Run i carries
+ *      one value per base, vals[val_offset[i] + (p - run_first[i])] for its base p, when val_offset[i] >= 0; or the single
+ *      value vals[~val_offset[i]] for all its bases when val_offset[i] < 0 (a wiggle line with a span).  Every base of
+ *      the target genome that some source base maps to (halMapSegment; HALGPU_NO_DUPES as in halgpu_liftover) receives
+ *      max(value, what it holds), a base nothing was written to holding 0.0 for that comparison; the n_preload
+ *      (preload_pos, preload_val) pairs (distinct target GENOME positions) are stored first as they are.
+ *      Output: the target bases that hold a value, ascending, with their values (host memory, halgpu_free_wig_result).
+ *      No arithmetic is done on the values, so they are bit-exact copies of inputs (or +0.0). ---- */
+typedef struct halgpu_wig_result {
+    size_t n;
+    int64_t *pos;   /* forward genome coordinates of tgt_genome, ascending */
+    double *val;
+    float kernel_ms;
+    int launches;
+    size_t n_retry;
+} halgpu_wig_result;
+int halgpu_wiggle_liftover(halgpu_ctx *ctx, int src_genome, int tgt_genome, uint32_t flags, size_t n_runs,
+                           const int64_t *run_first, const int64_t *run_last_incl, const int64_t *val_offset,
+                           const double *vals, size_t n_vals, size_t n_preload, const int64_t *preload_pos,
+                           const double *preload_val, halgpu_wig_result **out, char **err);
+void halgpu_free_wig_result(halgpu_wig_result *res);
 
 void halgpu_free_result(halgpu_lift_result *res);
 void halgpu_free_string(char *s);

@@ -54,8 +54,11 @@ def _lib():
                                  C.c_int, C.c_int, C.c_int64, C.c_void_p]
     L.oracle_column_liftover.restype = C.c_int64
     L.oracle_column_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_char]
+    L.oracle_liftover_frags.restype = C.c_int64
+    L.oracle_liftover_frags.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.oracle_fetch_frags.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.oracle_wiggle_liftover.restype = C.c_void_p
-    L.oracle_wiggle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p]
+    L.oracle_wiggle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p]
     L.oracle_last_error.restype = C.c_char_p
     L.oracle_last_error.argtypes = [C.c_void_p]
     L.oracle_depth.restype = C.c_int64
@@ -153,11 +156,22 @@ class Oracle:
             raise RuntimeError("oracle_hal2maf failed")
         return C.string_at(p, n.value)
 
-    def wiggle_liftover(self, src_name, tgt_name, wig_text, no_dupes=False, preload_text=None):
-        """Output text of halWiggleLiftover (str); raises RuntimeError carrying the reference's exception message."""
+    def liftover_frags(self, src, tgt, gs, ge, no_dupes=False):
+        """Per '+' interval the mapped fragments [(sLo, tLo, length, tRev)] (source forward; target reversed when tRev)."""
+        gs = np.ascontiguousarray(gs, dtype=np.int64)
+        ge = np.ascontiguousarray(ge, dtype=np.int64)
+        k = self.L.oracle_liftover_frags(self.h, src, tgt, int(no_dupes), len(gs), gs.ctypes.data, ge.ctypes.data)
+        off = np.zeros(len(gs) + 1, np.uint64)
+        s, t, ln, rv = np.zeros(k, np.int64), np.zeros(k, np.int64), np.zeros(k, np.int64), np.zeros(k, np.uint8)
+        self.L.oracle_fetch_frags(self.h, off.ctypes.data, s.ctypes.data, t.ctypes.data, ln.ctypes.data, rv.ctypes.data)
+        return [[(int(s[j]), int(t[j]), int(ln[j]), bool(rv[j])) for j in range(int(off[i]), int(off[i + 1]))] for i in range(len(gs))]
+
+    def wiggle_liftover(self, src_name, tgt_name, wig_text, no_dupes=False, preload_text=None, correct_path=False):
+        """Output text of halWiggleLiftover (str); raises RuntimeError carrying the reference's exception message.
+        correct_path: do not reproduce the reference's wrong turn at the MRCA (oracle/restate/wiggle.cpp)."""
         n = C.c_uint64(0)
         p = self.L.oracle_wiggle_liftover(self.h, self.genome_id(src_name), self.genome_id(tgt_name), int(no_dupes), wig_text.encode(),
-                                          None if preload_text is None else preload_text.encode(), C.byref(n))
+                                          None if preload_text is None else preload_text.encode(), int(correct_path), C.byref(n))
         if not p:
             raise RuntimeError(self.L.oracle_last_error(self.h).decode())
         return C.string_at(p, n.value).decode()

@@ -11,6 +11,8 @@ using namespace oracle;
 
 struct OracleHandle {
     HalView view;
+    std::vector<uint64_t> fragOffsets;
+    std::vector<Frag> frags;
     std::vector<uint64_t> offsets;
     std::vector<OutLine> lines;
     Stats stats;
@@ -163,13 +165,38 @@ int64_t oracle_column_liftover(void *hp, int src, int tgt, int noDupes, int64_t 
     return (int64_t)h->lines.size();
 }
 
+/* The mapped fragments (after insertAndBreakOverlaps, as handed to extractSegment) of n '+' intervals: returns their total
+ * number; oracle_fetch_frags copies offsets[n+1] and per fragment sLo, tLo, length, tRev. */
+int64_t oracle_liftover_frags(void *hp, int src, int tgt, int noDupes, int64_t n, const int64_t *gs, const int64_t *ge) {
+    OracleHandle *h = (OracleHandle *)hp;
+    Plan plan = makePlan(h->view, src, tgt);
+    h->fragOffsets.assign(1, 0);
+    h->frags.clear();
+    std::vector<OutLine> lines;
+    for (int64_t i = 0; i < n; i++) {
+        lines.clear();
+        liftInterval(h->view, plan, !noDupes, gs[i], ge[i], '+', lines, nullptr, &h->frags);
+        h->fragOffsets.push_back(h->frags.size());
+    }
+    return (int64_t)h->frags.size();
+}
+void oracle_fetch_frags(void *hp, uint64_t *offsets, int64_t *sLo, int64_t *tLo, int64_t *len, uint8_t *tRev) {
+    OracleHandle *h = (OracleHandle *)hp;
+    for (size_t i = 0; i < h->fragOffsets.size(); i++) offsets[i] = h->fragOffsets[i];
+    for (size_t i = 0; i < h->frags.size(); i++) {
+        const Frag &f = h->frags[i];
+        sLo[i] = f.sLo; tLo[i] = f.tLo; len[i] = f.sHi - f.sLo + 1; tRev[i] = f.tRev ? 1 : 0;
+    }
+}
+
 /* halWiggleLiftover text -> text (oracle/restate/wiggle.cpp).  Returns the output text (kept in the handle) and its length,
  * or NULL with the reference's exception message in the handle (oracle_last_error). */
-const char *oracle_wiggle_liftover(void *hp, int src, int tgt, int noDupes, const char *inText, const char *preloadText, uint64_t *len) {
+const char *oracle_wiggle_liftover(void *hp, int src, int tgt, int noDupes, const char *inText, const char *preloadText, int correctPath,
+                                   uint64_t *len) {
     OracleHandle *h = (OracleHandle *)hp;
     try {
         std::string pre = preloadText ? preloadText : "";
-        h->maf = wiggleLiftover(h->view, src, tgt, !noDupes, inText, preloadText ? &pre : nullptr);
+        h->maf = wiggleLiftover(h->view, src, tgt, !noDupes, inText, preloadText ? &pre : nullptr, correctPath != 0);
     } catch (std::exception &e) {
         h->err = e.what();
         return nullptr;

@@ -142,7 +142,8 @@ const SeqView *findSeq(const GenomeView &g, const std::string &name) {
 
 } // namespace
 
-std::string wiggleLiftover(const HalView &v, int src, int tgt, bool dupes, const std::string &inText, const std::string *preloadText) {
+std::string wiggleLiftover(const HalView &v, int src, int tgt, bool dupes, const std::string &inText, const std::string *preloadText,
+                           bool correctPath) {
     const GenomeView &S = v.genomes[src], &T = v.genomes[tgt];
     std::vector<double> vals((size_t)T.len, 0.0);
     std::vector<char> exists((size_t)T.len, 0);
@@ -163,7 +164,7 @@ std::string wiggleLiftover(const HalView &v, int src, int tgt, bool dupes, const
     const Plan plan = makePlan(v, src, tgt);
     /* which child of the MRCA does mapRecursiveDown pick?  the first one on the spanning set of {src, tgt} */
     bool wrongTurn = false;
-    if (plan.mrca != tgt && plan.mrca != src) {
+    if (!correctPath && plan.mrca != tgt && plan.mrca != src) {
         const int srcSide = plan.up[plan.up.size() - 2], tgtSide = plan.down[1];
         wrongTurn = v.genomes[srcSide].slot < v.genomes[tgtSide].slot;
     }

@@ -43,7 +43,7 @@ def emul_lib():
     csrc = os.path.join(ROOT, "hal_b200", "csrc")
     srcs = [os.path.join(csrc, f) for f in ("capi.cu", "engine.cu", "halmmap.cpp")]
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if os.path.isfile(os.path.join(csrc, f))] + \
-           [os.path.join(ROOT, "tests", "simt", "simt_emul.h")]
+           [os.path.join(ROOT, "tests", "simt", "simt_emul.h"), os.path.join(ROOT, "include", "halgpu.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cmd = ["g++", "-std=c++17", "-O2", "-DHALGPU_SIMT_EMUL", "-I" + os.path.join(ROOT, "tests", "simt"), "-I" + csrc,
                "-fPIC", "-shared", "-pthread"]
@@ -60,6 +60,19 @@ def emul_cli(emul_lib):
     host = os.path.join(ROOT, "hal_b200", "csrc", "host")
     srcs = [os.path.join(host, f) for f in ("halLiftoverMain.cpp", "gpu_liftover.cpp", "bed.cpp", "bed_fast.cpp")]
     deps = srcs + [os.path.join(host, f) for f in ("gpu_liftover.hpp", "bed.hpp", "bed_fast.hpp")] + [emul_lib]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs +
+                              ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    return out
+
+
+@pytest.fixture(scope="session")
+def emul_wig_cli(emul_lib):
+    """The halWiggleLiftover CLI linked against the emulated library."""
+    out = os.path.join(ROOT, "tests", "simt", "halWiggleLiftover_emul")
+    host = os.path.join(ROOT, "hal_b200", "csrc", "host")
+    srcs = [os.path.join(host, f) for f in ("halWiggleLiftoverMain.cpp", "wiggle_liftover.cpp")]
+    deps = srcs + [os.path.join(host, "wiggle_liftover.hpp"), emul_lib]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs +
                               ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])

@@ -129,6 +129,14 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, int delta) {
     return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline long long __double_as_longlong(double v) { return simt::fromBits<long long>(simt::toBits(v)); }
+inline double __longlong_as_double(long long v) { return simt::fromBits<double>(simt::toBits(v)); }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);

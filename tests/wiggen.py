@@ -12,6 +12,8 @@ def random_wig(rng, seqs, sections=(2, 6), max_lines=400, disorder=0.0):
         if kind.startswith("fixed"):
             step = rng.choice([1, 1, 1, 3, 10])
             span = rng.choice([1, 2, 5]) if kind == "fixedspan" else None
+            if span and span > step and rng.random() < 0.9:  # overlapping lines are "Coordinate out of order" inside a batch
+                step = span + rng.choice([0, 0, 3])
             n = rng.randint(1, max(1, min(max_lines, (ln - 10) // step)))
             start = rng.randint(1, max(1, ln - n * step - (span or 1)))
             out.append(f"fixedStep chrom={nm} start={start} step={step}" + (f" span={span}" if span else ""))
