@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--no-maf", action="store_true")
     ap.add_argument("--maf-columns", type=int, default=50_000_000)
     ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-wiggle", action="store_true")
+    ap.add_argument("--wiggle-bases", type=int, default=50_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -427,6 +429,41 @@ def main():
                 line["secondary_maf"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
                                                          "sample": f"{cores} processes of oracle/_ref/hal2maf, {win}-column windows (hal2mafMP style)"}
         os.remove(outp)
+    # secondary: halWiggleLiftover's mapping core: one value per base of L7, lifted to L0 through
+    # halgpu_wiggle_liftover with HOST buffers (runs + values in, set target bases out); the pair is L7 -> L0 because the
+    # reference's own halWiggleLiftover cannot map L0 -> L7 (its wrong turn at the MRCA, oracle/restate/wiggle.cpp)
+    if world == 1 and not args.no_wiggle:
+        wsrc, wtgt = a.genome_id("L7"), a.genome_id("L0")
+        nb = min(args.wiggle_bases, genome_len - 2 * SEG_LEN)
+        run = 2048
+        wf = np.arange(0, nb, run, dtype=np.int64)
+        wl = np.minimum(wf + run - 1, nb - 1)
+        wv = np.random.default_rng(9).random(nb) * 100.0
+        best = None
+        for i in range(3):
+            t0 = time.perf_counter()
+            wpos, wval, winfo = a.wiggle_liftover(wsrc, wtgt, wf, wl, wf.copy(), wv)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, winfo["kernel_ms"], len(wpos))
+        line["secondary_wiggle"] = {"metric": "wiggle_liftover_bases_per_sec", "value": nb / best[0], "unit": "source bases/s",
+                                    "seconds": best[0], "mapping_kernel_ms": best[1], "bases_in": int(nb), "bases_out": int(best[2]),
+                                    "runs": int(len(wf)), "h2d_bytes": int(nb * 8 + len(wf) * 24), "d2h_bytes": int(best[2] * 16),
+                                    "check": {"max_equals_input_max": bool(len(wval) and wval.max() <= wv.max()), "all_nonnegative": bool((wval >= 0).all())}}
+        if not args.no_cpu_baseline:
+            ref = os.path.join(ROOT, "oracle", "_ref", "halWiggleLiftover")
+            if os.path.exists(ref):
+                win = 20000
+                d = tempfile.mkdtemp(prefix="halb200_wig_")
+                for c in range(cores):
+                    with open(os.path.join(d, f"i{c}.wig"), "w") as f:
+                        f.write(f"fixedStep chrom=L7_seq start={c * win + 1} step=1\n" + "".join(f"{x:.4f}\n" for x in wv[c * win:(c + 1) * win]))
+                t0 = time.time()
+                procs = [subprocess.Popen([ref, hal, "L7", os.path.join(d, f"i{c}.wig"), "L0", os.path.join(d, f"o{c}.wig")]) for c in range(cores)]
+                assert all(p.wait() == 0 for p in procs)
+                dt = time.time() - t0
+                line["secondary_wiggle"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "source bases/s", "cores": cores, "kind": "reference",
+                                                            "sample": f"{cores} processes of oracle/_ref/halWiggleLiftover, {win} fixedStep bases each (text in, text out)"}
     # secondary: the whole halLiftover CLI (text I/O at GPU rate) on the same batch as a BED3 file:
     # process start + CUDA context + open/stage + multi-threaded tokeniser + halgpu_liftover + multi-threaded printer + file write
     if world == 1 and not args.no_cli:

@@ -185,3 +185,31 @@ def test_fast_path_matches_reference_binary(emul_cli, tmp_path, width, extras, a
         assert fast > 200
         assert open(out, "rb").read() == open(exp, "rb").read(), (threads, block)
         assert err.strip() == r.stderr.strip()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ref_bin("halLiftover") is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("width,extras,args", [(3, 0, []), (6, 1, ["--bedType", "6"]), (9, 0, ["--noDupes"])])
+def test_fast_path_cuda_matches_reference_binary(tmp_path, width, extras, args):
+    """The shipped CLI (CUDA library, multi-threaded text layer) against the reference CLI on 20k messy lines."""
+    import pyoracle
+    from hal_b200 import build
+    build.build()
+    cli = os.path.join(ROOT, "hal_b200", "bin", "halLiftover")
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    o = pyoracle.Oracle(hal)
+    seqs = [(n, l) for (n, s, l) in o.sequences(o.genome_id("L3"))]
+    o.close()
+    rng = random.Random(width)
+    bed = tmp_path / "in.bed"
+    bed.write_text(corpus(rng, seqs, width, 20000, extras, missing=("nope",)))
+    exp = str(tmp_path / "ref.bed")
+    r = subprocess.run([ref_bin("halLiftover")] + args + [hal, "L3", str(bed), "L0", exp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for threads, block in ((8, None), (5, 100000), (0, None)):
+        out = str(tmp_path / "o.bed")
+        rc, err, fast = run(cli, hal, "L3", str(bed), "L0", out, args=args, threads=threads, block=block)
+        assert rc == 0, err
+        assert (fast > 19000) == (threads > 0)
+        assert open(out, "rb").read() == open(exp, "rb").read(), (threads, block)
+        assert err.strip() == r.stderr.strip()
