@@ -64,14 +64,68 @@ def ensure_hal(segs):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region.  Only rank 0 samples (its own GPU): eight
-    pollers hitting the driver at 10 Hz stalled every rank's CUDA calls and tripled the 8-GPU step time."""
+    """SM clock / throttle-reason samples during the timed region.
 
-    def __init__(self, gpu, enabled=True):
-        self.rows, self.gpu, self.proc, self.enabled = [], gpu, None, enabled
+    NVML is queried in-process (pynvml, initialised in __init__, i.e. BEFORE the warm-up): starting an `nvidia-smi -lms`
+    child right at the timed region cost it ~50 ms of driver stalls (its NVML start-up serialises with this process's
+    cudaMallocAsync / cudaFree calls) and turned a 30 ms step into 80 ms.  `nvidia-smi` is only the fallback when pynvml
+    is missing, and then the sampler waits for its first row before the timed region starts.  Only rank 0 samples."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu, enabled=True, period_s=0.02):
+        self.rows, self.gpu, self.enabled, self.period = [], gpu, enabled, period_s
+        self.nvml = self.handle = self.proc = self.thread = None
+        self.stop = threading.Event()
+        if not enabled:
+            return
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(gpu)
+            try:  # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES is set: go through the PCI address
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.nvml = pynvml
+            self._sample()  # first query (lazy driver paths) outside the timed region
+            self.rows.clear()
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] pynvml unavailable ({e}); falling back to nvidia-smi")
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits])
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop.wait(self.period)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
 
     def __enter__(self):
         if not self.enabled:
+            return self
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
             return self
         try:
             self.proc = subprocess.Popen(
@@ -79,29 +133,29 @@ class ClockSampler:
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                  "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:  # its start-up must not overlap the timed region
+                time.sleep(0.02)
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-            self.t.join(timeout=2)
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def algorithmic_bytes_per_interval(hal, gs, ge, n_src_segs, sample=20000):
@@ -302,10 +356,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local, enabled=(rank == 0))  # NVML initialised here, before the warm-up
     for _ in range(args.warmup):
         nrec, *_ = step_resident(True)
     kms = []
-    with ClockSampler(local, enabled=(rank == 0)) as clocks:
+    with sampler as clocks:
         # the sampler is started BEFORE the barrier: spawning nvidia-smi takes rank 0 ~0.1 s, and ranks that entered the
         # timed loop earlier would sit in the first all-gather waiting for it (their event time is what MAX-over-ranks reports)
         barrier()
@@ -316,9 +371,12 @@ def main():
         # torch's stream: events on torch's current stream bracket all of it (device clock, includes in-step gaps).
         cur = torch.cuda.current_stream()
         e0.record(cur)
+        step_wall = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             nrec, k, launches, nretry = step_resident(True)
             kms.append(k)
+            step_wall.append((time.perf_counter() - ts) * 1e3)
         e1.record(cur)
         barrier()
         wall = time.perf_counter() - w0
@@ -375,7 +433,7 @@ def main():
                      "algorithmic_bytes_per_interval": per_interval,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"},
         "detail": {"output_lines_per_step": int(nrec), "retry_intervals": int(nretry), "wall_s_per_step": wall / args.steps,
-                   "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step,
+                   "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step, "step_wall_ms": [round(x, 3) for x in step_wall],
                    "oracle_sample_stats": ostats},
     }
     # secondary (BASELINE.json configs[4] shape on one GPU): halAlignmentDepth column sweep, ref = leaf L0, all targets

@@ -48,6 +48,7 @@ def _lib():
     L.oracle_liftover.restype = C.c_int64
     L.oracle_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.oracle_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    L.oracle_set_coalescence_limit.argtypes = [C.c_void_p, C.c_int]
     L.oracle_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.oracle_hal2maf.restype = C.c_void_p
     L.oracle_hal2maf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -90,13 +91,17 @@ class Oracle:
     def genome_length(self, g):
         return self.L.oracle_genome_length(self.h, g)
 
-    def liftover(self, src, tgt, gs, ge, strand=None, no_dupes=False):
+    def liftover(self, src, tgt, gs, ge, strand=None, no_dupes=False, coalescence_limit=None):
         """gs/ge: genome-global inclusive int64 arrays.  Returns dict of numpy arrays (CSR by interval)."""
         gs = np.ascontiguousarray(gs, dtype=np.int64)
         ge = np.ascontiguousarray(ge, dtype=np.int64)
         n = len(gs)
         st = np.full(n, ord('+'), dtype=np.uint8) if strand is None else np.ascontiguousarray(strand, dtype=np.uint8)
+        self.L.oracle_set_coalescence_limit(self.h, -1 if coalescence_limit is None else coalescence_limit)
         tot = self.L.oracle_liftover(self.h, src, tgt, int(no_dupes), n, gs.ctypes.data, ge.ctypes.data, st.ctypes.data)
+        self.L.oracle_set_coalescence_limit(self.h, -1)
+        if tot < 0:
+            raise RuntimeError(self.L.oracle_last_error(self.h).decode())
         r = dict(offsets=np.zeros(n + 1, np.uint64), tgtSeq=np.zeros(tot, np.int32), start=np.zeros(tot, np.int64),
                  end=np.zeros(tot, np.int64), strand=np.zeros(tot, np.uint8), srcStart=np.zeros(tot, np.int64),
                  srcStrand=np.zeros(tot, np.uint8))
@@ -176,7 +181,7 @@ class Oracle:
             raise RuntimeError(self.L.oracle_last_error(self.h).decode())
         return C.string_at(p, n.value).decode()
 
-    def liftover_bed(self, src_name, tgt_name, bed_text, no_dupes=False):
+    def liftover_bed(self, src_name, tgt_name, bed_text, no_dupes=False, coalescence_limit=None):
         """BED3..BED9 text in -> text out, formatted as halLiftover would (no BED12 regrouping / PSL)."""
         src, tgt = self.genome_id(src_name), self.genome_id(tgt_name)
         sseq = {n: (s, l) for (n, s, l) in self.sequences(src)}
@@ -201,7 +206,8 @@ class Oracle:
             gs.append(s0 + sseq[row[0]][0])
             ge.append(e0 - 1 + sseq[row[0]][0])
             st.append(ord(strand))
-        r = self.liftover(src, tgt, gs, ge, st, no_dupes)
+        r = self.liftover(src, tgt, gs, ge, st, no_dupes,
+                          None if coalescence_limit is None else self.genome_id(coalescence_limit))
         out = []
         off = r["offsets"]
         for i, (row, bt, strand) in enumerate(rows):

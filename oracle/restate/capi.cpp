@@ -11,6 +11,7 @@ using namespace oracle;
 
 struct OracleHandle {
     HalView view;
+    int coal = -1; /* coalescence limit of the following oracle_liftover calls (-1: MRCA) */
     std::vector<uint64_t> fragOffsets;
     std::vector<Frag> frags;
     std::vector<uint64_t> offsets;
@@ -51,7 +52,13 @@ const char *oracle_newick(void *hp) { return ((OracleHandle *)hp)->view.newick.c
 int64_t oracle_liftover(void *hp, int src, int tgt, int noDupes, int64_t n, const int64_t *gs, const int64_t *ge,
                         const char *strand) {
     OracleHandle *h = (OracleHandle *)hp;
-    Plan plan = makePlan(h->view, src, tgt);
+    Plan plan;
+    try {
+        plan = makePlan(h->view, src, tgt, h->coal);
+    } catch (std::exception &e) {
+        h->err = e.what();
+        return -1;
+    }
     h->offsets.assign(1, 0);
     h->lines.clear();
     h->stats = Stats();
@@ -61,6 +68,9 @@ int64_t oracle_liftover(void *hp, int src, int tgt, int noDupes, int64_t n, cons
     }
     return (int64_t)h->lines.size();
 }
+
+/* halLiftover --coalescenceLimit for the following oracle_liftover calls (genome id, -1 = MRCA) */
+void oracle_set_coalescence_limit(void *hp, int genome) { ((OracleHandle *)hp)->coal = genome; }
 
 void oracle_fetch(void *hp, uint64_t *offsets, int32_t *tgtSeq, int64_t *start, int64_t *end, char *strand,
                   int64_t *srcStart, char *srcStrand) {

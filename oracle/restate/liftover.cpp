@@ -21,7 +21,7 @@
 
 namespace oracle {
 
-Plan makePlan(const HalView &v, int src, int tgt) {
+Plan makePlan(const HalView &v, int src, int tgt, int coal) {
     Plan p;
     p.src = src;
     p.tgt = tgt;
@@ -34,6 +34,11 @@ Plan makePlan(const HalView &v, int src, int tgt) {
     p.up.assign(a.begin(), a.begin() + ia + 1);
     p.down.assign(b.begin(), b.begin() + ib + 1);
     std::reverse(p.down.begin(), p.down.end());
+    if (coal >= 0 && coal != p.mrca) {
+        int g = p.mrca;
+        while (g >= 0 && g != coal) { p.para.push_back(g); g = v.genomes[g].parent; }
+        if (g < 0) throw std::runtime_error("Hit root genome when attempting to map paralogies");
+    }
     return p;
 }
 
@@ -157,6 +162,67 @@ void levelDown(Ctx &c, const GenomeView &g, const GenomeView &ch, int k, bool du
     }
 }
 
+/* mapSelf (halSegmentMapper.cpp:263-330) inside genome g: a top fragment yields every member of its paralogy ring
+ * (itself first); a bottom fragment is first split over g's top segments (nothing at all in the root genome) */
+void selfMap(Ctx &c, const GenomeView &g, const std::vector<Frag> &in, std::vector<Frag> &out) {
+    auto ring = [&](const Frag &f0) {
+        Frag cur = f0;
+        int64_t first = f0.idx;
+        do {
+            out.push_back(cur);
+            int64_t nx = g.tNextPara(cur.idx);
+            if (nx >= 0) {
+                int64_t Sg = g.tStart(cur.idx), L = g.tStart(cur.idx + 1) - Sg;
+                bool flip = g.tRev(nx) != g.tRev(cur.idx);
+                hop(cur, Sg, L, g.tStart(nx), flip);
+                cur.idx = nx;
+                c.visitTop(g);
+            }
+        } while (g.tNextPara(cur.idx) >= 0 && cur.idx != first);
+    };
+    for (const Frag &f0 : in) {
+        if (f0.top) { ring(f0); continue; }
+        if (g.parent < 0) continue;
+        int64_t t = g.bTopParse(f0.idx);
+        while (g.tStart(t + 1) <= f0.tLo) t++;
+        for (; t < g.numTop && g.tStart(t) <= f0.tHi; t++) {
+            c.visitTop(g);
+            int64_t a = std::max(f0.tLo, g.tStart(t)), b = std::min(f0.tHi, g.tStart(t + 1) - 1);
+            Frag p = sub(f0, a, b);
+            p.top = true;
+            p.idx = t;
+            ring(p);
+        }
+    }
+}
+
+/* mapRecursiveParalogies (halSegmentMapper.cpp:525-576): level k of plan.para holds `in` (the interval's fragments mapped
+ * up to that genome).  Their paralogs there are mapped back down to the MRCA without dupes; the fragments themselves go
+ * one genome further up unless that is the limit.  Everything ends up in the MRCA. */
+void paralogies(Ctx &c, const HalView &v, const Plan &plan, size_t k, const std::vector<Frag> &in, std::vector<Frag> &results) {
+    results.clear();
+    if (in.empty() || k >= plan.para.size()) { results = in; return; }
+    const GenomeView &g = v.genomes[plan.para[k]];
+    std::vector<Frag> paralogs;
+    selfMap(c, g, in, paralogs);
+    if (k + 1 < plan.para.size()) {
+        std::vector<Frag> next;
+        levelUp(c, g, v.genomes[plan.para[k + 1]], in, next);
+        paralogies(c, v, plan, k + 1, next, results);
+    }
+    /* mapRecursiveDown(paralogs, ..., srcGenome = MRCA, doDupes = false): one level at a time, sort + unique after each */
+    std::vector<Frag> cur = paralogs, nxt;
+    for (size_t l = k; l > 0 && !cur.empty(); --l) {
+        nxt.clear();
+        const GenomeView &ch = v.genomes[plan.para[l - 1]];
+        levelDown(c, v.genomes[plan.para[l]], ch, ch.slot, false, cur, nxt);
+        cur.swap(nxt);
+    }
+    if (k > 0) sortUnique(cur);
+    results.insert(results.begin(), cur.begin(), cur.end()); /* results.splice(results.begin(), paralogsMappedToSrc) */
+    sortUnique(results);
+}
+
 inline bool lessTargetThenSource(const Frag &a, const Frag &b) {
     if (a.tLo != b.tLo) return a.tLo < b.tLo;
     if (a.tHi != b.tHi) return a.tHi < b.tHi;
@@ -201,6 +267,11 @@ void liftInterval(const HalView &v, const Plan &plan, bool dupes, int64_t gs, in
             cur.swap(nxt);
         }
         if (plan.up.size() > 1) sortUnique(cur);
+        /* paralogs that coalesce below the coalescence limit (mapSource, halSegmentMapper.cpp:617-623) */
+        if (!plan.para.empty() && dupes) {
+            paralogies(c, v, plan, 0, cur, nxt);
+            cur.swap(nxt);
+        }
         /* down phase (mapRecursiveDown) */
         for (size_t l = 0; l + 1 < plan.down.size(); l++) {
             nxt.clear();

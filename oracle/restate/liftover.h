@@ -32,9 +32,14 @@ struct Plan {
     int src, tgt, mrca;
     std::vector<int> up;   /* src ... mrca */
     std::vector<int> down; /* mrca ... tgt */
+    /* halLiftover --coalescenceLimit: mrca ... the child of the limit genome on the way up (empty when the limit is the
+     * MRCA, the default): the genomes whose paralogy rings mapRecursiveParalogies walks (halSegmentMapper.cpp:525-576) */
+    std::vector<int> para;
 };
 
-Plan makePlan(const HalView &v, int src, int tgt);
+/* coal: coalescence limit genome, -1 = the MRCA.  Throws when it is not the MRCA or one of its ancestors (the reference
+ * then runs off the root: "Hit root genome when attempting to map paralogies", halSegmentMapper.cpp:543-545). */
+Plan makePlan(const HalView &v, int src, int tgt, int coal = -1);
 
 /* Lift one interval [gs,ge] (genome-global inclusive) with BED strand ('+','-','.').
  * Appends the reference-ordered output lines (stable by srcStart) to out; optionally the
