@@ -176,9 +176,9 @@ class Alignment:
     def stream(self):
         return self.L.halgpu_stream(self.h)
 
-    def _call(self, fn, src, tgt, flags, n, a, b, s):
+    def _call(self, fn, src, tgt, flags, n, a, b, s, coal=-1):
         res, errp = C.POINTER(_Result)(), C.c_void_p()
-        rc = fn(self.h, src, tgt, -1, flags, n, a, b, s, C.byref(res), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        rc = fn(self.h, src, tgt, coal, flags, n, a, b, s, C.byref(res), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
         if rc != 0:
             msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else "liftover failed"
             if errp.value:
@@ -186,14 +186,15 @@ class Alignment:
             raise HalGpuError(msg)
         return res
 
-    def liftover(self, src, tgt, start, end_incl, strand=None, flags=0):
-        """Host arrays in (forward genome coordinates), numpy arrays out: (offsets[n+1], recs[REC_DTYPE], info)."""
+    def liftover(self, src, tgt, start, end_incl, strand=None, flags=0, coalescence_limit=-1):
+        """Host arrays in (forward genome coordinates), numpy arrays out: (offsets[n+1], recs[REC_DTYPE], info).
+        coalescence_limit: genome index for halLiftover --coalescenceLimit (-1: the MRCA)."""
         start = np.ascontiguousarray(start, dtype=np.int64)
         end_incl = np.ascontiguousarray(end_incl, dtype=np.int64)
         st = None if strand is None else np.ascontiguousarray(strand, dtype=np.uint8)
         n = len(start)
         res = self._call(self.L.halgpu_liftover, src, tgt, flags, n, start.ctypes.data, end_incl.ctypes.data,
-                         None if st is None else st.ctypes.data)
+                         None if st is None else st.ctypes.data, coalescence_limit)
         r = res.contents
         offsets = np.ctypeslib.as_array(C.cast(r.offsets, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
         if r.n_rec:

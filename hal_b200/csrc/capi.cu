@@ -99,13 +99,11 @@ static int liftDeviceWithBase(halgpu_ctx *ctx, int src, int tgt, int coalescence
                               const int64_t *dEnd, const uint8_t *dStrand, uint64_t offsetBase, halgpu_lift_result **out, char **err) {
     if (ctx == nullptr || out == nullptr) return fail(err, "halgpu_liftover: null argument");
     *out = nullptr;
-    if (coalescenceLimit != -1 && coalescenceLimit != halgpu_mrca(ctx, src, tgt)) {
-        return fail(err, "halgpu_liftover: --coalescenceLimit other than the MRCA is not supported");
-    }
+    if (coalescenceLimit < -1 || coalescenceLimit >= halgpu_num_genomes(ctx)) return fail(err, "halgpu_liftover: coalescence limit genome out of range");
     return guarded(err, [&] {
         rt::setDevice(ctx->impl->device());
         LiftOutput lo;
-        ctx->impl->liftover(src, tgt, flags, n, dStart, dEnd, dStrand, lo, offsetBase);
+        ctx->impl->liftover(src, tgt, flags, n, dStart, dEnd, dStrand, lo, offsetBase, nullptr, coalescenceLimit);
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = n; r->n_rec = lo.nRec; r->offsets = lo.offsets; r->recs = lo.recs; r->on_device = 1;
         r->kernel_ms = lo.kernelMs; r->launches = lo.launches; r->n_retry = lo.nRetry; r->psl = lo.psl;

@@ -40,8 +40,19 @@ struct PathStep {
     const int64_t *child; // down transitions: childEnc column of path[p] for the slot of path[p+1];
                           // up transitions: childEnc column of path[p+1] (the parent) for the slot of path[p]
     int64_t numTop, numBot;
-    int32_t up;  // 1: transition p -> p+1 goes to the parent
+    int32_t up;    // 1: transition p -> p+1 goes to the parent
+    int32_t flags; // STEP_* (only set on paths planned with a coalescence limit above the MRCA)
+    int32_t jump;  // STEP_PARA: path position at which this genome's paralogs start their way back down to the MRCA
     int32_t pad;
+};
+// halLiftover --coalescenceLimit (mapRecursiveParalogies, api/impl/halSegmentMapper.cpp:525-576): between the upward and the
+// downward part of the path sit the genomes from the MRCA up to the child of the limit (STEP_PARA entries, walked upward),
+// followed by the same genomes walked back down WITHOUT following paralogy rings (STEP_NODUPES entries).
+enum : int32_t {
+    STEP_PARA = 1,      // at this genome: every fragment (as top pieces) forks into (a) itself + its paralogy ring, which
+                        // continue at `jump`, and (b) itself mapped to the parent, unless STEP_PARA_LAST
+    STEP_NODUPES = 2,   // downward transition that does not start ring walks (mapRecursiveDown with doDupes = false)
+    STEP_PARA_LAST = 4  // the parent of this genome is the coalescence limit: nothing goes further up
 };
 
 struct LiftParams {

@@ -185,35 +185,58 @@ void Context::stageGenome(int gi) {
     if (g.numBottom > 0) buildBucket(d.bot, false, g.numBottom, g.length, d.botBucket, d.botShift, d.botBuckets);
 }
 
-const Plan &Context::plan(int src, int tgt) {
-    auto key = std::make_pair(src, tgt);
-    auto it = _plans.find(key);
-    if (it != _plans.end()) return it->second;
+const Plan &Context::plan(int src, int tgt, int coal) {
     const auto &G = _file->genomes();
     Plan p;
     p.src = src; p.tgt = tgt; p.mrca = _file->mrca(src, tgt);
     if (p.mrca < 0) throw HalError("source and target genomes share no ancestor");
-    for (int g = src; g != p.mrca; g = G[g].parent) p.path.push_back(g);
-    p.path.push_back(p.mrca);
-    p.upSteps = (int)p.path.size() - 1;
-    std::vector<int> down;
+    if (coal == p.mrca) coal = -1; // the default (liftover/impl/halBlockLiftover.cpp:36-38)
+    auto key = std::make_tuple(src, tgt, coal);
+    auto it = _plans.find(key);
+    if (it != _plans.end()) return it->second;
+    // genomes whose paralogy rings mapRecursiveParalogies walks: the MRCA ... the child of the limit
+    // (api/impl/halSegmentMapper.cpp:525-576); the limit must be an ancestor of the MRCA
+    std::vector<int> para;
+    if (coal >= 0) {
+        int g = p.mrca;
+        while (g >= 0 && g != coal) { para.push_back(g); g = G[g].parent; }
+        if (g < 0) throw HalError("Hit root genome when attempting to map paralogies");
+    }
+    p.coal = coal;
+    std::vector<int> up, down;
+    for (int g = src; g != p.mrca; g = G[g].parent) up.push_back(g);
     for (int g = tgt; g != p.mrca; g = G[g].parent) down.push_back(g);
     std::reverse(down.begin(), down.end());
-    p.path.insert(p.path.end(), down.begin(), down.end());
-    std::vector<PathStep> steps(p.path.size());
-    for (size_t i = 0; i < p.path.size(); ++i) {
-        const int g = p.path[i];
+    p.upSteps = (int)up.size();
+    // path positions: [up genomes] [para levels 0..K, upward] [para levels K..1, downward] [MRCA] [down genomes]
+    struct Entry { int g; int up; int flags; int jump; };
+    std::vector<Entry> ent;
+    for (int g : up) ent.push_back(Entry{g, 1, 0, 0});
+    const int K = (int)para.size() - 1;
+    const int firstPara = (int)ent.size();
+    const int mrcaPos = firstPara + (K >= 0 ? 2 * K + 1 : 0); // position of the MRCA entry the downward part starts from
+    for (int k = 0; k <= K; ++k) {
+        const int backDown = k == 0 ? mrcaPos : firstPara + (K + 1) + (K - k); // where level k's paralogs go down from
+        ent.push_back(Entry{para[k], 1, STEP_PARA | (k == K ? STEP_PARA_LAST : 0), backDown});
+    }
+    for (int k = K; k >= 1; --k) ent.push_back(Entry{para[k], 0, STEP_NODUPES, 0});
+    ent.push_back(Entry{p.mrca, 0, 0, 0});
+    for (int g : down) ent.push_back(Entry{g, 0, 0, 0});
+    p.path.clear();
+    for (const Entry &e : ent) p.path.push_back(e.g);
+    std::vector<PathStep> steps(ent.size());
+    for (size_t i = 0; i < ent.size(); ++i) {
+        const int g = ent[i].g;
         PathStep &s = steps[i];
         s.top = _g[g].top; s.bot = _g[g].bot; s.child = nullptr;
         s.numTop = G[g].numTop; s.numBot = G[g].numBottom;
-        s.up = (int)i < p.upSteps ? 1 : 0;
-        s.pad = 0;
-        if (!s.up && i + 1 < p.path.size()) {
-            const int c = p.path[i + 1];
-            s.child = _g[g].child + (size_t)G[c].slotInParent * (size_t)G[g].numBottom;
-        } else if (s.up) { // the parent's column for this genome's slot: canonical-paralog test
-            const int par = p.path[i + 1];
-            s.child = _g[par].child + (size_t)G[g].slotInParent * (size_t)G[par].numBottom;
+        s.up = ent[i].up; s.flags = ent[i].flags; s.jump = ent[i].jump; s.pad = 0;
+        if (i + 1 >= ent.size()) continue;
+        const int nx = ent[i + 1].g;
+        if (!s.up) { // this genome's childEnc column for the slot of the next genome down
+            s.child = _g[g].child + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
+        } else if (G[g].parent >= 0 && G[g].parent == nx) { // the parent's column for this genome's slot: canonical-paralog test
+            s.child = _g[nx].child + (size_t)G[g].slotInParent * (size_t)G[nx].numBottom;
         }
     }
     p.dSteps = static_cast<PathStep *>(rt::dmalloc(steps.size() * sizeof(PathStep)));
@@ -359,12 +382,14 @@ struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch
 } // namespace
 
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig) {
+                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig, int coal) {
     PhaseTimer pt;
     const auto &G = _file->genomes();
     if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
     if (n >= 0xffffffffull) throw HalError("batch too large (>= 2^32 intervals); split it");
-    const Plan &pl = plan(src, tgt);
+    if ((flags & (HALGPU_NO_DUPES | HALGPU_COLUMN_LIFTOVER)) != 0) coal = -1; // paralogs are only sought with dupes on (halSegmentMapper.cpp:619)
+    const Plan &pl = plan(src, tgt, coal);
+    const bool coalPath = pl.coal >= 0;
     const GenomeInfo &S = G[src];
     const bool srcIsTop = S.numTop > 0; // liftover/impl/halBlockLiftover.cpp:24-30
     if (!srcIsTop && S.numBottom == 0) throw HalError("source genome " + S.name + " has no segments");
@@ -426,17 +451,20 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
     if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
+    if (wig && coalPath) throw HalError("the wiggle liftover has no coalescence limit (the reference's halWiggleLiftover has none either)");
+    void (*const mapKernel)(const LiftParams) = wig ? liftoverKernel<true, false> : (coalPath ? liftoverKernel<false, true> : liftoverKernel<false, false>);
     // rung 1: all n intervals, scratch in shared memory
     const unsigned block = 128, warpsPerBlock = block / 32;
     {
         P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
         P.n = (int64_t)n; P.work = dWork;
         const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
-        rt::allowSmem(liftoverKernel<false>, smem);
-        rt::allowSmem(liftoverKernel<true>, smem);
+        rt::allowSmem(liftoverKernel<false, false>, smem);
+        rt::allowSmem(liftoverKernel<true, false>, smem);
+        rt::allowSmem(liftoverKernel<false, true>, smem);
         rt::Event e0, e1;
         e0.record(_stream);
-        rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
+        rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
         e1.record(_stream);
         rt::sync(_stream);
         out.kernelMs = rt::Event::elapsedMs(e0, e1);
@@ -505,7 +533,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             if (inSmem) { P.gscratch = nullptr; P.gscratchPerWarp = 0; }
             else { scratch.reset(new DevBuf(per * (uint64_t)warps)); P.gscratch = scratch->as<uint8_t>(); P.gscratchPerWarp = per; }
             const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
-            rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
+            rt::launch(mapKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
             rt::sync(_stream);
             continue;
         }
@@ -525,7 +553,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         rt::d2d(ids.p, list.p, nOver * sizeof(uint32_t), _stream);
         P.n = (int64_t)nOver; P.work = ids.as<uint32_t>();
         P.listCap = listCap; P.frameCap = frameCap; P.gscratch = scratch.as<uint8_t>(); P.gscratchPerWarp = per;
-        rt::launch(wig ? liftoverKernel<true> : liftoverKernel<false>, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
+        rt::launch(mapKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
         rt::sync(_stream);
     }
 

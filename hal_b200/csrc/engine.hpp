@@ -6,6 +6,7 @@
 #include "rt.hpp"
 #include <map>
 #include <memory>
+#include <tuple>
 #include <vector>
 
 namespace halgpu {
@@ -24,7 +25,8 @@ struct GenomeDev {
 
 struct Plan {
     int src = -1, tgt = -1, mrca = -1;
-    std::vector<int> path; // src .. mrca .. tgt
+    int coal = -1;         // coalescence limit genome when it lies above the MRCA, else -1
+    std::vector<int> path; // src .. mrca [.. child of the limit .. mrca] .. tgt (genome of every path position)
     int upSteps = 0;
     PathStep *dSteps = nullptr;
 };
@@ -64,7 +66,7 @@ class Context {
     // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
     // offsetBase is added to every CSR offset (the pipelined host entry point lifts a batch chunk by chunk)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr);
+                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr, int coal = -1);
 
     // wiggle liftover of nRuns source ranges [first, last] (genome coordinates) carrying per-base values (valOff >= 0) or
     // one value (valOff < 0: ~index), onto the target genome preloaded with nPre (position, value) pairs; host in, host out
@@ -82,14 +84,14 @@ class Context {
     void buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab);
     void stageGenome(int g);
     void buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb);
-    const Plan &plan(int src, int tgt);
+    const Plan &plan(int src, int tgt, int coal = -1);
     void *alloc(size_t bytes);
 
     std::unique_ptr<HalFile> _file;
     int _device;
     rt::Stream _stream, _copy;
     std::vector<GenomeDev> _g;
-    std::map<std::pair<int, int>, Plan> _plans;
+    std::map<std::tuple<int, int, int>, Plan> _plans; // (src, tgt, coalescence limit or -1)
     std::vector<void *> _owned;
     size_t _staged = 0;
     int _sms = 0;

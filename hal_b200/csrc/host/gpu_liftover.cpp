@@ -95,7 +95,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
     const std::string srcName = halgpu_genome_name(_ctx, srcGenome);
     _missed.clear();
     linesIn = intervalsLifted = linesOut = fastLines = 0;
-    gpuSeconds = textSeconds = writeSeconds = parseSeconds = 0;
+    gpuSeconds = textSeconds = writeSeconds = parseSeconds = readSeconds = 0;
 
     if (in->bad()) throw std::runtime_error("Error reading bed input stream");
     BedLine cur; // persists across lines like BedScanner::_bedLine
@@ -126,7 +126,13 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         intervalsLifted += n;
         return res;
     };
-    while (reader.next(block, blockLen)) {
+    while (true) {
+        {
+            auto tr = std::chrono::steady_clock::now();
+            const bool more = reader.next(block, blockLen);
+            readSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr).count();
+            if (!more) break;
+        }
         // ---- fast path: the whole block tokenised and formatted by `threads` threads (bed_fast.hpp) ----
         if (threads > 0 && !outPSL) {
             auto t0 = std::chrono::steady_clock::now();

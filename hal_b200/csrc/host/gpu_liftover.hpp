@@ -35,7 +35,7 @@ class GpuBlockLiftover {
     bool columnLiftover = false;
     // totals of the last convert()
     size_t linesIn = 0, intervalsLifted = 0, linesOut = 0;
-    double gpuSeconds = 0, textSeconds = 0, writeSeconds = 0, parseSeconds = 0; // halgpu_liftover calls / fast-path parse+format / ostream writes
+    double gpuSeconds = 0, textSeconds = 0, writeSeconds = 0, parseSeconds = 0, readSeconds = 0; // halgpu_liftover calls / fast-path parse+format / ostream writes
     size_t fastLines = 0;                                     // input lines that took the multi-threaded text path
 
   private:

@@ -4,6 +4,7 @@
 // be a HAL-MMAP file (convert HDF5 files with the reference's halExtract --outputFormat mmap).
 #include "gpu_liftover.hpp"
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -22,7 +23,7 @@ static void usage(ostream &os, const char *prog) {
        << "tgtGenome:   target genome name\ntgtBed:      path of output bed file.  set as stdout to stream to standard output.\n\n"
        << "OPTIONS:\n--append:             append results to tgtBed [default = 0]\n"
        << "--bedType <value>:    number of standard columns (3 to 12), columns beyond this are passed through. [default = 0]\n"
-       << "--coalescenceLimit <value>: coalescence limit genome (only the MRCA, the default, is supported) [default = \"\"]\n"
+       << "--coalescenceLimit <value>: coalescence limit genome: the genome at or above which paralogs coalesce (default: the MRCA of source and target) [default = \"\"]\n"
        << "--device <value>:     CUDA device index [default = 0]\n--help:               display this help page [default = 0]\n"
        << "--noDupes:            do not map between duplications in graph. [default = 0]\n"
        << "--columnLiftover:     (extension) use hal::ColumnLiftover instead of hal::BlockLiftover [default = 0]\n"
@@ -67,6 +68,9 @@ int main(int argc, char **argv) {
     }
     halgpu_ctx *ctx = nullptr;
     int rc = 0;
+    const auto tMain = chrono::steady_clock::now();
+    auto since = [](chrono::steady_clock::time_point t) { return chrono::duration<double>(chrono::steady_clock::now() - t).count(); };
+    double openSeconds = 0;
     try {
         const int bedType = opt.count("bedType") ? atoi(opt["bedType"].c_str()) : 0;
         bool outPSL = flag["outPSL"];
@@ -78,6 +82,7 @@ int main(int argc, char **argv) {
             halgpu_free_string(err);
             throw runtime_error(m);
         }
+        openSeconds = since(tMain);
         const int src = halgpu_genome_id(ctx, pos[1].c_str());
         if (src < 0) throw runtime_error(string("srcGenome, ") + pos[1] + ", not found in alignment");
         const int tgt = halgpu_genome_id(ctx, pos[3].c_str());
@@ -108,7 +113,8 @@ int main(int argc, char **argv) {
         if (getenv("HALGPU_TIMING")) {
             cerr << "[halLiftover] lines in " << lift.linesIn << " (" << lift.fastLines << " on the multi-threaded text path), intervals "
                  << lift.intervalsLifted << ", lines out " << lift.linesOut << "; text " << lift.textSeconds << " s (parse " << lift.parseSeconds << "), halgpu_liftover "
-                 << lift.gpuSeconds << " s, write " << lift.writeSeconds << " s, " << lift.textThreads << " text threads" << endl;
+                 << lift.gpuSeconds << " s, read " << lift.readSeconds << " s, write " << lift.writeSeconds << " s, " << lift.textThreads
+                 << " text threads; open+stage (incl. CUDA context) " << openSeconds << " s, total so far " << since(tMain) << " s" << endl;
         }
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;

@@ -163,8 +163,9 @@ struct WarpScratch {
     Frame *frames;
 };
 
-// WIG: the wiggle mode is a separate instantiation so that the BED path's register allocation is untouched by it
-template <bool WIG>
+// WIG / COAL: the wiggle mode and the coalescence-limit path are separate instantiations so that the default BED path's
+// register allocation is untouched by them
+template <bool WIG, bool COAL>
 __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
@@ -279,7 +280,41 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         if (valid && p < np - 1) {
             const PathStep st = steps[p];
             const int64_t tHi = tLo + len - 1;
-            if (st.up) {
+            if (COAL && (st.flags & STEP_PARA)) {
+                // mapRecursiveParalogies (halSegmentMapper.cpp:525-576) at one genome between the MRCA and the limit
+                if (!kindTop) { // mapSelf / mapUp of a bottom fragment: one top piece at a time (toParseUp), remainder to the pool
+                    int64_t t = cursor;
+                    if (t < 0) t = searchFrom<true>(st.top, ldBot(&st.bot[idx]).topParse, st.numTop, tLo);
+                    const int64_t tEnd = topStart(st.top, t + 1) - 1;
+                    if (tEnd < tHi) {
+                        push.sLo = sLo; push.tLo = tLo; push.len = len;
+                        subRange(push.sLo, push.tLo, push.len, sRev, tRev, tEnd + 1, tHi);
+                        push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1) | (idx << 3);
+                        push.aux = t + 1; push.p = p; push.type = 0;
+                        doPush = true;
+                        subRange(sLo, tLo, len, sRev, tRev, tLo, tEnd);
+                    }
+                    kindTop = true; idx = t; cursor = -1; // the fork happens in the next iteration, as a top piece
+                } else {
+                    const TopRec r = ldTop(&st.top[idx]);
+                    if (!(st.flags & STEP_PARA_LAST) && r.parentEnc >= 0) {
+                        // (b) mapUp(original, doDupes = true): a copy continues in the parent genome, one level further up
+                        const int64_t L = topStart(st.top, idx + 1) - r.start;
+                        const int64_t pi = r.parentEnc >> 1;
+                        const bool fl = (r.parentEnc & 1) != 0;
+                        const int64_t ps = botStart(steps[p + 1].bot, pi);
+                        const int64_t off = tLo - r.start;
+                        push.sLo = sLo; push.len = len;
+                        push.tLo = fl ? ps + L - off - len : ps + off;
+                        push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)((tRev != fl) ? 1 : 0) << 1) | (pi << 3);
+                        push.aux = -1; push.p = p + 1; push.type = 0;
+                        doPush = true;
+                    }
+                    // (a) mapSelf: this top and every member of its paralogy ring head back down to the MRCA
+                    landedDown = r.nextPara >= 0;
+                    p = st.jump;
+                }
+            } else if (st.up) {
                 if (!kindTop) { // bottom fragment: cut at the top-segment boundary (toParseUp, halTopSegmentIterator.cpp:55-81)
                     int64_t t = cursor;
                     if (t < 0) t = searchFrom<true>(st.top, ldBot(&st.bot[idx]).topParse, st.numTop, tLo);
@@ -333,7 +368,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                     const int64_t ci = ce >> 1;
                     const bool fl = (ce & 1) != 0;
                     int64_t cs;
-                    if (P.dupes) { // one 32-byte read gives the landing start AND tells whether a paralogy ring hangs here
+                    if (P.dupes && !(COAL && (st.flags & STEP_NODUPES))) { // one 32-byte read gives the landing start AND tells whether a paralogy ring hangs here
                         const TopRec rc = ldTop(&steps[p + 1].top[ci]);
                         cs = rc.start;
                         landedDown = rc.nextPara >= 0;
@@ -487,7 +522,9 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         const Frag a = listA[i], b = listA[i + 1];
         unsorted |= fragLess(b, a);
         const bool same = a.tLo == b.tLo && a.len == b.len;
-        clash |= !(same || b.tLo > a.tLo + a.len - 1);
+        // (COAL) a fragment and its own image mapped up and back down meet again in the MRCA: the reference drops such exact
+        // repeats with list::unique (halSegmentMapper.cpp:573-574); here they take the refinement path, which de-duplicates
+        clash |= !(same || b.tLo > a.tLo + a.len - 1) || (COAL && fragSameCoords(a, b));
         classes |= a.tLo == b.tLo;
         split |= !canMergeRight(a, b);
     }
@@ -501,7 +538,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         for (int i = lane; i + 1 < m; i += 32) {
             const Frag a = cur[i], b = cur[i + 1];
             const bool same = a.tLo == b.tLo && a.len == b.len;
-            clash |= !(same || b.tLo > a.tLo + a.len - 1);
+            clash |= !(same || b.tLo > a.tLo + a.len - 1) || (COAL && fragSameCoords(a, b));
             classes |= a.tLo == b.tLo;
         }
     }
@@ -747,7 +784,7 @@ __host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) 
 extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
 #endif
 
-template <bool WIG>
+template <bool WIG, bool COAL>
 __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
 #if defined(HALGPU_SIMT_EMUL)
     uint8_t *hg_dyn_smem = simt::dynamicSmem();
@@ -765,7 +802,7 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
     ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
     for (int64_t w = gwarp; w < P.n; w += nwarps) {
         const uint32_t item = P.work ? __ldg(&P.work[w]) : (uint32_t)w;
-        liftOneInterval<WIG>(P, ws, item, lane);
+        liftOneInterval<WIG, COAL>(P, ws, item, lane);
         __syncwarp();
     }
 }

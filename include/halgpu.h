@@ -97,7 +97,11 @@ void *halgpu_stream(const halgpu_ctx *ctx);                         /* the cudaS
  *      BlockLiftover::liftInterval, liftover/impl/halBlockLiftover.cpp:46-113).
  *      Inputs are forward GENOME coordinates: src_start = bed.start + seq.start,
  *      src_end_incl = bed.end - 1 + seq.start (halBlockLiftover.cpp:48-49); strand may be NULL ('+').
- *      coalescence_limit must be -1 (== MRCA, the CLI default).  Host buffers in, host result out;
+ *      coalescence_limit: -1 (== the MRCA, the CLI default) or a genome index (halLiftover --coalescenceLimit): with an
+ *      ancestor of the MRCA, paralogs that coalesce below it are mapped too (mapRecursiveParalogies,
+ *      api/impl/halSegmentMapper.cpp:525-576; ignored with HALGPU_NO_DUPES like in the reference, :619); a genome that
+ *      is not the MRCA or one of its ancestors fails with the reference's "Hit root genome ..." message.
+ *      Host buffers in, host result out;
  *      the host<->device copies are part of the call. ---- */
 int halgpu_liftover(halgpu_ctx *ctx, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
                     size_t n, const int64_t *src_start, const int64_t *src_end_incl, const uint8_t *strand,

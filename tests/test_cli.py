@@ -33,7 +33,7 @@ def check_all(cli, golden_cases, tmp_path, pick):
 
 def test_cli_emulated_matches_reference_outputs(emul_cli, golden_cases, tmp_path):
     check_all(emul_cli, golden_cases, tmp_path,
-              lambda c: "bed12" in c["name"] or c["name"].startswith("psl_") or c["name"].startswith("ref_") and "_all_" not in c["name"])
+              lambda c: "bed12" in c["name"] or c["name"].startswith(("psl_", "coal_")) or c["name"].startswith("ref_") and "_all_" not in c["name"])
 
 
 def test_cli_errors(emul_cli, tmp_path):

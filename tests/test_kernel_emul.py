@@ -110,3 +110,37 @@ def test_emulated_column_liftover_equals_oracle(emul_lib, oracle_lib, src, tgt, 
         assert got == exp, (i, gs[i], ge[i], chr(st[i]))
         assert (recs[off[i]:off[i + 1]]["src_start"] == -1).all()
     a.close()
+
+
+COAL_CASES = [("L3", "L2", "R"), ("L3", "A2", "A1"), ("L3", "A2", "R"), ("L2", "L3", "R"), ("A2", "L3", "A1"), ("L1", "L1", "R"),
+              ("L3", "L3", "A2"), ("A1", "L2", "R"), ("L0", "L1", "R"), ("L1", "A0", "R")]
+
+
+@pytest.mark.parametrize("src,tgt,limit", COAL_CASES)
+def test_emulated_coalescence_limit_equals_oracle(emul_lib, oracle_lib, src, tgt, limit):
+    """halLiftover --coalescenceLimit (mapRecursiveParalogies): the extended path of the kernel
+    against the oracle, whose restatement of it is pinned on the reference CLI (tests/test_oracle.py)."""
+    import hal_b200
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    a = hal_b200.Alignment(path, lib_path=emul_lib)
+    s, t, lim = a.genome_id(src), a.genome_id(tgt), a.genome_id(limit)
+    gs, ge, st = random_intervals(a.genome_length(s), 90, 250, seed=len(src + tgt + limit))
+    off, recs, _ = a.liftover(s, t, gs, ge, st, 0, coalescence_limit=lim)
+    exp = o.liftover(s, t, gs, ge, st, coalescence_limit=lim)
+    assert_same_as_oracle(off, recs, exp)
+    base = o.liftover(s, t, gs, ge, st)
+    assert len(exp["start"]) > len(base["start"]), "the limit should add paralogous lines on this fixture"
+    # with --noDupes the limit is ignored (halSegmentMapper.cpp:619)
+    off1, recs1, _ = a.liftover(s, t, gs, ge, st, 1, coalescence_limit=lim)
+    assert_same_as_oracle(off1, recs1, o.liftover(s, t, gs, ge, st, no_dupes=True))
+    a.close()
+
+
+def test_emulated_coalescence_limit_must_be_an_ancestor(emul_lib):
+    import hal_b200
+    a = hal_b200.Alignment(os.path.join(GOLDEN, "varlen8.hal"), lib_path=emul_lib)
+    gs, ge, st = random_intervals(a.genome_length(a.genome_id("L3")), 5, 100, seed=1)
+    with pytest.raises(hal_b200.HalGpuError, match="Hit root genome when attempting to map paralogies"):
+        a.liftover(a.genome_id("L3"), a.genome_id("L2"), gs, ge, st, 0, coalescence_limit=a.genome_id("A0"))
+    a.close()

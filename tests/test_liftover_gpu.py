@@ -56,7 +56,8 @@ def test_cuda_golden_text(hb, golden_cases):
             exp = open(os.path.join(GOLDEN, "cases", c["name"] + ".out.bed")).read()
             s, t = a.genome_id(c["src"]), a.genome_id(c["tgt"])
             rows, gs, ge, st = bed_to_batch(a.sequences(s), bed)
-            off, recs, _ = a.liftover(s, t, gs, ge, st, 1 if "--noDupes" in c["args"] else 0)
+            lim = a.genome_id(c["args"][c["args"].index("--coalescenceLimit") + 1]) if "--coalescenceLimit" in c["args"] else -1
+            off, recs, _ = a.liftover(s, t, gs, ge, st, 1 if "--noDupes" in c["args"] else 0, coalescence_limit=lim)
             assert batch_to_bed(rows, a.sequences(t), off, recs) == exp, c["name"]
     finally:
         for a in opened.values():
