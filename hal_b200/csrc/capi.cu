@@ -240,6 +240,11 @@ int halgpu_columns_depth(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, 
 
 int halgpu_column_runs(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, const int *targets, size_t nt, uint32_t flags,
                        halgpu_col_runs **out, char **err) {
+    return halgpu_column_runs_in_sweep(ctx, ref, first, last, first, targets, nt, flags, out, err);
+}
+
+int halgpu_column_runs_in_sweep(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, int64_t sweepFirst, const int *targets, size_t nt,
+                                uint32_t flags, halgpu_col_runs **out, char **err) {
     if (ctx == nullptr || out == nullptr || (nt > 0 && targets == nullptr)) return fail(err, "halgpu_column_runs: null argument");
     *out = nullptr;
     static_assert(sizeof(halgpu_col_row) == sizeof(ColRowRec), "row record layout");
@@ -248,7 +253,7 @@ int halgpu_column_runs(halgpu_ctx *ctx, int ref, int64_t first, int64_t last, co
         std::vector<int> t(targets, targets + nt);
         halgpu_col_runs *r = static_cast<halgpu_col_runs *>(std::calloc(1, sizeof(halgpu_col_runs)));
         try {
-            ctx->impl->columnRuns(ref, first, last, t, flags, *r);
+            ctx->impl->columnRuns(ref, first, last, t, flags, *r, sweepFirst);
         } catch (...) {
             halgpu_free_col_runs(r);
             throw;
@@ -287,6 +292,7 @@ void halgpu_free_col_runs(halgpu_col_runs *r) {
     rt::hostFree(r->run_col);
     rt::hostFree(r->row_offset);
     rt::hostFree(r->rows);
+    rt::hostFree(r->run_class);
     std::free(r);
 }
 

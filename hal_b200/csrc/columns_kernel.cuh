@@ -17,7 +17,7 @@
 
 namespace halgpu {
 
-enum : uint32_t { COL_COUNT_DUPES = 1u, COL_NO_ANCESTORS = 2u, COL_NO_DUPES = 4u, COL_ONLY_ORTHOLOGS = 8u };
+enum : uint32_t { COL_COUNT_DUPES = 1u, COL_NO_ANCESTORS = 2u, COL_NO_DUPES = 4u, COL_ONLY_ORTHOLOGS = 8u, COL_UNIQUE = 16u };
 
 struct DepthParams {
     const GenomeTab *genomes;
@@ -74,9 +74,32 @@ struct WalkStack {
     WalkStack stack;                                                                                               \
     stack.sPos = hgPos; stack.sA = hgA; stack.sB = hgB; stack.sMeta = hgMeta; stack.spill = hgSpill; stack.tid = (int)threadIdx.x;
 
-// Visitor: void emit(int g, int64_t pos, bool rev) for rows that pass the colMapInsert filters.
-template <class Emit>
-__device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, Emit &&emit) {
+struct NoRefHook {
+    __device__ __forceinline__ void operator()(int64_t) const {}
+};
+
+// ColumnIterator(unique = true) as used by MafExport (maf/impl/halMafExport.cpp:46-81): class of the column of reference
+// position p in a sweep that started at `window`, from the reference-genome bases its walk meets (before any row filter,
+// like the visit cache and _leftmostRefPos of api/impl/halColumnIterator.cpp:771-818):
+//   2  some reference-genome base lies in [window, p): an earlier column of the sweep put p into the visit cache, so
+//      nextFreeIndex (:749-762) skips p without walking it
+//   1  walked, but its left-most reference-genome base lies left of the window: isCanonicalOnRef (:208-212) is false and
+//      MafExport does not write it (its sequences still became ColumnMap keys)
+//   0  written
+struct UniqueClass {
+    int64_t window, p;
+    int cls;
+    __device__ __forceinline__ void operator()(int64_t pos) {
+        if (pos >= window && pos < p) cls = 2;
+        else if (pos < window && cls == 0) cls = 1;
+    }
+};
+
+// Visitor: void emit(int g, int64_t pos, bool rev) for rows that pass the colMapInsert filters; refHook(pos) sees every
+// base of the reference genome the walk meets, filtered or not.
+template <class Emit, class RefHook>
+__device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, Emit &&emit,
+                                           RefHook &&refHook) {
     const bool noDupes = (flags & COL_NO_DUPES) != 0, noAnc = (flags & COL_NO_ANCESTORS) != 0,
                onlyOrtho = (flags & COL_ONLY_ORTHOLOGS) != 0;
     int sp = 0;
@@ -89,6 +112,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
     };
     auto report = [&](int g, int64_t pos, bool rev) {
         const GenomeTab &T = G[g];
+        if (g == ref) refHook(pos);
         if (noAnc && T.nc > 0) return;
         if (!T.isTarget) return;
         emit(g, pos, rev);
@@ -190,7 +214,7 @@ __global__ void __launch_bounds__(128) depthKernel(const DepthParams P) {
         const bool ok = walkColumn(P.genomes, P.ref, P.first + i * P.step, P.flags, stack, [&](int g, int64_t, bool) {
             seen[g >> 6] |= 1ull << (g & 63);
             ++rows;
-        });
+        }, NoRefHook());
         if (!ok) *P.error = 1u;
         int d;
         if (P.flags & COL_COUNT_DUPES) {
@@ -219,6 +243,7 @@ struct ColSigParams {
     int32_t ref;
     uint32_t flags;
     int64_t first, n;
+    int64_t window;        // COL_UNIQUE: reference position the sweep started at (<= first)
     uint64_t *sigA, *sigB; // n entries each: 128-bit signature of the column's normalised rows
     uint32_t *nrows;       // n entries
     uint32_t *error;
@@ -233,6 +258,8 @@ struct ColEmitParams {
     const uint64_t *runRowOff; // per run: first row
     ColRowRec *rows;
     uint32_t *error;
+    int64_t window;           // COL_UNIQUE
+    uint8_t *runClass;        // COL_UNIQUE: per run, UniqueClass of its columns
 };
 
 __device__ __forceinline__ uint64_t hgMix(uint64_t x) {
@@ -242,7 +269,7 @@ __device__ __forceinline__ uint64_t hgMix(uint64_t x) {
 
 // walk column p and leave its rows sorted in ColumnMap order; returns the row count or -1 on overflow
 __device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, ColRowRec *rows,
-                                            uint64_t *keys) {
+                                            uint64_t *keys, UniqueClass &uc) {
     int n = 0;
     bool over = false;
     const bool ok = walkColumn(G, ref, p, flags, stack, [&](int g, int64_t pos, bool rev) {
@@ -256,7 +283,7 @@ __device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t
         while (j > 0 && keys[j - 1] > key) { rows[j] = rows[j - 1]; keys[j] = keys[j - 1]; --j; }
         rows[j] = r; keys[j] = key;
         ++n;
-    });
+    }, uc);
     return (ok && !over) ? n : -1;
 }
 
@@ -270,6 +297,8 @@ __global__ void __launch_bounds__(128) colSigKernel(const ColSigParams P) {
         uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xd1b54a32d192ed03ull;
         int n = 0;
         const GenomeTab *G = P.genomes;
+        UniqueClass uc;
+        uc.window = (P.flags & COL_UNIQUE) ? P.window : INT64_MIN; uc.p = (P.flags & COL_UNIQUE) ? P.first + i : INT64_MIN; uc.cls = 0;
         const bool ok = walkColumn(G, P.ref, P.first + i, P.flags, stack, [&](int g, int64_t pos, bool rev) {
             const GenomeTab &T = G[g];
             const int sq = T.numSeq > 1 ? seqOf(T.seqStart, T.numSeq, pos) : 0;
@@ -278,9 +307,10 @@ __global__ void __launch_bounds__(128) colSigKernel(const ColSigParams P) {
             a = hgMix(a ^ norm) + hgMix(id + 0x632be59bd9b4e019ull * (uint64_t)(n + 1));
             b = hgMix(b + id) ^ hgMix(norm * 0x9fb21c651e98df25ull + (uint64_t)n);
             ++n;
-        });
+        }, uc);
         if (!ok || n > HG_MAX_ROWS) { *P.error = 1u; P.nrows[i] = 0; P.sigA[i] = 0; P.sigB[i] = 0; continue; }
-        P.sigA[i] = a; P.sigB[i] = b; P.nrows[i] = (uint32_t)n;
+        // the class is part of the signature: a run never mixes written and skipped columns
+        P.sigA[i] = a ^ (0x2545f4914f6cdd1dull * (uint64_t)uc.cls); P.sigB[i] = b; P.nrows[i] = (uint32_t)n;
     }
 }
 
@@ -325,8 +355,11 @@ __global__ void __launch_bounds__(128) colEmitKernel(const ColEmitParams P) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += stride) {
         const int64_t i = P.runCol[r];
-        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys);
+        UniqueClass uc;
+        uc.window = (P.flags & COL_UNIQUE) ? P.window : INT64_MIN; uc.p = (P.flags & COL_UNIQUE) ? P.first + i : INT64_MIN; uc.cls = 0;
+        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys, uc);
         if (n < 0) { *P.error = 1u; continue; }
+        if (P.runClass) P.runClass[r] = (uint8_t)uc.cls;
         const uint64_t off = P.runRowOff[r];
         for (int k = 0; k < n; ++k) P.rows[off + k] = rows[k];
     }

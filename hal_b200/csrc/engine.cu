@@ -281,12 +281,16 @@ void Context::buildGenomeTab(int ref, const std::vector<int> &targets, std::vect
     }
 }
 
-void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out) {
+void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out,
+                         int64_t windowFirst) {
     const auto &G = _file->genomes();
     const int ng = (int)G.size();
     if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
     if (ng > 32767) throw HalError("too many genomes for the column row record");
     if (first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
+    const bool unique = (flags & COL_UNIQUE) != 0;
+    if (windowFirst < 0) windowFirst = first;
+    if (unique && windowFirst > first) throw HalError("the sweep start of a unique column range lies right of the range");
     DevBuf::current() = _stream;
     std::vector<GenomeTab> tab;
     buildGenomeTab(ref, targets, tab);
@@ -297,7 +301,7 @@ void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector
     DevBuf sigA(n * 8), sigB(n * 8), nrows((n + 1) * 4), isStart((n + 1) * 4), startRows((n + 1) * 4), runIndex((n + 2) * 8), rowOffset((n + 2) * 8);
     rt::Event e0, e1, e2, e3;
     ColSigParams sp;
-    sp.genomes = dTab.as<GenomeTab>(); sp.ref = ref; sp.flags = flags; sp.first = first; sp.n = n;
+    sp.genomes = dTab.as<GenomeTab>(); sp.ref = ref; sp.flags = flags; sp.first = first; sp.n = n; sp.window = windowFirst;
     sp.sigA = sigA.as<uint64_t>(); sp.sigB = sigB.as<uint64_t>(); sp.nrows = nrows.as<uint32_t>(); sp.error = dErr.as<uint32_t>();
     e0.record(_stream);
     rt::launch(colSigKernel, gridFor(n, 128, _sms), 128, 0, _stream, sp);
@@ -323,6 +327,8 @@ void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector
     ColEmitParams ep;
     ep.genomes = sp.genomes; ep.ref = ref; ep.flags = flags; ep.first = first; ep.n = (int64_t)nRuns;
     ep.runCol = rp.runCol; ep.runRowOff = rp.runRowOff; ep.rows = rows.as<ColRowRec>(); ep.error = sp.error;
+    DevBuf runClass(std::max<uint64_t>(nRuns, 1));
+    ep.window = windowFirst; ep.runClass = unique ? runClass.as<uint8_t>() : nullptr;
     e2.record(_stream);
     rt::launch(colEmitKernel, gridFor((int64_t)nRuns, 128, _sms), 128, 0, _stream, ep);
     e3.record(_stream);
@@ -333,6 +339,11 @@ void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector
     rt::d2h(out.run_col, runCol.p, (nRuns + 1) * 8, _stream);
     rt::d2h(out.row_offset, runRowOff.p, (nRuns + 1) * 8, _stream);
     rt::d2h(out.rows, rows.p, nRows * sizeof(halgpu_col_row), _stream);
+    out.run_class = nullptr;
+    if (unique) {
+        out.run_class = static_cast<uint8_t *>(rt::hostAlloc(std::max<uint64_t>(nRuns, 1)));
+        rt::d2h(out.run_class, runClass.p, nRuns, _stream);
+    }
     rt::sync(_stream);
     out.kernel_ms = rt::Event::elapsedMs(e0, e1) + rt::Event::elapsedMs(e2, e3);
 }

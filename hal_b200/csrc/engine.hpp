@@ -78,7 +78,9 @@ class Context {
                int32_t *dOut, float *kernelMs);
 
     // column runs of reference positions first..last; host (pinned) output owned by the caller
-    void columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out);
+    // windowFirst (COL_UNIQUE only): where the ColumnIterator sweep this range belongs to started (-1: at `first`)
+    void columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out,
+                    int64_t windowFirst = -1);
 
   private:
     void buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab);

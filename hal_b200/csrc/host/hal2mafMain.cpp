@@ -1,7 +1,8 @@
 // hal2maf -- GPU build of the reference CLI (maf/impl/hal2maf.cpp): same arguments, options, MAF text and
-// messages for the ColumnIterator flags the GPU column walk implements (unique=false, maxRefGap=0).
-// Not implemented (rejected with an error): --maxRefGap > 0, --unique, --global, --printTree, --refTargets.
+// messages for the ColumnIterator flags the GPU column walk implements (maxRefGap=0; --unique included).
+// Not implemented (rejected with an error): --maxRefGap > 0, --global, --printTree, --refTargets.
 #include "maf_export.hpp"
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -15,7 +16,7 @@ using namespace std;
 static void usage(ostream &os, const char *prog) {
     os << prog << " v-b200: Convert hal database to maf on a B200 GPU.\n\nUSAGE:\n" << prog << " [Options] <halFile> <mafFile>\n\n"
        << "OPTIONS:\n--refGenome <name>, --refSequence <name>, --start <n>, --length <n>, --rootGenome <name>, --targetGenomes <a,b,..>,\n"
-       << "--noDupes, --noAncestors, --onlySequenceNames, --onlyOrthologs, --keepEmptyRefBlocks, --append, --maxBlockLen <n>,\n"
+       << "--noDupes, --noAncestors, --onlySequenceNames, --onlyOrthologs, --unique, --keepEmptyRefBlocks, --append, --maxBlockLen <n>,\n"
        << "--device <n>, --help\n";
 }
 
@@ -36,7 +37,8 @@ int main(int argc, char **argv) {
     string halPath, mafPath, refGenomeName, rootGenomeName, targetGenomes, refSequenceName;
     int64_t start = 0, maxBlockLen = 1000;
     uint64_t length = 0;
-    bool noDupes = false, noAncestors = false, onlySequenceNames = false, append = false, onlyOrthologs = false, keepEmptyRefBlocks = false;
+    bool noDupes = false, noAncestors = false, onlySequenceNames = false, append = false, onlyOrthologs = false, keepEmptyRefBlocks = false,
+         unique = false;
     int device = 0;
     vector<string> pos;
     try {
@@ -59,7 +61,8 @@ int main(int argc, char **argv) {
             else if (a == "--keepEmptyRefBlocks") keepEmptyRefBlocks = true;
             else if (a == "--help") { usage(cerr, argv[0]); return 1; }
             else if (a == "--maxRefGap") { if (atoll(val().c_str()) != 0) throw runtime_error("--maxRefGap > 0 is not implemented in the GPU build"); }
-            else if (a == "--unique" || a == "--global" || a == "--printTree") throw runtime_error(a + " is not implemented in the GPU build");
+            else if (a == "--unique") unique = true;
+            else if (a == "--global" || a == "--printTree") throw runtime_error(a + " is not implemented in the GPU build");
             else if (a == "--refTargets") { if (!fixString(val()).empty()) throw runtime_error("--refTargets is not implemented in the GPU build"); }
             else if (a == "--format" || a == "--cacheMDC" || a == "--cacheRDC" || a == "--cacheBytes" || a == "--cacheW0" ||
                      a == "--mmapFileSize" || a == "--mmapSizeIncrease" || a == "--udcCacheDir") val();
@@ -135,7 +138,8 @@ int main(int argc, char **argv) {
         ostream &maf = mafPath != "stdout" ? mafFile : cout;
         halgpu::GpuMafExport ex(ctx);
         ex.setNoDupes(noDupes); ex.setNoAncestors(noAncestors); ex.setUcscNames(!onlySequenceNames); ex.setAppend(append);
-        ex.setMaxBlockLength(maxBlockLen); ex.setOnlyOrthologs(onlyOrthologs); ex.setKeepEmptyRefBlocks(keepEmptyRefBlocks);
+        ex.setMaxBlockLength(maxBlockLen); ex.setOnlyOrthologs(onlyOrthologs); ex.setKeepEmptyRefBlocks(keepEmptyRefBlocks); ex.setUnique(unique);
+        if (const char *cc = getenv("HALGPU_MAF_CHUNK_COLUMNS")) ex.chunkColumns = (size_t)std::max(1L, atol(cc)); // test hook
         if (refSeq >= 0) {
             ex.convertSequence(maf, ref, refSeq, start, length, targets);
         } else {

@@ -303,7 +303,8 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         mafStream << "##maf version=1 scoring=N/A\n" << "# hal " << halgpu_newick(_ctx) << std::endl << std::endl;
     }
     const uint32_t flags = (_noDupes ? (uint32_t)HALGPU_COL_NO_DUPES : 0u) | (_noAncestors ? (uint32_t)HALGPU_NO_ANCESTORS : 0u) |
-                           (_onlyOrthologs ? (uint32_t)HALGPU_ONLY_ORTHOLOGS : 0u);
+                           (_onlyOrthologs ? (uint32_t)HALGPU_ONLY_ORTHOLOGS : 0u) | (_unique ? (uint32_t)HALGPU_COL_UNIQUE : 0u);
+    const int64_t sweepFirst = S.start + startPosition; // the ColumnIterator of this call starts here (its visit cache spans all chunks)
     const Key refKey{m.rank[refGenome], refSequence};
     m.colKeys.clear(); // a fresh ColumnIterator per call
     uint64_t appendCount = 0;
@@ -323,8 +324,8 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         halgpu_col_runs *cr = nullptr;
         char *err = nullptr;
         auto t0 = std::chrono::steady_clock::now();
-        if (halgpu_column_runs(_ctx, refGenome, gFirst, gFirst + (int64_t)chunk - 1, targets.empty() ? nullptr : targets.data(), targets.size(),
-                               flags, &cr, &err) != 0) {
+        if (halgpu_column_runs_in_sweep(_ctx, refGenome, gFirst, gFirst + (int64_t)chunk - 1, sweepFirst, targets.empty() ? nullptr : targets.data(),
+                                        targets.size(), flags, &cr, &err) != 0) {
             std::string msg = err ? err : "halgpu_column_runs failed";
             halgpu_free_string(err);
             throw std::runtime_error(msg);
@@ -332,6 +333,8 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         for (size_t r = 0; r < cr->n_runs; ++r) {
             const int64_t col0 = cr->run_col[r], runLen = cr->run_col[r + 1] - col0;
+            const int cls = cr->run_class ? cr->run_class[r] : 0;
+            if (cls == 2) continue; // --unique: positions the iterator skips without walking them (nextFreeIndex)
             const halgpu_col_row *rr = cr->rows + cr->row_offset[r];
             const size_t nr = (size_t)(cr->row_offset[r + 1] - cr->row_offset[r]);
             m.rows.resize(nr);
@@ -342,6 +345,7 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
                 m.rows[i].rev = rr[i].rev != 0;
             }
             m.noteKeys();
+            if (cls == 1) continue; // --unique: walked (its sequences are ColumnMap keys now) but isCanonicalOnRef() is false
             int64_t j = 0;
             while (j < runLen) {
                 // exact per-column step (MafExport::convertSequence loop body, maf/impl/halMafExport.cpp:48-81)

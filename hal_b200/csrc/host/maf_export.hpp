@@ -31,6 +31,7 @@ class GpuMafExport {
     void setMaxBlockLength(int64_t v) { _maxLength = v <= 0 ? INT64_MAX : v; }
     void setOnlyOrthologs(bool v) { _onlyOrthologs = v; }
     void setKeepEmptyRefBlocks(bool v) { _keepEmptyRefBlocks = v; }
+    void setUnique(bool v) { _unique = v; } // MafExport::setUnique (maf/inc/halMafExport.h:51-53)
     size_t chunkColumns = 8u << 20; // columns per halgpu_column_runs call
     // totals
     uint64_t columns = 0, runs = 0, blocks = 0;
@@ -41,7 +42,7 @@ class GpuMafExport {
     std::unique_ptr<Impl> _impl;
     halgpu_ctx *_ctx;
     bool _noDupes = false, _noAncestors = false, _ucscNames = true, _append = false, _onlyOrthologs = false,
-         _keepEmptyRefBlocks = false;
+         _keepEmptyRefBlocks = false, _unique = false;
     int64_t _maxLength = 1000; // MafBlock::defaultMaxLength
 };
 

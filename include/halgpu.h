@@ -153,12 +153,24 @@ typedef struct halgpu_col_runs {
     uint64_t *row_offset;   /* n_runs + 1 entries */
     halgpu_col_row *rows;   /* n_rows entries */
     float kernel_ms;        /* device time of the column-walk kernels */
+    uint8_t *run_class;     /* HALGPU_COL_UNIQUE only (else NULL), n_runs entries: 0 = columns MafExport writes; 1 = walked by
+                             * the iterator but not written (left-most reference base left of the sweep start: isCanonicalOnRef
+                             * false) -- their sequences still become ColumnMap keys; 2 = skipped without being walked (the
+                             * position was visited through an earlier column of the sweep) */
 } halgpu_col_runs;
 
-enum { HALGPU_ONLY_ORTHOLOGS = 8u }; /* hal2maf --onlyOrthologs; also HALGPU_NO_ANCESTORS, HALGPU_COL_NO_DUPES */
+enum {
+    HALGPU_ONLY_ORTHOLOGS = 8u, /* hal2maf --onlyOrthologs; also HALGPU_NO_ANCESTORS, HALGPU_COL_NO_DUPES */
+    HALGPU_COL_UNIQUE = 16u     /* hal2maf --unique: ColumnIterator(unique = true) + MafExport's isCanonicalOnRef test
+                                 * (maf/impl/halMafExport.cpp:52,61; api/impl/halColumnIterator.cpp:208-212,749-762) */
+};
 
 int halgpu_column_runs(halgpu_ctx *ctx, int ref_genome, int64_t first, int64_t last, const int *targets, size_t n_targets,
                        uint32_t flags, halgpu_col_runs **out, char **err);
+/* same for a range that is one chunk of a longer sweep which started at sweep_first <= first (only matters with
+ * HALGPU_COL_UNIQUE, whose visit cache spans the whole sweep of one convertSequence call) */
+int halgpu_column_runs_in_sweep(halgpu_ctx *ctx, int ref_genome, int64_t first, int64_t last, int64_t sweep_first, const int *targets,
+                                size_t n_targets, uint32_t flags, halgpu_col_runs **out, char **err);
 void halgpu_free_col_runs(halgpu_col_runs *runs);
 /* packed DNA of a genome as staged (host pointer into the mapped file, 2 bases per byte, even index = high nibble;
  * replaces Genome::getDnaIterator for bulk text emission, api/inc/halDnaIterator.h:131-138) */

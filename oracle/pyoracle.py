@@ -52,7 +52,7 @@ def _lib():
     L.oracle_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.oracle_hal2maf.restype = C.c_void_p
     L.oracle_hal2maf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_int, C.c_int64, C.c_void_p]
+                                 C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
     L.oracle_column_liftover.restype = C.c_int64
     L.oracle_column_liftover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_char]
     L.oracle_liftover_frags.restype = C.c_int64
@@ -146,7 +146,7 @@ class Oracle:
         return [(int(r["tgtSeq"][j]), int(r["start"][j]), int(r["end"][j]), chr(r["strand"][j])) for j in range(k)]
 
     def hal2maf(self, ref_name, ref_seq=None, start=0, length=0, targets=(), no_dupes=False, no_ancestors=False,
-                only_orthologs=False, only_sequence_names=False, keep_empty_ref_blocks=False, max_block_len=0):
+                only_orthologs=False, only_sequence_names=False, keep_empty_ref_blocks=False, max_block_len=0, unique=False):
         """MAF text of `hal2maf --refGenome ref [--refSequence s --start a --length n] ...` (bytes)."""
         g = self.genome_id(ref_name)
         si = -1
@@ -156,7 +156,7 @@ class Oracle:
         n = C.c_uint64(0)
         p = self.L.oracle_hal2maf(self.h, g, si, start, length, t.ctypes.data if len(t) else None, len(t), int(no_dupes),
                                   int(no_ancestors), int(only_orthologs), int(only_sequence_names), int(keep_empty_ref_blocks),
-                                  max_block_len, C.byref(n))
+                                  max_block_len, int(unique), C.byref(n))
         if not p:
             raise RuntimeError("oracle_hal2maf failed")
         return C.string_at(p, n.value)

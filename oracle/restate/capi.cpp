@@ -113,7 +113,7 @@ int64_t oracle_depth(void *hp, int ref, int64_t first, int64_t last, int64_t ste
  * the text kept inside the handle until the next call; *len receives its length.  NULL on error. */
 const char *oracle_hal2maf(void *hp, int ref, int refSeq, int64_t start, int64_t length, const int *targets, int nt, int noDupes,
                            int noAncestors, int onlyOrthologs, int onlySequenceNames, int keepEmptyRefBlocks, int64_t maxBlockLen,
-                           uint64_t *len) {
+                           int unique, uint64_t *len) {
     OracleHandle *h = (OracleHandle *)hp;
     try {
         MafOpts o;
@@ -122,6 +122,7 @@ const char *oracle_hal2maf(void *hp, int ref, int refSeq, int64_t start, int64_t
         o.fullNames = !onlySequenceNames;
         o.keepEmptyRefBlocks = keepEmptyRefBlocks != 0;
         if (maxBlockLen > 0) o.maxBlockLen = maxBlockLen;
+        o.unique = unique != 0;
         h->maf.clear();
         hal2maf(h->view, ref, refSeq, start, length, o, h->maf);
     } catch (std::exception &e) {

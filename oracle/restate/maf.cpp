@@ -216,8 +216,28 @@ void convertSequence(const HalView &v, Block &blk, int ref, int seq, int64_t sta
     size_t numBlocks = 0;
     for (int64_t i = 0; i < length; ++i) {
         const int64_t sp = start + i;
-        loadColumn(v, ref, S.start + sp, o, cm, rows);
-        if (i == 0) {
+        if (o.unique) {
+            /* ColumnIterator(unique = true) + MafExport's isCanonicalOnRef test (maf/impl/halMafExport.cpp:52,61;
+             * api/impl/halColumnIterator.cpp:208-212, 749-762, 771-818).  Every walked column puts its reference-genome bases
+             * right of the window start into the visit cache and nextFreeIndex skips cached positions WITHOUT walking them:
+             * a position is walked iff no reference-genome row of its column lies in [window start, position).  A walked
+             * column is written iff its left-most reference-genome base is not left of the window start -- but it has been
+             * walked, so its sequences are ColumnMap keys from then on (which matters to canAppendColumn). */
+            const int64_t w0 = S.start + start, me = S.start + sp;
+            column(v, ref, me, o.col, rows);
+            bool walked = true, canonical = true;
+            for (const ColRow &r : rows) {
+                if (r.genome != ref) continue;
+                walked &= !(r.pos >= w0 && r.pos < me);
+                canonical &= !(r.pos < w0);
+            }
+            if (!walked) continue;
+            loadColumn(v, ref, me, o, cm, rows);
+            if (!canonical) continue;
+        } else {
+            loadColumn(v, ref, S.start + sp, o, cm, rows);
+        }
+        if (appendCount == 0) {
             blk.initBlock(cm, refKey, sp);
         } else if (!blk.canAppend(cm)) {
             if (numBlocks++ % 1000 == 0) { /* defragment: drop ColumnMap keys without rows */

@@ -11,6 +11,7 @@ struct MafOpts {
     bool fullNames = true;            /* !--onlySequenceNames */
     bool keepEmptyRefBlocks = false;
     int64_t maxBlockLen = 1000;       /* MafBlock::defaultMaxLength */
+    bool unique = false;              /* hal2maf --unique: only columns whose left-most reference-genome base is the column's own */
 };
 
 /* hal2maf for one reference genome: refSeq < 0 -> every sequence (one convertSequence call each, shared MafBlock);

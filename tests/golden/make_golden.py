@@ -183,6 +183,12 @@ def main():
     addm("maf_varlen_L2_root", v, ["--refGenome", "L2", "--refSequence", "L2_s2", "--length", "2500", "--rootGenome", "A1"])
     addm("maf_varlen_L3_names_len7", v, ["--refGenome", "L3", "--refSequence", "L3_s0", "--length", "1500", "--onlySequenceNames", "--maxBlockLen", "7"])
     addm("maf_varlen_A0_keepempty", v, ["--refGenome", "A0", "--refSequence", "A0_s2", "--length", "2500", "--keepEmptyRefBlocks"])
+    # hal2maf --unique (ColumnIterator unique + isCanonicalOnRef): windows whose columns have reference-genome paralogs
+    addm("maf_varlen_L0_unique_win", v, ["--refGenome", "L0", "--refSequence", "L0_s1", "--start", "11000", "--length", "4000", "--unique"])
+    addm("maf_varlen_A0_unique_win", v, ["--refGenome", "A0", "--refSequence", "A0_s2", "--start", "300", "--length", "3000", "--unique"])
+    addm("maf_varlen_L3_unique_len9", v, ["--refGenome", "L3", "--refSequence", "L3_s1", "--start", "100", "--length", "2500", "--unique", "--maxBlockLen", "9"])
+    addm("maf_ref_child1_unique", t, ["--refGenome", "child1", "--unique"])
+    addm("maf_small_G2_unique", s, ["--refGenome", "Genome_2", "--unique"])
     json.dump(mcases, open(os.path.join(HERE, "cases", "maf_index.json"), "w"), indent=1)
     json.dump(dcases, open(os.path.join(HERE, "cases", "depth_index.json"), "w"), indent=1)
     addp("psl_varlen_L0_L3", v, "L0", "L3", rand_bed(v, "L0", 300, 300, 401, "+-"), ("--outPSL",))

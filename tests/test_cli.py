@@ -100,7 +100,7 @@ def test_maf_cli_emulated_matches_reference_outputs(emul_maf_cli, tmp_path):
     check_maf(emul_maf_cli, tmp_path)
     r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--noAncestors"], capture_output=True, text=True)
     assert r.returncode == 1 and "the --noAncestors option is invalid" in r.stderr
-    r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--unique"], capture_output=True, text=True)
+    r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--printTree"], capture_output=True, text=True)
     assert r.returncode == 1 and "not implemented in the GPU build" in r.stderr
 
 
@@ -108,11 +108,26 @@ def test_maf_cli_emulated_matches_reference_outputs(emul_maf_cli, tmp_path):
 def test_maf_cli_emulated_whole_genome_live(emul_maf_cli, tmp_path):
     """multi-sequence whole-genome export: 4 convertSequence calls sharing one MafBlock"""
     hal = os.path.join(GOLDEN, "varlen8.hal")
-    for args in (["--refGenome", "L1"], ["--refGenome", "A2", "--maxBlockLen", "50"]):
+    for args in (["--refGenome", "L1"], ["--refGenome", "A2", "--maxBlockLen", "50"], ["--refGenome", "L0", "--unique"]):
         a, b = str(tmp_path / "a.maf"), str(tmp_path / "b.maf")
         subprocess.check_call([ref_bin("hal2maf"), hal, a] + args)
         subprocess.check_call([emul_maf_cli, hal, b] + args)
         assert open(a, "rb").read() == open(b, "rb").read(), args
+
+
+@pytest.mark.skipif(ref_bin("hal2maf") is None, reason="oracle/_ref not built")
+def test_maf_cli_emulated_unique_across_chunks(emul_maf_cli, tmp_path):
+    """--unique keeps one visit cache per convertSequence sweep: the column range is processed in chunks, every chunk must
+    classify its columns against the START OF THE SWEEP (halgpu_column_runs_in_sweep)."""
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    args = ["--refGenome", "L0", "--refSequence", "L0_s1", "--start", "9000", "--length", "7000", "--unique"]
+    a, b = str(tmp_path / "a.maf"), str(tmp_path / "b.maf")
+    subprocess.check_call([ref_bin("hal2maf"), hal, a] + args)
+    subprocess.check_call([emul_maf_cli, hal, b] + args, env=dict(os.environ, HALGPU_MAF_CHUNK_COLUMNS="613"))
+    assert open(a, "rb").read() == open(b, "rb").read()
+    plain = str(tmp_path / "p.maf")
+    subprocess.check_call([ref_bin("hal2maf"), hal, plain] + args[:-1])
+    assert open(plain, "rb").read() != open(a, "rb").read(), "the window should contain reference paralogs"
 
 
 @pytest.mark.gpu
@@ -123,7 +138,8 @@ def test_maf_cli_cuda_matches_reference_outputs(tmp_path):
     check_maf(cli, tmp_path)
     if ref_bin("hal2maf"):
         hal = os.path.join(GOLDEN, "varlen8.hal")
-        for args in (["--refGenome", "L1"], ["--refGenome", "R"], ["--refGenome", "A2", "--maxBlockLen", "50"], ["--refGenome", "L3", "--noDupes"]):
+        for args in (["--refGenome", "L1"], ["--refGenome", "R"], ["--refGenome", "A2", "--maxBlockLen", "50"], ["--refGenome", "L3", "--noDupes"],
+                     ["--refGenome", "L0", "--unique"], ["--refGenome", "A0", "--unique", "--onlyOrthologs"]):
             a, b = str(tmp_path / "a.maf"), str(tmp_path / "b.maf")
             subprocess.check_call([ref_bin("hal2maf"), hal, a] + args)
             subprocess.check_call([cli, hal, b] + args)
