@@ -392,6 +392,33 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - w0) / args.steps
 
+    # BASELINE.json configs[4] on N > 1 GPUs: the halAlignmentDepth sweep of the whole reference genome, one window per rank,
+    # ONE all-gather of the per-column values (hal_b200/parallel.py); strong scaling: the sweep is the same 50 M columns
+    depth_multi = None
+    if dist and not args.no_depth:
+        from hal_b200 import parallel
+        lo, hi = parallel.shard_bounds(genome_len, world)[rank]
+        d_win = torch.empty(hi - lo, dtype=torch.int32, device="cuda")
+        dms = []
+        for i in range(2 + 3):
+            barrier()
+            cur = torch.cuda.current_stream()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record(cur)
+            a.depth(src, lo, hi - 1, 1, (), 0, out_ptr=d_win.data_ptr())  # returns with the library's stream idle
+            whole = parallel.all_gather_columns(d_win, genome_len)
+            d1.record(cur)
+            barrier()
+            if i >= 2:
+                dms.append(d0.elapsed_time(d1))
+        t = torch.tensor([float(np.mean(dms))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        depth_multi = {"metric": "alignment_depth_columns_per_sec", "value": genome_len / (float(t[0]) / 1e3), "unit": "columns/s",
+                       "ms_per_sweep": float(t[0]), "columns": genome_len, "rows_per_column": 16, "scaling": "strong",
+                       "parallelism": f"reference windows x{world}, one all-gather of {genome_len * 4} B",
+                       "check": {"depth15_fraction": float((whole == 15).float().mean()), "gathered": int(whole.numel())}}
+        del whole, d_win
+
     ms_step = max(dev_ms, 0.0) / args.steps
     if dist:
         t = torch.tensor([ms_step, e2e_s, float(np.mean(kms))], device="cuda", dtype=torch.float64)
@@ -436,6 +463,8 @@ def main():
                    "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step, "step_wall_ms": [round(x, 3) for x in step_wall],
                    "oracle_sample_stats": ostats},
     }
+    if depth_multi is not None:
+        line["secondary"] = depth_multi
     # secondary (BASELINE.json configs[4] shape on one GPU): halAlignmentDepth column sweep, ref = leaf L0, all targets
     if world == 1 and not args.no_depth:
         d_out = torch.empty(genome_len, dtype=torch.int32, device="cuda")

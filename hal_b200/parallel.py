@@ -2,6 +2,9 @@
 the interval batch is cut into contiguous shards, one per rank, and the fixed-width output records are brought
 together with one all-gather (records padded to the largest per-rank count).  No collective sits inside the walk.
 
+Column sweeps (halAlignmentDepth, BASELINE.json configs[4]) shard the same way: contiguous windows of reference positions,
+one per rank, and one all-gather of the fixed-size per-column values.
+
 Pure torch.distributed: works with the nccl backend on GPUs and with gloo on CPU (tests/test_parallel.py)."""
 import torch
 import torch.distributed as dist
@@ -61,3 +64,21 @@ def all_gather_records(counts_per_interval, recs_u8, foreign=True):
     offsets = torch.zeros(all_counts.numel() + 1, dtype=torch.int64, device=dev)
     torch.cumsum(all_counts, 0, dtype=torch.int64, out=offsets[1:])
     return offsets, recs
+
+
+def all_gather_columns(values, n_total):
+    """values: this rank's per-column tensor (its window of shard_bounds(n_total, world), in rank order).  Returns the
+    whole sweep (n_total values) on every rank with ONE all-gather: windows differ by at most one column, so every rank
+    pads to the largest window and the (at most world - 1) pad slots are dropped afterwards."""
+    world = dist.get_world_size()
+    bounds = shard_bounds(n_total, world)
+    width = max(hi - lo for lo, hi in bounds)
+    send = values
+    if values.numel() != width:
+        send = torch.zeros(width, dtype=values.dtype, device=values.device)
+        send[: values.numel()] = values
+    out = torch.empty(world * width, dtype=values.dtype, device=values.device)
+    dist.all_gather_into_tensor(out, send.contiguous())
+    if all(hi - lo == width for lo, hi in bounds):
+        return out
+    return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(bounds)])

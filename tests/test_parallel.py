@@ -56,3 +56,35 @@ def test_two_rank_gloo_equals_single_process(emul_lib, tmp_path):
     a.close()
     assert np.array_equal(np.load(tmp_path / "offsets.npy"), off.astype(np.int64))
     assert np.array_equal(np.load(tmp_path / "recs.npy"), recs.view(np.uint8))
+
+
+def _depth_worker(rank, world, port, emul_lib, hal, out_dir):
+    sys.path.insert(0, ROOT)
+    import hal_b200
+    from hal_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = hal_b200.Alignment(hal, lib_path=emul_lib)
+    g = a.genome_id("L1")
+    n = 4001  # odd: the windows differ by one column
+    lo, hi = parallel.shard_bounds(n, world)[rank]
+    d, _ = a.depth(g, lo, hi - 1, 1, (), hal_b200.HALGPU_COUNT_DUPES)
+    whole = parallel.all_gather_columns(torch.from_numpy(d), n)
+    if rank == 1:
+        np.save(os.path.join(out_dir, "depth.npy"), whole.numpy())
+    a.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_depth_sweep_equals_single_process(emul_lib, tmp_path):
+    """halAlignmentDepth sweep sharded by reference window + one all-gather == the single-process sweep"""
+    import hal_b200
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_depth_worker, args=(2, port, emul_lib, hal, str(tmp_path)), nprocs=2, join=True)
+    a = hal_b200.Alignment(hal, lib_path=emul_lib)
+    d, _ = a.depth(a.genome_id("L1"), 0, 4000, 1, (), hal_b200.HALGPU_COUNT_DUPES)
+    a.close()
+    assert np.array_equal(np.load(tmp_path / "depth.npy"), d)
