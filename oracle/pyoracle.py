@@ -161,11 +161,13 @@ class Oracle:
             raise RuntimeError("oracle_hal2maf failed")
         return C.string_at(p, n.value)
 
-    def liftover_frags(self, src, tgt, gs, ge, no_dupes=False):
+    def liftover_frags(self, src, tgt, gs, ge, no_dupes=False, coalescence_limit=None):
         """Per '+' interval the mapped fragments [(sLo, tLo, length, tRev)] (source forward; target reversed when tRev)."""
         gs = np.ascontiguousarray(gs, dtype=np.int64)
         ge = np.ascontiguousarray(ge, dtype=np.int64)
+        self.L.oracle_set_coalescence_limit(self.h, -1 if coalescence_limit is None else coalescence_limit)
         k = self.L.oracle_liftover_frags(self.h, src, tgt, int(no_dupes), len(gs), gs.ctypes.data, ge.ctypes.data)
+        self.L.oracle_set_coalescence_limit(self.h, -1)
         off = np.zeros(len(gs) + 1, np.uint64)
         s, t, ln, rv = np.zeros(k, np.int64), np.zeros(k, np.int64), np.zeros(k, np.int64), np.zeros(k, np.uint8)
         self.L.oracle_fetch_frags(self.h, off.ctypes.data, s.ctypes.data, t.ctypes.data, ln.ctypes.data, rv.ctypes.data)

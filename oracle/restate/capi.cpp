@@ -180,7 +180,7 @@ int64_t oracle_column_liftover(void *hp, int src, int tgt, int noDupes, int64_t 
  * number; oracle_fetch_frags copies offsets[n+1] and per fragment sLo, tLo, length, tRev. */
 int64_t oracle_liftover_frags(void *hp, int src, int tgt, int noDupes, int64_t n, const int64_t *gs, const int64_t *ge) {
     OracleHandle *h = (OracleHandle *)hp;
-    Plan plan = makePlan(h->view, src, tgt);
+    Plan plan = makePlan(h->view, src, tgt, h->coal);
     h->fragOffsets.assign(1, 0);
     h->frags.clear();
     std::vector<OutLine> lines;

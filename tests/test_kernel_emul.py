@@ -144,3 +144,18 @@ def test_emulated_coalescence_limit_must_be_an_ancestor(emul_lib):
     with pytest.raises(hal_b200.HalGpuError, match="Hit root genome when attempting to map paralogies"):
         a.liftover(a.genome_id("L3"), a.genome_id("L2"), gs, ge, st, 0, coalescence_limit=a.genome_id("A0"))
     a.close()
+
+
+def test_emulated_reference_coalescence_limit_kat(emul_lib):
+    """the same known-answer test (halMappedSegmentTest.cpp:478-613) through the kernel"""
+    import hal_b200
+    a = hal_b200.Alignment(os.path.join(GOLDEN, "refMapExtraParalogsTest.hal"), lib_path=emul_lib)
+    s, t, root = a.genome_id("grandChild2"), a.genome_id("grandChild1"), a.genome_id("root")
+    gs, ge = np.array([0], np.int64), np.array([2], np.int64)
+    off, recs, _ = a.liftover(s, t, gs, ge)
+    assert [(int(r["start"]), int(r["end"]), chr(r["strand"])) for r in recs] == [(0, 3, "-")]
+    off, recs, _ = a.liftover(s, t, gs, ge, coalescence_limit=root)
+    # the three paralogous target segments are adjacent and collinear on the reverse strand but share ONE source piece:
+    # extractSegment cannot merge them (source deltas differ), so three lines
+    assert sorted((int(r["start"]), int(r["end"]), chr(r["strand"])) for r in recs) == [(0, 3, "-"), (3, 6, "-"), (6, 9, "-")]
+    a.close()
