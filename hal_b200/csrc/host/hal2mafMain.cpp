@@ -140,6 +140,8 @@ int main(int argc, char **argv) {
         ex.setNoDupes(noDupes); ex.setNoAncestors(noAncestors); ex.setUcscNames(!onlySequenceNames); ex.setAppend(append);
         ex.setMaxBlockLength(maxBlockLen); ex.setOnlyOrthologs(onlyOrthologs); ex.setKeepEmptyRefBlocks(keepEmptyRefBlocks); ex.setUnique(unique);
         if (const char *cc = getenv("HALGPU_MAF_CHUNK_COLUMNS")) ex.chunkColumns = (size_t)std::max(1L, atol(cc)); // test hook
+        if (const char *cc = getenv("HALGPU_MAF_QUEUE_BYTES")) ex.queueBytes = (size_t)std::max(0L, atol(cc));      // test hook
+        if (const char *cc = getenv("HALGPU_TEXT_THREADS")) ex.formatThreads = (unsigned)std::max(1L, atol(cc));
         if (refSeq >= 0) {
             ex.convertSequence(maf, ref, refSeq, start, length, targets);
         } else {

@@ -3,6 +3,7 @@
 #include <charconv>
 #include <chrono>
 #include <stdexcept>
+#include <thread>
 
 namespace halgpu {
 
@@ -15,9 +16,19 @@ struct Key { // ColumnIterator::SequenceLess order: genome name bytes, then sequ
     bool operator!=(const Key &o) const { return !(*this == o); }
 };
 
+// The row text of an entry is kept as a list of pieces -- runs of gaps, runs of consecutive bases of one strand -- while the
+// (sequential, history dependent) block state machine runs; the characters themselves are decoded from the packed DNA only
+// when a finished block is formatted, by many threads at once ("MAF row formatter").
+struct Piece {
+    int64_t pos;   // genome coordinate of the first base (walks down when rev); unused for gaps
+    int64_t count;
+    int8_t kind;   // 0 gap, 1 forward bases, 2 reverse-complemented bases
+};
+
 struct Entry { // MafBlockEntry (maf/inc/halMafBlock.h:70-115)
     const std::string *name = nullptr; // cached "Genome.Sequence" (or bare sequence name)
-    std::string text;
+    std::vector<Piece> text;
+    bool anyBase = false;
     int genome = -1, seq = -1;
     int64_t start = -1, length = 0, srcLength = 0;
     char strand = '+';
@@ -97,7 +108,7 @@ struct GpuMafExport::Impl {
                 e->lastUsed = 0;
             }
             if (!deleted) {
-                e->start = -1; e->strand = '+'; e->length = 0; e->text.clear();
+                e->start = -1; e->strand = '+'; e->length = 0; e->text.clear(); e->anyBase = false;
                 if (w != i) entries[w] = std::move(entries[i]);
                 ++w;
             }
@@ -117,7 +128,7 @@ struct GpuMafExport::Impl {
         } else {
             e->start = -1; e->length = 0; e->strand = '+';
         }
-        if (clearText) e->text.clear();
+        if (clearText) { e->text.clear(); e->anyBase = false; }
     }
     void initBlock(const Key &refKey, int64_t refSeqPos) { // MafBlock::initBlock (:294-368)
         resetEntries();
@@ -189,11 +200,7 @@ struct GpuMafExport::Impl {
         }
         for (; e < entries.size(); ++e) pairing.emplace_back(entries[e].e.get(), -1);
     }
-    void appendBases(std::string &text, int g, int64_t pos, bool rev, int64_t count) const { // DnaIterator::getBase x count
-        const uint8_t *d = dna[g];
-        const size_t at = text.size();
-        text.resize(at + (size_t)count);
-        char *o = &text[at];
+    static void decodeBases(char *o, const uint8_t *d, int64_t pos, bool rev, int64_t count) { // DnaIterator::getBase x count
         if (!rev) {
             for (int64_t i = 0; i < count; ++i) { const int64_t p = pos + i; const uint8_t b = d[p >> 1]; o[i] = NIB[(p & 1) ? (b & 0xF) : (b >> 4)]; }
         } else {
@@ -208,9 +215,18 @@ struct GpuMafExport::Impl {
                 const Row &d = rows[pr.second];
                 if (e->start == -1) initEntry(e, d.key, &d, false); // updateEntry (:109-113): keeps the accumulated '-'
                 e->length += count;
-                appendBases(e->text, d.genome, d.pos, d.rev, count);
+                const int8_t kind = d.rev ? 2 : 1;
+                if (!e->text.empty() && e->text.back().kind == kind &&
+                    d.pos == (d.rev ? e->text.back().pos - e->text.back().count : e->text.back().pos + e->text.back().count)) {
+                    e->text.back().count += count;
+                } else {
+                    e->text.push_back(Piece{d.pos, count, kind});
+                }
+                e->anyBase = true;
+            } else if (!e->text.empty() && e->text.back().kind == 0) {
+                e->text.back().count += count;
             } else {
-                e->text.append((size_t)count, '-');
+                e->text.push_back(Piece{0, count, 0});
             }
         }
     }
@@ -220,30 +236,104 @@ struct GpuMafExport::Impl {
             if (pr.second >= 0) cap = std::min(cap, maxLength - pr.first->length);
         return cap < 0 ? 0 : cap;
     }
-    bool referenceIsAllGaps() const {
-        if (reference == nullptr) return false;
-        for (char c : reference->text) if (c != '-') return false;
-        return true;
+    bool referenceIsAllGaps() const { // MafBlock::referenceIsAllGaps: the reference row's text holds nothing but '-'
+        return reference != nullptr && !reference->anyBase;
     }
-    static void printEntry(std::string &out, const Entry &e, int64_t start) { // operator<<(MafBlockEntry) (:452-456)
-        char buf[24];
-        out += "s\t"; out += *e.name; out += '\t';
-        auto r = std::to_chars(buf, buf + sizeof buf, start); out.append(buf, r.ptr); out += '\t';
-        r = std::to_chars(buf, buf + sizeof buf, e.length); out.append(buf, r.ptr); out += '\t';
-        out += e.strand; out += '\t';
-        r = std::to_chars(buf, buf + sizeof buf, e.srcLength); out.append(buf, r.ptr); out += '\t';
-        out += e.text; out += '\n';
+    // ---- deferred printing: finished blocks are queued as row descriptors and formatted by formatQueued() ----
+    struct RowJob {
+        const std::string *name;
+        int64_t start, length, srcLength;
+        size_t firstPiece, numPieces;
+        int genome;
+        char strand;
+    };
+    struct BlockJob {
+        size_t firstRow, numRows, textBytes;
+    };
+    std::vector<Piece> jobPieces;
+    std::vector<RowJob> jobRows;
+    std::vector<BlockJob> jobBlocks;
+    size_t queuedBytes = 0;
+    unsigned formatThreads = 1;
+
+    void queueEntry(const Entry &e, int64_t start) { // operator<<(MafBlockEntry) (:452-456), text deferred
+        RowJob r;
+        r.name = e.name; r.start = start; r.length = e.length; r.srcLength = e.srcLength; r.genome = e.genome; r.strand = e.strand;
+        r.firstPiece = jobPieces.size(); r.numPieces = e.text.size();
+        jobPieces.insert(jobPieces.end(), e.text.begin(), e.text.end());
+        size_t len = 0;
+        for (const Piece &p : e.text) len += (size_t)p.count;
+        jobBlocks.back().textBytes += len + e.name->size() + 64;
+        jobRows.push_back(r);
+        ++jobBlocks.back().numRows;
     }
-    void printBlock(std::string &out) const { // MafBlock::printBlock (:499-519)
-        out += "a\n";
+    void queueBlock() { // MafBlock::printBlock (:499-519)
+        jobBlocks.push_back(BlockJob{jobRows.size(), 0, 2});
         if (reference->start == -1) {
-            if (refIndex != -1) printEntry(out, *reference, refIndex);
+            if (refIndex != -1) queueEntry(*reference, refIndex);
         } else {
-            printEntry(out, *reference, reference->start);
+            queueEntry(*reference, reference->start);
         }
         for (const Slot &s : entries) {
-            if (s.e->start != -1 && s.e.get() != reference) printEntry(out, *s.e, s.e->start);
+            if (s.e->start != -1 && s.e.get() != reference) queueEntry(*s.e, s.e->start);
         }
+        queuedBytes += jobBlocks.back().textBytes;
+    }
+    void formatRow(std::string &out, const RowJob &r) const {
+        char buf[24];
+        out += "s\t"; out += *r.name; out += '\t';
+        auto c = std::to_chars(buf, buf + sizeof buf, r.start); out.append(buf, c.ptr); out += '\t';
+        c = std::to_chars(buf, buf + sizeof buf, r.length); out.append(buf, c.ptr); out += '\t';
+        out += r.strand; out += '\t';
+        c = std::to_chars(buf, buf + sizeof buf, r.srcLength); out.append(buf, c.ptr); out += '\t';
+        for (size_t i = 0; i < r.numPieces; ++i) {
+            const Piece &p = jobPieces[r.firstPiece + i];
+            const size_t at = out.size();
+            if (p.kind == 0) {
+                out.append((size_t)p.count, '-');
+            } else {
+                out.resize(at + (size_t)p.count);
+                decodeBases(&out[at], dna[r.genome], p.pos, p.kind == 2, p.count);
+            }
+        }
+        out += '\n';
+    }
+    // Writes every queued block ("a\n" + rows + blank line) except that the LAST one gets no blank line when `last` is set
+    // (MafExport::convertSequence ends with `mafStream << _mafBlock << endl`).
+    void formatQueued(std::ostream &os, bool last) {
+        const size_t nb = jobBlocks.size();
+        if (nb == 0) return;
+        unsigned T = std::max(1u, std::min<unsigned>(formatThreads, (unsigned)(queuedBytes >> 20) + 1));
+        std::vector<size_t> cut(T + 1, nb); // contiguous groups of blocks with about equal text
+        cut[0] = 0;
+        size_t acc = 0, t = 1;
+        for (size_t b = 0; b < nb && t < T; ++b) {
+            acc += jobBlocks[b].textBytes;
+            if (acc >= queuedBytes * t / T) cut[t++] = b + 1;
+        }
+        std::vector<std::string> outs(T);
+        auto work = [&](unsigned k) {
+            std::string &out = outs[k];
+            size_t bytes = 0;
+            for (size_t b = cut[k]; b < cut[k + 1]; ++b) bytes += jobBlocks[b].textBytes;
+            out.reserve(bytes);
+            for (size_t b = cut[k]; b < cut[k + 1]; ++b) {
+                out += "a\n";
+                const BlockJob &B = jobBlocks[b];
+                for (size_t r = B.firstRow; r < B.firstRow + B.numRows; ++r) formatRow(out, jobRows[r]);
+                if (!(last && b + 1 == nb)) out += '\n';
+            }
+        };
+        if (T == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < T; ++k) th.emplace_back(work, k);
+            for (auto &x : th) x.join();
+        }
+        for (const std::string &o : outs) os.write(o.data(), (std::streamsize)o.size());
+        jobPieces.clear(); jobRows.clear(); jobBlocks.clear();
+        queuedBytes = 0;
     }
     void defragment() { // ColumnIterator::defragment (api/impl/halColumnIterator.cpp:192-206): drop keys without rows
         std::vector<Key> keep;
@@ -284,6 +374,11 @@ GpuMafExport::GpuMafExport(halgpu_ctx *ctx) : _impl(new Impl), _ctx(ctx) {
 
 GpuMafExport::~GpuMafExport() {}
 
+unsigned GpuMafExport::defaultFormatThreads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 32u));
+}
+
 void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int refSequence, int64_t startPosition, uint64_t length,
                                    const std::vector<int> &targets) {
     Impl &m = *_impl;
@@ -309,14 +404,13 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
     m.colKeys.clear(); // a fresh ColumnIterator per call
     uint64_t appendCount = 0;
     size_t numBlocks = 0;
-    std::string out;
+    m.formatThreads = formatThreads;
     auto flush = [&]() {
         if (appendCount > 0 && (_keepEmptyRefBlocks || !m.referenceIsAllGaps())) {
-            m.printBlock(out);
-            out += '\n';
+            m.queueBlock();
             ++blocks;
         }
-        if (out.size() > (8u << 20)) { mafStream.write(out.data(), (std::streamsize)out.size()); out.clear(); }
+        if (m.queuedBytes > queueBytes) m.formatQueued(mafStream, false);
     };
     for (uint64_t done = 0; done < length;) {
         const uint64_t chunk = std::min<uint64_t>(chunkColumns, length - done);
@@ -372,12 +466,12 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         done += chunk;
     }
     if (appendCount > 0 && (_keepEmptyRefBlocks || !m.referenceIsAllGaps())) {
-        m.printBlock(out);
+        m.queueBlock();
         ++blocks;
-        mafStream.write(out.data(), (std::streamsize)out.size());
+        m.formatQueued(mafStream, true);
         mafStream << std::endl;
     } else {
-        mafStream.write(out.data(), (std::streamsize)out.size());
+        m.formatQueued(mafStream, false);
     }
 }
 

@@ -33,6 +33,9 @@ class GpuMafExport {
     void setKeepEmptyRefBlocks(bool v) { _keepEmptyRefBlocks = v; }
     void setUnique(bool v) { _unique = v; } // MafExport::setUnique (maf/inc/halMafExport.h:51-53)
     size_t chunkColumns = 8u << 20; // columns per halgpu_column_runs call
+    unsigned formatThreads = defaultFormatThreads(); // threads that decode and print the rows of finished blocks
+    static unsigned defaultFormatThreads();
+    size_t queueBytes = (size_t)256 << 20;           // finished blocks are formatted and written once about this much text is queued
     // totals
     uint64_t columns = 0, runs = 0, blocks = 0;
     double gpuSeconds = 0;

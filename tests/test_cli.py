@@ -87,11 +87,13 @@ def test_depth_cli_cuda_matches_reference_outputs(tmp_path):
 
 def check_maf(cli, tmp_path, whole_genome_hal=None):
     import json
-    for c in json.load(open(os.path.join(GOLDEN, "cases", "maf_index.json"))):
+    for k, c in enumerate(json.load(open(os.path.join(GOLDEN, "cases", "maf_index.json")))):
         out = str(tmp_path / "o.maf")
         if os.path.exists(out):
             os.remove(out)
-        r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"]), out] + c["args"], capture_output=True, text=True)
+        # the row text is decoded by a pool of threads from queued block descriptors: vary the pool and the queue size
+        env = dict(os.environ, HALGPU_TEXT_THREADS=str(1 + k % 5), HALGPU_MAF_QUEUE_BYTES=str([1 << 28, 0, 5000, 200000][k % 4]))
+        r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"]), out] + c["args"], capture_output=True, text=True, env=env)
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == open(os.path.join(GOLDEN, "cases", c["name"] + ".maf"), "rb").read(), c["name"]
 
