@@ -560,6 +560,27 @@ def main():
                                     "seconds": best[0], "mapping_kernel_ms": best[1], "bases_in": int(nb), "bases_out": int(best[2]),
                                     "runs": int(len(wf)), "h2d_bytes": int(nb * 8 + len(wf) * 24), "d2h_bytes": int(best[2] * 16),
                                     "check": {"max_equals_input_max": bool(len(wval) and wval.max() <= wv.max()), "all_nonnegative": bool((wval >= 0).all())}}
+        try:
+            # roofline of the wiggle-mode kernel, same accounting as the headline: algorithmic bytes = per source base 8 B of value
+            # + 16 B read-modify-write of the target key, + the index records the reference walk visits (oracle visit count on a
+            # sample of the runs) + 24 B per run of input; DRAM traffic from the committed ncu capture
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            from pyoracle import Oracle
+            o = Oracle(hal)
+            k = min(200, len(wf))
+            st_ = o.liftover(o.genome_id("L7"), o.genome_id("L0"), wf[:k], wl[:k])["stats"]
+            o.close()
+            per_base = 24.0 + st_["visitBytes"] / float((wl[:k] - wf[:k] + 1).sum()) + 24.0 / run
+            ach = per_base * nb / (best[1] / 1e3) / 1e9
+            wtraffic = None
+            try:
+                wtraffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("wiggleKernel_dram_bytes_per_launch")
+            except (OSError, ValueError):
+                pass
+            line["secondary_wiggle"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": wtraffic,
+                                                    "kernel": "liftoverKernel<true,false>", "kernel_ms": best[1], "algorithmic_bytes_per_source_base": per_base}
+        except Exception as e:  # noqa: BLE001
+            line["secondary_wiggle"]["roofline"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
             ref = os.path.join(ROOT, "oracle", "_ref", "halWiggleLiftover")
             if os.path.exists(ref):
