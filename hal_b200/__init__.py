@@ -17,6 +17,7 @@ HALGPU_NO_DUPES = 1
 HALGPU_NO_SORT = 2
 HALGPU_PSL = 4
 HALGPU_COLUMN_LIFTOVER = 8
+HALGPU_RAW_FRAGMENTS = 16
 HALGPU_COUNT_DUPES = 1
 HALGPU_NO_ANCESTORS = 2
 HALGPU_COL_NO_DUPES = 4
@@ -45,6 +46,9 @@ class _WigResult(C.Structure):
 REC_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("src_start", "<i8"), ("tgt_seq", "<i4"),
                       ("strand", "u1"), ("src_strand", "u1"), ("n_frag", "<u2")])
 assert REC_DTYPE.itemsize == 32
+# HALGPU_RAW_FRAGMENTS: the same 32-byte slots hold halgpu_frag records (recs.view(FRAG_DTYPE))
+FRAG_DTYPE = np.dtype([("src_start", "<i8"), ("tgt_start", "<i8"), ("length", "<i8"), ("flags", "<u4"), ("pad", "<u4")])
+assert FRAG_DTYPE.itemsize == 32
 
 # every symbol include/halgpu.h declares
 ABI_SYMBOLS = [

@@ -37,6 +37,8 @@ const GenomeInfo *genome(const halgpu_ctx *ctx, int g) {
 }
 } // namespace
 
+static_assert(sizeof(halgpu_frag) == sizeof(halgpu_lift_rec), "fragment records share the result buffer");
+
 extern "C" {
 
 int halgpu_open(const char *path, int device, halgpu_ctx **out, char **err) {

@@ -463,16 +463,18 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
     if (wig && coalPath) throw HalError("the wiggle liftover has no coalescence limit (the reference's halWiggleLiftover has none either)");
-    void (*const mapKernel)(const LiftParams) = wig ? liftoverKernel<true, false> : (coalPath ? liftoverKernel<false, true> : liftoverKernel<false, false>);
+    const bool raw = (flags & HALGPU_RAW_FRAGMENTS) != 0;
+    if (raw && (coalPath || wig || (flags & (HALGPU_PSL | HALGPU_COLUMN_LIFTOVER)) != 0)) {
+        throw HalError("HALGPU_RAW_FRAGMENTS cannot be combined with a coalescence limit, PSL counts or ColumnLiftover mode");
+    }
+    void (*const mapKernel)(const LiftParams) = wig ? liftoverKernel<LIFT_WIG> : (coalPath ? liftoverKernel<LIFT_COAL> : (raw ? liftoverKernel<LIFT_RAW> : liftoverKernel<LIFT_BED>));
     // rung 1: all n intervals, scratch in shared memory
     const unsigned block = 128, warpsPerBlock = block / 32;
     {
         P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
         P.n = (int64_t)n; P.work = dWork;
         const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
-        rt::allowSmem(liftoverKernel<false, false>, smem);
-        rt::allowSmem(liftoverKernel<true, false>, smem);
-        rt::allowSmem(liftoverKernel<false, true>, smem);
+        rt::allowSmem(mapKernel, smem);
         rt::Event e0, e1;
         e0.record(_stream);
         rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);

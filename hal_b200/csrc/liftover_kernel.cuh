@@ -34,6 +34,8 @@ struct Frag { // 32 B
     int64_t meta; // bit0 sRev, bit1 tRev, bit2 kindTop, bits 3.. : segment index (phase 1) / sequence id (phase 2)
 };
 
+static_assert(sizeof(Frag) == sizeof(halgpu_frag) && sizeof(Frag) == sizeof(halgpu_lift_rec), "HALGPU_RAW_FRAGMENTS hands Frag records out as halgpu_frag");
+
 struct Frame { // 48 B
     int64_t sLo, tLo, len, meta;
     int64_t aux;  // PARSE: index of the next segment of the other array; RING: first ring member
@@ -163,10 +165,12 @@ struct WarpScratch {
     Frame *frames;
 };
 
-// WIG / COAL: the wiggle mode and the coalescence-limit path are separate instantiations so that the default BED path's
-// register allocation is untouched by them
-template <bool WIG, bool COAL>
+// MODE: the wiggle mode, the coalescence-limit path and the raw-fragment mode are separate instantiations so that the
+// default BED path's code and register allocation are untouched by them
+enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 3 };
+template <int MODE>
 __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
+    constexpr bool WIG = MODE == LIFT_WIG, COAL = MODE == LIFT_COAL, RAW = MODE == LIFT_RAW;
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';
@@ -445,6 +449,22 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     int m = listCount;
     if (m == 0) {
         if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = 0; P.outOffset[item] = 0; }
+        return;
+    }
+    if (RAW) {
+        // halgpu_liftover(HALGPU_RAW_FRAGMENTS): hand the mapped fragments out as they are (halgpu_frag has Frag's layout);
+        // refinement and merging then happen over MANY intervals at once on the caller's side (halSynteny lifts whole
+        // chromosomes: insertAndBreakOverlaps / extractSegment become global there)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)m);
+        base = __shfl_sync(HG_FULL, base, 0);
+        if (base + (unsigned long long)m > P.poolCap) {
+            if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+            return;
+        }
+        Frag *dst = reinterpret_cast<Frag *>(P.pool) + base;
+        for (int i = lane; i < m; i += 32) dst[i] = listA[i];
+        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)m; P.outOffset[item] = base; }
         return;
     }
     // target sequence of every fragment (MappedSegment::getSequence)
@@ -784,7 +804,7 @@ __host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) 
 extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
 #endif
 
-template <bool WIG, bool COAL>
+template <int MODE>
 __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
 #if defined(HALGPU_SIMT_EMUL)
     uint8_t *hg_dyn_smem = simt::dynamicSmem();
@@ -802,7 +822,7 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
     ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
     for (int64_t w = gwarp; w < P.n; w += nwarps) {
         const uint32_t item = P.work ? __ldg(&P.work[w]) : (uint32_t)w;
-        liftOneInterval<WIG, COAL>(P, ws, item, lane);
+        liftOneInterval<MODE>(P, ws, item, lane);
         __syncwarp();
     }
 }

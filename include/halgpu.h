@@ -43,6 +43,16 @@ typedef struct halgpu_lift_rec {
     uint16_t n_frag;     /* mapped fragments merged into this line (saturates at 65535) */
 } halgpu_lift_rec;
 
+/* One mapped fragment (HALGPU_RAW_FRAGMENTS): `length` source bases starting at src_start (forward GENOME coordinates of the
+ * source genome) are homologous to the `length` target bases starting at tgt_start (forward GENOME coordinates of the target
+ * genome, NOT sequence relative); with bit 1 of flags set the target piece is read on the reverse strand (its first base
+ * pairs with the LAST source base), bit 0 likewise for the source piece ('-' input intervals).  32 bytes. */
+typedef struct halgpu_frag {
+    int64_t src_start, tgt_start, length;
+    uint32_t flags; /* bit 0: source reversed, bit 1: target reversed */
+    uint32_t pad;
+} halgpu_frag;
+
 /* Result of one liftover batch, CSR by input interval, lines of one interval in the reference's
  * output order (stable by src_start, liftover/impl/halLiftover.cpp:90). */
 typedef struct halgpu_lift_result {
@@ -64,6 +74,11 @@ enum {
     HALGPU_NO_DUPES = 1u,     /* halLiftover --noDupes (liftover/impl/halLiftoverMain.cpp:24) */
     HALGPU_NO_SORT = 2u,      /* do not reorder the batch by source position inside the call */
     HALGPU_PSL = 4u,          /* also compare source and target DNA of every mapped fragment (halLiftover --outPSL) */
+    HALGPU_RAW_FRAGMENTS = 16u, /* return the mapped fragments of every interval -- halMapSegment's output for each of its source
+                                 * segments, before insertAndBreakOverlaps and extractSegment -- as halgpu_frag records in
+                                 * result->recs (same size as halgpu_lift_rec; cast), in no particular order within an
+                                 * interval.  For callers that refine and merge across intervals themselves (halSynteny lifts
+                                 * whole chromosomes).  Not with HALGPU_PSL, HALGPU_COLUMN_LIFTOVER or a coalescence limit. */
     HALGPU_COLUMN_LIFTOVER = 8u /* hal::ColumnLiftover::liftInterval semantics (liftover/impl/halColumnLiftover.cpp:21-92)
                                  * instead of BlockLiftover's: per target sequence and strand the maximal runs of target
                                  * bases homologous to the interval, forward runs first; src_start = -1; with

@@ -80,6 +80,19 @@ def emul_wig_cli(emul_lib):
 
 
 @pytest.fixture(scope="session")
+def emul_synteny_cli(emul_lib):
+    """The halSynteny CLI linked against the emulated library."""
+    out = os.path.join(ROOT, "tests", "simt", "halSynteny_emul")
+    host = os.path.join(ROOT, "hal_b200", "csrc", "host")
+    srcs = [os.path.join(host, f) for f in ("halSyntenyMain.cpp", "synteny.cpp")]
+    deps = srcs + [os.path.join(host, "synteny.hpp"), emul_lib]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs +
+                              ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    return out
+
+
+@pytest.fixture(scope="session")
 def emul_depth_cli(emul_lib):
     out = os.path.join(ROOT, "tests", "simt", "halAlignmentDepth_emul")
     src = os.path.join(ROOT, "hal_b200", "csrc", "host", "halAlignmentDepthMain.cpp")
