@@ -21,6 +21,8 @@ from wiggen import random_wig  # noqa: E402
 EMUL = os.path.join(ROOT, "tests", "simt", "libhalgpu_emul.so")
 MAF = os.path.join(ROOT, "tests", "simt", "hal2maf_emul")
 WIG = os.path.join(ROOT, "tests", "simt", "halWiggleLiftover_emul")
+SYN = os.path.join(ROOT, "tests", "simt", "halSynteny_emul")
+REF_SYN = os.path.join(ROOT, "oracle", "_ref", "halSynteny")
 
 
 def rand_tree(rng, names):
@@ -111,6 +113,17 @@ def main():
             if (exp is not None and (r.returncode != 0 or open(out).read() != exp)) or (exp is None and r.stderr.strip() != err):
                 bad += 1
                 print("WIGGLE DIFF", tag, src, tgt, nd, r.stderr[:200], err)
+        # halSynteny against the reference binary (there is no separate restatement of dag_merge in the oracle)
+        if os.path.exists(REF_SYN) and os.path.exists(SYN):
+            src, tgt = rng.choice(names), rng.choice(names)
+            if src != tgt:
+                args = ["--queryGenome", src, "--targetGenome", tgt, "--minBlockSize", str(rng.choice([1, 30, 500])), "--maxAnchorDistance", str(rng.choice([1, 50, 5000]))]
+                pa, pb = os.path.join(d, "a.psl"), os.path.join(d, "b.psl")
+                ra = subprocess.run([REF_SYN] + args + [hal, pa], capture_output=True, text=True)
+                rb = subprocess.run([SYN] + args + [hal, pb], capture_output=True, text=True)
+                if ra.returncode != rb.returncode or (ra.returncode == 0 and open(pa).read() != open(pb).read()):
+                    bad += 1
+                    print("SYNTENY DIFF", tag, args, ra.stderr[:100], rb.stderr[:100])
         a.close()
         o.close()
         print("round", it, "done", tag, flush=True)
