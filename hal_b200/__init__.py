@@ -18,6 +18,7 @@ HALGPU_NO_SORT = 2
 HALGPU_PSL = 4
 HALGPU_COLUMN_LIFTOVER = 8
 HALGPU_RAW_FRAGMENTS = 16
+HALGPU_SEED_BOTTOM = 32
 HALGPU_COUNT_DUPES = 1
 HALGPU_NO_ANCESTORS = 2
 HALGPU_COL_NO_DUPES = 4

@@ -402,7 +402,9 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     const Plan &pl = plan(src, tgt, coal);
     const bool coalPath = pl.coal >= 0;
     const GenomeInfo &S = G[src];
-    const bool srcIsTop = S.numTop > 0; // liftover/impl/halBlockLiftover.cpp:24-30
+    // liftover/impl/halBlockLiftover.cpp:24-30; BlockMapper::map (halBlockMapper.cpp:76-83) seeds from the BOTTOM array when the
+    // source genome is the MRCA: HALGPU_SEED_BOTTOM
+    const bool srcIsTop = S.numTop > 0 && !((flags & HALGPU_SEED_BOTTOM) != 0 && S.numBottom > 0);
     if (!srcIsTop && S.numBottom == 0) throw HalError("source genome " + S.name + " has no segments");
     out = LiftOutput();
     out.n = n;
@@ -464,10 +466,12 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
     if (wig && coalPath) throw HalError("the wiggle liftover has no coalescence limit (the reference's halWiggleLiftover has none either)");
     const bool raw = (flags & HALGPU_RAW_FRAGMENTS) != 0;
-    if (raw && (coalPath || wig || (flags & (HALGPU_PSL | HALGPU_COLUMN_LIFTOVER)) != 0)) {
-        throw HalError("HALGPU_RAW_FRAGMENTS cannot be combined with a coalescence limit, PSL counts or ColumnLiftover mode");
+    if (raw && (wig || (flags & (HALGPU_PSL | HALGPU_COLUMN_LIFTOVER)) != 0)) {
+        throw HalError("HALGPU_RAW_FRAGMENTS cannot be combined with PSL counts or ColumnLiftover mode");
     }
-    void (*const mapKernel)(const LiftParams) = wig ? liftoverKernel<LIFT_WIG> : (coalPath ? liftoverKernel<LIFT_COAL> : (raw ? liftoverKernel<LIFT_RAW> : liftoverKernel<LIFT_BED>));
+    void (*const mapKernel)(const LiftParams) =
+        wig ? liftoverKernel<LIFT_WIG>
+            : (raw ? (coalPath ? liftoverKernel<LIFT_RAW_COAL> : liftoverKernel<LIFT_RAW>) : (coalPath ? liftoverKernel<LIFT_COAL> : liftoverKernel<LIFT_BED>));
     // rung 1: all n intervals, scratch in shared memory
     const unsigned block = 128, warpsPerBlock = block / 32;
     {

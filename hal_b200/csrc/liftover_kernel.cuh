@@ -167,10 +167,10 @@ struct WarpScratch {
 
 // MODE: the wiggle mode, the coalescence-limit path and the raw-fragment mode are separate instantiations so that the
 // default BED path's code and register allocation are untouched by them
-enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 3 };
+enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 4, LIFT_RAW_COAL = 6 }; // COAL and RAW are bits
 template <int MODE>
 __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
-    constexpr bool WIG = MODE == LIFT_WIG, COAL = MODE == LIFT_COAL, RAW = MODE == LIFT_RAW;
+    constexpr bool WIG = MODE == LIFT_WIG, COAL = (MODE & LIFT_COAL) != 0, RAW = (MODE & LIFT_RAW) != 0;
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';

@@ -78,7 +78,9 @@ enum {
                                  * segments, before insertAndBreakOverlaps and extractSegment -- as halgpu_frag records in
                                  * result->recs (same size as halgpu_lift_rec; cast), in no particular order within an
                                  * interval.  For callers that refine and merge across intervals themselves (halSynteny lifts
-                                 * whole chromosomes).  Not with HALGPU_PSL, HALGPU_COLUMN_LIFTOVER or a coalescence limit. */
+                                 * whole chromosomes).  Not with HALGPU_PSL or HALGPU_COLUMN_LIFTOVER. */
+    HALGPU_SEED_BOTTOM = 32u,   /* take the source segments from the genome's BOTTOM array even if it has a top array
+                                 * (BlockMapper::map does so when the source genome is the MRCA, halBlockMapper.cpp:76-83) */
     HALGPU_COLUMN_LIFTOVER = 8u /* hal::ColumnLiftover::liftInterval semantics (liftover/impl/halColumnLiftover.cpp:21-92)
                                  * instead of BlockLiftover's: per target sequence and strand the maximal runs of target
                                  * bases homologous to the interval, forward runs first; src_start = -1; with

@@ -1,0 +1,62 @@
+"""Regenerates tests/golden/blockviz/cases.json (run where oracle/_ref/blockVizCli exists): queries against the REFERENCE's
+blockViz C API (blockViz/impl/halBlockViz.cpp compiled from /root/reference behind tests/cpp/blockviz_cli.cpp) and its answers."""
+import json
+import os
+import random
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref", "blockVizCli")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from pyoracle import Oracle  # noqa: E402
+
+
+def ancestors(o, g):
+    out, i = [], o.genome_id(g)
+    while i >= 0:
+        out.append(o.genomes[i])
+        i = o.L.oracle_genome_parent(o.h, i)
+    return out
+
+
+def main():
+    rng = random.Random(31)
+    cases = []
+    for hal, n in (("varlen8.hal", 40), ("refBedLiftoverTest.hal", 12), ("randgenSmallSeed0.hal", 10), ("refMapExtraParalogsTest.hal", 6)):
+        o = Oracle(os.path.join(HERE, hal))
+        fixed = [["species"], ["maxlod"], ["chroms", o.genomes[-1]], ["limits", o.genomes[-1], o.genomes[1]]]
+        nm, _, ln = o.sequences(o.genome_id(o.genomes[-1]))[0]
+        fixed.append(["dna", o.genomes[-1], nm, "3", str(min(ln, 70))])
+        fixed.append(["blocks", "nope", o.genomes[0], nm, "0", "10", "0", "0", "0", "0", "-"])
+        fixed.append(["blocks", o.genomes[0], o.genomes[-1], nm, "9", "3", "0", "0", "0", "0", "-"])
+        fixed.append(["blocks", o.genomes[0], o.genomes[-1], nm, "0", "10", "1", "0", "2", "0", "-"])
+        queries = fixed
+        for _ in range(n):
+            q, t = rng.choice(o.genomes), rng.choice(o.genomes)
+            nm, _, ln = rng.choice(o.sequences(o.genome_id(t)))
+            L = rng.randint(1, min(ln, rng.choice([30, 400, 2500])))
+            a = rng.randint(0, ln - L)
+            dup = rng.choice([0, 1, 2])
+            rev = 1 if (dup < 2 and rng.random() < 0.25) else 0
+            lim = "-"
+            if rng.random() < 0.3:
+                common = [x for x in ancestors(o, q) if x in ancestors(o, t)]
+                lim = rng.choice(common)
+            args = ["blocks", q, t, nm, str(a), str(a + L), str(rev), str(rng.choice([0, 0, 2])), str(dup), "0", lim]
+            if rng.random() < 0.15:
+                args.append(rng.choice(o.sequences(o.genome_id(q)))[0])
+            queries.append(args)
+        for args in queries:
+            r = subprocess.run([REF, os.path.join(HERE, hal)] + args, capture_output=True, text=True)
+            if r.returncode < 0:
+                continue
+            cases.append(dict(hal=hal, args=args, rc=r.returncode, out=r.stdout))
+    os.makedirs(os.path.join(HERE, "blockviz"), exist_ok=True)
+    json.dump(cases, open(os.path.join(HERE, "blockviz", "cases.json"), "w"), indent=0)
+    print(len(cases), "cases,", sum(1 for c in cases if "\nD\t" in c["out"]), "with target dupes,", sum(1 for c in cases if c["rc"] != 0), "errors")
+
+
+if __name__ == "__main__":
+    main()
