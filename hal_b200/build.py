@@ -63,9 +63,9 @@ def build(force=False, verbose=False):
     if force or _newer(syn, syn_srcs + [os.path.join(host, "synteny.hpp"), LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", syn] + syn_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     viz = os.path.join(HERE, "libhalBlockVizGpu.so")  # the reference's blockViz C API (include/halBlockViz.h) over libhalgpu
-    viz_src = os.path.join(host, "blockviz.cpp")
-    if force or _newer(viz, [viz_src, os.path.join(os.path.dirname(HERE), "include", "halBlockViz.h"), LIB]):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", viz, viz_src, "-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN"])
+    viz_srcs = [os.path.join(host, "blockviz.cpp"), os.path.join(host, "maf_export.cpp")]
+    if force or _newer(viz, viz_srcs + [os.path.join(host, "maf_export.hpp"), os.path.join(os.path.dirname(HERE), "include", "halBlockViz.h"), LIB]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-o", viz] + viz_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN"])
     vizcli = os.path.join(BIN, "blockVizCli")  # text driver of the C API (tests/cpp/blockviz_cli.cpp)
     vizcli_src = os.path.join(os.path.dirname(HERE), "tests", "cpp", "blockviz_cli.cpp")
     if os.path.exists(vizcli_src) and (force or _newer(vizcli, [vizcli_src, viz])):

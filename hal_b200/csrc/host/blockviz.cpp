@@ -10,6 +10,7 @@
 // heuristics over that set and run here on the host, restated from the lines cited.
 #include "../../../include/halBlockViz.h"
 #include "../../../include/halgpu.h"
+#include "maf_export.hpp"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -624,13 +626,65 @@ struct hal_block_results_t *halGetBlocksInTargetRange_filterByChrom(int halHandl
     return r;
 }
 
-hal_int_t halGetMaf(FILE *, int, struct hal_species_t *, char *, char *, hal_int_t, hal_int_t, int, int, int, char **errStr) {
-    handleError("halGetMaf is not implemented in the GPU build (use hal2maf)", errStr);
-    return -1;
+hal_int_t halGetMaf(FILE *outFile, int halHandle, struct hal_species_t *qSpeciesNames, char *tSpecies, char *tChrom, hal_int_t tStart,
+                    hal_int_t tEnd, int maxRefGap, int maxBlockLength, int doDupes, char **errStr) {
+    std::lock_guard<std::mutex> g(gLock);
+    hal_int_t numBytes = 0;
+    try { // halBlockViz.cpp:407-473
+        if (tEnd - tStart < 0) {
+            handleError("halGetMaf invalid query range [" + std::to_string(tStart) + "," + std::to_string(tEnd) + ")", errStr);
+            return -1;
+        }
+        if (maxRefGap != 0) {
+            handleError("halGetMaf: maxRefGap > 0 (gapped column iterators) is not implemented in the GPU build", errStr);
+            return -1;
+        }
+        halgpu_ctx *ctx = ctxOf(halHandle);
+        const int t = halgpu_genome_id(ctx, tSpecies);
+        std::set<int> qSet;
+        const halgpu_seq *tseq = nullptr;
+        size_t nts = 0;
+        for (hal_species_t *q = qSpeciesNames; q != nullptr; q = q->next) { // checkGenomes per query species
+            const int qi = halgpu_genome_id(ctx, q->name);
+            if (qi < 0) throw std::runtime_error("Query species " + std::string(q->name) + " not found in alignment with handle " + std::to_string(halHandle));
+            if (t < 0) throw std::runtime_error("Reference species " + std::string(tSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
+            halgpu_sequence_table(ctx, t, &tseq, &nts);
+            if (findSeq(tseq, nts, tChrom) < 0) throw std::runtime_error("Unable to locate sequence " + std::string(tChrom) + " in genome " + tSpecies);
+            qSet.insert(qi);
+        }
+        if (t < 0) throw std::runtime_error("Reference species " + std::string(tSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
+        halgpu_sequence_table(ctx, t, &tseq, &nts);
+        const int ts = findSeq(tseq, nts, tChrom);
+        if (ts < 0) throw std::runtime_error("Unable to locate sequence " + std::string(tChrom) + " in genome " + tSpecies);
+        const int64_t myEnd = tEnd > 0 ? tEnd : tseq[ts].length;
+        const int64_t absStart = tseq[ts].start + tStart, absEnd = tseq[ts].start + myEnd - 1;
+        if (absStart > absEnd) {
+            handleError("halGetMaf invalid range", errStr);
+            return -1;
+        }
+        if (absEnd > tseq[ts].start + tseq[ts].length) { // MMapSequence::getEndPosition() == start + length
+            handleError("halGetMaf target end position outside of target sequence", errStr);
+            return -1;
+        }
+        std::ostringstream mafBuffer;
+        halgpu::GpuMafExport mafExport(ctx);
+        mafExport.setNoDupes(doDupes == 0);
+        mafExport.setUcscNames(true);
+        mafExport.setMaxBlockLengthRaw((int64_t)maxBlockLength);
+        // sic: the reference hands convertSequence the ABSOLUTE start (:452), which only equals the sequence-relative one
+        // it expects for the first sequence of a genome; kept
+        mafExport.convertSequence(mafBuffer, t, ts, absStart, (uint64_t)(1 + absEnd - absStart), std::vector<int>(qSet.begin(), qSet.end()));
+        const std::string buf = mafBuffer.str();
+        if (!buf.empty()) numBytes = (hal_int_t)fwrite(buf.c_str(), buf.length(), sizeof(char), outFile); // (fwrite's ITEM count, i.e. 1)
+    } catch (std::exception &e) {
+        handleError("halGetMaf error writing MAF blocks: " + std::string(e.what()), errStr);
+        return -1;
+    }
+    return numBytes;
 }
-hal_int_t halGetMAF(FILE *, int, struct hal_species_t *, char *, char *, hal_int_t, hal_int_t, int, char **errStr) {
-    handleError("halGetMAF is not implemented in the GPU build (use hal2maf)", errStr);
-    return -1;
+hal_int_t halGetMAF(FILE *outFile, int halHandle, struct hal_species_t *qSpeciesNames, char *tSpecies, char *tChrom, hal_int_t tStart,
+                    hal_int_t tEnd, int doDupes, char **errStr) { // deprecated spelling (halBlockViz.cpp:475-479)
+    return halGetMaf(outFile, halHandle, qSpeciesNames, tSpecies, tChrom, tStart, tEnd, 0, 0, doDupes, errStr);
 }
 
 struct hal_species_t *halGetSpecies(int halHandle, char **errStr) {

@@ -29,6 +29,9 @@ class GpuMafExport {
     void setUcscNames(bool v) { _ucscNames = v; }
     void setAppend(bool v) { _append = v; }
     void setMaxBlockLength(int64_t v) { _maxLength = v <= 0 ? INT64_MAX : v; }
+    // MafBlock::setMaxLength as it is (maf/inc/halMafBlock.h:132-134): 0 makes canAppendColumn fail on every column, i.e.
+    // one-column blocks in a release build of the reference (its assert build aborts) -- what halGetMAF's 0 means
+    void setMaxBlockLengthRaw(int64_t v) { _maxLength = v; }
     void setOnlyOrthologs(bool v) { _onlyOrthologs = v; }
     void setKeepEmptyRefBlocks(bool v) { _keepEmptyRefBlocks = v; }
     void setUnique(bool v) { _unique = v; } // MafExport::setUnique (maf/inc/halMafExport.h:51-53)

@@ -5,10 +5,10 @@
  * errStr == NULL the reference throws, this library aborts with the message), so client code compiles unchanged.
  *
  * Implemented on the GPU path: halGetBlocksInTargetRange[_filterByChrom] with mapBackAdjacencies == 0 (all three
- * duplication modes, sequence modes, coalescence limit, reversed target range).  Host-only queries: halOpen (a HAL-MMAP
- * file), halClose, halCloseGenome, halGetSpecies, halGetPossibleCoalescenceLimits, halGetChroms, halGetDna,
- * halGetMaxLODQueryLength.  Not implemented (return the failure value with a message): LOD list files (halOpenLOD),
- * mapBackAdjacencies != 0, halGetMaf / halGetMAF, halGetGenomeMetadata.
+ * duplication modes, sequence modes, coalescence limit, reversed target range) and halGetMaf / halGetMAF with
+ * maxRefGap == 0.  Host-only queries: halOpen (a HAL-MMAP file), halClose, halCloseGenome, halGetSpecies,
+ * halGetPossibleCoalescenceLimits, halGetChroms, halGetDna, halGetMaxLODQueryLength.  Not implemented (return the failure
+ * value with a message): LOD list files (halOpenLOD), mapBackAdjacencies != 0, maxRefGap > 0, halGetGenomeMetadata.
  */
 #ifndef HAL_BLOCK_VIZ_H
 #define HAL_BLOCK_VIZ_H

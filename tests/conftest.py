@@ -97,11 +97,12 @@ def emul_blockviz_cli(emul_lib):
     """tests/cpp/blockviz_cli.cpp against this repo's blockViz implementation linked with the emulated library."""
     d = os.path.join(ROOT, "tests", "simt")
     lib, out = os.path.join(d, "libhalBlockVizGpu_emul.so"), os.path.join(d, "blockVizCli_emul")
-    src = os.path.join(ROOT, "hal_b200", "csrc", "host", "blockviz.cpp")
+    host = os.path.join(ROOT, "hal_b200", "csrc", "host")
+    srcs = [os.path.join(host, "blockviz.cpp"), os.path.join(host, "maf_export.cpp")]
     drv = os.path.join(ROOT, "tests", "cpp", "blockviz_cli.cpp")
-    deps = [src, drv, os.path.join(ROOT, "include", "halBlockViz.h"), emul_lib]
+    deps = srcs + [drv, os.path.join(host, "maf_export.hpp"), os.path.join(ROOT, "include", "halBlockViz.h"), emul_lib]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib, src, "-L" + d, "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib] + srcs + ["-L" + d, "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", out, drv, "-L" + d, "-lhalBlockVizGpu_emul",
                                "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
     return out

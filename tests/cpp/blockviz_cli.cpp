@@ -4,6 +4,7 @@
 // against whichever halBlockViz.h the build points it at.
 //
 // usage: blockVizCli <hal> species | chroms <genome> | dna <genome> <chrom> <start> <end> | limits <q> <t> | maxlod
+//        blockVizCli <hal> maf <tSpecies> <tChrom> <tStart> <tEnd> <maxRefGap> <maxBlockLength> <doDupes> <q1,q2,...>   (MAF to stdout)
 //        blockVizCli <hal> blocks <qSpecies> <tSpecies> <tChrom> <tStart> <tEnd> <tReversed> <seqMode> <dupMode> <adj> <limit|-> [qChromFilter]
 #include "halBlockViz.h"
 #include <cstdio>
@@ -38,6 +39,23 @@ int main(int argc, char **argv) {
         halFreeSpeciesList(s);
     } else if (cmd == "maxlod") {
         printf("%ld\n", halGetMaxLODQueryLength(h, &err));
+    } else if (cmd == "maf" && argc >= 11) {
+        hal_species_t *head = NULL, *tail = NULL;
+        std::string names = argv[10];
+        size_t at = 0;
+        while (at <= names.size()) {
+            size_t c = names.find(',', at);
+            if (c == std::string::npos) c = names.size();
+            hal_species_t *s = (hal_species_t *)calloc(1, sizeof(hal_species_t));
+            s->name = strdup(names.substr(at, c - at).c_str());
+            if (!head) head = s; else tail->next = s;
+            tail = s;
+            at = c + 1;
+        }
+        hal_int_t n = halGetMaf(stdout, h, head, argv[3], argv[4], atol(argv[5]), atol(argv[6]), atoi(argv[7]), atoi(argv[8]), atoi(argv[9]), &err);
+        fflush(stdout);
+        if (n < 0) { printf("ERROR %s\n", err ? err : "?"); rc = 1; } else printf("RETURNED %ld\n", n);
+        halFreeSpeciesList(head);
     } else if (cmd == "blocks" && argc >= 13) {
         const char *limit = strcmp(argv[12], "-") ? argv[12] : NULL;
         hal_block_results_t *r;

@@ -32,6 +32,13 @@ def main():
         fixed.append(["blocks", "nope", o.genomes[0], nm, "0", "10", "0", "0", "0", "0", "-"])
         fixed.append(["blocks", o.genomes[0], o.genomes[-1], nm, "9", "3", "0", "0", "0", "0", "-"])
         fixed.append(["blocks", o.genomes[0], o.genomes[-1], nm, "0", "10", "1", "0", "2", "0", "-"])
+        t0 = o.genomes[-1]
+        others = ",".join(g for g in o.genomes[:3] if g != t0)
+        fixed.append(["maf", t0, nm, "0", str(min(ln, 600)), "0", "1000", "1", others])
+        fixed.append(["maf", t0, nm, "5", str(min(ln, 300)), "0", "9", "0", o.genomes[0]])
+        if len(o.sequences(o.genome_id(t0))) > 1:  # a later sequence: the reference passes the ABSOLUTE start to convertSequence
+            nm2, _, ln2 = o.sequences(o.genome_id(t0))[1]
+            fixed.append(["maf", t0, nm2, "10", str(min(ln2, 200)), "0", "1000", "1", o.genomes[0]])
         queries = fixed
         for _ in range(n):
             q, t = rng.choice(o.genomes), rng.choice(o.genomes)

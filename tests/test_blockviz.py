@@ -18,14 +18,14 @@ from conftest import GOLDEN, ROOT, ref_bin
 CASES = json.load(open(os.path.join(GOLDEN, "blockviz", "cases.json")))
 
 
-def check_cases(cli):
+def check_cases(cli, step=1):
     kinds = set()
-    for c in CASES:
+    for c in CASES[::step] + [c for c in CASES if c["args"][0] != "blocks"]:
         r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"])] + c["args"], capture_output=True, text=True)
         assert r.returncode == c["rc"], (c["args"], r.stdout, r.stderr)
         assert r.stdout == c["out"], c["args"]
         kinds.add(c["args"][0])
-    assert kinds >= {"species", "chroms", "dna", "limits", "maxlod", "blocks"}
+    assert kinds >= {"species", "chroms", "dna", "limits", "maxlod", "blocks", "maf"}
 
 
 def test_blockviz_emulated_matches_reference_answers(emul_blockviz_cli):
@@ -56,6 +56,8 @@ def test_blockviz_unsupported_calls_fail_with_a_message(emul_blockviz_cli):
     hal = os.path.join(GOLDEN, "varlen8.hal")
     r = subprocess.run([emul_blockviz_cli, hal, "blocks", "L0", "L3", "L3_s1", "0", "100", "0", "0", "2", "1", "-"], capture_output=True, text=True)
     assert r.returncode == 1 and "mapBackAdjacencies is not implemented" in r.stdout
+    r = subprocess.run([emul_blockviz_cli, hal, "maf", "L3", "L3_s0", "0", "100", "3", "1000", "1", "L0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "maxRefGap > 0" in r.stdout
 
 
 def test_blockviz_library_exports_every_declared_symbol(product_lib):
@@ -73,4 +75,4 @@ def test_blockviz_library_exports_every_declared_symbol(product_lib):
 def test_blockviz_cuda_matches_reference_answers():
     from hal_b200 import build
     build.build()
-    check_cases(os.path.join(ROOT, "hal_b200", "bin", "blockVizCli"))
+    check_cases(os.path.join(ROOT, "hal_b200", "bin", "blockVizCli"), step=2)  # (every query is a process + CUDA context)
