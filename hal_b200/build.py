@@ -62,14 +62,14 @@ def build(force=False, verbose=False):
     syn_srcs = [os.path.join(host, f) for f in ("halSyntenyMain.cpp", "synteny.cpp")]
     if force or _newer(syn, syn_srcs + [os.path.join(host, "synteny.hpp"), LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", syn] + syn_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
-    viz = os.path.join(HERE, "libhalBlockVizGpu.so")  # the reference's blockViz C API (include/halBlockViz.h) over libhalgpu
+    viz = os.path.join(HERE, "libhalBlockVizGpu.so")  # the reference's blockViz C API (include/halgpu_blockviz.h) over libhalgpu
     viz_srcs = [os.path.join(host, "blockviz.cpp"), os.path.join(host, "maf_export.cpp")]
-    if force or _newer(viz, viz_srcs + [os.path.join(host, "maf_export.hpp"), os.path.join(os.path.dirname(HERE), "include", "halBlockViz.h"), LIB]):
+    if force or _newer(viz, viz_srcs + [os.path.join(host, "maf_export.hpp"), os.path.join(os.path.dirname(HERE), "include", "halgpu_blockviz.h"), LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-o", viz] + viz_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN"])
     vizcli = os.path.join(BIN, "blockVizCli")  # text driver of the C API (tests/cpp/blockviz_cli.cpp)
     vizcli_src = os.path.join(os.path.dirname(HERE), "tests", "cpp", "blockviz_cli.cpp")
     if os.path.exists(vizcli_src) and (force or _newer(vizcli, [vizcli_src, viz])):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", vizcli, vizcli_src,
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DHALGPU_BLOCKVIZ_HEADER", "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", vizcli, vizcli_src,
                                "-L" + HERE, "-lhalBlockVizGpu", "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     dep = os.path.join(BIN, "halAlignmentDepth")
     dep_src = os.path.join(host, "halAlignmentDepthMain.cpp")

@@ -1,5 +1,5 @@
 // libhalBlockVizGpu -- the reference's blockViz C API (blockViz/inc/halBlockViz.h, blockViz/impl/halBlockViz.cpp) over the
-// B200 context (include/halgpu.h).  See include/halBlockViz.h for what is implemented.
+// B200 context (include/halgpu.h).  See include/halgpu_blockviz.h for what is implemented.
 //
 // halGetBlocksInTargetRange = BlockMapper::init / map (liftover/impl/halBlockMapper.cpp:37-103) + readBlocks
 // (halBlockViz.cpp:759-827).  BlockMapper::map is halMapSegment for every reference segment of the range -- that part runs
@@ -8,7 +8,7 @@
 // MappedSegmentSet of the whole range (common refinement of the fragments' query extents), chainReferenceParalogies
 // (:1072-1175), the extractSegment sweep with its cut sets, readBlock and processTargetDupes (:939-1070) are sequential
 // heuristics over that set and run here on the host, restated from the lines cited.
-#include "../../../include/halBlockViz.h"
+#include "../../../include/halgpu_blockviz.h"
 #include "../../../include/halgpu.h"
 #include "maf_export.hpp"
 #include <algorithm>

@@ -1,8 +1,10 @@
 /*
- * halBlockViz.h -- the reference's block-visualisation C API (blockViz/inc/halBlockViz.h, the interface the UCSC browser
+ * halgpu_blockviz.h -- the reference's block-visualisation C API (blockViz/inc/halBlockViz.h, the interface the UCSC browser
  * links against) as exported by hal_b200/libhalBlockVizGpu.so on top of the B200 context of include/halgpu.h.
  * Same names, struct layouts, argument meaning and error convention (NULL / -1 plus a malloc'd message in *errStr; with
- * errStr == NULL the reference throws, this library aborts with the message), so client code compiles unchanged.
+ * errStr == NULL the reference throws, this library aborts with the message).  The ABI is identical, so client code built
+ * against the reference's own halBlockViz.h links against this library unchanged; this header exists for builds without the
+ * reference tree.
  *
  * Implemented on the GPU path: halGetBlocksInTargetRange[_filterByChrom] with mapBackAdjacencies == 0 (all three
  * duplication modes, sequence modes, coalescence limit, reversed target range) and halGetMaf / halGetMAF with

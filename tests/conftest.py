@@ -100,10 +100,10 @@ def emul_blockviz_cli(emul_lib):
     host = os.path.join(ROOT, "hal_b200", "csrc", "host")
     srcs = [os.path.join(host, "blockviz.cpp"), os.path.join(host, "maf_export.cpp")]
     drv = os.path.join(ROOT, "tests", "cpp", "blockviz_cli.cpp")
-    deps = srcs + [drv, os.path.join(host, "maf_export.hpp"), os.path.join(ROOT, "include", "halBlockViz.h"), emul_lib]
+    deps = srcs + [drv, os.path.join(host, "maf_export.hpp"), os.path.join(ROOT, "include", "halgpu_blockviz.h"), emul_lib]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", lib] + srcs + ["-L" + d, "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", out, drv, "-L" + d, "-lhalBlockVizGpu_emul",
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DHALGPU_BLOCKVIZ_HEADER", "-I" + os.path.join(ROOT, "include"), "-o", out, drv, "-L" + d, "-lhalBlockVizGpu_emul",
                                "-lhalgpu_emul", "-Wl,-rpath,$ORIGIN", "-pthread"])
     return out
 

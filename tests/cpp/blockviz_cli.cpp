@@ -1,12 +1,16 @@
 // TEST HARNESS -- prints everything the blockViz C API returns for one query, as text, so that the reference's
 // libHalBlockViz (compiled into oracle/_ref/blockVizCli from /root/reference) and this repo's GPU implementation of the same
 // API (hal_b200/libhalBlockVizGpu.so) can be compared byte for byte.  It only uses the public C API; it is compiled
-// against whichever halBlockViz.h the build points it at.
+// against the reference's halBlockViz.h (oracle build) or include/halgpu_blockviz.h (-DHALGPU_BLOCKVIZ_HEADER).
 //
 // usage: blockVizCli <hal> species | chroms <genome> | dna <genome> <chrom> <start> <end> | limits <q> <t> | maxlod
 //        blockVizCli <hal> maf <tSpecies> <tChrom> <tStart> <tEnd> <maxRefGap> <maxBlockLength> <doDupes> <q1,q2,...>   (MAF to stdout)
 //        blockVizCli <hal> blocks <qSpecies> <tSpecies> <tChrom> <tStart> <tEnd> <tReversed> <seqMode> <dupMode> <adj> <limit|-> [qChromFilter]
-#include "halBlockViz.h"
+#ifdef HALGPU_BLOCKVIZ_HEADER
+#include "halgpu_blockviz.h" // this repo's declaration of the same API
+#else
+#include "halBlockViz.h" // the reference's header (oracle build)
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

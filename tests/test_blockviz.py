@@ -1,5 +1,5 @@
 """The reference's blockViz C API (blockViz/inc/halBlockViz.h) re-implemented over the GPU context:
-hal_b200/libhalBlockVizGpu.so + include/halBlockViz.h.  A text driver of the API (tests/cpp/blockviz_cli.cpp) is linked once
+hal_b200/libhalBlockVizGpu.so + include/halgpu_blockviz.h.  A text driver of the API (tests/cpp/blockviz_cli.cpp) is linked once
 against the reference's own implementation (oracle/_ref/blockVizCli) and once against this one; their outputs must be identical.
 
 CPU tier: emulated library vs committed answers of the reference (tests/golden/blockviz) and vs the reference live.
@@ -63,12 +63,12 @@ def test_blockviz_unsupported_calls_fail_with_a_message(emul_blockviz_cli):
 def test_blockviz_library_exports_every_declared_symbol(product_lib):
     lib = os.path.join(ROOT, "hal_b200", "libhalBlockVizGpu.so")
     assert os.path.exists(lib), "hal_b200/build.py builds it next to libhalgpu.so"
-    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "halBlockViz.h")).read(), flags=re.S)
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "halgpu_blockviz.h")).read(), flags=re.S)
     syms = sorted(set(re.findall(r"\b(hal[A-Z][A-Za-z_]+)\s*\(", text)))
     assert len(syms) >= 20
     L = ctypes.CDLL(lib)
     for s in syms:
-        assert hasattr(L, s), f"{s} declared in include/halBlockViz.h but not exported"
+        assert hasattr(L, s), f"{s} declared in include/halgpu_blockviz.h but not exported"
 
 
 @pytest.mark.gpu

@@ -23,6 +23,8 @@ MAF = os.path.join(ROOT, "tests", "simt", "hal2maf_emul")
 WIG = os.path.join(ROOT, "tests", "simt", "halWiggleLiftover_emul")
 SYN = os.path.join(ROOT, "tests", "simt", "halSynteny_emul")
 REF_SYN = os.path.join(ROOT, "oracle", "_ref", "halSynteny")
+VIZ = os.path.join(ROOT, "tests", "simt", "blockVizCli_emul")
+REF_VIZ = os.path.join(ROOT, "oracle", "_ref", "blockVizCli")
 
 
 def rand_tree(rng, names):
@@ -124,6 +126,22 @@ def main():
                 if ra.returncode != rb.returncode or (ra.returncode == 0 and open(pa).read() != open(pb).read()):
                     bad += 1
                     print("SYNTENY DIFF", tag, args, ra.stderr[:100], rb.stderr[:100])
+        # the blockViz C API against the reference's implementation behind the same text driver
+        if os.path.exists(REF_VIZ) and os.path.exists(VIZ):
+            for _ in range(6):
+                q, t = rng.choice(names), rng.choice(names)
+                nm, _, ln = rng.choice(o.sequences(o.genome_id(t)))
+                L = rng.randint(1, min(ln, rng.choice([40, 600, 20000])))
+                st0 = rng.randint(0, ln - L)
+                dup = rng.choice([0, 1, 2])
+                args = ["blocks", q, t, nm, str(st0), str(st0 + L), "1" if (dup < 2 and rng.random() < 0.25) else "0", str(rng.choice([0, 2])), str(dup), "0", "-"]
+                if rng.random() < 0.25:
+                    args = ["maf", t, nm, str(st0), str(st0 + L), "0", str(rng.choice([1000, 7])), str(rng.choice([0, 1])), ",".join(rng.sample(names, min(2, len(names))))]
+                ra = subprocess.run([REF_VIZ, hal] + args, capture_output=True, text=True)
+                rb = subprocess.run([VIZ, hal] + args, capture_output=True, text=True)
+                if ra.returncode >= 0 and (ra.returncode, ra.stdout) != (rb.returncode, rb.stdout):
+                    bad += 1
+                    print("BLOCKVIZ DIFF", tag, " ".join(args), ra.stdout[:120].replace("\n", " | "), "//", rb.stdout[:120].replace("\n", " | "))
         a.close()
         o.close()
         print("round", it, "done", tag, flush=True)
