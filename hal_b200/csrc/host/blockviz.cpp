@@ -298,13 +298,217 @@ hal_target_dupe_list_t *processTargetDupes(const std::vector<Seg> &para, const s
     return head;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BlockMapper::mapAdjacencies (liftover/impl/halBlockMapper.cpp:121-245), _maxAdjScan == 1: for every element of the set
+// (in set order, while the set grows) the query segment to its right and the one to its left -- or what is left of its own
+// segment -- are cut by the neighbouring set element (cutByNext, :272-329), mapped BACK to the reference genome, and the
+// results that land on the reference sequence without overlapping their neighbours in the set join it ("off-screen" blocks).
+// The back-mapping of every candidate piece is done beforehand in ONE raw-fragment GPU call (uncut pieces; cutting a piece
+// restricts its fragments), the sequential part below only slices and inserts.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SegSetLess {
+    bool operator()(const Seg &a, const Seg &b) const { return segLess(a, b); }
+};
+typedef std::set<Seg, SegSetLess> SegSet;
+
+struct QueryArray { // the query genome's segment array the mapped segments live in
+    const uint8_t *base;
+    size_t stride;
+    int64_t n;
+    int64_t start(int64_t i) const { int64_t v; memcpy(&v, base + stride * (size_t)i, 8); return v; }
+    int64_t indexOf(int64_t pos) const {
+        int64_t lo = 0, hi = n;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (start(mid) <= pos) lo = mid; else hi = mid; }
+        return lo;
+    }
+};
+
+struct Piece { // an adjacent query piece in forward coordinates, oriented like the element it belongs to
+    int64_t lo, hi, idx;
+    bool valid;
+};
+
+// restriction of raw back-mapped fragments (source = query piece, forward; target = reference) to source range [lo, hi]
+void restrictFrags(const halgpu_frag *f, size_t n, int64_t lo, int64_t hi, bool reversed, std::vector<Seg> &out) {
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t s0 = f[i].src_start, s1 = s0 + f[i].length - 1;
+        const int64_t a = std::max(s0, lo), b = std::min(s1, hi);
+        if (a > b) continue;
+        const bool tRev = (f[i].flags & 2u) != 0;
+        // source offset u = a - s0 (source forward in the precomputed call); target piece accordingly
+        const int64_t m = b - a + 1, u = a - s0;
+        Seg g;
+        g.sLo = a; g.len = m;
+        g.qLo = tRev ? f[i].tgt_start + f[i].length - u - m : f[i].tgt_start + u; // ("q" fields hold the mapped side = reference here)
+        g.sRev = reversed;           // a reversed iterator maps with both strands flipped
+        g.qRev = tRev != reversed;
+        g.qSeq = 0; g.alive = true; g.inPara = false;
+        out.push_back(g);
+    }
+}
+
+void mapAdjacencies(halgpu_ctx *ctx, int tGenome, int qGenome, bool doDupes, bool qTop, const halgpu_seq *qseq, size_t nqs, const halgpu_seq &refSeq,
+                    std::vector<Seg> &segsVec) {
+    QueryArray Q;
+    size_t stride = 40;
+    if (qTop) {
+        Q.base = static_cast<const uint8_t *>(halgpu_genome_top_segments(ctx, qGenome));
+        Q.n = halgpu_genome_num_top(ctx, qGenome);
+    } else {
+        Q.base = static_cast<const uint8_t *>(halgpu_genome_bottom_segments(ctx, qGenome, &stride));
+        Q.n = halgpu_genome_num_bottom(ctx, qGenome);
+    }
+    Q.stride = stride;
+    if (Q.base == nullptr || Q.n <= 0 || segsVec.empty()) return;
+    // [minIndex, maxIndex) of every query sequence: segments of a sequence are contiguous, sequences in order
+    std::vector<int64_t> firstIdx(nqs + 1, 0);
+    for (size_t i = 0; i < nqs; ++i) firstIdx[i + 1] = firstIdx[i] + (qTop ? qseq[i].num_top : qseq[i].num_bottom);
+    auto rightPiece = [&](const Seg &e) { // queryIt->toRight() from the element's slice
+        Piece p;
+        const int64_t idx = Q.indexOf(e.qLo), S = Q.start(idx), E = Q.start(idx + 1) - 1;
+        const int64_t mn = firstIdx[(size_t)e.qSeq], mx = firstIdx[(size_t)e.qSeq + 1];
+        if (!e.qRev) {
+            if (e.qHi() == E) { p.idx = idx + 1; p.valid = p.idx >= mn && p.idx < mx; if (p.valid) { p.lo = Q.start(p.idx); p.hi = Q.start(p.idx + 1) - 1; } }
+            else { p.idx = idx; p.lo = e.qHi() + 1; p.hi = E; p.valid = true; }
+        } else {
+            if (e.qLo == S) { p.idx = idx - 1; p.valid = p.idx >= mn && p.idx < mx; if (p.valid) { p.lo = Q.start(p.idx); p.hi = Q.start(p.idx + 1) - 1; } }
+            else { p.idx = idx; p.lo = S; p.hi = e.qLo - 1; p.valid = true; }
+        }
+        return p;
+    };
+    auto leftPiece = [&](const Seg &e) { // queryIt->toLeft()
+        Piece p;
+        const int64_t idx = Q.indexOf(e.qLo), S = Q.start(idx), E = Q.start(idx + 1) - 1;
+        const int64_t mn = firstIdx[(size_t)e.qSeq], mx = firstIdx[(size_t)e.qSeq + 1];
+        if (!e.qRev) {
+            if (e.qLo == S) { p.idx = idx - 1; p.valid = p.idx >= mn && p.idx < mx; if (p.valid) { p.lo = Q.start(p.idx); p.hi = Q.start(p.idx + 1) - 1; } }
+            else { p.idx = idx; p.lo = S; p.hi = e.qLo - 1; p.valid = true; }
+        } else {
+            if (e.qHi() == E) { p.idx = idx + 1; p.valid = p.idx >= mn && p.idx < mx; if (p.valid) { p.lo = Q.start(p.idx); p.hi = Q.start(p.idx + 1) - 1; } }
+            else { p.idx = idx; p.lo = e.qHi() + 1; p.hi = E; p.valid = true; }
+        }
+        return p;
+    };
+    // ---- one GPU call: every candidate piece mapped back to the reference genome ----
+    std::vector<int64_t> gs, ge;
+    std::map<std::pair<int64_t, int64_t>, size_t> candidate; // (lo, hi) -> interval
+    auto addCandidate = [&](const Piece &p) {
+        if (!p.valid) return;
+        auto key = std::make_pair(p.lo, p.hi);
+        if (candidate.count(key)) return;
+        candidate[key] = gs.size();
+        gs.push_back(p.lo);
+        ge.push_back(p.hi);
+    };
+    for (const Seg &e : segsVec) { addCandidate(rightPiece(e)); addCandidate(leftPiece(e)); }
+    halgpu_lift_result *res = nullptr;
+    if (!gs.empty()) {
+        char *err = nullptr;
+        const uint32_t flags = HALGPU_RAW_FRAGMENTS | (doDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (qTop ? 0u : (uint32_t)HALGPU_SEED_BOTTOM);
+        if (halgpu_liftover(ctx, qGenome, tGenome, -1, flags, gs.size(), gs.data(), ge.data(), nullptr, &res, &err) != 0) {
+            std::string m = err ? err : "halgpu_liftover failed";
+            halgpu_free_string(err);
+            throw std::runtime_error(m);
+        }
+    }
+    const halgpu_frag *raw = res ? reinterpret_cast<const halgpu_frag *>(res->recs) : nullptr;
+
+    SegSet segSet(segsVec.begin(), segsVec.end());
+    SegSet adjSet;
+    auto overlapsPos = [](const Seg &s, int64_t pos) { return pos >= s.qLo && pos <= s.qHi(); };
+    for (SegSet::const_iterator it = segSet.begin(); it != segSet.end(); ++it) {
+        if (adjSet.count(*it)) continue;
+        const Seg e = *it;
+        std::vector<Seg> back; // halMapSegment results of the right and the left piece
+        for (int side = 0; side < 2; ++side) {
+            Piece p = side == 0 ? rightPiece(e) : leftPiece(e);
+            if (!p.valid) continue;
+            const auto key = std::make_pair(p.lo, p.hi);
+            // neighbour in the CURRENT set: right scan -> next element (previous for a reversed iterator); left scan the other way
+            const bool wantNext = (side == 0) != e.qRev;
+            SegSet::const_iterator nb = it;
+            bool haveNb = true;
+            if (wantNext) { ++nb; haveNb = nb != segSet.end(); }
+            else if (nb == segSet.begin()) haveNb = false;
+            else --nb;
+            bool wasCut = false;
+            if (haveNb && Q.indexOf(nb->qLo) == p.idx) { // cutByNext(queryIt, neighbour's target, right)
+                const bool right = side == 0 ? !e.qRev : e.qRev;
+                if (right) {
+                    if (p.lo >= nb->qLo) wasCut = true;
+                    else if (p.hi >= nb->qLo) p.hi = nb->qLo - 1;
+                } else {
+                    if (p.hi <= nb->qHi()) wasCut = true;
+                    else if (p.lo <= nb->qHi()) p.lo = nb->qHi() + 1;
+                }
+            }
+            if (wasCut) continue;
+            const size_t iv = candidate[key];
+            restrictFrags(raw + res->offsets[iv], (size_t)(res->offsets[iv + 1] - res->offsets[iv]), p.lo, p.hi, e.qRev, back);
+        }
+        if (back.empty()) continue;
+        // backResults: one MappedSegmentSet (insertAndBreakOverlaps over the mapped = reference side)
+        std::vector<int64_t> bps;
+        for (const Seg &b : back) { bps.push_back(b.qLo); bps.push_back(b.qLo + b.len); }
+        std::sort(bps.begin(), bps.end());
+        bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+        std::vector<Seg> refined;
+        for (const Seg &b : back) {
+            auto c = std::upper_bound(bps.begin(), bps.end(), b.qLo);
+            int64_t a = b.qLo;
+            for (; c != bps.end() && *c <= b.qHi(); ++c) { refined.push_back(sub(b, a, *c - 1)); a = *c; }
+            refined.push_back(sub(b, a, b.qHi()));
+        }
+        std::sort(refined.begin(), refined.end(), segLess);
+        refined.erase(std::unique(refined.begin(), refined.end(), [](const Seg &x, const Seg &y) { return x.qLo == y.qLo && x.len == y.len && x.sLo == y.sLo; }),
+                      refined.end());
+        // flip (source <-> target), make the reference side forward, keep what lies on the reference sequence and does not
+        // overlap its neighbours in the set (:196-216)
+        SegSet outSet;
+        for (const Seg &b : refined) {
+            if (b.qLo < refSeq.start || b.qLo >= refSeq.start + refSeq.length) continue; // mseg->getSequence() == _refSequence
+            Seg m;
+            m.sLo = b.qLo; m.qLo = b.sLo; m.len = b.len;
+            m.sRev = b.qRev; m.qRev = b.sRev;
+            if (m.sRev) { m.sRev = false; m.qRev = !m.qRev; } // fullReverse
+            m.qSeq = e.qSeq; m.alive = true; m.inPara = false;
+            SegSet::const_iterator j = segSet.lower_bound(m);
+            if (j != segSet.begin()) --j;
+            bool overlaps = false;
+            for (size_t count = 0; count < 3 && j != segSet.end() && !overlaps; ++count, ++j) {
+                overlaps = overlapsPos(m, j->qStartPos()) || overlapsPos(m, j->qEndPos()) || overlapsPos(*j, m.qStartPos()) || overlapsPos(*j, m.qEndPos());
+            }
+            if (!overlaps) outSet.insert(m);
+        }
+        // one copy per query interval: the one whose reference piece is nearest to this element's (:219-243)
+        for (SegSet::const_iterator i = outSet.begin(); i != outSet.end();) {
+            SegSet::const_iterator j = i;
+            ++j;
+            while (j != outSet.end() && (j->qStartPos() == i->qStartPos() || j->qEndPos() == i->qStartPos())) ++j;
+            SegSet::const_iterator best = i;
+            int64_t bestDelta = std::numeric_limits<int64_t>::max();
+            for (SegSet::const_iterator k = i; k != j; ++k) {
+                const int64_t d1 = k->sStartPos() - e.sStartPos(), d2 = k->sEndPos() - e.sStartPos();
+                const int64_t delta = std::min(d1 < 0 ? -d1 : d1, d2 < 0 ? -d2 : d2);
+                if (delta < bestDelta) { bestDelta = delta; best = k; }
+            }
+            segSet.insert(*best);
+            adjSet.insert(*best);
+            i = j;
+        }
+    }
+    if (res) halgpu_free_result(res);
+    segsVec.assign(segSet.begin(), segSet.end());
+}
+
 int findSeq(const halgpu_seq *seqs, size_t n, const char *name) {
     for (size_t i = 0; i < n; ++i) if (strcmp(seqs[i].name, name) == 0) return (int)i;
     return -1;
 }
 
 hal_block_results_t *readBlocks(halgpu_ctx *ctx, int tGenome, int tSeqIdx, int64_t absStart, int64_t absEnd, bool tReversed, int qGenome,
-                                bool getSeq, bool doDupes, bool doTargetDupes, const char *limitName) {
+                                bool getSeq, bool doDupes, bool doTargetDupes, bool doAdjes, const char *limitName) {
     const halgpu_seq *tseq = nullptr, *qseq = nullptr;
     size_t nts = 0, nqs = 0;
     halgpu_sequence_table(ctx, tGenome, &tseq, &nts);
@@ -389,6 +593,14 @@ hal_block_results_t *readBlocks(halgpu_ctx *ctx, int tGenome, int tSeqIdx, int64
     std::sort(segs.begin(), segs.end(), segLess);
     segs.erase(std::unique(segs.begin(), segs.end(), [](const Seg &x, const Seg &y) { return x.qLo == y.qLo && x.len == y.len && x.sLo == y.sLo; }), segs.end());
 
+    if (doAdjes) {
+        // kind of the mapped segments in the query genome: arrived from the parent (top) unless the query genome is the MRCA and
+        // was reached from below (bottom) -- but with a coalescence limit above the MRCA everything in the MRCA went through
+        // mapSelf, which turns bottom segments into their top pieces; a self-alignment stays on the top array
+        const bool coalActive = doDupes && coal >= 0 && coal != mrca;
+        const bool qTop = !(mrca == qGenome && qGenome != tGenome) || coalActive;
+        mapAdjacencies(ctx, tGenome, qGenome, doDupes, qTop, qseq, nqs, tseq[tSeqIdx], segs);
+    }
     if (doDupes && qGenome != tGenome) chainReferenceParalogies(segs);
     std::vector<Seg> paraSet;
     for (const Seg &s : segs) if (s.inPara) paraSet.push_back(s);
@@ -557,10 +769,6 @@ struct hal_block_results_t *halGetBlocksInTargetRange(int halHandle, char *qSpec
             handleError("tReversed cannot be set in conjunction with dupMode=HAL_QUERY_AND_TARGET_DUPS", errStr);
             return nullptr;
         }
-        if (mapBackAdjacencies != 0) {
-            handleError("halGetBlocksInTargetRange: mapBackAdjacencies is not implemented in the GPU build", errStr);
-            return nullptr;
-        }
         const bool getSeq = seqMode != HAL_NO_SEQUENCE; // a single HAL file is always level of detail 0
         halgpu_ctx *ctx = ctxOf(halHandle);
         // checkGenomes
@@ -586,7 +794,7 @@ struct hal_block_results_t *halGetBlocksInTargetRange(int halHandle, char *qSpec
             return nullptr;
         }
         return readBlocks(ctx, t, ts, absStart, absEnd, tReversed != 0, q, getSeq, dupMode != HAL_NO_DUPS, dupMode == HAL_QUERY_AND_TARGET_DUPS,
-                          coalescenceLimitName);
+                          mapBackAdjacencies != 0, coalescenceLimitName);
     } catch (std::exception &e) {
         handleError("halGetBlocksInTargetRange error reading blocks: " + std::string(e.what()), errStr);
         return nullptr;

@@ -6,11 +6,10 @@
  * against the reference's own halBlockViz.h links against this library unchanged; this header exists for builds without the
  * reference tree.
  *
- * Implemented on the GPU path: halGetBlocksInTargetRange[_filterByChrom] with mapBackAdjacencies == 0 (all three
- * duplication modes, sequence modes, coalescence limit, reversed target range) and halGetMaf / halGetMAF with
- * maxRefGap == 0.  Host-only queries: halOpen (a HAL-MMAP file), halClose, halCloseGenome, halGetSpecies,
+ * Implemented on the GPU path: halGetBlocksInTargetRange[_filterByChrom] (all three duplication modes, sequence modes,
+ * coalescence limit, reversed target range, mapBackAdjacencies) and halGetMaf / halGetMAF with maxRefGap == 0.  Host-only queries: halOpen (a HAL-MMAP file), halClose, halCloseGenome, halGetSpecies,
  * halGetPossibleCoalescenceLimits, halGetChroms, halGetDna, halGetMaxLODQueryLength.  Not implemented (return the failure
- * value with a message): LOD list files (halOpenLOD), mapBackAdjacencies != 0, maxRefGap > 0, halGetGenomeMetadata.
+ * value with a message): LOD list files (halOpenLOD), maxRefGap > 0, halGetGenomeMetadata.
  */
 #ifndef HAL_BLOCK_VIZ_H
 #define HAL_BLOCK_VIZ_H

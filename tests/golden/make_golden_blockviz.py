@@ -39,6 +39,10 @@ def main():
         if len(o.sequences(o.genome_id(t0))) > 1:  # a later sequence: the reference passes the ABSOLUTE start to convertSequence
             nm2, _, ln2 = o.sequences(o.genome_id(t0))[1]
             fixed.append(["maf", t0, nm2, "10", str(min(ln2, 200)), "0", "1000", "1", o.genomes[0]])
+        if hal == "varlen8.hal":  # whole chromosomes with target duplications (hal_target_dupe_list_t), +- adjacencies
+            fixed.append(["blocks", "L1", "L2", "L2_s1", "0", "0", "0", "0", "2", "0", "-"])
+            fixed.append(["blocks", "L1", "L0", "L0_s2", "0", "0", "0", "0", "2", "1", "-"])
+            fixed.append(["blocks", "L1", "L3", "L3_s3", "200", "3000", "0", "0", "2", "1", "-"])
         queries = fixed
         for _ in range(n):
             q, t = rng.choice(o.genomes), rng.choice(o.genomes)
@@ -51,7 +55,8 @@ def main():
             if rng.random() < 0.3:
                 common = [x for x in ancestors(o, q) if x in ancestors(o, t)]
                 lim = rng.choice(common)
-            args = ["blocks", q, t, nm, str(a), str(a + L), str(rev), str(rng.choice([0, 0, 2])), str(dup), "0", lim]
+            adj = "1" if (rev == 0 and rng.random() < 0.4) else "0"
+            args = ["blocks", q, t, nm, str(a), str(a + L), str(rev), str(rng.choice([0, 0, 2])), str(dup), adj, lim]
             if rng.random() < 0.15:
                 args.append(rng.choice(o.sequences(o.genome_id(q)))[0])
             queries.append(args)

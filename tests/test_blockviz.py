@@ -26,6 +26,7 @@ def check_cases(cli, step=1):
         assert r.stdout == c["out"], c["args"]
         kinds.add(c["args"][0])
     assert kinds >= {"species", "chroms", "dna", "limits", "maxlod", "blocks", "maf"}
+    assert any("\nD\t" in c["out"] for c in CASES) and any(c["args"][0] == "blocks" and c["args"][9] == "1" for c in CASES)
 
 
 def test_blockviz_emulated_matches_reference_answers(emul_blockviz_cli):
@@ -38,13 +39,15 @@ def test_blockviz_emulated_vs_reference_live(emul_blockviz_cli):
     hal = os.path.join(GOLDEN, "varlen8.hal")
     o = pyoracle.Oracle(hal)
     rng = random.Random(2)
-    for _ in range(40):
+    for _ in range(25):
         q, t = rng.choice(o.genomes), rng.choice(o.genomes)
         nm, _, ln = rng.choice(o.sequences(o.genome_id(t)))
         L = rng.randint(1, min(ln, 1500))
         a = rng.randint(0, ln - L)
         dup = rng.choice([0, 1, 2])
-        args = ["blocks", q, t, nm, str(a), str(a + L), "1" if (dup < 2 and rng.random() < 0.3) else "0", str(rng.choice([0, 2])), str(dup), "0", "-"]
+        rev = "1" if (dup < 2 and rng.random() < 0.3) else "0"
+        adj = "1" if (rev == "0" and rng.random() < 0.5) else "0"
+        args = ["blocks", q, t, nm, str(a), str(a + L), rev, str(rng.choice([0, 2])), str(dup), adj, "-"]
         r = subprocess.run([ref_bin("blockVizCli"), hal] + args, capture_output=True, text=True)
         m = subprocess.run([emul_blockviz_cli, hal] + args, capture_output=True, text=True)
         if r.returncode < 0:
@@ -54,8 +57,6 @@ def test_blockviz_emulated_vs_reference_live(emul_blockviz_cli):
 
 def test_blockviz_unsupported_calls_fail_with_a_message(emul_blockviz_cli):
     hal = os.path.join(GOLDEN, "varlen8.hal")
-    r = subprocess.run([emul_blockviz_cli, hal, "blocks", "L0", "L3", "L3_s1", "0", "100", "0", "0", "2", "1", "-"], capture_output=True, text=True)
-    assert r.returncode == 1 and "mapBackAdjacencies is not implemented" in r.stdout
     r = subprocess.run([emul_blockviz_cli, hal, "maf", "L3", "L3_s0", "0", "100", "3", "1000", "1", "L0"], capture_output=True, text=True)
     assert r.returncode == 1 and "maxRefGap > 0" in r.stdout
 

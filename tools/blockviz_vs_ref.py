@@ -43,7 +43,8 @@ def main():
             aq, at = ancestors(o, q), ancestors(o, t)
             common = [x for x in aq if x in at]
             lim = rng.choice(common)
-        args = ["blocks", q, t, nm, str(a), str(b), str(rev), str(seq), str(dup), "0", lim]
+        adj = "1" if (rev == 0 and rng.random() < 0.5) else "0"
+        args = ["blocks", q, t, nm, str(a), str(b), str(rev), str(seq), str(dup), adj, lim]
         if rng.random() < 0.15:
             args.append(rng.choice(o.sequences(o.genome_id(q)))[0])
         r = subprocess.run([ref, hal] + args, capture_output=True, text=True)

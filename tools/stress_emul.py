@@ -134,7 +134,8 @@ def main():
                 L = rng.randint(1, min(ln, rng.choice([40, 600, 20000])))
                 st0 = rng.randint(0, ln - L)
                 dup = rng.choice([0, 1, 2])
-                args = ["blocks", q, t, nm, str(st0), str(st0 + L), "1" if (dup < 2 and rng.random() < 0.25) else "0", str(rng.choice([0, 2])), str(dup), "0", "-"]
+                rev = "1" if (dup < 2 and rng.random() < 0.25) else "0"
+                args = ["blocks", q, t, nm, str(st0), str(st0 + L), rev, str(rng.choice([0, 2])), str(dup), "1" if (rev == "0" and rng.random() < 0.5) else "0", "-"]
                 if rng.random() < 0.25:
                     args = ["maf", t, nm, str(st0), str(st0 + L), "0", str(rng.choice([1000, 7])), str(rng.choice([0, 1])), ",".join(rng.sample(names, min(2, len(names))))]
                 ra = subprocess.run([REF_VIZ, hal] + args, capture_output=True, text=True)
