@@ -27,11 +27,19 @@
 namespace {
 
 std::mutex gLock; // the reference serialises every call on one mutex too (halBlockViz.cpp:29-38)
-struct Handle {
-    halgpu_ctx *ctx;
+// LodManager (lod/impl/halLodManager.cpp): the alignments of one handle by minimum query length; a plain HAL file is the
+// single entry 0.  Contexts (one staged copy on the GPU each) are opened on first use.
+struct LodEntry {
     std::string path;
+    halgpu_ctx *ctx = nullptr;
+};
+struct Handle {
+    std::string path;
+    std::map<uint64_t, LodEntry> lod;
+    uint64_t maxLodLowerBound = (uint64_t)std::numeric_limits<int64_t>::max();
 };
 std::map<int, Handle> gHandles;
+const char *const kMaxLodToken = "max";
 
 void handleError(const std::string &msg, char **errStr) {
     if (errStr == nullptr) {
@@ -46,10 +54,118 @@ char *copyCString(const std::string &s) {
     memcpy(o, s.c_str(), s.size() + 1);
     return o;
 }
-halgpu_ctx *ctxOf(int handle) { // checkHandle
+Handle &handleOf(int handle) { // checkHandle
     auto it = gHandles.find(handle);
     if (it == gHandles.end()) throw std::runtime_error("Handle " + std::to_string(handle) + "not found in alignment map");
+    return it->second;
+}
+// LodManager::getAlignment (halLodManager.cpp:112-133): the entry with the largest minimum length <= queryLength, or level 0
+// when DNA is needed
+halgpu_ctx *alignmentFor(int handle, uint64_t queryLength, bool needDNA) {
+    Handle &h = handleOf(handle);
+    auto it = h.lod.begin();
+    if (!needDNA) {
+        it = h.lod.upper_bound(queryLength);
+        --it;
+    }
+    if (it->first == h.maxLodLowerBound) {
+        throw std::runtime_error("Query length " + std::to_string(queryLength) + " above maximum LOD size of " + std::to_string(h.maxLodLowerBound - 1));
+    }
+    if (it->second.ctx == nullptr) {
+        char *err = nullptr;
+        int device = 0;
+        if (const char *d = getenv("HALGPU_DEVICE")) device = atoi(d);
+        if (halgpu_open(it->second.path.c_str(), device, &it->second.ctx, &err) != 0) {
+            std::string m = err ? err : "cannot open";
+            halgpu_free_string(err);
+            throw std::runtime_error(m);
+        }
+        if (halgpu_num_genomes(it->second.ctx) == 0) throw std::runtime_error("No genomes found in base alignment specified in " + it->second.path);
+    }
     return it->second.ctx;
+}
+bool isLod0(int handle, uint64_t queryLength) { // LodManager::isLod0
+    Handle &h = handleOf(handle);
+    auto it = h.lod.upper_bound(queryLength);
+    --it;
+    return it == h.lod.begin();
+}
+halgpu_ctx *ctxOf(int handle) { return alignmentFor(handle, std::numeric_limits<uint64_t>::max(), false); } // "the lowest level of detail"
+bool isHalFile(const char *path) { // detectHalAlignmentFormat: the HAL-MMAP header string
+    FILE *f = fopen(path, "rb");
+    if (f == nullptr) return false;
+    char hdr[9] = {0};
+    const size_t n = fread(hdr, 1, 8, f);
+    fclose(f);
+    return n == 8 && memcmp(hdr, "HAL-MMAP", 8) == 0;
+}
+// LodManager::loadLODFile (halLodManager.cpp:44-104): lines "<minQueryLength> <path|max>"
+void loadLodFile(Handle &h, const std::string &lodPath) {
+    FILE *f = fopen(lodPath.c_str(), "r");
+    if (f == nullptr) throw std::runtime_error("Error opening " + lodPath);
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    fclose(f);
+    size_t lineNum = 1, at = 0;
+    bool foundMax = false;
+    while (at <= text.size()) {
+        size_t nl = text.find('\n', at);
+        if (nl == std::string::npos) nl = text.size();
+        const std::string line = text.substr(at, nl - at);
+        at = nl + 1;
+        if (line.empty()) continue;
+        std::istringstream ss(line);
+        uint64_t minLen = 0;
+        std::string path;
+        ss >> minLen >> path;
+        if (foundMax) {
+            throw std::runtime_error("Error on line " + std::to_string(lineNum) + " of " + lodPath + ": Limit token (" + kMaxLodToken + ") can only appear on final line.");
+        }
+        LodEntry e;
+        if (path == kMaxLodToken) {
+            foundMax = true;
+            h.maxLodLowerBound = minLen;
+            e.path = kMaxLodToken;
+        } else if (!path.empty() && (path[0] == '/' || path.find(":/") != std::string::npos)) { // LodManager::resolvePath
+            e.path = path;
+        } else {
+            const size_t sl = lodPath.find_last_of('/');
+            e.path = sl == std::string::npos ? path : lodPath.substr(0, sl + 1) + path;
+        }
+        h.lod.insert(std::make_pair(minLen, e));
+        ++lineNum;
+    }
+}
+void checkLodMap(const Handle &h, const std::string &path) { // LodManager::checkMap
+    if (h.lod.empty()) throw std::runtime_error("No entries were found in " + path);
+    if (h.lod.begin()->first != 0) {
+        throw std::runtime_error("No alignment with range value 0 found in " + path + ". A record of the form \"0 pathToOriginalHALFile\" must be present");
+    }
+    if (h.maxLodLowerBound == 0) throw std::runtime_error("Maximum LOD query length must be > 0");
+}
+int openLodOrHal(const char *inputPath, bool isLod, char **errStr) {
+    for (auto &kv : gHandles) if (kv.second.path == inputPath) return kv.first; // findOrAllocHandle: one handle per path
+    Handle h;
+    h.path = inputPath;
+    try {
+        if (isLod) {
+            loadLodFile(h, inputPath);
+        } else {
+            LodEntry e;
+            e.path = inputPath;
+            h.lod.insert(std::make_pair((uint64_t)0, e));
+        }
+        checkLodMap(h, inputPath);
+    } catch (std::exception &e) {
+        handleError("openLodOrHal error: " + std::string(inputPath) + ": " + e.what(), errStr);
+        return -1;
+    }
+    int id = 0;
+    while (gHandles.count(id)) ++id;
+    gHandles[id] = h;
+    return id;
 }
 
 // branch lengths of the newick string (Alignment::getBranchLength): name -> length of the branch to its parent
@@ -507,7 +623,7 @@ int findSeq(const halgpu_seq *seqs, size_t n, const char *name) {
     return -1;
 }
 
-hal_block_results_t *readBlocks(halgpu_ctx *ctx, int tGenome, int tSeqIdx, int64_t absStart, int64_t absEnd, bool tReversed, int qGenome,
+hal_block_results_t *readBlocks(halgpu_ctx *ctx, halgpu_ctx *seqCtx, int tGenome, int tSeqIdx, int64_t absStart, int64_t absEnd, bool tReversed, int qGenome,
                                 bool getSeq, bool doDupes, bool doTargetDupes, bool doAdjes, const char *limitName) {
     const halgpu_seq *tseq = nullptr, *qseq = nullptr;
     size_t nts = 0, nqs = 0;
@@ -645,9 +761,23 @@ hal_block_results_t *readBlocks(halgpu_ctx *ctx, int tGenome, int tSeqIdx, int64
         const int64_t tEnd = std::max(fq.sHi(), lq.sHi()) - tseq[tSeqIdx].start;
         cur->size = (hal_int_t)(1 + tEnd - cur->tStart);
         cur->strand = fq.qRev ? '-' : '+';
-        if (getSeq) {
-            std::string qd = dnaOf(ctx, qGenome, qseq[fq.qSeq].start + cur->qStart, cur->size);
-            const std::string td = dnaOf(ctx, tGenome, tseq[tSeqIdx].start + cur->tStart, cur->size);
+        if (getSeq) { // DNA comes from the level-0 alignment, looked up by genome and sequence NAME (halBlockViz.cpp:867-899)
+            auto locate = [&](const char *genomeName, const char *seqName, int &g, int64_t &start) {
+                g = halgpu_genome_id(seqCtx, genomeName);
+                if (g < 0) throw std::runtime_error("Unable to open genome " + std::string(genomeName) + " for DNA sequence extraction");
+                const halgpu_seq *ss = nullptr;
+                size_t nn = 0;
+                halgpu_sequence_table(seqCtx, g, &ss, &nn);
+                const int si = findSeq(ss, nn, seqName);
+                if (si < 0) throw std::runtime_error("Unable to open sequence " + std::string(seqName) + " for DNA sequence extraction");
+                start = ss[si].start;
+            };
+            int qg, tg;
+            int64_t qs0, ts0;
+            locate(qGenomeName.c_str(), qseq[fq.qSeq].name, qg, qs0);
+            locate(halgpu_genome_name(ctx, tGenome), tseq[tSeqIdx].name, tg, ts0);
+            std::string qd = dnaOf(seqCtx, qg, qs0 + cur->qStart, cur->size);
+            const std::string td = dnaOf(seqCtx, tg, ts0 + cur->tStart, cur->size);
             if (cur->strand == '-') reverseComplement(qd);
             cur->qSequence = copyCString(qd);
             cur->tSequence = copyCString(td);
@@ -667,27 +797,22 @@ extern "C" {
 
 int halOpen(char *halFilePath, char **errStr) {
     std::lock_guard<std::mutex> g(gLock);
-    for (auto &kv : gHandles) if (kv.second.path == halFilePath) return kv.first; // findOrAllocHandle: one handle per path
-    halgpu_ctx *ctx = nullptr;
-    char *err = nullptr;
-    int device = 0;
-    if (const char *d = getenv("HALGPU_DEVICE")) device = atoi(d);
-    if (halgpu_open(halFilePath, device, &ctx, &err) != 0) {
-        std::string m = "error opening path " + std::string(halFilePath) + ": " + (err ? err : "?");
-        halgpu_free_string(err);
-        handleError(m, errStr);
+    const int h = openLodOrHal(halFilePath, false, errStr);
+    if (h < 0) return h;
+    try { // the reference opens lazily too, but a missing / non-HAL file is better reported here
+        alignmentFor(h, 0, true);
+    } catch (std::exception &e) {
+        gHandles.erase(h);
+        handleError("openLodOrHal error: " + std::string(halFilePath) + ": " + e.what(), errStr);
         return -1;
     }
-    int h = 0;
-    while (gHandles.count(h)) ++h;
-    gHandles[h] = Handle{ctx, halFilePath};
     return h;
 }
-int halOpenLOD(char *lodFilePath, char **errStr) {
-    handleError("halOpenLOD: level-of-detail list files are not supported by the GPU build (open the HAL file itself): " + std::string(lodFilePath), errStr);
-    return -1;
+int halOpenHalOrLod(char *lodFilePath, char **errStr) {
+    std::lock_guard<std::mutex> g(gLock);
+    return openLodOrHal(lodFilePath, !isHalFile(lodFilePath), errStr);
 }
-int halOpenHalOrLod(char *path, char **errStr) { return halOpen(path, errStr); }
+int halOpenLOD(char *lodFilePath, char **errStr) { return halOpenHalOrLod(lodFilePath, errStr); } // deprecated spelling
 
 int halClose(int handle, char **errStr) {
     std::lock_guard<std::mutex> g(gLock);
@@ -696,7 +821,7 @@ int halClose(int handle, char **errStr) {
         handleError("halClose error closing handle " + std::to_string(handle) + ": not found", errStr);
         return -1;
     }
-    halgpu_close(it->second.ctx);
+    for (auto &kv : it->second.lod) halgpu_close(kv.second.ctx);
     gHandles.erase(it);
     return 0;
 }
@@ -769,18 +894,27 @@ struct hal_block_results_t *halGetBlocksInTargetRange(int halHandle, char *qSpec
             handleError("tReversed cannot be set in conjunction with dupMode=HAL_QUERY_AND_TARGET_DUPS", errStr);
             return nullptr;
         }
-        const bool getSeq = seqMode != HAL_NO_SEQUENCE; // a single HAL file is always level of detail 0
-        halgpu_ctx *ctx = ctxOf(halHandle);
-        // checkGenomes
-        const int q = halgpu_genome_id(ctx, qSpecies);
-        if (q < 0) throw std::runtime_error("Query species " + std::string(qSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
-        const int t = halgpu_genome_id(ctx, tSpecies);
-        if (t < 0) throw std::runtime_error("Reference species " + std::string(tSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
+        bool getSeq; // halBlockViz.cpp:268-279
+        switch (seqMode) {
+        case HAL_NO_SEQUENCE: getSeq = false; break;
+        case HAL_FORCE_LOD0_SEQUENCE: getSeq = true; break;
+        case HAL_LOD0_SEQUENCE:
+        default: getSeq = isLod0(halHandle, (uint64_t)rangeLength);
+        }
+        halgpu_ctx *ctx = alignmentFor(halHandle, (uint64_t)rangeLength, getSeq);
+        int q = -1, t = -1, ts = -1;
         const halgpu_seq *tseq = nullptr;
         size_t nts = 0;
-        halgpu_sequence_table(ctx, t, &tseq, &nts);
-        const int ts = findSeq(tseq, nts, tChrom);
-        if (ts < 0) throw std::runtime_error("Unable to locate sequence " + std::string(tChrom) + " in genome " + tSpecies);
+        auto checkGenomes = [&](halgpu_ctx *c, const std::string &chrom) {
+            q = halgpu_genome_id(c, qSpecies);
+            if (q < 0) throw std::runtime_error("Query species " + std::string(qSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
+            t = halgpu_genome_id(c, tSpecies);
+            if (t < 0) throw std::runtime_error("Reference species " + std::string(tSpecies) + " not found in alignment with handle " + std::to_string(halHandle));
+            halgpu_sequence_table(c, t, &tseq, &nts);
+            ts = findSeq(tseq, nts, chrom.c_str());
+            if (ts < 0) throw std::runtime_error("Unable to locate sequence " + chrom + " in genome " + tSpecies);
+        };
+        checkGenomes(ctx, tChrom);
         const int64_t myEnd = tEnd > 0 ? tEnd : tseq[ts].length;
         const int64_t absStart = tseq[ts].start + tStart, absEnd = tseq[ts].start + myEnd - 1;
         if (absStart > absEnd) {
@@ -793,7 +927,12 @@ struct hal_block_results_t *halGetBlocksInTargetRange(int halHandle, char *qSpec
             handleError("halGetBlocksInTargetRange target end position outside of target sequence", errStr);
             return nullptr;
         }
-        return readBlocks(ctx, t, ts, absStart, absEnd, tReversed != 0, q, getSeq, dupMode != HAL_NO_DUPS, dupMode == HAL_QUERY_AND_TARGET_DUPS,
+        if (tEnd == 0) { // the query length is known now: a proper level-of-detail choice (:299-306)
+            ctx = alignmentFor(halHandle, (uint64_t)(absEnd - absStart), false);
+            checkGenomes(ctx, tChrom);
+        }
+        halgpu_ctx *seqCtx = getSeq ? alignmentFor(halHandle, (uint64_t)(absEnd - absStart), true) : nullptr;
+        return readBlocks(ctx, seqCtx, t, ts, absStart, absEnd, tReversed != 0, q, getSeq, dupMode != HAL_NO_DUPS, dupMode == HAL_QUERY_AND_TARGET_DUPS,
                           mapBackAdjacencies != 0, coalescenceLimitName);
     } catch (std::exception &e) {
         handleError("halGetBlocksInTargetRange error reading blocks: " + std::string(e.what()), errStr);
@@ -847,7 +986,7 @@ hal_int_t halGetMaf(FILE *outFile, int halHandle, struct hal_species_t *qSpecies
             handleError("halGetMaf: maxRefGap > 0 (gapped column iterators) is not implemented in the GPU build", errStr);
             return -1;
         }
-        halgpu_ctx *ctx = ctxOf(halHandle);
+        halgpu_ctx *ctx = alignmentFor(halHandle, 0, true);
         const int t = halgpu_genome_id(ctx, tSpecies);
         std::set<int> qSet;
         const halgpu_seq *tseq = nullptr;
@@ -971,7 +1110,7 @@ struct hal_chromosome_t *halGetChroms(int halHandle, char *speciesName, char **e
 char *halGetDna(int halHandle, char *speciesName, char *chromName, hal_int_t start, hal_int_t end, char **errStr) {
     std::lock_guard<std::mutex> g(gLock);
     try {
-        halgpu_ctx *ctx = ctxOf(halHandle);
+        halgpu_ctx *ctx = alignmentFor(halHandle, 0, true);
         const int gi = halgpu_genome_id(ctx, speciesName);
         if (gi < 0) {
             handleError("halGetChroms: species with name " + std::string(speciesName) + " not found in alignment with handle " + std::to_string(halHandle), errStr);
@@ -1003,7 +1142,7 @@ hal_int_t halGetMaxLODQueryLength(int halHandle, char **errStr) {
         handleError("halGetMaxLODQueryLength error getting Max LOD Query Length.  handle " + std::to_string(halHandle) + ": not found", errStr);
         return -1;
     }
-    return (hal_int_t)(std::numeric_limits<int64_t>::max() - 1); // LodManager::getMaxQueryLength() of a single HAL file
+    return (hal_int_t)(gHandles[halHandle].maxLodLowerBound - 1); // LodManager::getMaxQueryLength()
 }
 
 struct hal_metadata_t *halGetGenomeMetadata(int, const char *, char **errStr) {

@@ -19,7 +19,7 @@
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: see source\n"); return 2; }
     char *err = NULL;
-    int h = halOpen(argv[1], &err);
+    int h = halOpenHalOrLod(argv[1], &err); // a HAL file or a level-of-detail list
     if (h < 0) { printf("ERROR %s\n", err ? err : "?"); return 1; }
     const std::string cmd = argv[2];
     int rc = 0;

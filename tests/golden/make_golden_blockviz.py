@@ -65,6 +65,25 @@ def main():
             if r.returncode < 0:
                 continue
             cases.append(dict(hal=hal, args=args, rc=r.returncode, out=r.stdout))
+    # level-of-detail list (tests/golden/varlen8.lod.txt: 0 varlen8.hal / 500 varlen8_lod1.hal / 20000 max; varlen8_lod1.hal =
+    # halTreeGen --mode varlen, same tree and names, --segs 400 --minLen 20 --maxLen 120 --seqs 4 --seed 12 --pDup 0.1 --pInv 0.2):
+    # which file answers depends on the query length, DNA always comes from level 0, lengths >= 20000 are refused
+    a, b = Oracle(os.path.join(HERE, "varlen8.hal")), Oracle(os.path.join(HERE, "varlen8_lod1.hal"))
+    lod = "varlen8.lod.txt"
+    lodq = [["species"], ["maxlod"], ["dna", "L3", "L3_s0", "0", "50"], ["chroms", "L2"]]
+    for _ in range(24):
+        q, t = rng.choice(a.genomes), rng.choice(a.genomes)
+        si = rng.randrange(4)
+        nm, _, la = a.sequences(a.genome_id(t))[si]
+        lb = b.sequences(b.genome_id(t))[si][2]
+        ln = min(la, lb)
+        L = rng.randint(1, min(ln, rng.choice([100, 499, 500, 501, 3000, 19999, 20000, 25000])))
+        st = rng.randint(0, ln - L)
+        lodq.append(["blocks", q, t, nm, str(st), str(st + L), "0", str(rng.choice([0, 1, 2])), str(rng.choice([0, 1, 2])), rng.choice(["0", "1"]), "-"])
+    for args in lodq:
+        r = subprocess.run([REF, os.path.join(HERE, lod)] + args, capture_output=True, text=True)
+        if r.returncode >= 0:
+            cases.append(dict(hal=lod, args=args, rc=r.returncode, out=r.stdout))
     os.makedirs(os.path.join(HERE, "blockviz"), exist_ok=True)
     json.dump(cases, open(os.path.join(HERE, "blockviz", "cases.json"), "w"), indent=0)
     print(len(cases), "cases,", sum(1 for c in cases if "\nD\t" in c["out"]), "with target dupes,", sum(1 for c in cases if c["rc"] != 0), "errors")
