@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
     "halgpu_free_string", "halgpu_launch_count", "halgpu_columns_depth", "halgpu_columns_depth_device",
     "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna", "halgpu_host_alloc", "halgpu_host_free",
-    "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_column_runs_in_sweep", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
+    "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_column_runs_in_sweep", "halgpu_genome_metadata", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
 ]
 
 

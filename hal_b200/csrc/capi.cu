@@ -303,6 +303,15 @@ const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int g) {
     return i ? i->dna : nullptr;
 }
 
+int halgpu_genome_metadata(const halgpu_ctx *ctx, int g, size_t index, const char **key, const char **value) {
+    const GenomeInfo *i = genome(ctx, g);
+    if (i == nullptr || key == nullptr || value == nullptr || index >= i->metadata.size()) return 1;
+    auto it = i->metadata.begin();
+    std::advance(it, (long)index);
+    *key = it->first.c_str();
+    *value = it->second.c_str();
+    return 0;
+}
 const void *halgpu_genome_top_segments(const halgpu_ctx *ctx, int g) {
     const GenomeInfo *i = genome(ctx, g);
     return i ? i->top : nullptr;

@@ -134,6 +134,22 @@ HalFile::HalFile(const std::string &path) : _path(path) {
             throw HalError("Problem: genome has length " + std::to_string(gi.length) + ", however sequences total " +
                            std::to_string(expectStart));
         }
+        // metadata: MMapMetaDataData {keysOffset, valuesOffset} -> two MMapArray<size_t> of offsets to MMapStrings
+        // (api/mmap_impl/mmapMetaData.h:10-16,66-76)
+        const uint64_t metaOff = u64(b + 64);
+        if (metaOff != 0) {
+            const uint64_t keysOff = u64(metaOff), valsOff = u64(metaOff + 8);
+            const uint64_t nk = u64(keysOff + 16), nv = u64(valsOff + 16);
+            if (nk != nv) throw HalError("# keys != # values in metadata");
+            auto str = [&](uint64_t off) {
+                const uint64_t len = u64(off + 16);
+                const char *p = reinterpret_cast<const char *>(at(off + ARRAY_HEADER_BYTES, len, "metadata string"));
+                return std::string(p, strnlen(p, len));
+            };
+            for (uint64_t i = 0; i < nk; ++i) {
+                gi.metadata.insert(std::make_pair(str(u64(keysOff + ARRAY_HEADER_BYTES + 8 * i)), str(u64(valsOff + ARRAY_HEADER_BYTES + 8 * i))));
+            }
+        }
     }
     // tree
     size_t pos = 0;

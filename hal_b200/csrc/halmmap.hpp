@@ -41,6 +41,7 @@ struct GenomeInfo {
     const uint8_t *dna = nullptr;    // (length+1)/2 bytes, even index = high nibble
     std::vector<SequenceInfo> sequences;
     std::map<std::string, int> sequenceByName;
+    std::map<std::string, std::string> metadata; // Genome::getMetaData()->getMap() (api/mmap_impl/mmapMetaData.h)
 };
 
 class HalFile {

@@ -1145,9 +1145,26 @@ hal_int_t halGetMaxLODQueryLength(int halHandle, char **errStr) {
     return (hal_int_t)(gHandles[halHandle].maxLodLowerBound - 1); // LodManager::getMaxQueryLength()
 }
 
-struct hal_metadata_t *halGetGenomeMetadata(int, const char *, char **errStr) {
-    handleError("halGetGenomeMetadata is not implemented in the GPU build", errStr);
-    return nullptr;
+struct hal_metadata_t *halGetGenomeMetadata(int halHandle, const char *genomeName, char **errStr) {
+    std::lock_guard<std::mutex> g(gLock);
+    try { // halBlockViz.cpp:1177-1213
+        halgpu_ctx *ctx = ctxOf(halHandle);
+        const int gi = halgpu_genome_id(ctx, genomeName);
+        if (gi < 0) throw std::runtime_error("Genome " + std::string(genomeName) + " not found in alignment");
+        hal_metadata_t *head = nullptr, *prev = nullptr;
+        const char *k = nullptr, *v = nullptr;
+        for (size_t i = 0; halgpu_genome_metadata(ctx, gi, i, &k, &v) == 0; ++i) {
+            hal_metadata_t *cur = static_cast<hal_metadata_t *>(calloc(1, sizeof(hal_metadata_t)));
+            cur->key = copyCString(k);
+            cur->value = copyCString(v);
+            if (prev != nullptr) prev->next = cur; else head = cur;
+            prev = cur;
+        }
+        return head;
+    } catch (std::exception &e) {
+        handleError("halGetGenomeMetadata: " + std::string(e.what()), errStr);
+        return nullptr;
+    }
 }
 
 } // extern "C"

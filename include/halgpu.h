@@ -196,6 +196,9 @@ const uint8_t *halgpu_genome_dna(const halgpu_ctx *ctx, int genome);
  * start is the genome length): top records are 40 B (api/mmap_impl/mmapTopSegmentData.h:40-44), bottom records
  * *stride B (mmapBottomSegmentData.h:35-52); the first int64 of every record is its start position.  Replaces
  * Genome::getTopSegmentIterator / getBottomSegmentIterator for host code that only needs segment boundaries. */
+/* metadata of a genome (replaces Genome::getMetaData()->getMap(), api/inc/halMetaData.h): entry `index` in key order;
+ * returns 0 and sets *key / *value (owned by the context) while index < the number of entries, else 1 */
+int halgpu_genome_metadata(const halgpu_ctx *ctx, int genome, size_t index, const char **key, const char **value);
 const void *halgpu_genome_top_segments(const halgpu_ctx *ctx, int genome);
 const void *halgpu_genome_bottom_segments(const halgpu_ctx *ctx, int genome, size_t *stride);
 

@@ -9,7 +9,7 @@
  * Implemented on the GPU path: halGetBlocksInTargetRange[_filterByChrom] (all three duplication modes, sequence modes,
  * coalescence limit, reversed target range, mapBackAdjacencies) and halGetMaf / halGetMAF with maxRefGap == 0.  Host-only queries: halOpen (a HAL-MMAP file), halClose, halCloseGenome, halGetSpecies,
  * halGetPossibleCoalescenceLimits, halGetChroms, halGetDna, halGetMaxLODQueryLength.  Not implemented (return the failure
- * value with a message): maxRefGap > 0, halGetGenomeMetadata.
+ * value with a message): maxRefGap > 0 (gapped column iterators).
  */
 #ifndef HAL_BLOCK_VIZ_H
 #define HAL_BLOCK_VIZ_H

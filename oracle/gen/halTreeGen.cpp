@@ -298,6 +298,7 @@ int main(int argc, char **argv) {
     Opts o;
     o.mode = "varlen"; o.newick = "((L0,L1)A0,(L2)A1)R;"; o.seed = 1; o.segs = 200; o.minLen = 5; o.maxLen = 40;
     o.seqs = 1; o.branch = -1; o.pInv = 0.2; o.pDup = 0.1; o.pIns = 0.05; o.pDel = 0.05; o.pMut = 0.1; o.fileGB = 1;
+    vector<string> meta;
     for (int i = 1; i < argc; i++) {
         string a = argv[i];
         if (a.compare(0, 2, "--") == 0 && i + 1 < argc) {
@@ -309,6 +310,7 @@ int main(int argc, char **argv) {
             else if (a == "--pDup") o.pDup = atof(v.c_str()); else if (a == "--pIns") o.pIns = atof(v.c_str());
             else if (a == "--pDel") o.pDel = atof(v.c_str()); else if (a == "--pMut") o.pMut = atof(v.c_str());
             else if (a == "--fileGB") o.fileGB = atol(v.c_str());
+            else if (a == "--meta") meta.push_back(v); /* genome:key=value, written through Genome::getMetaData()->set */
             else { cerr << "unknown option " << a << endl; return 1; }
         } else {
             o.out = a;
@@ -322,6 +324,12 @@ int main(int argc, char **argv) {
         addTree(aln, root, NULL, o);
         if (o.mode == "randgen") buildRandgen(aln, o);
         else buildVarlen(aln, root, o);
+        for (size_t i = 0; i < meta.size(); i++) {
+            const size_t c = meta[i].find(':'), e = meta[i].find('=');
+            Genome *g = aln->openGenome(meta[i].substr(0, c));
+            if (g == NULL || c == string::npos || e == string::npos) throw hal_exception("bad --meta " + meta[i]);
+            g->getMetaData()->set(meta[i].substr(c + 1, e - c - 1), meta[i].substr(e + 1));
+        }
         aln->close();
     } catch (exception &e) {
         cerr << "halTreeGen: " << e.what() << endl;

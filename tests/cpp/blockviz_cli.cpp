@@ -3,7 +3,7 @@
 // API (hal_b200/libhalBlockVizGpu.so) can be compared byte for byte.  It only uses the public C API; it is compiled
 // against the reference's halBlockViz.h (oracle build) or include/halgpu_blockviz.h (-DHALGPU_BLOCKVIZ_HEADER).
 //
-// usage: blockVizCli <hal> species | chroms <genome> | dna <genome> <chrom> <start> <end> | limits <q> <t> | maxlod
+// usage: blockVizCli <hal> species | meta <genome> | chroms <genome> | dna <genome> <chrom> <start> <end> | limits <q> <t> | maxlod
 //        blockVizCli <hal> maf <tSpecies> <tChrom> <tStart> <tEnd> <maxRefGap> <maxBlockLength> <doDupes> <q1,q2,...>   (MAF to stdout)
 //        blockVizCli <hal> blocks <qSpecies> <tSpecies> <tChrom> <tStart> <tEnd> <tReversed> <seqMode> <dupMode> <adj> <limit|-> [qChromFilter]
 #ifdef HALGPU_BLOCKVIZ_HEADER
@@ -28,6 +28,11 @@ int main(int argc, char **argv) {
         if (!s) { printf("ERROR %s\n", err ? err : "?"); rc = 1; }
         for (hal_species_t *p = s; p; p = p->next) printf("%s\t%ld\t%ld\t%s\t%g\n", p->name, p->length, p->numChroms, p->parentName, p->parentBranchLength);
         halFreeSpeciesList(s);
+    } else if (cmd == "meta") {
+        hal_metadata_t *m = halGetGenomeMetadata(h, argv[3], &err);
+        if (!m && err) { printf("ERROR %s\n", err); rc = 1; }
+        for (hal_metadata_t *p = m; p; p = p->next) printf("%s=%s\n", p->key, p->value);
+        halFreeMetadataList(m);
     } else if (cmd == "chroms") {
         hal_chromosome_t *c = halGetChroms(h, argv[3], &err);
         if (!c) { printf("ERROR %s\n", err ? err : "?"); rc = 1; }

@@ -66,10 +66,14 @@ def main():
                 continue
             cases.append(dict(hal=hal, args=args, rc=r.returncode, out=r.stdout))
     # level-of-detail list (tests/golden/varlen8.lod.txt: 0 varlen8.hal / 500 varlen8_lod1.hal / 20000 max; varlen8_lod1.hal =
-    # halTreeGen --mode varlen, same tree and names, --segs 400 --minLen 20 --maxLen 120 --seqs 4 --seed 12 --pDup 0.1 --pInv 0.2):
+    # halTreeGen --mode varlen, same tree and names, --segs 400 --minLen 20 --maxLen 120 --seqs 4 --seed 12 --pDup 0.1 --pInv 0.2
+    # --meta 'L3:assembly=lod1 test' --meta L3:zebra=1 --meta 'R:note=root genome'):
     # which file answers depends on the query length, DNA always comes from level 0, lengths >= 20000 are refused
     a, b = Oracle(os.path.join(HERE, "varlen8.hal")), Oracle(os.path.join(HERE, "varlen8_lod1.hal"))
     lod = "varlen8.lod.txt"
+    for args in (["meta", "L3"], ["meta", "R"], ["meta", "L0"], ["meta", "nope"]):  # --meta of halTreeGen: L3:assembly, L3:zebra, R:note
+        r = subprocess.run([REF, os.path.join(HERE, "varlen8_lod1.hal")] + args, capture_output=True, text=True)
+        cases.append(dict(hal="varlen8_lod1.hal", args=args, rc=r.returncode, out=r.stdout))
     lodq = [["species"], ["maxlod"], ["dna", "L3", "L3_s0", "0", "50"], ["chroms", "L2"]]
     for _ in range(24):
         q, t = rng.choice(a.genomes), rng.choice(a.genomes)

@@ -25,7 +25,7 @@ def check_cases(cli, step=1):
         assert r.returncode == c["rc"], (c["args"], r.stdout, r.stderr)
         assert r.stdout == c["out"], c["args"]
         kinds.add(c["args"][0])
-    assert kinds >= {"species", "chroms", "dna", "limits", "maxlod", "blocks", "maf"}
+    assert kinds >= {"species", "chroms", "dna", "limits", "maxlod", "blocks", "maf", "meta"}
     assert any(c["hal"].endswith(".lod.txt") and c["args"][0] == "blocks" for c in CASES)  # level-of-detail list files
     assert any("\nD\t" in c["out"] for c in CASES) and any(c["args"][0] == "blocks" and c["args"][9] == "1" for c in CASES)
 
