@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
     wig = os.path.join(BIN, "halWiggleLiftover")
     wig_srcs = [os.path.join(host, f) for f in ("halWiggleLiftoverMain.cpp", "wiggle_liftover.cpp")]
     if force or _newer(wig, wig_srcs + [os.path.join(host, "wiggle_liftover.hpp"), LIB]):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", wig] + wig_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", wig] + wig_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     syn = os.path.join(BIN, "halSynteny")
     syn_srcs = [os.path.join(host, f) for f in ("halSyntenyMain.cpp", "synteny.cpp")]
     if force or _newer(syn, syn_srcs + [os.path.join(host, "synteny.hpp"), LIB]):

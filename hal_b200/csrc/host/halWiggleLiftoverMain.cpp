@@ -93,7 +93,8 @@ int main(int argc, char **argv) {
         if (getenv("HALGPU_TIMING")) {
             cerr << "[halWiggleLiftover] lines in " << lift.linesIn << ", source bases " << lift.basesIn << " in " << lift.runs << " runs, target bases out "
                  << lift.basesOut << "; parse " << lift.parseSeconds << " s, halgpu_wiggle_liftover " << lift.gpuSeconds << " s (mapping kernel "
-                 << lift.kernelMs << " ms), write " << lift.writeSeconds << " s" << endl;
+                 << lift.kernelMs << " ms), write " << lift.writeSeconds << " s; " << (lift.fastParsed ? "multi-threaded" : "serial") << " scanner, "
+                 << lift.textThreads << " text threads" << endl;
         }
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;

@@ -2,11 +2,13 @@
 #include <algorithm>
 #include <charconv>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <istream>
 #include <map>
 #include <ostream>
 #include <stdexcept>
+#include <thread>
 
 namespace halgpu {
 
@@ -155,6 +157,144 @@ template <class V> size_t scanWiggle(const char *text, size_t n, WigScanner &sc,
     return lineNumber;
 }
 
+
+// Multi-threaded pre-parse of the data lines (SURVEY.md 8(f) rank 1 applied to wiggle text).  The lines are cut into chunks,
+// every thread classifies its lines -- header candidate / "value" / "position value" -- and converts the numbers in a strict
+// dialect (whole tokens, nothing else on the line); headers are then parsed by the very same WigScanner::scanHeader and the
+// visitors are called in input order with the state scanLine would have produced.  Anything the strict pre-parse does not
+// recognise (or a line form that does not fit its section) makes it return false BEFORE any visitor ran, and the caller
+// falls back to scanWiggle(), which owns the reference's tolerant parsing and its messages.
+struct FastWigChunk {
+    std::vector<uint8_t> kind;    // per non-blank line: 0 header candidate, 1 "value", 2 "position value"
+    std::vector<double> value;    // per line of kind 1 / 2 (kind 0: unused slot)
+    std::vector<int64_t> pos;     // per line of kind 2
+    std::vector<std::pair<const char *, const char *>> header; // text of the kind-0 lines
+    bool bad = false;
+};
+
+inline bool strictDouble(const char *b, const char *e, double &v) { // the whole token, in the grammar `ss >> double` gathers
+    const char *q = b;
+    return b < e && !isSpace(*b) && extractDouble(q, e, v) && q == e;
+}
+inline bool strictInt64(const char *b, const char *e, int64_t &v) {
+    const char *q = b;
+    return b < e && !isSpace(*b) && extractInt(q, e, v) && q == e;
+}
+
+template <class V> bool fastScanWiggle(const char *text, size_t n, unsigned nThreads, WigScanner &sc, size_t &linesOut, V &&visit) {
+    size_t grain = (size_t)1 << 20;
+    if (const char *gs = std::getenv("HALGPU_WIG_GRAIN")) grain = (size_t)std::max(1L, std::atol(gs)); // test hook
+    nThreads = std::max(1u, std::min<unsigned>(nThreads, (unsigned)(n / grain) + 1));
+    std::vector<size_t> cut(nThreads + 1, n);
+    cut[0] = 0;
+    for (unsigned t = 1; t < nThreads; ++t) {
+        const size_t c = std::max(cut[t - 1], n * t / nThreads);
+        const char *nl = c < n ? static_cast<const char *>(std::memchr(text + c, '\n', n - c)) : nullptr;
+        cut[t] = nl ? (size_t)(nl - text) + 1 : n;
+    }
+    std::vector<FastWigChunk> chunks(nThreads);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nThreads; ++t) {
+        th.emplace_back([&, t] {
+            FastWigChunk &C = chunks[t];
+            const char *p = text + cut[t], *const e = text + cut[t + 1];
+            const size_t guess = (size_t)(e - p) / 6 + 16;
+            C.kind.reserve(guess);
+            C.value.reserve(guess);
+            while (true) {
+                while (p < e && isSpace(*p)) ++p;
+                if (p >= e) break;
+                const char *nl = static_cast<const char *>(std::memchr(p, '\n', (size_t)(e - p)));
+                const char *le = nl ? nl : e;
+                if (*p == 'f' || *p == 'v') {
+                    C.kind.push_back(0);
+                    C.value.push_back(0);
+                    C.header.emplace_back(p, le);
+                } else {
+                    const char *t1 = p;
+                    while (t1 < le && !isSpace(*t1)) ++t1;
+                    const char *q = t1;
+                    while (q < le && isSpace(*q)) ++q;
+                    double v = 0;
+                    if (q == le) { // one token
+                        if (!strictDouble(p, t1, v)) { C.bad = true; return; }
+                        C.kind.push_back(1);
+                        C.value.push_back(v);
+                    } else { // two tokens, then only blanks
+                        const char *t2 = q;
+                        while (t2 < le && !isSpace(*t2)) ++t2;
+                        const char *r = t2;
+                        while (r < le && isSpace(*r)) ++r;
+                        int64_t pos = 0;
+                        if (r != le || !strictInt64(p, t1, pos) || !strictDouble(q, t2, v)) { C.bad = true; return; }
+                        C.kind.push_back(2);
+                        C.value.push_back(v);
+                        C.pos.push_back(pos);
+                    }
+                }
+                if (!nl) break;
+                p = nl + 1;
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    for (const FastWigChunk &C : chunks) if (C.bad) return false;
+    // dry run over the headers and the line forms: every section must consist of lines of the form its header announces
+    {
+        WigScanner probe = sc;
+        bool have = probe.haveHeader;
+        try {
+            for (const FastWigChunk &C : chunks) {
+                size_t h = 0;
+                for (size_t i = 0; i < C.kind.size(); ++i) {
+                    if (C.kind[i] == 0) {
+                        if (!probe.scanHeader(C.header[h].first, C.header[h].second)) return false;
+                        ++h;
+                        have = true;
+                    } else if (!have || C.kind[i] != (probe.fixedStep ? 1 : 2)) {
+                        return false;
+                    }
+                }
+            }
+        } catch (std::exception &) {
+            return false; // a malformed header: the serial scanner reports it with the right line number
+        }
+    }
+    // the real pass: visitors in input order
+    size_t lineNumber = 0;
+    try {
+        for (const FastWigChunk &C : chunks) {
+            size_t h = 0, k2 = 0;
+            for (size_t i = 0; i < C.kind.size(); ++i) {
+                ++lineNumber;
+                if (C.kind[i] == 0) {
+                    sc.scanHeader(C.header[h].first, C.header[h].second);
+                    ++h;
+                    sc.haveHeader = true;
+                    visit(0);
+                    continue;
+                }
+                if (sc.fixedStep) { // WiggleScanner::scanLine
+                    sc.first = sc.start + sc.offset * sc.step;
+                    ++sc.offset;
+                } else {
+                    sc.first = C.pos[k2++];
+                    --sc.start;
+                }
+                sc.value = C.value[i];
+                sc.last = sc.first;
+                if (sc.span > 1) sc.last += sc.span - 1;
+                visit(1);
+            }
+        }
+    } catch (std::exception &ex) {
+        throw std::runtime_error(std::string(ex.what()) + " in input wiggle line " + std::to_string(lineNumber));
+    }
+    visit(2);
+    linesOut = lineNumber;
+    return true;
+}
+
 std::string slurp(std::istream &in) {
     std::string s;
     char buf[1 << 16];
@@ -165,6 +305,11 @@ std::string slurp(std::istream &in) {
 double seconds(std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 
 } // namespace
+
+unsigned GpuWiggleLiftover::defaultTextThreads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 32u));
+}
 
 void GpuWiggleLiftover::preloadOutput(int tgtGenome, std::istream *inputFile) {
     if (_ctx == nullptr || inputFile == nullptr) throw std::runtime_error("GpuWiggleLiftover::preloadOutput: null argument");
@@ -274,7 +419,7 @@ void GpuWiggleLiftover::convert(int srcGenome, std::istream *inputFile, int tgtG
     };
     const halgpu_seq *srcSeq = nullptr;
     WigScanner sc;
-    linesIn = scanWiggle(text.data(), text.size(), sc, [&](int kind) {
+    auto visitor = [&](int kind) {
         if (kind == 0) { // WiggleLiftover::visitHeader
             flushBatch();
             auto it = byName.find(sc.sequenceName);
@@ -314,7 +459,16 @@ void GpuWiggleLiftover::convert(int srcGenome, std::istream *inputFile, int tgtG
             for (int64_t k = 0; k < span; ++k) vals.push_back(sc.value);
             runLast.back() = absLast;
         }
-    });
+    };
+    unsigned threads = textThreads;
+    if (const char *tt = std::getenv("HALGPU_TEXT_THREADS")) threads = (unsigned)std::max(0L, std::atol(tt));
+    size_t fastLinesSeen = 0;
+    if (threads > 0 && fastScanWiggle(text.data(), text.size(), threads, sc, fastLinesSeen, visitor)) {
+        linesIn = fastLinesSeen;
+        fastParsed = true;
+    } else {
+        linesIn = scanWiggle(text.data(), text.size(), sc, visitor);
+    }
     runs = runFirst.size();
     parseSeconds = seconds(t0);
 
@@ -333,47 +487,75 @@ void GpuWiggleLiftover::convert(int srcGenome, std::istream *inputFile, int tgtG
     kernelMs = res->kernel_ms;
     basesOut = res->n;
 
-    // WiggleLiftover::write (halWiggleLiftover.cpp:160-198)
+    // WiggleLiftover::write (halWiggleLiftover.cpp:160-198).  Whether position i opens a new "fixedStep" block depends on the
+    // previous position and on the writer's current sequence, which is sticky: MMapSequence::getEndPosition() is start +
+    // length, one PAST the last base (api/mmap_impl/mmapSequence.h:50-52), so a run that continues contiguously into the next
+    // sequence gets no header there and a header printed at exactly that position still names the previous sequence (kept:
+    // HAL-MMAP files are what this build reads).  The state after position j is simply "the sequence containing it" unless j
+    // is the first base of its sequence, so every formatting thread can recover its starting state by looking back.
     t0 = std::chrono::steady_clock::now();
-    std::string out;
-    out.reserve(std::min<size_t>(res->n * 8 + 256, (size_t)64 << 20));
-    int64_t seqIdx = -1, prevPos = -1;
-    bool needHeader = true;
-    for (size_t i = 0; i < res->n; ++i) {
-        const int64_t pos = res->pos[i];
-        // MMapSequence::getEndPosition() is start + length, one PAST the last base (api/mmap_impl/mmapSequence.h:50-52):
-        // a run that continues contiguously into the next sequence gets no header there, and a header printed at exactly
-        // that position still names the previous sequence.  Kept, since HAL-MMAP files are what this build reads.
+    auto seqOfPos = [&](int64_t pos) { // Genome::getSequenceBySite
+        size_t lo = 0, hi = nt;
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) >> 1;
+            if (tseq[mid].start <= pos) lo = mid; else hi = mid;
+        }
+        return (int64_t)lo;
+    };
+    auto step = [&](int64_t &seqIdx, int64_t &prevPos, int64_t pos, bool &needHeader) { // one iteration of the reference's loop
         if (seqIdx < 0 || pos < tseq[seqIdx].start || pos > tseq[seqIdx].start + tseq[seqIdx].length) {
-            size_t lo = 0, hi = nt; // Genome::getSequenceBySite
-            while (hi - lo > 1) {
-                const size_t mid = (lo + hi) >> 1;
-                if (tseq[mid].start <= pos) lo = mid; else hi = mid;
-            }
-            seqIdx = (int64_t)lo;
+            seqIdx = seqOfPos(pos);
             needHeader = true;
         } else if (pos != prevPos + 1) {
             needHeader = true;
         }
-        if (needHeader) {
-            out += "fixedStep\tchrom=";
-            out += tseq[seqIdx].name;
-            out += "\tstart=";
-            out += std::to_string(1 + pos - tseq[seqIdx].start);
-            out += "\tstep=1\n";
-            needHeader = false;
-        }
-        char buf[40]; // operator<<(double): %g with precision 6
-        auto r = std::to_chars(buf, buf + sizeof buf, res->val[i], std::chars_format::general, 6);
-        out.append(buf, r.ptr);
-        out += '\n';
         prevPos = pos;
-        if (out.size() > ((size_t)32 << 20)) {
-            outputFile->write(out.data(), (std::streamsize)out.size());
-            out.clear();
+    };
+    size_t fgrain = (size_t)1 << 18;
+    if (const char *gs = std::getenv("HALGPU_WIG_GRAIN")) fgrain = (size_t)std::max(1L, std::atol(gs)); // test hook
+    unsigned fthreads = std::max(1u, std::min<unsigned>(threads, (unsigned)(res->n / fgrain) + 1));
+    std::vector<std::string> outs(fthreads);
+    auto formatRange = [&](unsigned t) {
+        const size_t a = res->n * t / fthreads, b = res->n * (t + 1) / fthreads;
+        std::string &out = outs[t];
+        out.reserve((b - a) * 9 + 256);
+        int64_t seqIdx = -1, prevPos = -1;
+        if (a > 0) { // recover the writer's state after element a - 1
+            size_t j = a - 1;
+            while (j > 0 && res->pos[j] == tseq[seqOfPos(res->pos[j])].start) --j;
+            bool dummy = false;
+            if (!(j == 0 && res->pos[0] == tseq[seqOfPos(res->pos[0])].start)) {
+                seqIdx = seqOfPos(res->pos[j]);
+                prevPos = res->pos[j];
+                ++j;
+            }
+            for (; j < a; ++j) step(seqIdx, prevPos, res->pos[j], dummy);
         }
+        for (size_t i = a; i < b; ++i) {
+            const int64_t pos = res->pos[i];
+            bool needHeader = false;
+            step(seqIdx, prevPos, pos, needHeader);
+            if (needHeader) {
+                out += "fixedStep\tchrom=";
+                out += tseq[seqIdx].name;
+                out += "\tstart=";
+                out += std::to_string(1 + pos - tseq[seqIdx].start);
+                out += "\tstep=1\n";
+            }
+            char buf[40]; // operator<<(double): %g with precision 6
+            auto r = std::to_chars(buf, buf + sizeof buf, res->val[i], std::chars_format::general, 6);
+            out.append(buf, r.ptr);
+            out += '\n';
+        }
+    };
+    if (fthreads == 1) {
+        formatRange(0);
+    } else {
+        std::vector<std::thread> fth;
+        for (unsigned t = 0; t < fthreads; ++t) fth.emplace_back(formatRange, t);
+        for (auto &x : fth) x.join();
     }
-    outputFile->write(out.data(), (std::streamsize)out.size());
+    for (const std::string &o : outs) outputFile->write(o.data(), (std::streamsize)o.size());
     writeSeconds = seconds(t0);
     halgpu_free_wig_result(res);
     _prePos.clear();

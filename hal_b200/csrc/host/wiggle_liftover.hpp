@@ -37,6 +37,11 @@ class GpuWiggleLiftover {
     size_t maxRunBases = 2048;
     // a line whose span reaches this many bases is sent as one run with a single value instead of per-base copies
     int64_t singleValueSpan = 64;
+    // threads of the strict multi-threaded pre-parse of the data lines and of the output formatter (0: serial scanner only;
+    // env HALGPU_TEXT_THREADS overrides)
+    unsigned textThreads = defaultTextThreads();
+    static unsigned defaultTextThreads();
+    bool fastParsed = false; // the last convert() took the multi-threaded pre-parse
     // totals of the last convert()
     size_t linesIn = 0, runs = 0, basesIn = 0, basesOut = 0;
     double parseSeconds = 0, gpuSeconds = 0, writeSeconds = 0;
