@@ -36,6 +36,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class Secondary:
+    """A secondary measurement must never take the headline line down: an exception inside the block is recorded under the
+    secondary's key as {"error": ...} and the bench goes on."""
+
+    def __init__(self, line, key):
+        self.line, self.key = line, key
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is None or not issubclass(et, Exception):
+            return False
+        cur = self.line.get(self.key)
+        if not isinstance(cur, dict):
+            cur = self.line[self.key] = {}
+        cur["error"] = ("%s: %s" % (et.__name__, ev))[:300]
+        log("secondary", self.key, "failed:", cur["error"])
+        return True
+
+
 def make_intervals(n, genome_len, seed):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -468,55 +489,57 @@ def main():
         line["secondary"] = depth_multi
     # secondary (BASELINE.json configs[4] shape on one GPU): halAlignmentDepth column sweep, ref = leaf L0, all targets
     if world == 1 and not args.no_depth:
-        d_out = torch.empty(genome_len, dtype=torch.int32, device="cuda")
-        dk = []
-        for i in range(2 + 3):
-            _, ms = a.depth(src, 0, genome_len - 1, 1, (), 0, out_ptr=d_out.data_ptr())
-            if i >= 2:
-                dk.append(ms)
-        torch.cuda.synchronize()
-        dms = float(np.mean(dk))
-        line["secondary"] = {"metric": "alignment_depth_columns_per_sec", "value": genome_len / (dms / 1e3), "unit": "columns/s",
-                             "kernel_ms": dms, "columns": genome_len, "rows_per_column": 16,
-                             "check": {"depth15_fraction": float((d_out == 15).float().mean())}}
-        if not args.no_cpu_baseline:
-            ref = os.path.join(ROOT, "oracle", "_ref", "halAlignmentDepth")
-            if os.path.exists(ref):
-                win = 100000
-                t0 = time.time()
-                procs = [subprocess.Popen([ref, hal, SRC, "--start", str(c * win), "--length", str(win)], stdout=subprocess.DEVNULL)
-                         for c in range(cores)]
-                assert all(p.wait() == 0 for p in procs)
-                dt = time.time() - t0
-                line["secondary"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
-                                                     "sample": f"{cores} processes of oracle/_ref/halAlignmentDepth, {win} columns each"}
+        with Secondary(line, "secondary"):
+            d_out = torch.empty(genome_len, dtype=torch.int32, device="cuda")
+            dk = []
+            for i in range(2 + 3):
+                _, ms = a.depth(src, 0, genome_len - 1, 1, (), 0, out_ptr=d_out.data_ptr())
+                if i >= 2:
+                    dk.append(ms)
+            torch.cuda.synchronize()
+            dms = float(np.mean(dk))
+            line["secondary"] = {"metric": "alignment_depth_columns_per_sec", "value": genome_len / (dms / 1e3), "unit": "columns/s",
+                                 "kernel_ms": dms, "columns": genome_len, "rows_per_column": 16,
+                                 "check": {"depth15_fraction": float((d_out == 15).float().mean())}}
+            if not args.no_cpu_baseline:
+                ref = os.path.join(ROOT, "oracle", "_ref", "halAlignmentDepth")
+                if os.path.exists(ref):
+                    win = 100000
+                    t0 = time.time()
+                    procs = [subprocess.Popen([ref, hal, SRC, "--start", str(c * win), "--length", str(win)], stdout=subprocess.DEVNULL)
+                             for c in range(cores)]
+                    assert all(p.wait() == 0 for p in procs)
+                    dt = time.time() - t0
+                    line["secondary"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
+                                                         "sample": f"{cores} processes of oracle/_ref/halAlignmentDepth, {win} columns each"}
     # secondary (BASELINE.json configs[2]): hal2maf block extraction, ref = root, through the product CLI (GPU column
     # runs + host block state machine + text), whole genome, output to a file on the box
     if world == 1 and not args.no_maf:
-        cli = os.path.join(ROOT, "hal_b200", "bin", "hal2maf")
-        mcols = min(genome_len, args.maf_columns)
-        outp = os.path.join(os.path.dirname(hal), "bench_out.maf")
-        if os.path.exists(outp):
+        with Secondary(line, "secondary_maf"):
+            cli = os.path.join(ROOT, "hal_b200", "bin", "hal2maf")
+            mcols = min(genome_len, args.maf_columns)
+            outp = os.path.join(os.path.dirname(hal), "bench_out.maf")
+            if os.path.exists(outp):
+                os.remove(outp)
+            t0 = time.time()
+            subprocess.check_call([cli, hal, outp, "--refGenome", "R", "--refSequence", "R_seq", "--start", "0", "--length", str(mcols)])
+            dt = time.time() - t0
+            msize = os.path.getsize(outp)
+            line["secondary_maf"] = {"metric": "hal2maf_columns_per_sec", "value": mcols / dt, "unit": "columns/s", "seconds": dt,
+                                     "columns": mcols, "maf_bytes": msize, "includes": "open+stage (%.2f s), GPU column runs, host blocker, text, file write" % stage_s}
+            if not args.no_cpu_baseline:
+                ref = os.path.join(ROOT, "oracle", "_ref", "hal2maf")
+                if os.path.exists(ref):
+                    win = 40000
+                    d = tempfile.mkdtemp(prefix="halb200_maf_")
+                    t0 = time.time()
+                    procs = [subprocess.Popen([ref, hal, os.path.join(d, f"o{c}.maf"), "--refGenome", "R", "--refSequence", "R_seq", "--start",
+                                               str(c * win), "--length", str(win)]) for c in range(cores)]
+                    assert all(p.wait() == 0 for p in procs)
+                    dt = time.time() - t0
+                    line["secondary_maf"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
+                                                             "sample": f"{cores} processes of oracle/_ref/hal2maf, {win}-column windows (hal2mafMP style)"}
             os.remove(outp)
-        t0 = time.time()
-        subprocess.check_call([cli, hal, outp, "--refGenome", "R", "--refSequence", "R_seq", "--start", "0", "--length", str(mcols)])
-        dt = time.time() - t0
-        msize = os.path.getsize(outp)
-        line["secondary_maf"] = {"metric": "hal2maf_columns_per_sec", "value": mcols / dt, "unit": "columns/s", "seconds": dt,
-                                 "columns": mcols, "maf_bytes": msize, "includes": "open+stage (%.2f s), GPU column runs, host blocker, text, file write" % stage_s}
-        if not args.no_cpu_baseline:
-            ref = os.path.join(ROOT, "oracle", "_ref", "hal2maf")
-            if os.path.exists(ref):
-                win = 40000
-                d = tempfile.mkdtemp(prefix="halb200_maf_")
-                t0 = time.time()
-                procs = [subprocess.Popen([ref, hal, os.path.join(d, f"o{c}.maf"), "--refGenome", "R", "--refSequence", "R_seq", "--start",
-                                           str(c * win), "--length", str(win)]) for c in range(cores)]
-                assert all(p.wait() == 0 for p in procs)
-                dt = time.time() - t0
-                line["secondary_maf"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "columns/s", "cores": cores, "kind": "reference",
-                                                         "sample": f"{cores} processes of oracle/_ref/hal2maf, {win}-column windows (hal2mafMP style)"}
-        os.remove(outp)
     # secondary ("report BOTH"): the divergent variant of C2 -- branch length 0.05, i.e. random-parent
     # transpositions (paralogy rings), inversions and insertions on every branch -- same batch, same direction
     if world == 1 and args.divergent:
@@ -543,64 +566,66 @@ def main():
     # halgpu_wiggle_liftover with HOST buffers (runs + values in, set target bases out); the pair is L7 -> L0 because the
     # reference's own halWiggleLiftover cannot map L0 -> L7 (its wrong turn at the MRCA, oracle/restate/wiggle.cpp)
     if world == 1 and not args.no_wiggle:
-        wsrc, wtgt = a.genome_id("L7"), a.genome_id("L0")
-        nb = min(args.wiggle_bases, genome_len - 2 * SEG_LEN)
-        run = 2048
-        wf = np.arange(0, nb, run, dtype=np.int64)
-        wl = np.minimum(wf + run - 1, nb - 1)
-        wv = np.random.default_rng(9).random(nb) * 100.0
-        best = None
-        for i in range(3):
-            t0 = time.perf_counter()
-            wpos, wval, winfo = a.wiggle_liftover(wsrc, wtgt, wf, wl, wf.copy(), wv)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, winfo["kernel_ms"], len(wpos))
-        line["secondary_wiggle"] = {"metric": "wiggle_liftover_bases_per_sec", "value": nb / best[0], "unit": "source bases/s",
-                                    "seconds": best[0], "mapping_kernel_ms": best[1], "bases_in": int(nb), "bases_out": int(best[2]),
-                                    "runs": int(len(wf)), "h2d_bytes": int(nb * 8 + len(wf) * 24), "d2h_bytes": int(best[2] * 16),
-                                    "check": {"max_equals_input_max": bool(len(wval) and wval.max() <= wv.max()), "all_nonnegative": bool((wval >= 0).all())}}
-        try:
-            # roofline of the wiggle-mode kernel, same accounting as the headline: algorithmic bytes = per source base 8 B of value
-            # + 16 B read-modify-write of the target key, + the index records the reference walk visits (oracle visit count on a
-            # sample of the runs) + 24 B per run of input; DRAM traffic from the committed ncu capture
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            from pyoracle import Oracle
-            o = Oracle(hal)
-            k = min(200, len(wf))
-            st_ = o.liftover(o.genome_id("L7"), o.genome_id("L0"), wf[:k], wl[:k])["stats"]
-            o.close()
-            per_base = 24.0 + st_["visitBytes"] / float((wl[:k] - wf[:k] + 1).sum()) + 24.0 / run
-            ach = per_base * nb / (best[1] / 1e3) / 1e9
-            wtraffic = None
+        with Secondary(line, "secondary_wiggle"):
+            wsrc, wtgt = a.genome_id("L7"), a.genome_id("L0")
+            nb = min(args.wiggle_bases, genome_len - 2 * SEG_LEN)
+            run = 2048
+            wf = np.arange(0, nb, run, dtype=np.int64)
+            wl = np.minimum(wf + run - 1, nb - 1)
+            wv = np.random.default_rng(9).random(nb) * 100.0
+            best = None
+            for i in range(3):
+                t0 = time.perf_counter()
+                wpos, wval, winfo = a.wiggle_liftover(wsrc, wtgt, wf, wl, wf.copy(), wv)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, winfo["kernel_ms"], len(wpos))
+            line["secondary_wiggle"] = {"metric": "wiggle_liftover_bases_per_sec", "value": nb / best[0], "unit": "source bases/s",
+                                        "seconds": best[0], "mapping_kernel_ms": best[1], "bases_in": int(nb), "bases_out": int(best[2]),
+                                        "runs": int(len(wf)), "h2d_bytes": int(nb * 8 + len(wf) * 24), "d2h_bytes": int(best[2] * 16),
+                                        "check": {"max_equals_input_max": bool(len(wval) and wval.max() <= wv.max()), "all_nonnegative": bool((wval >= 0).all())}}
             try:
-                wtraffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("wiggleKernel_dram_bytes_per_launch")
-            except (OSError, ValueError):
-                pass
-            line["secondary_wiggle"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": wtraffic,
-                                                    "kernel": "liftoverKernel<true,false>", "kernel_ms": best[1], "algorithmic_bytes_per_source_base": per_base}
-        except Exception as e:  # noqa: BLE001
-            line["secondary_wiggle"]["roofline"] = {"error": str(e)[:200]}
-        if not args.no_cpu_baseline:
-            ref = os.path.join(ROOT, "oracle", "_ref", "halWiggleLiftover")
-            if os.path.exists(ref):
-                win = 20000
-                d = tempfile.mkdtemp(prefix="halb200_wig_")
-                for c in range(cores):
-                    with open(os.path.join(d, f"i{c}.wig"), "w") as f:
-                        f.write(f"fixedStep chrom=L7_seq start={c * win + 1} step=1\n" + "".join(f"{x:.4f}\n" for x in wv[c * win:(c + 1) * win]))
-                t0 = time.time()
-                procs = [subprocess.Popen([ref, hal, "L7", os.path.join(d, f"i{c}.wig"), "L0", os.path.join(d, f"o{c}.wig")]) for c in range(cores)]
-                assert all(p.wait() == 0 for p in procs)
-                dt = time.time() - t0
-                line["secondary_wiggle"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "source bases/s", "cores": cores, "kind": "reference",
-                                                            "sample": f"{cores} processes of oracle/_ref/halWiggleLiftover, {win} fixedStep bases each (text in, text out)"}
+                # roofline of the wiggle-mode kernel, same accounting as the headline: algorithmic bytes = per source base 8 B of value
+                # + 16 B read-modify-write of the target key, + the index records the reference walk visits (oracle visit count on a
+                # sample of the runs) + 24 B per run of input; DRAM traffic from the committed ncu capture
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                from pyoracle import Oracle
+                o = Oracle(hal)
+                k = min(200, len(wf))
+                st_ = o.liftover(o.genome_id("L7"), o.genome_id("L0"), wf[:k], wl[:k])["stats"]
+                o.close()
+                per_base = 24.0 + st_["visitBytes"] / float((wl[:k] - wf[:k] + 1).sum()) + 24.0 / run
+                ach = per_base * nb / (best[1] / 1e3) / 1e9
+                wtraffic = None
+                try:
+                    wtraffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("wiggleKernel_dram_bytes_per_launch")
+                except (OSError, ValueError):
+                    pass
+                line["secondary_wiggle"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": wtraffic,
+                                                        "kernel": "liftoverKernel<LIFT_WIG>", "kernel_ms": best[1], "algorithmic_bytes_per_source_base": per_base}
+            except Exception as e:  # noqa: BLE001
+                line["secondary_wiggle"]["roofline"] = {"error": str(e)[:200]}
+            if not args.no_cpu_baseline:
+                ref = os.path.join(ROOT, "oracle", "_ref", "halWiggleLiftover")
+                if os.path.exists(ref):
+                    win = 20000
+                    d = tempfile.mkdtemp(prefix="halb200_wig_")
+                    for c in range(cores):
+                        with open(os.path.join(d, f"i{c}.wig"), "w") as f:
+                            f.write(f"fixedStep chrom=L7_seq start={c * win + 1} step=1\n" + "".join(f"{x:.4f}\n" for x in wv[c * win:(c + 1) * win]))
+                    t0 = time.time()
+                    procs = [subprocess.Popen([ref, hal, "L7", os.path.join(d, f"i{c}.wig"), "L0", os.path.join(d, f"o{c}.wig")]) for c in range(cores)]
+                    assert all(p.wait() == 0 for p in procs)
+                    dt = time.time() - t0
+                    line["secondary_wiggle"]["cpu_baseline"] = {"value": cores * win / dt, "unit": "source bases/s", "cores": cores, "kind": "reference",
+                                                                "sample": f"{cores} processes of oracle/_ref/halWiggleLiftover, {win} fixedStep bases each (text in, text out)"}
     # secondary: the whole halLiftover CLI (text I/O at GPU rate) on the same batch as a BED3 file:
     # process start + CUDA context + open/stage + multi-threaded tokeniser + halgpu_liftover + multi-threaded printer + file write
     if world == 1 and not args.no_cli:
-        a.close()
-        a = None
-        line["secondary_cli"] = cli_throughput(hal, gs, ge, SRC + "_seq")
+        with Secondary(line, "secondary_cli"):
+            a.close()
+            a = None
+            line["secondary_cli"] = cli_throughput(hal, gs, ge, SRC + "_seq")
     if not args.no_cpu_baseline:
         sample = args.cpu_sample or min(2_000_000, max(2000, cores * 6000))
         r = reference_throughput(hal, gs, ge, SRC + "_seq", sample, cores)

@@ -11,6 +11,8 @@
 
 #if defined(HALGPU_SIMT_EMUL)
 #include "simt_emul.h"
+#include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <chrono>
 #include <numeric>
@@ -36,8 +38,14 @@ typedef int Stream;
 inline void setDevice(int) {}
 inline Stream createStream() { return 0; }
 inline void destroyStream(Stream) {}
-inline void *dmalloc(size_t n) { void *p = std::calloc(n ? n : 1, 1); if (!p) throw GpuError("out of memory"); return p; }
-inline void dfree(void *p) { std::free(p); }
+inline void *dmalloc(size_t n) { // 256-byte aligned like cudaMalloc; calloc keeps large untouched buffers lazily zeroed
+    void *raw = std::calloc((n ? n : 1) + 256 + sizeof(void *), 1);
+    if (!raw) throw GpuError("out of memory");
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + sizeof(void *) + 255) & ~(uintptr_t)255;
+    reinterpret_cast<void **>(a)[-1] = raw;
+    return reinterpret_cast<void *>(a);
+}
+inline void dfree(void *p) { if (p) std::free(reinterpret_cast<void **>(p)[-1]); }
 inline void *dmallocAsync(size_t n, Stream) { return dmalloc(n); }
 inline void dfreeAsync(void *p, Stream) { dfree(p); }
 inline void *hostAlloc(size_t n) { return std::malloc(n ? n : 1); }
