@@ -76,7 +76,7 @@ def build(force=False, verbose=False):
     if force or _newer(dep, [dep_src, LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", dep, dep_src, "-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     maf = os.path.join(BIN, "hal2maf")
-    maf_srcs = [os.path.join(host, f) for f in ("hal2mafMain.cpp", "maf_export.cpp")]
+    maf_srcs = [os.path.join(host, f) for f in ("hal2mafMain.cpp", "maf_export.cpp", "bed.cpp")]
     if force or _newer(maf, maf_srcs + [os.path.join(host, "maf_export.hpp"), LIB]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", maf] + maf_srcs + ["-L" + HERE, "-lhalgpu", "-Wl,-rpath,$ORIGIN/.."])
     return LIB

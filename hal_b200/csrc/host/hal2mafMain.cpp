@@ -1,12 +1,18 @@
 // hal2maf -- GPU build of the reference CLI (maf/impl/hal2maf.cpp): same arguments, options, MAF text and
 // messages for the ColumnIterator flags the GPU column walk implements (maxRefGap=0; --unique included).
-// Not implemented (rejected with an error): --maxRefGap > 0, --global, --printTree, --refTargets.
+// --refTargets <bed|stdin> drives one convertSequence per BED interval / BED12 block like MafBed (maf/impl/halMafBed.cpp:24-54).
+// Not implemented (rejected with an error): --maxRefGap > 0, --global, --printTree.
+#include "bed.hpp"
 #include "maf_export.hpp"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <cctype>
+#include <cstring>
 #include <iostream>
+#include <iterator>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -15,7 +21,7 @@ using namespace std;
 
 static void usage(ostream &os, const char *prog) {
     os << prog << " v-b200: Convert hal database to maf on a B200 GPU.\n\nUSAGE:\n" << prog << " [Options] <halFile> <mafFile>\n\n"
-       << "OPTIONS:\n--refGenome <name>, --refSequence <name>, --start <n>, --length <n>, --rootGenome <name>, --targetGenomes <a,b,..>,\n"
+       << "OPTIONS:\n--refGenome <name>, --refSequence <name>, --refTargets <bed|stdin>, --start <n>, --length <n>, --rootGenome <name>, --targetGenomes <a,b,..>,\n"
        << "--noDupes, --noAncestors, --onlySequenceNames, --onlyOrthologs, --unique, --keepEmptyRefBlocks, --append, --maxBlockLen <n>,\n"
        << "--device <n>, --help\n";
 }
@@ -33,8 +39,60 @@ static string fixString(const string &s) { // maf/impl/hal2maf.cpp:94-101
     return s;
 }
 
+// hal2mafWithTargets + MafBed::visitLine (maf/impl/hal2maf.cpp:105-119, halMafBed.cpp:24-54) under BedScanner::scan
+// (liftover/impl/halBedScanner.cpp:40-61): one convertSequence per BED<=9 line or per BED12 block, with the reference's
+// messages.  The reference never tests the stream it opens (it tests a second, unopened one), so an unreadable path is an
+// empty scan there and here.
+static void refTargets(halgpu::GpuMafExport &ex, ostream &maf, halgpu_ctx *ctx, int ref, const halgpu_seq *seqs, size_t nseq, const string &path,
+                       const vector<int> &targets) {
+    ifstream bedFile;
+    if (path != "stdin") bedFile.open(path);
+    istream &bed = path != "stdin" ? static_cast<istream &>(bedFile) : cin;
+    if (bed.bad()) throw runtime_error("Error reading bed input stream");
+    const string text((istreambuf_iterator<char>(bed)), istreambuf_iterator<char>());
+    map<string, int> seqByName;
+    for (size_t i = 0; i < nseq; ++i) seqByName[seqs[i].name] = (int)i;
+    halgpu::BedLine cur; // one object for the whole scan, like BedScanner::_bedLine
+    string lineBuf;
+    size_t lineNumber = 0;
+    const char *p = text.data(), *const end = p + text.size();
+    auto skipWs = [&]() { while (p < end && isspace((unsigned char)*p)) ++p; };
+    skipWs();
+    while (p < end) {
+        ++lineNumber;
+        const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+        lineBuf.assign(p, nl ? nl : end);
+        p = nl ? nl + 1 : end;
+        try {
+            cur.parse(lineBuf, 0);
+            const auto it = seqByName.find(cur.chrName);
+            if (it == seqByName.end()) {
+                cerr << "Line " << lineNumber << ": BED sequence " << cur.chrName << " not found in genome " << halgpu_genome_name(ctx, ref) << '\n';
+            } else if (cur.bedType <= 9) {
+                if (cur.end <= cur.start || cur.end > seqs[it->second].length) {
+                    cerr << "Line " << lineNumber << ": BED coordinates invalid\n";
+                } else {
+                    ex.convertSequence(maf, ref, it->second, cur.start, (uint64_t)(cur.end - cur.start), targets);
+                }
+            } else {
+                for (size_t i = 0; i < cur.blocks.size(); ++i) {
+                    const int64_t bs = cur.start + cur.blocks[i].start, bl = cur.blocks[i].length;
+                    if (bl == 0 || bs + bl >= seqs[it->second].length) {
+                        cerr << "Line " << lineNumber << ", block " << i << ": BED coordinates invalid\n";
+                    } else {
+                        ex.convertSequence(maf, ref, it->second, bs, (uint64_t)bl, targets);
+                    }
+                }
+            }
+        } catch (exception &e) {
+            throw runtime_error(string(e.what()) + " in input bed line " + to_string(lineNumber));
+        }
+        skipWs();
+    }
+}
+
 int main(int argc, char **argv) {
-    string halPath, mafPath, refGenomeName, rootGenomeName, targetGenomes, refSequenceName;
+    string halPath, mafPath, refGenomeName, rootGenomeName, targetGenomes, refSequenceName, refTargetsPath;
     int64_t start = 0, maxBlockLen = 1000;
     uint64_t length = 0;
     bool noDupes = false, noAncestors = false, onlySequenceNames = false, append = false, onlyOrthologs = false, keepEmptyRefBlocks = false,
@@ -63,7 +121,7 @@ int main(int argc, char **argv) {
             else if (a == "--maxRefGap") { if (atoll(val().c_str()) != 0) throw runtime_error("--maxRefGap > 0 is not implemented in the GPU build"); }
             else if (a == "--unique") unique = true;
             else if (a == "--global" || a == "--printTree") throw runtime_error(a + " is not implemented in the GPU build");
-            else if (a == "--refTargets") { if (!fixString(val()).empty()) throw runtime_error("--refTargets is not implemented in the GPU build"); }
+            else if (a == "--refTargets") refTargetsPath = fixString(val());
             else if (a == "--format" || a == "--cacheMDC" || a == "--cacheRDC" || a == "--cacheBytes" || a == "--cacheW0" ||
                      a == "--mmapFileSize" || a == "--mmapSizeIncrease" || a == "--udcCacheDir") val();
             else if (a == "--inMemory") {}
@@ -74,7 +132,10 @@ int main(int argc, char **argv) {
         halPath = pos[0];
         mafPath = pos[1];
         if (rootGenomeName != "" && targetGenomes != "") throw runtime_error("--rootGenome and --targetGenomes options are mutually exclusive");
-        if (refSequenceName == "" && (start != 0 || length != 0)) throw runtime_error("--start and --length require --refSequence");
+        if (refSequenceName == "" && (start != 0 || length != 0)) throw runtime_error("--start and --length require --refSequenceName");
+        if (!refTargetsPath.empty() && (start != 0 || length != 0 || !refSequenceName.empty())) {
+            throw runtime_error("--refSequence, --start, and --length options are unsupported when using BED input");
+        }
     } catch (exception &e) {
         cerr << e.what() << endl;
         usage(cerr, argv[0]);
@@ -142,7 +203,9 @@ int main(int argc, char **argv) {
         if (const char *cc = getenv("HALGPU_MAF_CHUNK_COLUMNS")) ex.chunkColumns = (size_t)std::max(1L, atol(cc)); // test hook
         if (const char *cc = getenv("HALGPU_MAF_QUEUE_BYTES")) ex.queueBytes = (size_t)std::max(0L, atol(cc));      // test hook
         if (const char *cc = getenv("HALGPU_TEXT_THREADS")) ex.formatThreads = (unsigned)std::max(1L, atol(cc));
-        if (refSeq >= 0) {
+        if (!refTargetsPath.empty()) {
+            refTargets(ex, maf, ctx, ref, seqs, nseq, refTargetsPath, targets);
+        } else if (refSeq >= 0) {
             ex.convertSequence(maf, ref, refSeq, start, length, targets);
         } else {
             for (size_t i = 0; i < nseq; ++i) ex.convertSequence(maf, ref, (int)i, start, length, targets);

@@ -122,8 +122,8 @@ def emul_depth_cli(emul_lib):
 def emul_maf_cli(emul_lib):
     out = os.path.join(ROOT, "tests", "simt", "hal2maf_emul")
     host = os.path.join(ROOT, "hal_b200", "csrc", "host")
-    srcs = [os.path.join(host, f) for f in ("hal2mafMain.cpp", "maf_export.cpp")]
-    deps = srcs + [os.path.join(host, "maf_export.hpp"), emul_lib]
+    srcs = [os.path.join(host, f) for f in ("hal2mafMain.cpp", "maf_export.cpp", "bed.cpp")]
+    deps = srcs + [os.path.join(host, "maf_export.hpp"), os.path.join(host, "bed.hpp"), emul_lib]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out] + srcs + ["-L" + os.path.dirname(emul_lib), "-lhalgpu_emul",
                                "-Wl,-rpath,$ORIGIN", "-pthread"])

@@ -98,8 +98,32 @@ def check_maf(cli, tmp_path, whole_genome_hal=None):
         assert open(out, "rb").read() == open(os.path.join(GOLDEN, "cases", c["name"] + ".maf"), "rb").read(), c["name"]
 
 
+def check_maf_targets(cli, tmp_path):
+    """hal2maf --refTargets (MafBed, maf/impl/halMafBed.cpp): one convertSequence per BED interval / BED12 block; output, the
+    per-line messages and the scanner's error text equal the reference's (tests/golden/make_golden_maf_targets.py)"""
+    import json
+    d = os.path.join(GOLDEN, "maf_targets")
+    for c in json.load(open(os.path.join(d, "index.json"))):
+        out = str(tmp_path / "t.maf")
+        if os.path.exists(out):
+            os.remove(out)
+        r = subprocess.run([cli, os.path.join(GOLDEN, c["hal"]), out, "--refTargets", os.path.join(d, c["name"] + ".bed")] + c["args"],
+                           capture_output=True, text=True)
+        assert r.returncode == c.get("returncode", 0), r.stderr
+        err = "".join(x + "\n" for x in r.stderr.splitlines() if not x.startswith("[halgpu"))
+        assert err == c["stderr"], c["name"]
+        want = os.path.join(d, c["name"] + ".maf")
+        assert os.path.exists(out) == os.path.exists(want), c["name"]
+        if os.path.exists(want):
+            assert open(out, "rb").read() == open(want, "rb").read(), c["name"]
+
+
 def test_maf_cli_emulated_matches_reference_outputs(emul_maf_cli, tmp_path):
     check_maf(emul_maf_cli, tmp_path)
+    check_maf_targets(emul_maf_cli, tmp_path)
+    r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--refTargets", "x.bed", "--refSequence", "R_s0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "unsupported when using BED input" in r.stderr
     r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--noAncestors"], capture_output=True, text=True)
     assert r.returncode == 1 and "the --noAncestors option is invalid" in r.stderr
     r = subprocess.run([emul_maf_cli, os.path.join(GOLDEN, "varlen8.hal"), str(tmp_path / "x.maf"), "--printTree"], capture_output=True, text=True)
@@ -138,6 +162,7 @@ def test_maf_cli_cuda_matches_reference_outputs(tmp_path):
     build.build()
     cli = os.path.join(ROOT, "hal_b200", "bin", "hal2maf")
     check_maf(cli, tmp_path)
+    check_maf_targets(cli, tmp_path)
     if ref_bin("hal2maf"):
         hal = os.path.join(GOLDEN, "varlen8.hal")
         for args in (["--refGenome", "L1"], ["--refGenome", "R"], ["--refGenome", "A2", "--maxBlockLen", "50"], ["--refGenome", "L3", "--noDupes"],
