@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--maf-columns", type=int, default=50_000_000)
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-wiggle", action="store_true")
-    ap.add_argument("--divergent", action="store_true", help="also lift the batch over the branch-length-0.05 variant of C2 (opt-in: not yet run at full size on a GPU)")
+    ap.add_argument("--no-divergent", action="store_true", help="skip the branch-length-0.05 variant of C2 (SURVEY 8(d): report both variants)")
     ap.add_argument("--wiggle-bases", type=int, default=50_000_000)
     args = ap.parse_args()
 
@@ -542,7 +542,7 @@ def main():
             os.remove(outp)
     # secondary ("report BOTH"): the divergent variant of C2 -- branch length 0.05, i.e. random-parent
     # transpositions (paralogy rings), inversions and insertions on every branch -- same batch, same direction
-    if world == 1 and args.divergent:
+    if world == 1 and not args.no_divergent:
         try:
             dhal = ensure_hal(args.segs, "0.05")
             with hal_b200.Alignment(dhal, device=local) as b:
