@@ -27,3 +27,29 @@ for hal in tests/golden/refBedLiftoverTest.hal tests/golden/varlen8.hal; do
     python tools/maf_targets_vs_ref.py $A/hal2maf_emul $hal 1 | tail -n 1
     python tools/cli_sanitized_vs_plain.py $A $hal | tail -n 1
 done
+
+# ThreadSanitizer over the multi-threaded text layers (BED tokeniser/printer against the stub ABI library, MAF row pool and
+# wiggle scanner/writer against the plain emulated library): no report, output equal to the serial path.
+T=$A/tsan; mkdir -p "$T"; cd "$T"
+FT="-std=c++17 -O1 -g -fsanitize=thread"
+cp $R/tests/simt/libhalgpu_emul.so .
+g++ -std=c++17 -O2 -fPIC -shared -o libhalgpu_stub.so $R/tests/cpp/halgpu_stub.cpp
+g++ $FT -pthread -o halLiftover_stub $H/halLiftoverMain.cpp $H/gpu_liftover.cpp $H/bed.cpp $H/bed_fast.cpp -L. -lhalgpu_stub '-Wl,-rpath,$ORIGIN'
+g++ $FT -o hal2maf_emul $H/hal2mafMain.cpp $H/maf_export.cpp $H/bed.cpp $L
+g++ $FT -o halWiggleLiftover_emul $H/halWiggleLiftoverMain.cpp $H/wiggle_liftover.cpp $L
+export TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0"
+python - <<'PY'
+import random
+rng = random.Random(1)
+with open("in.bed", "w") as f:
+    for i in range(200000):
+        a = rng.randrange(0, 900000)
+        f.write(f"{rng.choice(['chrA', 'chrB'])}\t{a}\t{a + rng.randrange(1, 500)}\tn{i}\t{rng.randrange(1000)}\t{rng.choice('+-')}\n")
+PY
+HALGPU_TEXT_THREADS=6 HALGPU_BLOCK_BYTES=1500000 ./halLiftover_stub x S in.bed T out.bed
+HALGPU_TEXT_THREADS=0 ./halLiftover_stub x S in.bed T out0.bed
+cmp out.bed out0.bed && echo "tsan BED: clean"
+G=$R/tests/golden
+HALGPU_TEXT_THREADS=5 HALGPU_MAF_QUEUE_BYTES=20000 ./hal2maf_emul $G/varlen8.hal o.maf --refGenome L0
+$R/tests/simt/hal2maf_emul $G/varlen8.hal o0.maf --refGenome L0
+cmp o.maf o0.maf && echo "tsan MAF: clean"
