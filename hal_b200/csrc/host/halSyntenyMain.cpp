@@ -3,6 +3,7 @@
 // `--device` selects the GPU.  The alignment must be a HAL-MMAP file (or a PSL file with --alignmentIsPsl, which needs no GPU
 // work at all: blocks are read, chained by dag_merge and written back).
 #include "synteny.hpp"
+#include <chrono>
 #include <algorithm>
 #include <cstdlib>
 #include <fstream>
@@ -94,15 +95,18 @@ int main(int argc, char **argv) {
             out.exceptions(ofstream::failbit | ofstream::badbit);
             out.open(pos[1], ofstream::out);
             halgpu::GpuHal2Psl h2p(ctx);
+            double mergeSeconds = 0;
             for (const string &c : chroms) {
                 const vector<halgpu::PslBlock> blocks = h2p.convert2psl(src, tgt, c);
+                const auto t0 = chrono::steady_clock::now();
                 halgpu::writePsl(halgpu::dagMerge(blocks, minBlockSize, maxAnchorDistance), out);
+                mergeSeconds += chrono::duration<double>(chrono::steady_clock::now() - t0).count();
             }
             out.close();
             if (getenv("HALGPU_TIMING")) {
                 cerr << "[halSynteny] " << h2p.intervals << " GPU intervals, " << h2p.fragments << " mapped fragments, " << h2p.refined
                      << " after refinement, " << h2p.lines << " blocks; halgpu_liftover " << h2p.gpuSeconds << " s, host refine/merge "
-                     << h2p.hostSeconds << " s" << endl;
+                     << h2p.hostSeconds << " s, dag merge + write " << mergeSeconds << " s" << endl;
             }
         }
     } catch (exception &e) {

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <queue>
 #include <ostream>
 #include <set>
 #include <sstream>
@@ -253,16 +254,26 @@ std::vector<PslBlock> GpuHal2Psl::convert2psl(int srcGenome, int tgtGenome, cons
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 
-inline bool areSyntenic(const PslBlock &a, const PslBlock &b) { // assumes a.start < b.start
+// one vertex of the merge DAG: the block's coordinates with its target-name / strand strings interned to integers
+struct Vertex {
+    uint64_t qStart, qEnd, tStart, tEnd, size;
+    int tName, strand;
+};
+inline bool areSyntenic(const Vertex &a, const Vertex &b) { // assumes a.start < b.start
     return a.qEnd <= b.qStart && a.tEnd <= b.tStart && a.tName == b.tName && a.strand == b.strand;
 }
-inline bool isNotOverlappingOrderedPair(const PslBlock &a, const PslBlock &b, uint64_t threshold) {
+inline bool isNotOverlappingOrderedPair(const Vertex &a, const Vertex &b, uint64_t threshold) {
     return areSyntenic(a, b) && b.qStart - a.qEnd < threshold && b.tStart - a.tEnd < threshold;
 }
-std::vector<int> getNext(int pos, const std::vector<PslBlock> &group, uint64_t maxAnchorDistance) {
+// get_next (psl_merger.cpp): the candidates after `pos` up to the first one that could itself follow the first candidate.
+// The vertices are sorted by qStart, so once a block starts `threshold` or more past this block's query end no later block can
+// pass the distance test: the scan stops there (the reference scans to the end of the group, with the same result).
+std::vector<int> getNext(int pos, const std::vector<Vertex> &group, uint64_t maxAnchorDistance) {
     std::vector<int> f;
+    const Vertex &a = group[pos];
     for (int i = pos + 1; i < (int)group.size(); ++i) {
-        if (isNotOverlappingOrderedPair(group[pos], group[i], maxAnchorDistance)) {
+        if (group[i].qStart >= a.qEnd && group[i].qStart - a.qEnd >= maxAnchorDistance) break;
+        if (isNotOverlappingOrderedPair(a, group[i], maxAnchorDistance)) {
             if (f.empty()) {
                 f.push_back(i);
             } else if (isNotOverlappingOrderedPair(group[f[0]], group[i], maxAnchorDistance)) {
@@ -277,42 +288,63 @@ std::vector<int> getNext(int pos, const std::vector<PslBlock> &group, uint64_t m
 
 } // namespace
 
+// dag_merge (psl_merger.cpp): repeat { weigh the DAG of the still-visible blocks: weight(v) = size(v) + the largest weight among
+// its visible predecessors (the first such predecessor in vertex order is remembered); take the heaviest vertex (the last one
+// among equals), trace its chain back, emit it, hide its vertices } until every block is hidden.  The reference re-weighs the
+// whole DAG for every chain; only the vertices downstream of the chain just hidden can change, so here those are re-weighed in
+// ascending vertex order (a min-heap of dirty vertices) with the same recurrence -- same weights, same predecessors, same chains.
 std::vector<std::vector<PslBlock>> dagMerge(const std::vector<PslBlock> &blocks, uint64_t minBlockBreath, uint64_t maxAnchorDistance) {
     std::map<std::string, std::vector<PslBlock>> blocksByQName;
     for (const PslBlock &b : blocks) blocksByQName[b.qName].push_back(b);
     std::vector<std::vector<PslBlock>> paths;
     for (auto &kv : blocksByQName) {
-        std::vector<PslBlock> group = kv.second;
-        std::sort(group.begin(), group.end(), [](PslBlock a, PslBlock b) { // qStartLess (by value, like the reference's functor)
+        std::vector<PslBlock> &group = kv.second;
+        std::sort(group.begin(), group.end(), [](const PslBlock &a, const PslBlock &b) { // qStartLess; std::sort like the reference: same permutation of ties
             if (a.qStart < b.qStart) return true;
             if (a.qStart == b.qStart) return a.tStart < b.tStart;
             return false;
         });
         const int n = (int)group.size();
-        std::vector<std::vector<int>> dag(n);
-        std::vector<char> dagKnown(n, 0), hidden(n, 0);
-        int numHidden = 0;
-        std::vector<int> prev(n);
-        std::vector<uint64_t> weight(n);
-        std::vector<char> seen(n);
-        while (numHidden != n) {
-            // weigh_dag
-            std::fill(seen.begin(), seen.end(), 0);
+        std::vector<Vertex> vx(n);
+        {
+            std::map<std::string, int> ids;
+            auto intern = [&](const std::string &x) { return ids.emplace(x, (int)ids.size()).first->second; };
             for (int i = 0; i < n; ++i) {
-                if (hidden[i]) continue;
-                if (!dagKnown[i]) { dag[i] = getNext(i, group, maxAnchorDistance); dagKnown[i] = 1; }
-                if (!seen[i]) { seen[i] = 1; prev[i] = -1; weight[i] = group[i].size; }
-                for (int j : dag[i]) {
-                    if (hidden[j]) continue;
-                    const uint64_t alt = weight[i] + group[j].size;
-                    if (!seen[j] || weight[j] < alt) { seen[j] = 1; prev[j] = i; weight[j] = alt; }
-                }
+                const PslBlock &b = group[i];
+                vx[i] = Vertex{b.qStart, b.qEnd, b.tStart, b.tEnd, b.size, intern("t" + b.tName), intern("s" + b.strand)};
             }
-            // traceback from the heaviest vertex (the LAST one among equals: >= in get_maxed_vertex)
+        }
+        std::vector<std::vector<int>> dag(n), pred(n);
+        for (int i = 0; i < n; ++i) {
+            dag[i] = getNext(i, vx, maxAnchorDistance);
+            for (int j : dag[i]) pred[j].push_back(i); // ascending i
+        }
+        std::vector<char> hidden(n, 0), dirty(n, 0);
+        std::vector<int> prev(n, -1);
+        std::vector<uint64_t> weight(n);
+        auto reweigh = [&](int j) { // weigh_dag's relaxations into j, in the order the reference applies them
+            bool seen = false;
+            uint64_t w = vx[j].size;
+            int p = -1;
+            for (int i : pred[j]) {
+                if (hidden[i]) continue;
+                const uint64_t alt = weight[i] + vx[j].size;
+                if (!seen || w < alt) { seen = true; w = alt; p = i; }
+            }
+            const bool changed = w != weight[j];
+            weight[j] = w;
+            prev[j] = p;
+            return changed;
+        };
+        for (int j = 0; j < n; ++j) { weight[j] = 0; reweigh(j); }
+        std::priority_queue<int, std::vector<int>, std::greater<int>> work;
+        int numHidden = 0;
+        while (numHidden != n) {
+            // the heaviest visible vertex (the LAST one among equals: >= in get_maxed_vertex)
             int start = -1;
             uint64_t best = 0;
             for (int i = 0; i < n; ++i) {
-                if (!seen[i]) continue;
+                if (hidden[i]) continue;
                 if (start < 0 || weight[i] >= best) { best = weight[i]; start = i; }
             }
             if (start < 0) break;
@@ -320,6 +352,18 @@ std::vector<std::vector<PslBlock>> dagMerge(const std::vector<PslBlock> &blocks,
             for (int p = prev[start]; p != -1; p = prev[p]) path.push_back(p);
             for (int v : path) {
                 if (!hidden[v]) { hidden[v] = 1; ++numHidden; }
+            }
+            for (int v : path) {
+                for (int j : dag[v]) if (!hidden[j] && !dirty[j]) { dirty[j] = 1; work.push(j); }
+            }
+            while (!work.empty()) {
+                const int j = work.top();
+                work.pop();
+                dirty[j] = 0;
+                if (hidden[j]) continue;
+                if (reweigh(j)) {
+                    for (int k : dag[j]) if (!hidden[k] && !dirty[k]) { dirty[k] = 1; work.push(k); }
+                }
             }
             std::vector<PslBlock> blockPath;
             for (auto it = path.rbegin(); it != path.rend(); ++it) blockPath.push_back(group[*it]);
