@@ -355,6 +355,8 @@ def main():
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
+    last_info = {}
+
     def step_resident(gather):
         res = a.liftover_ptrs(src, tgt, n, d_gs.data_ptr(), d_ge.data_ptr(), None, 0, device=True)
         if gather and dist:
@@ -364,6 +366,7 @@ def main():
             recs = torch.as_tensor(_Arr(res.recs_ptr, max(res.n_rec, 1) * 32), device="cuda")[: res.n_rec * 32]
             parallel.all_gather_records(offs[1:] - offs[:-1], recs)
         out = (res.n_rec, res.kernel_ms, res.launches, res.n_retry)
+        last_info.update(fast_ms=res.fast_ms, n_complex=res.n_complex)
         res.close()
         return out
 
@@ -482,7 +485,7 @@ def main():
                      "algorithmic_bytes_per_interval": per_interval,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"},
         "detail": {"output_lines_per_step": int(nrec), "retry_intervals": int(nretry), "wall_s_per_step": wall / args.steps,
-                   "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step, "step_wall_ms": [round(x, 3) for x in step_wall],
+                   "stage_seconds": stage_s, "staged_bytes": a.staged_bytes, "kernel_share_of_step": kmean / ms_step, "fast_kernel_ms": last_info.get("fast_ms"), "complex_intervals": last_info.get("n_complex"), "step_wall_ms": [round(x, 3) for x in step_wall],
                    "oracle_sample_stats": ostats},
     }
     if depth_multi is not None:
@@ -552,14 +555,14 @@ def main():
                     t0 = time.perf_counter()
                     res = b.liftover_ptrs(bs, bt, n, d_gs.data_ptr(), d_ge.data_ptr(), None, 0, device=True)
                     dt = time.perf_counter() - t0
-                    cur = (dt, res.kernel_ms, res.n_rec, res.n_retry, res.launches)
+                    cur = (dt, res.kernel_ms, res.n_rec, res.n_retry, res.launches, res.fast_ms, res.n_complex)
                     res.close()
                     if i > 0 and (best is None or dt < best[0]):
                         best = cur
             line["secondary_divergent"] = {"metric": "liftover_intervals_per_sec", "value": n / best[0], "unit": "intervals/s",
                                            "workload": "C2 with --branch 0.05 (transpositions/paralogy rings, inversions, insertions)",
                                            "seconds": best[0], "kernel_ms": best[1], "output_lines": int(best[2]),
-                                           "retry_intervals": int(best[3]), "launches": int(best[4])}
+                                           "retry_intervals": int(best[3]), "launches": int(best[4]), "fast_kernel_ms": best[5], "complex_intervals": int(best[6])}
         except Exception as e:  # noqa: BLE001 -- a secondary line must not take the headline down
             line["secondary_divergent"] = {"error": str(e)[:300]}
     # secondary: halWiggleLiftover's mapping core: one value per base of L7, lifted to L0 through

@@ -19,6 +19,7 @@ HALGPU_PSL = 4
 HALGPU_COLUMN_LIFTOVER = 8
 HALGPU_RAW_FRAGMENTS = 16
 HALGPU_SEED_BOTTOM = 32
+HALGPU_NO_FAST = 64
 HALGPU_COUNT_DUPES = 1
 HALGPU_NO_ANCESTORS = 2
 HALGPU_COL_NO_DUPES = 4
@@ -36,7 +37,7 @@ class _Seq(C.Structure):
 class _Result(C.Structure):
     _fields_ = [("n", C.c_size_t), ("n_rec", C.c_size_t), ("offsets", C.c_void_p), ("recs", C.c_void_p),
                 ("on_device", C.c_int), ("kernel_ms", C.c_float), ("launches", C.c_int), ("n_retry", C.c_size_t),
-                ("psl", C.c_void_p)]
+                ("psl", C.c_void_p), ("fast_ms", C.c_float), ("n_complex", C.c_size_t), ("owner", C.c_void_p)]
 
 
 class _WigResult(C.Structure):
@@ -122,6 +123,7 @@ class DeviceResult:
         self.n, self.n_rec = r.n, r.n_rec
         self.offsets_ptr, self.recs_ptr = r.offsets, r.recs
         self.kernel_ms, self.launches, self.n_retry = r.kernel_ms, r.launches, r.n_retry
+        self.fast_ms, self.n_complex = r.fast_ms, r.n_complex
 
     def close(self):
         if self._res is not None:
@@ -207,7 +209,7 @@ class Alignment:
             recs = np.frombuffer(buf, dtype=REC_DTYPE).copy()
         else:
             recs = np.zeros(0, dtype=REC_DTYPE)
-        info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry)
+        info = dict(kernel_ms=r.kernel_ms, launches=r.launches, n_retry=r.n_retry, fast_ms=r.fast_ms, n_complex=r.n_complex)
         if r.psl and r.n_rec:
             info["psl"] = np.ctypeslib.as_array(C.cast(r.psl, C.POINTER(C.c_uint32)), shape=(r.n_rec, 4)).copy()
         self.L.halgpu_free_result(res)

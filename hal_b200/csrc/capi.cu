@@ -109,6 +109,7 @@ static int liftDeviceWithBase(halgpu_ctx *ctx, int src, int tgt, int coalescence
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = n; r->n_rec = lo.nRec; r->offsets = lo.offsets; r->recs = lo.recs; r->on_device = 1;
         r->kernel_ms = lo.kernelMs; r->launches = lo.launches; r->n_retry = lo.nRetry; r->psl = lo.psl;
+        r->fast_ms = lo.fastMs; r->n_complex = lo.nComplex; r->owner = ctx;
         *out = r;
     });
 }
@@ -190,6 +191,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                 if (wantPsl) rt::d2h(r->psl + 4 * nRec, dev->psl, dev->n_rec * 16, cs);
                 nRec += dev->n_rec;
                 r->kernel_ms += dev->kernel_ms; r->launches += dev->launches; r->n_retry += dev->n_retry;
+                r->fast_ms += dev->fast_ms; r->n_complex += dev->n_complex;
             }
             rt::sync(cs);
             r->n_rec = nRec; // (offsets already carry each chunk's base: added on the device)
@@ -324,10 +326,13 @@ const void *halgpu_genome_bottom_segments(const halgpu_ctx *ctx, int g, size_t *
 
 void halgpu_free_result(halgpu_lift_result *r) {
     if (r == nullptr) return;
-    if (r->on_device) {
-        rt::dfree(r->offsets);
-        rt::dfree(r->recs);
-        rt::dfree(r->psl);
+    if (r->on_device) { // the buffers return to the owning context's cache: no cudaFree, no device synchronisation
+        halgpu_ctx *owner = static_cast<halgpu_ctx *>(r->owner);
+        if (owner != nullptr) {
+            owner->impl->release(r->offsets);
+            owner->impl->release(r->recs);
+            owner->impl->release(r->psl);
+        }
     } else {
         rt::hostFree(r->offsets);
         rt::hostFree(r->recs);

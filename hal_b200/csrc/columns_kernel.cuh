@@ -137,8 +137,8 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
             const TopRec r = ldTop(&T.top[w.a]);
             if (r.parentEnc < 0 || T.parent < 0 || !G[T.parent].inScope) break;
             const GenomeTab P = G[T.parent];
-            const int64_t pi = r.parentEnc >> 1;
-            if (noDupes && (ldS(&P.child[(int64_t)T.slot * P.numBot + pi]) >> 1) != w.a) break; // isCanonicalParalog
+            const int64_t pi = linkIdx(r.parentEnc);
+            if (noDupes && linkIdx(ldS(&P.child[(int64_t)T.slot * P.numBot + pi])) != w.a) break; // isCanonicalParalog
             const int64_t L = topStart(T.top, w.a + 1) - r.start, f = w.pos - r.start;
             const bool fl = (r.parentEnc & 1) != 0;
             const int64_t ps = botStart(P.bot, pi);
@@ -165,7 +165,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
             if (!G[c].inScope) break;
             const GenomeTab C = G[c];
             const int64_t b0 = botStart(T.bot, w.a), L = botStart(T.bot, w.a + 1) - b0, f = w.pos - b0;
-            const int64_t ci = ce >> 1;
+            const int64_t ci = linkIdx(ce);
             const bool fl = (ce & 1) != 0;
             const int64_t cs = topStart(C.top, ci);
             const int64_t cp = fl ? cs + L - 1 - f : cs + f;

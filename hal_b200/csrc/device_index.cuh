@@ -2,10 +2,19 @@
 //
 // The file's AoS records (top 40 B, bottom 8*(2+nc)+roundup8(nc) B) are re-packed
 // once at staging time into sector-friendly arrays; the file format itself is untouched.
-//   TopRec   32 B  == one DRAM sector: start | parent<<1|reversed | bottomParseIndex | nextParalogyIndex
+//   TopRec   32 B  == one DRAM sector: start | parent link | bottomParseIndex | nextParalogyIndex
 //   BotCore  16 B : start | topParseIndex          (what every walk needs from a bottom record)
-//   childEnc  8 B : child<<1|reversed, one array per child slot (a walk only ever follows ONE slot per level,
+//   childEnc  8 B : child link, one array per child slot (a walk only ever follows ONE slot per level,
 //                   so the other slots' columns are never fetched -- AoS bottoms of an 8-child genome are 88 B)
+// A link (parent link of a top record, child link of a bottom record) is -1 for "none", else
+//   bit 0      reversed
+//   bits 1-32  index of the homologous segment in the other genome
+//   bits 33-62 collinear run, in bases, capped at LINK_RUN_CAP: counted from the START of this segment, how far the
+//              vertical map stays ONE affine map -- the following segments all have links, the same orientation and
+//              indices advancing by +1 (forward) / -1 (reversed).  For child links the run is additionally 0 when the
+//              landing top segment carries a paralogy ring and stops before the first following segment whose landing
+//              top does (mapSelf fans out there, api/impl/halSegmentMapper.cpp:263-288).  Computed once at staging
+//              (stage_kernels.cuh: linkRunKernel); the file format has no such field.
 // Both arrays keep the file's +1 sentinel record so that length(i) = start(i+1) - start(i)
 // (api/mmap_impl/mmapTopSegment.h:78-80).
 #pragma once
@@ -21,9 +30,17 @@
 
 namespace halgpu {
 
+static const int64_t LINK_RUN_CAP = (1ll << 30) - 1;
+__host__ __device__ inline int64_t linkIdx(int64_t e) { return (e >> 1) & 0xffffffffll; }
+__host__ __device__ inline bool linkRev(int64_t e) { return (e & 1) != 0; }
+__host__ __device__ inline int64_t linkRun(int64_t e) { return e >> 33; } // e >= 0
+__host__ __device__ inline int64_t makeLink(int64_t idx, bool rev, int64_t run) {
+    return (run << 33) | (idx << 1) | (rev ? 1 : 0);
+}
+
 struct alignas(32) TopRec {
     int64_t start;
-    int64_t parentEnc; // -1: no parent; else (parentIndex << 1) | parentReversed
+    int64_t parentEnc; // -1: no parent; else a link (see above) to the parent genome's bottom segment
     int64_t botParse;  // bottomParseIndex (-1 for leaves)
     int64_t nextPara;  // nextParalogyIndex (-1: none)
 };
@@ -44,6 +61,9 @@ struct PathStep {
     int32_t flags; // STEP_* (only set on paths planned with a coalescence limit above the MRCA)
     int32_t jump;  // STEP_PARA: path position at which this genome's paralogs start their way back down to the MRCA
     int32_t pad;
+    // position -> segment index tables of this genome (fastLiftKernel re-locates a fragment after every hop)
+    const uint32_t *topBucket, *botBucket;
+    int32_t topShift, botShift;
 };
 // halLiftover --coalescenceLimit (mapRecursiveParalogies, api/impl/halSegmentMapper.cpp:525-576): between the upward and the
 // downward part of the path sit the genomes from the MRCA up to the child of the limit (STEP_PARA entries, walked upward),
@@ -75,13 +95,15 @@ struct LiftParams {
     int32_t pad0;
     // batch
     int64_t n;               // work items of this launch
-    const uint32_t *work;    // optional: work[w] = interval id (sorted order or retry subset); NULL: identity
+    const uint32_t *work;    // optional: work[w] = interval id (retry subsets, the complex list); NULL: identity
+    const unsigned long long *work64; // optional, instead of work: the sorted batch, interval id in the low 32 bits
+    const unsigned long long *nDev; // optional: the number of work items lives on the device (complex list length)
     const int64_t *gs, *ge;  // genome-global inclusive
     const uint8_t *strand;   // may be NULL
     // outputs
-    uint32_t *outCount;      // per interval
-    uint64_t *outOffset;     // per interval: first record in pool
-    uint32_t *status;        // per interval: ST_*
+    unsigned long long *outLoc; // per interval: (first record in pool << LOC_COUNT_BITS) | number of records; 0 until written
+    uint32_t *status;        // per interval: ST_* (zeroed == ST_OK by the engine; only failures are written)
+    unsigned long long *failCount; // 4 counters indexed by ST_*: intervals that ended in that state (ST_OK is not counted)
     halgpu_lift_rec *pool;
     uint32_t *pslPool;        // optional (HALGPU_PSL): 4 counters per pool record (matches, misMatches, repMatches, nCount), zeroed
     const uint8_t *srcDna, *tgtDna; // packed nibbles of the source / target genome (PSL only)
@@ -131,5 +153,31 @@ static const unsigned long long WIG_UNSET = 0x7fffffffffffffffull;
 static const unsigned long long WIG_ZERO = 0x8000000000000000ull;
 
 enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2, ST_BAD_INPUT = 3 };
+#define HG_LOC_COUNT_BITS 25 // an interval yields at most 2^24 records (engine.cu: listCap ladder)
+
+// fastLiftKernel (liftover_kernel.cuh): one LANE per interval.  An interval whose whole source range maps through every
+// genome of the path as ONE affine piece without meeting a paralogy ring yields exactly one output line; everything
+// else is appended to the complex list and walked by liftoverKernel (one warp per interval).
+struct FastParams {
+    const PathStep *steps;
+    int32_t P;
+    int32_t srcIsTop;
+    int64_t srcLen;
+    const int64_t *tgtSeqStart;
+    int32_t tgtNumSeq;
+    int32_t pad0;
+    int64_t n;
+    const int64_t *gs, *ge;               // input order
+    const uint8_t *strand;                // may be NULL
+    const unsigned long long *sortedGs;   // optional: gs in visiting order ...
+    const unsigned long long *sortedVal;  // ... with (interval id | min(length, 2^32 - 1) << 32)
+    unsigned long long *tileCursor;       // next tile of 32 work items
+    unsigned long long *outLoc;
+    halgpu_lift_rec *pool;
+    unsigned long long *poolCursor;
+    uint64_t poolCap;
+    uint32_t *complexList;                // interval ids left to liftoverKernel
+    unsigned long long *complexCount;
+};
 
 } // namespace halgpu

@@ -75,6 +75,24 @@ struct DevBuf { // RAII for per-batch device scratch (stream-ordered)
     template <class T> T *as() const { return static_cast<T *>(p); }
     void *release() { void *q = p; p = nullptr; return q; }
 };
+// buffers of one batch, handed back to the context's cache when the batch ends
+struct Lease {
+    DeviceCache &cache;
+    std::vector<void *> held;
+    explicit Lease(DeviceCache &c) : cache(c) {}
+    ~Lease() { for (void *p : held) cache.give(p); }
+    Lease(const Lease &) = delete;
+    Lease &operator=(const Lease &) = delete;
+    void *take(size_t bytes) { void *p = cache.take(bytes); held.push_back(p); return p; }
+    template <class T> T *as(size_t count) { return static_cast<T *>(take(count * sizeof(T))); }
+    void giveNow(void *p) {
+        for (size_t i = 0; i < held.size(); ++i) if (held[i] == p) { held.erase(held.begin() + (long)i); cache.give(p); return; }
+    }
+    void *detach(void *p) { // ownership leaves with the result
+        for (size_t i = 0; i < held.size(); ++i) if (held[i] == p) { held.erase(held.begin() + (long)i); return p; }
+        return p;
+    }
+};
 unsigned gridFor(int64_t n, unsigned block, int sms) {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = (int64_t)sms * 32;
@@ -83,6 +101,35 @@ unsigned gridFor(int64_t n, unsigned block, int sms) {
     return (unsigned)g;
 }
 } // namespace
+
+DeviceCache::~DeviceCache() {
+    for (auto &kv : _sizeOf) rt::dfree(kv.first);
+}
+void *DeviceCache::take(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    {
+        std::lock_guard<std::mutex> g(_m);
+        auto it = _idle.lower_bound(bytes);
+        if (it != _idle.end() && it->first <= 2 * bytes + (1u << 20)) {
+            void *p = it->second;
+            _idle.erase(it);
+            return p;
+        }
+    }
+    const size_t cap = (bytes + bytes / 8 + 255) & ~(size_t)255;
+    void *p = rt::dmalloc(cap);
+    std::lock_guard<std::mutex> g(_m);
+    _sizeOf[p] = cap;
+    _held += cap;
+    return p;
+}
+void DeviceCache::give(void *p) {
+    if (p == nullptr) return;
+    std::lock_guard<std::mutex> g(_m);
+    auto it = _sizeOf.find(p);
+    if (it == _sizeOf.end()) { rt::dfree(p); return; } // not ours (defensive)
+    _idle.emplace(it->second, p);
+}
 
 void *Context::alloc(size_t bytes) {
     void *p = rt::dmalloc(bytes);
@@ -100,7 +147,10 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     _g.resize(_file->genomes().size());
     try {
         for (size_t g = 0; g < _g.size(); ++g) stageGenome((int)g);
+        for (size_t g = 0; g < _g.size(); ++g) stageLinkRuns((int)g); // needs every genome's arrays in place
         rt::sync(_stream);
+        _hostCtr = static_cast<unsigned long long *>(rt::hostAlloc(32 * sizeof(unsigned long long)));
+        for (auto &e : _ev) e.reset(new rt::Event);
     } catch (...) {
         for (void *p : _owned) rt::dfree(p);
         rt::destroyStream(_stream);
@@ -110,6 +160,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
 }
 
 Context::~Context() {
+    rt::hostFree(_hostCtr);
     for (auto &kv : _plans) rt::dfree(kv.second.dSteps);
     for (void *p : _owned) rt::dfree(p);
     rt::destroyStream(_stream);
@@ -185,6 +236,36 @@ void Context::stageGenome(int gi) {
     if (g.numBottom > 0) buildBucket(d.bot, false, g.numBottom, g.length, d.botBucket, d.botShift, d.botBuckets);
 }
 
+void Context::stageLinkRuns(int gi) {
+    // the run field of every vertical link (device_index.cuh): parent links of this genome's tops, child links of its bottoms
+    const GenomeInfo &g = _file->genomes()[gi];
+    GenomeDev &d = _g[gi];
+    const int64_t nMax = std::max(g.numTop, g.numBottom);
+    if (nMax == 0) return;
+    DevBuf::current() = _stream;
+    DevBuf mark((size_t)nMax * 4), next((size_t)nMax * 4);
+    size_t tmpBytes = 0;
+    rt::suffixMinU32Tmp(nullptr, tmpBytes, mark.as<uint32_t>(), next.as<uint32_t>(), (size_t)nMax, _stream);
+    DevBuf tmp(tmpBytes);
+    auto run = [&](int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n, const TopRec *landTop) {
+        LinkRunParams lp;
+        lp.links = links; lp.starts = starts; lp.linkStride = linkStride; lp.startStride = startStride; lp.n = n;
+        lp.landTop = landTop; lp.mark = mark.as<uint32_t>();
+        rt::launch(linkBreakKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
+        size_t tb = tmpBytes;
+        rt::suffixMinU32Tmp(tmp.p, tb, mark.as<uint32_t>(), next.as<uint32_t>(), (size_t)n, _stream);
+        lp.mark = next.as<uint32_t>();
+        rt::launch(linkRunKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
+    };
+    if (g.numTop > 0 && g.parent >= 0) {
+        run(&d.top[0].parentEnc, sizeof(TopRec) / 8, &d.top[0].start, sizeof(TopRec) / 8, g.numTop, nullptr);
+    }
+    for (size_t k = 0; k < g.children.size() && g.numBottom > 0; ++k) {
+        run(d.child + k * (size_t)g.numBottom, 1, &d.bot[0].start, sizeof(BotCore) / 8, g.numBottom, _g[g.children[k]].top);
+    }
+    rt::sync(_stream);
+}
+
 const Plan &Context::plan(int src, int tgt, int coal) {
     const auto &G = _file->genomes();
     Plan p;
@@ -231,6 +312,7 @@ const Plan &Context::plan(int src, int tgt, int coal) {
         s.top = _g[g].top; s.bot = _g[g].bot; s.child = nullptr;
         s.numTop = G[g].numTop; s.numBot = G[g].numBottom;
         s.up = ent[i].up; s.flags = ent[i].flags; s.jump = ent[i].jump; s.pad = 0;
+        s.topBucket = _g[g].topBucket; s.botBucket = _g[g].botBucket; s.topShift = _g[g].topShift; s.botShift = _g[g].botShift;
         if (i + 1 >= ent.size()) continue;
         const int nx = ent[i + 1].g;
         if (!s.up) { // this genome's childEnc column for the slot of the next genome down
@@ -394,6 +476,11 @@ struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch
 
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
                        const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig, int coal) {
+    // One batch == one pass of the hot path.  Everything up to the single stream synchronisation is enqueued without
+    // waiting: sort -> fastLiftKernel (one lane per interval) -> liftoverKernel over the complex list (one warp per
+    // interval) -> scan -> gather -> read-back of the counters.  Buffers come from the context's cache, so a warm batch
+    // allocates nothing.  Only a batch with intervals that overflowed their scratch or the record pool (counted by the
+    // kernels themselves) enters the retry ladder, which synchronises per rung.
     PhaseTimer pt;
     const auto &G = _file->genomes();
     if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
@@ -406,208 +493,270 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     // source genome is the MRCA: HALGPU_SEED_BOTTOM
     const bool srcIsTop = S.numTop > 0 && !((flags & HALGPU_SEED_BOTTOM) != 0 && S.numBottom > 0);
     if (!srcIsTop && S.numBottom == 0) throw HalError("source genome " + S.name + " has no segments");
+    const bool raw = (flags & HALGPU_RAW_FRAGMENTS) != 0;
+    const bool wantPsl = (flags & HALGPU_PSL) != 0;
+    const bool columnMerge = (flags & HALGPU_COLUMN_LIFTOVER) != 0;
+    if (wig && coalPath) throw HalError("the wiggle liftover has no coalescence limit (the reference's halWiggleLiftover has none either)");
+    if (raw && (wig || wantPsl || columnMerge)) throw HalError("HALGPU_RAW_FRAGMENTS cannot be combined with PSL counts or ColumnLiftover mode");
     out = LiftOutput();
     out.n = n;
-    DevBuf::current() = _stream;
     const int launches0 = (int)rt::g_launches;
+    // the one-lane-per-interval kernel computes BlockLiftover lines only (no PSL base counts, no raw fragments, ...)
+    const bool fast = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !(flags & HALGPU_NO_FAST) && n > 0 &&
+                      pl.path.size() <= (size_t)HG_FAST_MAX_PATH && std::getenv("HALGPU_NO_FAST") == nullptr;
 
-    DevBuf outCount((n + 1) * sizeof(uint32_t)), outOffset((n + 1) * sizeof(uint64_t)), status((n + 1) * sizeof(uint32_t));
-    rt::dmemset(outCount.p, 0, (n + 1) * sizeof(uint32_t), _stream);
-    rt::dmemset(status.p, 0xff, (n + 1) * sizeof(uint32_t), _stream);
-    DevBuf cursor(8 * sizeof(unsigned long long)); // [0] pool cursor, [1] list count, [4..7] per-status counts
-    rt::dmemset(cursor.p, 0, 8 * sizeof(unsigned long long), _stream);
+    Lease L(_cache);
+    try {
+        enum { C_POOL = 0, C_COLLECT = 1, C_TILE = 2, C_COMPLEX = 3, C_FAIL = 4, C_TOTAL = 8, C_WORDS = 16 };
+        unsigned long long *outLoc = L.as<unsigned long long>(n + 2);
+        uint32_t *status = L.as<uint32_t>(n + 1);
+        unsigned long long *ctr = L.as<unsigned long long>(C_WORDS);
+        rt::dmemset(outLoc, 0, (n + 2) * sizeof(unsigned long long), _stream);
+        rt::dmemset(status, 0, (n + 1) * sizeof(uint32_t), _stream);
+        rt::dmemset(ctr, 0, C_WORDS * sizeof(unsigned long long), _stream);
+        pt.mark("alloc0");
 
-    pt.mark("alloc0");
-    // visit the batch in source order so that neighbouring warps walk neighbouring records (L2 reuse)
-    std::unique_ptr<DevBuf> work, keysIn, keysOut, valsIn;
-    const uint32_t *dWork = nullptr;
-    if (!(flags & HALGPU_NO_SORT) && n > 1) {
-        keysIn.reset(new DevBuf(n * 8)); keysOut.reset(new DevBuf(n * 8));
-        valsIn.reset(new DevBuf(n * 4)); work.reset(new DevBuf(n * 4));
-        IotaParams ip;
-        ip.out = valsIn->as<uint32_t>(); ip.keys = keysIn->as<uint64_t>(); ip.gs = dGs; ip.n = (int64_t)n;
-        rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
-        int endBit = 1;
-        while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
-        rt::sortPairsU64U32(keysIn->as<uint64_t>(), keysOut->as<uint64_t>(), valsIn->as<uint32_t>(), work->as<uint32_t>(), n, endBit, _stream);
-        dWork = work->as<uint32_t>();
-        keysIn.reset(); keysOut.reset(); valsIn.reset();
-    }
+        // visit the batch in source order so that neighbouring lanes / warps walk neighbouring records (coalescing, L2 reuse).
+        // Only the upper bits of the start decide the order: ~32 source segments per sort bucket are as good as an exact order.
+        const unsigned long long *sortedGs = nullptr, *sortedVal = nullptr;
+        if (!(flags & HALGPU_NO_SORT) && n > 1) {
+            uint64_t *keysIn = L.as<uint64_t>(n), *valsIn = L.as<uint64_t>(n), *keysOut = L.as<uint64_t>(n), *valsOut = L.as<uint64_t>(n);
+            IotaParams ip;
+            ip.vals = valsIn; ip.keys = keysIn; ip.gs = dGs; ip.ge = dGe; ip.n = (int64_t)n;
+            rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
+            int endBit = 1;
+            while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
+            const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
+            int bits = ((endBit - coarse) / 8) * 8;
+            if (bits < 8) bits = std::min(8, endBit);
+            const int beginBit = std::max(0, endBit - bits);
+            size_t tmpBytes = 0;
+            rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+            void *tmp = L.take(tmpBytes);
+            rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+            sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
+            sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
+        }
+        if (pt.on) rt::sync(_stream);
+        pt.mark("sort");
 
-    if (pt.on) rt::sync(_stream);
-    pt.mark("sort");
-    uint64_t poolCap = wig ? 1 : (uint64_t)n + (uint64_t)n / 4 + 4096; // (the wiggle mode emits no records)
-    std::unique_ptr<DevBuf> pool(new DevBuf(poolCap * sizeof(halgpu_lift_rec)));
-    const bool wantPsl = (flags & HALGPU_PSL) != 0;
-    std::unique_ptr<DevBuf> pslPool;
-    if (wantPsl) {
-        pslPool.reset(new DevBuf(poolCap * 16));
-        rt::dmemset(pslPool->p, 0, poolCap * 16, _stream);
-    }
+        uint64_t poolCap = wig ? 1 : (uint64_t)n + (uint64_t)n / 4 + 4096; // (the wiggle mode emits no records)
+        halgpu_lift_rec *pool = L.as<halgpu_lift_rec>(poolCap);
+        uint32_t *pslPool = nullptr;
+        if (wantPsl) {
+            pslPool = L.as<uint32_t>(poolCap * 4);
+            rt::dmemset(pslPool, 0, poolCap * 16, _stream);
+        }
 
-    LiftParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.steps = pl.dSteps; P.P = (int32_t)pl.path.size(); P.dupes = (flags & HALGPU_NO_DUPES) ? 0 : 1;
-    P.columnMerge = (flags & HALGPU_COLUMN_LIFTOVER) ? 1 : 0;
-    P.upCanonicalOnly = (P.columnMerge && !P.dupes) ? 1 : 0;
-    P.srcIsTop = srcIsTop ? 1 : 0;
-    P.srcShift = srcIsTop ? _g[src].topShift : _g[src].botShift;
-    P.srcN = srcIsTop ? S.numTop : S.numBottom;
-    P.srcLen = S.length;
-    P.srcBucket = srcIsTop ? _g[src].topBucket : _g[src].botBucket;
-    P.srcNumBuckets = srcIsTop ? _g[src].topBuckets : _g[src].botBuckets;
-    P.tgtSeqStart = _g[tgt].seqStart; P.tgtNumSeq = (int32_t)G[tgt].sequences.size();
-    P.gs = dGs; P.ge = dGe; P.strand = dStrand;
-    P.outCount = outCount.as<uint32_t>(); P.outOffset = outOffset.as<uint64_t>(); P.status = status.as<uint32_t>();
-    P.pool = pool->as<halgpu_lift_rec>(); P.poolCursor = cursor.as<unsigned long long>(); P.poolCap = poolCap;
-    P.pslPool = wantPsl ? pslPool->as<uint32_t>() : nullptr;
-    P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
-    if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
+        LiftParams P;
+        std::memset(&P, 0, sizeof(P));
+        P.steps = pl.dSteps; P.P = (int32_t)pl.path.size(); P.dupes = (flags & HALGPU_NO_DUPES) ? 0 : 1;
+        P.columnMerge = columnMerge ? 1 : 0;
+        P.upCanonicalOnly = (P.columnMerge && !P.dupes) ? 1 : 0;
+        P.srcIsTop = srcIsTop ? 1 : 0;
+        P.srcShift = srcIsTop ? _g[src].topShift : _g[src].botShift;
+        P.srcN = srcIsTop ? S.numTop : S.numBottom;
+        P.srcLen = S.length;
+        P.srcBucket = srcIsTop ? _g[src].topBucket : _g[src].botBucket;
+        P.srcNumBuckets = srcIsTop ? _g[src].topBuckets : _g[src].botBuckets;
+        P.tgtSeqStart = _g[tgt].seqStart; P.tgtNumSeq = (int32_t)G[tgt].sequences.size();
+        P.gs = dGs; P.ge = dGe; P.strand = dStrand;
+        P.outLoc = outLoc; P.status = status; P.failCount = ctr + C_FAIL;
+        P.pool = pool; P.poolCursor = ctr + C_POOL; P.poolCap = poolCap;
+        P.pslPool = pslPool;
+        P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
+        if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
-    if (wig && coalPath) throw HalError("the wiggle liftover has no coalescence limit (the reference's halWiggleLiftover has none either)");
-    const bool raw = (flags & HALGPU_RAW_FRAGMENTS) != 0;
-    if (raw && (wig || (flags & (HALGPU_PSL | HALGPU_COLUMN_LIFTOVER)) != 0)) {
-        throw HalError("HALGPU_RAW_FRAGMENTS cannot be combined with PSL counts or ColumnLiftover mode");
-    }
-    void (*const mapKernel)(const LiftParams) =
-        wig ? liftoverKernel<LIFT_WIG>
-            : (raw ? (coalPath ? liftoverKernel<LIFT_RAW_COAL> : liftoverKernel<LIFT_RAW>) : (coalPath ? liftoverKernel<LIFT_COAL> : liftoverKernel<LIFT_BED>));
-    // rung 1: all n intervals, scratch in shared memory
-    const unsigned block = 128, warpsPerBlock = block / 32;
-    {
-        P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
-        P.n = (int64_t)n; P.work = dWork;
-        const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
-        rt::allowSmem(mapKernel, smem);
-        rt::Event e0, e1;
-        e0.record(_stream);
-        rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
-        e1.record(_stream);
-        rt::sync(_stream);
-        out.kernelMs = rt::Event::elapsedMs(e0, e1);
-    }
-    pt.mark("kernel");
-
-    // retry ladder: pool growth, then larger per-warp scratch in global memory
-    DevBuf list((n + 1) * sizeof(uint32_t));
-    unsigned long long *dCount = cursor.as<unsigned long long>() + 1;
-    auto collect = [&](uint32_t want, const uint32_t *subset, int64_t cnt) -> uint64_t {
-        rt::dmemset(dCount, 0, sizeof(unsigned long long), _stream);
-        CollectParams cp;
-        cp.status = P.status; cp.list = list.as<uint32_t>(); cp.count = dCount; cp.subset = subset; cp.n = cnt; cp.want = want;
-        rt::launch(collectKernel, gridFor(cnt, 256, _sms), 256, 0, _stream, cp);
-        unsigned long long c = 0;
-        rt::d2h(&c, dCount, sizeof(c), _stream);
-        rt::sync(_stream);
-        return c;
-    };
-    int listCap = 64, frameCap = 32;
-    for (int round = 0; round < 64; ++round) {
-        // one pass over the statuses; in the common case (everything ST_OK) this is the only check
-        unsigned long long counts[4] = {0, 0, 0, 0};
+        void (*const mapKernel)(const LiftParams) =
+            wig ? liftoverKernel<LIFT_WIG>
+                : (raw ? (coalPath ? liftoverKernel<LIFT_RAW_COAL> : liftoverKernel<LIFT_RAW>) : (coalPath ? liftoverKernel<LIFT_COAL> : liftoverKernel<LIFT_BED>));
+        const unsigned block = 128, warpsPerBlock = block / 32;
+        uint32_t *complexList = nullptr;
+        // rung 1: the whole batch; the walk keeps its lists in shared memory
+        _ev[0]->record(_stream);
+        if (fast) {
+            complexList = L.as<uint32_t>(n + 1);
+            FastParams F;
+            std::memset(&F, 0, sizeof(F));
+            F.steps = pl.dSteps; F.P = P.P; F.srcIsTop = P.srcIsTop; F.srcLen = S.length;
+            F.tgtSeqStart = P.tgtSeqStart; F.tgtNumSeq = P.tgtNumSeq;
+            F.n = (int64_t)n; F.gs = dGs; F.ge = dGe; F.strand = dStrand;
+            F.sortedGs = sortedGs; F.sortedVal = sortedVal;
+            F.tileCursor = ctr + C_TILE; F.outLoc = outLoc; F.pool = pool; F.poolCursor = ctr + C_POOL; F.poolCap = poolCap;
+            F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
+            const int64_t tiles = ((int64_t)n + 31) / 32;
+            const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)_sms * 8));
+            rt::launch(fastLiftKernel, fgrid, 256, 0, _stream, F);
+            _ev[1]->record(_stream);
+        }
         {
-            unsigned long long *dCounts = cursor.as<unsigned long long>() + 4;
-            rt::dmemset(dCounts, 0, 4 * sizeof(unsigned long long), _stream);
-            StatusCountParams sp;
-            sp.status = P.status; sp.counts = dCounts; sp.n = (int64_t)n;
-            rt::launch(statusCountKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, sp);
-            rt::d2h(counts, dCounts, sizeof(counts), _stream);
-            rt::sync(_stream);
+            P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
+            P.n = (int64_t)n;
+            if (fast) { P.work = complexList; P.nDev = ctr + C_COMPLEX; }
+            else P.work64 = sortedVal;
+            const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
+            rt::allowSmem(mapKernel, smem);
+            rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
+            P.work = nullptr; P.work64 = nullptr; P.nDev = nullptr;
         }
-        if (counts[ST_BAD_INPUT] > 0) {
-            throw HalError(std::to_string(counts[ST_BAD_INPUT]) + " interval(s) lie outside genome " + S.name + " (length " + std::to_string(S.length) + ")");
-        }
-        if (counts[ST_POOL_FULL] == 0 && counts[ST_SCRATCH_OVERFLOW] == 0) break;
-        // (a) intervals that found the output pool full: grow it (old records stay valid) and redo them
-        uint64_t nFull = counts[ST_POOL_FULL] ? collect(ST_POOL_FULL, nullptr, (int64_t)n) : 0;
-        if (nFull > 0) {
-            unsigned long long used = 0;
-            rt::d2h(&used, P.poolCursor, sizeof(used), _stream);
-            rt::sync(_stream);
-            const uint64_t newCap = std::max<uint64_t>(poolCap * 2, used * 2);
-            std::unique_ptr<DevBuf> np(new DevBuf(newCap * sizeof(halgpu_lift_rec)));
-            rt::d2d(np->p, pool->p, poolCap * sizeof(halgpu_lift_rec), _stream);
-            rt::sync(_stream);
-            pool.swap(np);
-            if (wantPsl) { // counters of the records already written move along; the new tail starts at zero
-                std::unique_ptr<DevBuf> nq(new DevBuf(newCap * 16));
-                rt::dmemset(nq->p, 0, newCap * 16, _stream);
-                rt::d2d(nq->p, pslPool->p, poolCap * 16, _stream);
-                rt::sync(_stream);
-                pslPool.swap(nq);
-                P.pslPool = pslPool->as<uint32_t>();
-            }
-            poolCap = newCap;
-            P.pool = pool->as<halgpu_lift_rec>(); P.poolCap = poolCap;
-            DevBuf ids(nFull * sizeof(uint32_t));
-            rt::d2d(ids.p, list.p, nFull * sizeof(uint32_t), _stream);
-            P.n = (int64_t)nFull; P.work = ids.as<uint32_t>();
-            const bool inSmem = listCap == 64;
-            const uint64_t per = liftScratchBytes(listCap, frameCap);
-            const int64_t warps = std::min<int64_t>((int64_t)nFull, (int64_t)_sms * 8);
-            std::unique_ptr<DevBuf> scratch;
-            P.listCap = listCap; P.frameCap = frameCap;
-            if (inSmem) { P.gscratch = nullptr; P.gscratchPerWarp = 0; }
-            else { scratch.reset(new DevBuf(per * (uint64_t)warps)); P.gscratch = scratch->as<uint8_t>(); P.gscratchPerWarp = per; }
-            const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
-            rt::launch(mapKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
-            rt::sync(_stream);
-            continue;
-        }
-        // (b) intervals whose fragment lists outgrew the scratch: next rung
-        uint64_t nOver = collect(ST_SCRATCH_OVERFLOW, nullptr, (int64_t)n);
-        if (nOver == 0) break;
-        if (out.nRetry == 0) out.nRetry = nOver;
-        listCap *= (listCap == 64 ? 64 : 16); // 64 -> 4096 -> 65536 -> 1M
-        frameCap = listCap / 4;
-        if (listCap > (1 << 24)) throw HalError("an interval maps to more than 16M fragments; not supported");
-        const uint64_t per = liftScratchBytes(listCap, frameCap);
-        int64_t warps = std::min<int64_t>((int64_t)nOver, (int64_t)_sms * 8);
-        const uint64_t budget = 8ull << 30; // scratch budget
-        if ((uint64_t)warps * per > budget) warps = std::max<int64_t>(1, (int64_t)(budget / per));
-        DevBuf scratch(per * (uint64_t)warps);
-        DevBuf ids(nOver * sizeof(uint32_t));
-        rt::d2d(ids.p, list.p, nOver * sizeof(uint32_t), _stream);
-        P.n = (int64_t)nOver; P.work = ids.as<uint32_t>();
-        P.listCap = listCap; P.frameCap = frameCap; P.gscratch = scratch.as<uint8_t>(); P.gscratchPerWarp = per;
-        rt::launch(mapKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
-        rt::sync(_stream);
-    }
+        _ev[2]->record(_stream);
+        if (pt.on) rt::sync(_stream);
+        pt.mark("kernel");
 
-    pt.mark("status");
-    if (wig) { // values went straight into wig->keys; there is no record list to assemble
+        // CSR assembly in input order, enqueued right behind the kernels; redone only if the retry ladder had to run
+        uint64_t *csr = nullptr;
+        halgpu_lift_rec *recs = nullptr;
+        uint32_t *psl = nullptr;
+        uint64_t recCap = 0;
+        void *scanTmp = nullptr;
+        size_t scanTmpBytes = 0;
+        const uint64_t countMask = (1ull << HG_LOC_COUNT_BITS) - 1ull;
+        auto assemble = [&]() {
+            if (wig) return;
+            if (csr == nullptr) {
+                csr = L.as<uint64_t>(n + 2);
+                rt::exclusiveScanMaskedTmp(nullptr, scanTmpBytes, outLoc, csr, n, countMask, _stream);
+                scanTmp = L.take(scanTmpBytes);
+            }
+            if (recs == nullptr || recCap < P.poolCap) {
+                if (recs) L.giveNow(recs);
+                if (psl) L.giveNow(psl);
+                recCap = P.poolCap;
+                recs = L.as<halgpu_lift_rec>(recCap);
+                psl = wantPsl ? L.as<uint32_t>(recCap * 4) : nullptr;
+            }
+            size_t tb = scanTmpBytes;
+            rt::exclusiveScanMaskedTmp(scanTmp, tb, outLoc, csr, n, countMask, _stream);
+            GatherParams gp;
+            gp.pslPool = P.pslPool; gp.psl = psl;
+            gp.outLoc = outLoc; gp.csr = csr; gp.pool = P.pool; gp.recs = recs; gp.n = (int64_t)n;
+            rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
+            rt::d2d(ctr + C_TOTAL, csr + n, sizeof(uint64_t), _stream);
+            if (offsetBase != 0) { // chunk-local offsets -> offsets of the whole batch (halgpu_liftover lifts chunk by chunk)
+                AddBaseParams ab;
+                ab.v = csr; ab.n = (int64_t)n + 1; ab.base = offsetBase;
+                rt::launch(addBaseKernel, gridFor((int64_t)n + 1, 256, _sms), 256, 0, _stream, ab);
+            }
+        };
+        auto readBack = [&]() { // the batch's one synchronisation
+            rt::d2h(_hostCtr, ctr, C_WORDS * sizeof(unsigned long long), _stream);
+            rt::sync(_stream);
+        };
+        assemble();
+        readBack();
+        out.kernelMs = rt::Event::elapsedMs(*_ev[0], *_ev[2]);
+        if (fast) { out.fastMs = rt::Event::elapsedMs(*_ev[0], *_ev[1]); out.nComplex = (size_t)_hostCtr[C_COMPLEX]; }
+        pt.mark("assemble");
+
+        // retry ladder: pool growth, then larger per-warp scratch in global memory
+        uint32_t *list = nullptr;
+        auto collect = [&](uint32_t want) -> uint64_t {
+            if (list == nullptr) list = L.as<uint32_t>(n + 1);
+            rt::dmemset(ctr + C_COLLECT, 0, sizeof(unsigned long long), _stream);
+            CollectParams cp;
+            cp.status = status; cp.list = list; cp.count = ctr + C_COLLECT; cp.subset = nullptr; cp.n = (int64_t)n; cp.want = want;
+            rt::launch(collectKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, cp);
+            unsigned long long c = 0;
+            rt::d2h(&c, ctr + C_COLLECT, sizeof(c), _stream);
+            rt::sync(_stream);
+            return c;
+        };
+        int listCap = 64, frameCap = 32;
+        bool redo = false;
+        for (int round = 0; round < 64; ++round) {
+            const unsigned long long *fails = _hostCtr + C_FAIL;
+            if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] round %d fails %llu %llu %llu pool %llu complex %llu total %llu\n", round, fails[1], fails[2], fails[3], _hostCtr[C_POOL], _hostCtr[C_COMPLEX], _hostCtr[C_TOTAL]);
+            if (fails[ST_BAD_INPUT] > 0) {
+                throw HalError(std::to_string(fails[ST_BAD_INPUT]) + " interval(s) lie outside genome " + S.name + " (length " + std::to_string(S.length) + ")");
+            }
+            if (fails[ST_POOL_FULL] == 0 && fails[ST_SCRATCH_OVERFLOW] == 0) break;
+            redo = true;
+            rt::Event r0, r1;
+            // (a) intervals that found the output pool full: grow it (old records stay valid) and redo them
+            const uint64_t nFull = fails[ST_POOL_FULL] ? collect(ST_POOL_FULL) : 0;
+            if (nFull > 0) {
+                const uint64_t used = _hostCtr[C_POOL];
+                const uint64_t newCap = std::max<uint64_t>(poolCap * 2, used * 2);
+                halgpu_lift_rec *np = L.as<halgpu_lift_rec>(newCap);
+                rt::d2d(np, pool, poolCap * sizeof(halgpu_lift_rec), _stream);
+                if (wantPsl) { // counters of the records already written move along; the new tail starts at zero
+                    uint32_t *nq = L.as<uint32_t>(newCap * 4);
+                    rt::dmemset(nq, 0, newCap * 16, _stream);
+                    rt::d2d(nq, pslPool, poolCap * 16, _stream);
+                    rt::sync(_stream);
+                    L.giveNow(pslPool);
+                    pslPool = nq;
+                    P.pslPool = pslPool;
+                }
+                rt::sync(_stream);
+                L.giveNow(pool);
+                pool = np;
+                poolCap = newCap;
+                P.pool = pool; P.poolCap = poolCap;
+                uint32_t *ids = L.as<uint32_t>(nFull);
+                rt::d2d(ids, list, nFull * sizeof(uint32_t), _stream);
+                rt::dmemset(ctr + C_FAIL + ST_POOL_FULL, 0, sizeof(unsigned long long), _stream); // all of them run again
+                P.n = (int64_t)nFull; P.work = ids;
+                const bool inSmem = listCap == 64;
+                const uint64_t per = liftScratchBytes(listCap, frameCap);
+                const int64_t warps = std::min<int64_t>((int64_t)nFull, (int64_t)_sms * 8);
+                void *scratch = nullptr;
+                P.listCap = listCap; P.frameCap = frameCap;
+                if (inSmem) { P.gscratch = nullptr; P.gscratchPerWarp = 0; }
+                else { scratch = L.take(per * (uint64_t)warps); P.gscratch = static_cast<uint8_t *>(scratch); P.gscratchPerWarp = per; }
+                const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
+                r0.record(_stream);
+                rt::launch(mapKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
+                r1.record(_stream);
+                readBack();
+                out.kernelMs += rt::Event::elapsedMs(r0, r1);
+                L.giveNow(ids);
+                if (scratch) L.giveNow(scratch);
+                continue;
+            }
+            // (b) intervals whose fragment lists outgrew the scratch: next rung
+            const uint64_t nOver = collect(ST_SCRATCH_OVERFLOW);
+            if (nOver == 0) break;
+            if (out.nRetry == 0) out.nRetry = nOver;
+            listCap *= (listCap == 64 ? 64 : 16); // 64 -> 4096 -> 65536 -> 1M
+            frameCap = listCap / 4;
+            if (listCap > (1 << 24)) throw HalError("an interval maps to more than 16M fragments; not supported");
+            const uint64_t per = liftScratchBytes(listCap, frameCap);
+            int64_t warps = std::min<int64_t>((int64_t)nOver, (int64_t)_sms * 8);
+            const uint64_t budget = 8ull << 30; // scratch budget
+            if ((uint64_t)warps * per > budget) warps = std::max<int64_t>(1, (int64_t)(budget / per));
+            void *scratch = L.take(per * (uint64_t)warps);
+            uint32_t *ids = L.as<uint32_t>(nOver);
+            rt::d2d(ids, list, nOver * sizeof(uint32_t), _stream);
+            rt::dmemset(ctr + C_FAIL + ST_SCRATCH_OVERFLOW, 0, sizeof(unsigned long long), _stream); // all of them run again
+            P.n = (int64_t)nOver; P.work = ids;
+            P.listCap = listCap; P.frameCap = frameCap; P.gscratch = static_cast<uint8_t *>(scratch); P.gscratchPerWarp = per;
+            r0.record(_stream);
+            rt::launch(mapKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
+            r1.record(_stream);
+            readBack();
+            out.kernelMs += rt::Event::elapsedMs(r0, r1);
+            L.giveNow(ids);
+            L.giveNow(scratch);
+        }
+        if (redo) {
+            assemble();
+            readBack();
+        }
+        pt.mark("retries");
+        if (wig) { // values went straight into wig->keys; there is no record list to assemble
+            out.launches = (int)rt::g_launches - launches0;
+            return;
+        }
+        out.offsets = static_cast<uint64_t *>(L.detach(csr));
+        out.recs = static_cast<halgpu_lift_rec *>(L.detach(recs));
+        out.psl = wantPsl ? static_cast<uint32_t *>(L.detach(psl)) : nullptr;
+        out.nRec = (size_t)_hostCtr[C_TOTAL];
         out.launches = (int)rt::g_launches - launches0;
-        return;
+    } catch (...) {
+        try { rt::sync(_stream); } catch (...) {} // nothing of this batch may still run when its buffers return to the cache
+        throw;
     }
-    // CSR assembly in input order
-    DevBuf *csr = new DevBuf((n + 2) * sizeof(uint64_t));
-    std::unique_ptr<DevBuf> csrHold(csr);
-    rt::exclusiveScanU32(P.outCount, csr->as<uint64_t>(), n, _stream);
-    uint64_t total = 0;
-    rt::d2h(&total, csr->as<uint64_t>() + n, sizeof(total), _stream);
-    rt::sync(_stream);
-    pt.mark("scan");
-    DevBuf *recs = new DevBuf(std::max<uint64_t>(total, 1) * sizeof(halgpu_lift_rec));
-    std::unique_ptr<DevBuf> recsHold(recs);
-    std::unique_ptr<DevBuf> pslHold;
-    if (wantPsl) pslHold.reset(new DevBuf(std::max<uint64_t>(total, 1) * 16));
-    GatherParams gp;
-    gp.pslPool = P.pslPool; gp.psl = wantPsl ? pslHold->as<uint32_t>() : nullptr;
-    gp.outCount = P.outCount; gp.outOffset = P.outOffset; gp.csr = csr->as<uint64_t>();
-    gp.pool = pool->as<halgpu_lift_rec>(); gp.recs = recs->as<halgpu_lift_rec>(); gp.n = (int64_t)n;
-    rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
-    if (offsetBase != 0) {
-        AddBaseParams ab;
-        ab.v = csr->as<uint64_t>(); ab.n = (int64_t)n + 1; ab.base = offsetBase;
-        rt::launch(addBaseKernel, gridFor((int64_t)n + 1, 256, _sms), 256, 0, _stream, ab);
-    }
-    rt::sync(_stream);
-    pt.mark("gather");
-    out.offsets = static_cast<uint64_t *>(csrHold->release());
-    out.recs = static_cast<halgpu_lift_rec *>(recsHold->release());
-    out.psl = wantPsl ? static_cast<uint32_t *>(pslHold->release()) : nullptr;
-    out.nRec = total;
-    out.launches = (int)rt::g_launches - launches0;
 }
 
 void Context::wiggle(int src, int tgt, uint32_t flags, size_t nRuns, const int64_t *first, const int64_t *last, const int64_t *valOff,

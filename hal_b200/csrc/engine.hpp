@@ -6,6 +6,7 @@
 #include "rt.hpp"
 #include <map>
 #include <memory>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -31,13 +32,30 @@ struct Plan {
     PathStep *dSteps = nullptr;
 };
 
-struct LiftOutput { // device-side result of one batch
+struct LiftOutput { // device-side result of one batch; the buffers belong to the context's cache (Context::release)
     uint64_t *offsets = nullptr; // n + 1
     halgpu_lift_rec *recs = nullptr;
     uint32_t *psl = nullptr;     // 4 per record when HALGPU_PSL
     size_t n = 0, nRec = 0, nRetry = 0;
-    float kernelMs = 0;
+    size_t nComplex = 0;         // intervals the one-lane-per-interval kernel handed to the warp-per-interval walk
+    float kernelMs = 0;          // mapping kernels of the batch (fast + walk + retries)
+    float fastMs = 0;            // fastLiftKernel alone (0 when the batch did not use it)
     int launches = 0;
+};
+
+// Device buffers recycled across batches: once warm, a batch performs no cudaMalloc / cudaFree at all.
+class DeviceCache {
+  public:
+    ~DeviceCache();
+    void *take(size_t bytes);
+    void give(void *p);
+    size_t bytesHeld() const { return _held; }
+
+  private:
+    std::mutex _m;
+    std::multimap<size_t, void *> _idle;
+    std::map<void *, size_t> _sizeOf;
+    size_t _held = 0;
 };
 
 struct WigScatter { // wiggle mode of the mapping kernel (device pointers)
@@ -63,7 +81,7 @@ class Context {
     rt::Stream copyStream() const { return _copy; } // host<->device traffic of the pipelined host-buffer entry point
     size_t stagedBytes() const { return _staged; }
     int device() const { return _device; }
-    // device pointers in, device result out (caller frees offsets/recs with rt::dfree)
+    // device pointers in, device result out (the caller hands offsets/recs/psl back with release())
     // offsetBase is added to every CSR offset (the pipelined host entry point lifts a batch chunk by chunk)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
                   const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr, int coal = -1);
@@ -82,7 +100,11 @@ class Context {
     void columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out,
                     int64_t windowFirst = -1);
 
+    void release(void *deviceBuffer) { _cache.give(deviceBuffer); } // result buffers of liftover()
+    DeviceCache &cache() { return _cache; }
+
   private:
+    void stageLinkRuns(int g);
     void buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab);
     void stageGenome(int g);
     void buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb);
@@ -97,6 +119,9 @@ class Context {
     std::vector<void *> _owned;
     size_t _staged = 0;
     int _sms = 0;
+    DeviceCache _cache;
+    unsigned long long *_hostCtr = nullptr; // pinned: the counters of one batch, read back with its single synchronisation
+    std::unique_ptr<rt::Event> _ev[4];
 };
 
 } // namespace halgpu

@@ -160,6 +160,17 @@ __device__ __forceinline__ void warpRankSort(const Frag *src, Frag *dst, int m, 
     __syncwarp();
 }
 
+// per-interval bookkeeping: only failures touch the status array and the failure counters (the engine zeroes both)
+__device__ __forceinline__ void liftFail(const LiftParams &P, uint32_t item, uint32_t st) {
+    P.status[item] = st;
+    P.outLoc[item] = 0ull;
+    atomicAdd(P.failCount + st, 1ull);
+}
+__device__ __forceinline__ void liftDone(const LiftParams &P, uint32_t item, unsigned long long base, uint32_t count) {
+    P.status[item] = ST_OK;
+    P.outLoc[item] = (base << HG_LOC_COUNT_BITS) | (unsigned long long)count;
+}
+
 struct WarpScratch {
     Frag *listA, *listB;
     Frame *frames;
@@ -175,7 +186,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';
     if (gs < 0 || ge < gs || ge >= P.srcLen) { // reported by the engine as an error; nothing is read for this item
-        if (lane == 0) { P.status[item] = ST_BAD_INPUT; P.outCount[item] = 0; }
+        if (lane == 0) liftFail(P, item, ST_BAD_INPUT);
         return;
     }
     const PathStep *steps = P.steps;
@@ -304,7 +315,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                     if (!(st.flags & STEP_PARA_LAST) && r.parentEnc >= 0) {
                         // (b) mapUp(original, doDupes = true): a copy continues in the parent genome, one level further up
                         const int64_t L = topStart(st.top, idx + 1) - r.start;
-                        const int64_t pi = r.parentEnc >> 1;
+                        const int64_t pi = linkIdx(r.parentEnc);
                         const bool fl = (r.parentEnc & 1) != 0;
                         const int64_t ps = botStart(steps[p + 1].bot, pi);
                         const int64_t off = tLo - r.start;
@@ -336,11 +347,11 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                 const TopRec r = ldTop(&st.top[idx]); // toParent, halBottomSegmentIterator.cpp:40-49
                 if (r.parentEnc < 0) {
                     valid = false;
-                } else if (P.upCanonicalOnly && (ldS(&st.child[r.parentEnc >> 1]) >> 1) != idx) {
+                } else if (P.upCanonicalOnly && linkIdx(ldS(&st.child[linkIdx(r.parentEnc)])) != idx) {
                     valid = false; // ColumnIterator noDupes: only the canonical paralog goes up (halColumnIterator.cpp:559-560)
                 } else {
                     const int64_t L = topStart(st.top, idx + 1) - r.start;
-                    const int64_t pi = r.parentEnc >> 1;
+                    const int64_t pi = linkIdx(r.parentEnc);
                     const bool fl = (r.parentEnc & 1) != 0;
                     const int64_t ps = botStart(steps[p + 1].bot, pi);
                     const int64_t off = tLo - r.start;
@@ -369,7 +380,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                 } else {
                     const int64_t b0 = botStart(st.bot, idx);
                     const int64_t L = botStart(st.bot, idx + 1) - b0;
-                    const int64_t ci = ce >> 1;
+                    const int64_t ci = linkIdx(ce);
                     const bool fl = (ce & 1) != 0;
                     int64_t cs;
                     if (P.dupes && !(COAL && (st.flags & STEP_NODUPES))) { // one 32-byte read gives the landing start AND tells whether a paralogy ring hangs here
@@ -441,14 +452,14 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     }
 
     if (overflow) {
-        if (lane == 0) { P.status[item] = ST_SCRATCH_OVERFLOW; P.outCount[item] = 0; }
+        if (lane == 0) liftFail(P, item, ST_SCRATCH_OVERFLOW);
         return;
     }
 
     // ---- phase 2 ----
     int m = listCount;
     if (m == 0) {
-        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = 0; P.outOffset[item] = 0; }
+        if (lane == 0) liftDone(P, item, 0, 0);
         return;
     }
     if (RAW) {
@@ -459,12 +470,12 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)m);
         base = __shfl_sync(HG_FULL, base, 0);
         if (base + (unsigned long long)m > P.poolCap) {
-            if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+            if (lane == 0) liftFail(P, item, ST_POOL_FULL);
             return;
         }
         Frag *dst = reinterpret_cast<Frag *>(P.pool) + base;
         for (int i = lane; i < m; i += 32) dst[i] = listA[i];
-        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)m; P.outOffset[item] = base; }
+        if (lane == 0) liftDone(P, item, base, (uint32_t)m);
         return;
     }
     // target sequence of every fragment (MappedSegment::getSequence)
@@ -515,7 +526,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)nl);
         base = __shfl_sync(HG_FULL, base, 0);
         if (base + (unsigned long long)nl > P.poolCap) {
-            if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+            if (lane == 0) liftFail(P, item, ST_POOL_FULL);
             return;
         }
         for (int r = lane; r < nl; r += 32) {
@@ -532,7 +543,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
             o.n_frag = (uint16_t)(l.sLo > 65535 ? 65535 : l.sLo);
             P.pool[base + r] = o;
         }
-        if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)nl; P.outOffset[item] = base; }
+        if (lane == 0) liftDone(P, item, base, (uint32_t)nl);
         return;
     }
     // one pass over neighbouring pairs: order of the MappedSegmentSet, its "identical or disjoint" invariant
@@ -618,7 +629,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
         }
         __syncwarp();
         if (total > listCap) {
-            if (lane == 0) { P.status[item] = ST_SCRATCH_OVERFLOW; P.outCount[item] = 0; }
+            if (lane == 0) liftFail(P, item, ST_SCRATCH_OVERFLOW);
             return;
         }
         m = total;
@@ -734,7 +745,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     if (lane == 0) base = atomicAdd(P.poolCursor, (unsigned long long)nLines);
     base = __shfl_sync(HG_FULL, base, 0);
     if (base + (unsigned long long)nLines > P.poolCap) {
-        if (lane == 0) { P.status[item] = ST_POOL_FULL; P.outCount[item] = 0; }
+        if (lane == 0) liftFail(P, item, ST_POOL_FULL);
         return;
     }
     for (int r = lane; r < nLines; r += 32) {
@@ -792,7 +803,7 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                 if (cnt[c]) atomicAdd(dst + c, cnt[c]);
         }
     }
-    if (lane == 0) { P.status[item] = ST_OK; P.outCount[item] = (uint32_t)nLines; P.outOffset[item] = base; }
+    if (lane == 0) liftDone(P, item, base, (uint32_t)nLines);
 }
 
 // bytes of scratch one warp needs for the given capacities
@@ -820,10 +831,132 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
     ws.listA = reinterpret_cast<Frag *>(basePtr);
     ws.listB = ws.listA + P.listCap;
     ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
-    for (int64_t w = gwarp; w < P.n; w += nwarps) {
-        const uint32_t item = P.work ? __ldg(&P.work[w]) : (uint32_t)w;
+    const int64_t n = P.nDev ? (int64_t)*P.nDev : P.n; // the complex list's length is only known on the device
+    for (int64_t w = gwarp; w < n; w += nwarps) {
+        const uint32_t item = P.work64 ? (uint32_t)P.work64[w] : (P.work ? __ldg(&P.work[w]) : (uint32_t)w);
         liftOneInterval<MODE>(P, ws, item, lane);
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fastLiftKernel -- one LANE per interval.
+//
+// BlockLiftover::liftInterval (liftover/impl/halBlockLiftover.cpp:46-113) cuts the interval at every segment boundary of
+// every genome on the path (toRight seeds, toParseUp/Down pieces), maps the pieces one by one (halMapSegment) and then
+// merges neighbours that are adjacent on both sides with equal strands (BlockMapper::extractSegment,
+// liftover/impl/halBlockMapper.cpp:331-394).  When the WHOLE interval lies, in every genome of the path, inside one
+// collinear run of the vertical links (the run field of a link, device_index.cuh) all those pieces are images of one affine
+// map: they tile one target range, no paralogy ring adds anything (a ring at a landing top ends the run), so the set holds
+// pairwise disjoint, pairwise mergeable neighbours and extractSegment returns exactly ONE line -- provided the target range
+// stays inside one target sequence (:364-371).  That line is computed here with one record read per hop instead of one per
+// piece.  Anything else (an unaligned piece, a rearrangement or a ring inside the interval, a sequence boundary, bad
+// input) goes to the complex list and is walked piece by piece by liftoverKernel.
+// ---------------------------------------------------------------------------------------------------------------
+#define HG_FAST_MAX_PATH 24
+
+template <bool TOP> __device__ __forceinline__ int64_t locateSeg(const PathStep &st, int64_t pos) {
+    if (TOP) return searchFrom<true>(st.top, (int64_t)__ldg(&st.topBucket[pos >> st.topShift]), st.numTop, pos);
+    return searchFrom<false>(st.bot, (int64_t)__ldg(&st.botBucket[pos >> st.botShift]), st.numBot, pos);
+}
+
+__global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
+    __shared__ PathStep sSteps[HG_FAST_MAX_PATH];
+    for (int i = (int)threadIdx.x; i < P.P; i += (int)blockDim.x) sSteps[i] = P.steps[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nTiles = (P.n + 31) >> 5;
+    while (true) {
+        unsigned long long tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tileCursor, 1ull);
+        tile = __shfl_sync(HG_FULL, tile, 0);
+        if ((int64_t)tile >= nTiles) break;
+        const int64_t w = (int64_t)tile * 32 + lane;
+        const bool have = w < P.n;
+        uint32_t item = 0;
+        int64_t gs = 0, ge = -1;
+        if (have) {
+            if (P.sortedGs) {
+                const unsigned long long v = P.sortedVal[w];
+                item = (uint32_t)v;
+                gs = (int64_t)P.sortedGs[w];
+                const unsigned long long l32 = v >> 32;
+                ge = l32 == 0xffffffffull ? ldS(&P.ge[item]) : gs + (int64_t)l32 - 1;
+            } else {
+                item = (uint32_t)w;
+                gs = ldS(&P.gs[w]); ge = ldS(&P.ge[w]);
+            }
+        }
+        bool ok = have && gs >= 0 && ge >= gs && ge < P.srcLen;
+        int64_t tLo = gs;
+        const int64_t len = ge - gs + 1;
+        bool rev = false;
+        if (ok) {
+            const int np = P.P;
+            for (int p = 0; p < np - 1; ++p) {
+                const PathStep &st = sSteps[p];
+                if (st.up) { // toParent (api/impl/halBottomSegmentIterator.cpp:40-49) over a whole run
+                    const int64_t idx = locateSeg<true>(st, tLo);
+                    const TopRec r = ldTop(&st.top[idx]);
+                    const int64_t off = tLo - r.start;
+                    if (r.parentEnc < 0 || off + len > linkRun(r.parentEnc)) { ok = false; break; }
+                    const int64_t ps = botStart(sSteps[p + 1].bot, linkIdx(r.parentEnc));
+                    if (linkRev(r.parentEnc)) {
+                        const int64_t L = topStart(st.top, idx + 1) - r.start;
+                        tLo = ps + L - off - len;
+                        rev = !rev;
+                    } else {
+                        tLo = ps + off;
+                    }
+                } else { // toChild (api/impl/halTopSegmentIterator.cpp:36-45) over a whole run
+                    const int64_t idx = locateSeg<false>(st, tLo);
+                    const int64_t ce = ldS(&st.child[idx]);
+                    const int64_t b0 = botStart(st.bot, idx);
+                    const int64_t off = tLo - b0;
+                    if (ce < 0 || off + len > linkRun(ce)) { ok = false; break; }
+                    const int64_t cs = topStart(sSteps[p + 1].top, linkIdx(ce));
+                    if (linkRev(ce)) {
+                        const int64_t L = botStart(st.bot, idx + 1) - b0;
+                        tLo = cs + L - off - len;
+                        rev = !rev;
+                    } else {
+                        tLo = cs + off;
+                    }
+                }
+            }
+        }
+        int seq = 0;
+        int64_t seqStart = 0;
+        if (ok && P.tgtNumSeq > 1) {
+            seq = seqOf(P.tgtSeqStart, P.tgtNumSeq, tLo);
+            seqStart = ldS(&P.tgtSeqStart[seq]);
+            if (tLo + len > ldS(&P.tgtSeqStart[seq + 1])) ok = false; // the pieces would not merge across sequences
+        }
+        const unsigned okm = __ballot_sync(HG_FULL, ok);
+        const unsigned cm = __ballot_sync(HG_FULL, have && !ok);
+        unsigned long long base = 0, cbase = 0;
+        if (lane == 0) {
+            if (okm) base = atomicAdd(P.poolCursor, (unsigned long long)__popc(okm));
+            if (cm) cbase = atomicAdd(P.complexCount, (unsigned long long)__popc(cm));
+        }
+        base = __shfl_sync(HG_FULL, base, 0);
+        cbase = __shfl_sync(HG_FULL, cbase, 0);
+        if (ok) { // (the engine sizes the pool for at least one record per interval, so slot < poolCap)
+            const unsigned long long slot = base + (unsigned long long)lanePrefix(okm, lane);
+            const uint8_t bs = P.strand ? P.strand[item] : (uint8_t)'+';
+            const bool flip = bs == '-';
+            const unsigned long long st8 = bs == '.' ? (unsigned long long)'.' : (unsigned long long)((flip != rev) ? '-' : '+');
+            const unsigned long long ss8 = bs == '.' ? (unsigned long long)'.' : (unsigned long long)(flip ? '-' : '+');
+            longlong2 a, b; // halgpu_lift_rec as two 16-byte stores
+            a.x = tLo - seqStart; a.y = tLo + len - seqStart;
+            b.x = gs;
+            b.y = (long long)((unsigned long long)(uint32_t)seq | (st8 << 32) | (ss8 << 40) | (1ull << 48));
+            longlong2 *dst = reinterpret_cast<longlong2 *>(&P.pool[slot]);
+            dst[0] = a; dst[1] = b;
+            P.outLoc[item] = (slot << HG_LOC_COUNT_BITS) | 1ull;
+        } else if (have) {
+            P.complexList[cbase + (unsigned long long)lanePrefix(cm, lane)] = item;
+        }
     }
 }
 

@@ -20,6 +20,7 @@
 #else
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/reverse_iterator.h>
 #include <cuda_runtime.h>
 #endif
 
@@ -85,6 +86,28 @@ inline void selectFlagged(const uint8_t *flag, int64_t *out, unsigned long long 
     unsigned long long c = 0;
     for (size_t i = 0; i < n; ++i) if (flag[i]) out[c++] = (int64_t)i;
     *dCount = c;
+}
+// The *Tmp primitives take their temporary storage from the caller (tmp == nullptr: only report the size needed).
+inline void sortPairsU64U64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keysIn, uint64_t *keysOut, const uint64_t *valsIn, uint64_t *valsOut,
+                               size_t n, int beginBit, int endBit, Stream) {
+    if (tmp == nullptr) { tmpBytes = 1; return; }
+    std::vector<uint32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    const uint64_t mask = (endBit >= 64 ? ~0ull : ((1ull << endBit) - 1ull)) & ~((1ull << beginBit) - 1ull);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (keysIn[a] & mask) < (keysIn[b] & mask); });
+    for (size_t i = 0; i < n; ++i) { keysOut[i] = keysIn[idx[i]]; valsOut[i] = valsIn[idx[i]]; }
+}
+// out[i] = sum of (in[j] & mask) for j < i, i in [0, n]  (n + 1 entries are read and written)
+inline void exclusiveScanMaskedTmp(void *tmp, size_t &tmpBytes, const unsigned long long *in, uint64_t *out, size_t n, uint64_t mask, Stream) {
+    if (tmp == nullptr) { tmpBytes = 1; return; }
+    uint64_t s = 0;
+    for (size_t i = 0; i <= n; ++i) { out[i] = s; s += in[i] & mask; }
+}
+// out[i] = min(in[i], in[i + 1], ..., in[n - 1])
+inline void suffixMinU32Tmp(void *tmp, size_t &tmpBytes, const uint32_t *in, uint32_t *out, size_t n, Stream) {
+    if (tmp == nullptr) { tmpBytes = 1; return; }
+    uint32_t m = 0xffffffffu;
+    for (size_t i = n; i-- > 0;) { m = std::min(m, in[i]); out[i] = m; }
 }
 
 #else // ---------------------------------------------------------------- CUDA
@@ -171,6 +194,31 @@ inline void selectFlagged(const uint8_t *flag, int64_t *out, unsigned long long 
     g_launches += 1;
     dfreeAsync(tmp, s);
     check(e, "select");
+}
+// The *Tmp primitives take their temporary storage from the caller (tmp == nullptr: only report the size needed), so a
+// batch allocates nothing once the engine's buffer cache is warm.
+inline void sortPairsU64U64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keysIn, uint64_t *keysOut, const uint64_t *valsIn, uint64_t *valsOut,
+                               size_t n, int beginBit, int endBit, Stream s) {
+    check(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, beginBit, endBit, s), "radix sort");
+    if (tmp != nullptr) g_launches += 1;
+}
+struct MaskU64 {
+    uint64_t mask;
+    __host__ __device__ uint64_t operator()(unsigned long long v) const { return (uint64_t)v & mask; }
+};
+inline void exclusiveScanMaskedTmp(void *tmp, size_t &tmpBytes, const unsigned long long *in, uint64_t *out, size_t n, uint64_t mask, Stream s) {
+    auto it = thrust::make_transform_iterator(in, MaskU64{mask});
+    check(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, it, out, (int64_t)(n + 1), s), "scan");
+    if (tmp != nullptr) g_launches += 1;
+}
+struct MinU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; }
+};
+inline void suffixMinU32Tmp(void *tmp, size_t &tmpBytes, const uint32_t *in, uint32_t *out, size_t n, Stream s) {
+    auto rin = thrust::make_reverse_iterator(in + n);
+    auto rout = thrust::make_reverse_iterator(out + n);
+    check(cub::DeviceScan::InclusiveScan(tmp, tmpBytes, rin, rout, MinU32(), (int64_t)n, s), "suffix min");
+    if (tmp != nullptr) g_launches += 1;
 }
 #endif
 

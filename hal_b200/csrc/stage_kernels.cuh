@@ -19,7 +19,7 @@ __global__ void packTopKernel(const PackTopParams p) {
         const bool rev = p.raw[40 * i + 32] != 0;
         TopRec o;
         o.start = start;
-        o.parentEnc = parent < 0 ? -1 : ((parent << 1) | (rev ? 1 : 0));
+        o.parentEnc = parent < 0 ? -1 : makeLink(parent, rev, 0); // the run field is filled in by linkRunKernel
         o.botParse = botParse;
         o.nextPara = para;
         p.out[i] = o;
@@ -46,7 +46,7 @@ __global__ void packBotKernel(const PackBotParams p) {
             for (int k = 0; k < p.nc; ++k) {
                 const int64_t c = r[2 + k];
                 const bool rev = rec[16 + 8 * p.nc + k] != 0;
-                p.child[(int64_t)k * p.numBot + i] = c < 0 ? -1 : ((c << 1) | (rev ? 1 : 0));
+                p.child[(int64_t)k * p.numBot + i] = c < 0 ? -1 : makeLink(c, rev, 0);
             }
         }
     }
@@ -72,17 +72,59 @@ __global__ void bucketKernel(const BucketParams p) {
     }
 }
 
+// Collinear runs of the vertical links (device_index.cuh).  linkBreakKernel marks the segments after which the run ends,
+// a suffix-min scan turns the marks into "index of the next break at or after i", linkRunKernel stores the distance in bases.
+struct LinkRunParams {
+    int64_t *links;        // link of segment i at links[i * linkStride]
+    const int64_t *starts; // start of segment i at starts[i * startStride]; entry n is the sentinel (genome length)
+    int64_t linkStride, startStride, n;
+    const TopRec *landTop; // child links: top array of the child genome (paralogy rings end a run); NULL for parent links
+    uint32_t *mark;        // n entries: i if the run ends with segment i, else 0xffffffff  ->  after the scan: next break >= i
+};
+__device__ __forceinline__ bool linkRing(const LinkRunParams &p, int64_t e) {
+    return p.landTop != nullptr && p.landTop[linkIdx(e)].nextPara >= 0;
+}
+__global__ void linkBreakKernel(const LinkRunParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        bool cont = false;
+        if (i + 1 < p.n) {
+            const int64_t a = p.links[i * p.linkStride], b = p.links[(i + 1) * p.linkStride];
+            if (a >= 0 && b >= 0 && linkRev(a) == linkRev(b) && linkIdx(b) == linkIdx(a) + (linkRev(a) ? -1 : 1)) {
+                cont = !linkRing(p, a) && !linkRing(p, b);
+            }
+        }
+        p.mark[i] = cont ? 0xffffffffu : (uint32_t)i;
+    }
+}
+__global__ void linkRunKernel(const LinkRunParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const int64_t e = p.links[i * p.linkStride];
+        if (e < 0) continue;
+        int64_t run = 0;
+        if (!linkRing(p, e)) {
+            run = p.starts[((int64_t)p.mark[i] + 1) * p.startStride] - p.starts[i * p.startStride];
+            if (run > LINK_RUN_CAP) run = LINK_RUN_CAP;
+        }
+        p.links[i * p.linkStride] = makeLink(linkIdx(e), linkRev(e), run);
+    }
+}
+
+// sort input: key = source start (sorted on its upper bits only), value = interval id | min(length, 2^32 - 1) << 32
 struct IotaParams {
-    uint32_t *out;
+    uint64_t *vals;
     uint64_t *keys;
-    const int64_t *gs;
+    const int64_t *gs, *ge;
     int64_t n;
 };
 __global__ void iotaKeysKernel(const IotaParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        p.out[i] = (uint32_t)i;
-        p.keys[i] = (uint64_t)p.gs[i];
+        const int64_t a = p.gs[i], len = p.ge[i] - a + 1;
+        const uint64_t l32 = (len <= 0 || len >= 0xffffffffll) ? 0xffffffffull : (uint64_t)len;
+        p.vals[i] = (uint64_t)i | (l32 << 32);
+        p.keys[i] = (uint64_t)a;
     }
 }
 
@@ -106,23 +148,6 @@ __global__ void collectKernel(const CollectParams p) {
     }
 }
 
-// how many intervals ended in each state (one pass; the id lists are only built when a retry is needed)
-struct StatusCountParams {
-    const uint32_t *status;
-    unsigned long long *counts; // 4 entries, indexed by ST_*
-    int64_t n;
-};
-__global__ void statusCountKernel(const StatusCountParams p) {
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    unsigned local[4] = {0u, 0u, 0u, 0u};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const uint32_t s = p.status[i];
-        if (s < 4u) local[s]++;
-    }
-    for (int k = 1; k < 4; ++k)
-        if (local[k]) atomicAdd(p.counts + k, (unsigned long long)local[k]);
-}
-
 struct AddBaseParams {
     uint64_t *v;
     int64_t n;
@@ -135,8 +160,7 @@ __global__ void addBaseKernel(const AddBaseParams p) { // chunk-local CSR offset
 
 // pool (allocation order) -> CSR (input order)
 struct GatherParams {
-    const uint32_t *outCount;
-    const uint64_t *outOffset;
+    const unsigned long long *outLoc;
     const uint64_t *csr;
     const halgpu_lift_rec *pool;
     halgpu_lift_rec *recs;
@@ -147,9 +171,12 @@ struct GatherParams {
 __global__ void gatherKernel(const GatherParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const uint32_t c = p.outCount[i];
-        const uint64_t from = p.outOffset[i], to = p.csr[i];
-        for (uint32_t k = 0; k < c; ++k) p.recs[to + k] = p.pool[from + k];
+        const unsigned long long loc = p.outLoc[i];
+        const uint32_t c = (uint32_t)(loc & ((1ull << HG_LOC_COUNT_BITS) - 1ull));
+        const uint64_t from = loc >> HG_LOC_COUNT_BITS, to = p.csr[i];
+        const longlong2 *src = reinterpret_cast<const longlong2 *>(p.pool + from);
+        longlong2 *dst = reinterpret_cast<longlong2 *>(p.recs + to);
+        for (uint32_t k = 0; k < 2 * c; ++k) dst[k] = src[k];
         if (p.pslPool)
             for (uint32_t k = 0; k < 4 * c; ++k) p.psl[4 * to + k] = p.pslPool[4 * from + k];
     }

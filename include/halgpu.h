@@ -68,6 +68,11 @@ typedef struct halgpu_lift_result {
     /* HALGPU_PSL only (else NULL): per output line the four PSL base counts of BlockLiftover::readPSLInfo
      * (liftover/impl/halBlockLiftover.cpp:115-162): matches, misMatches, repMatches, nCount -- 4 x uint32 per record */
     uint32_t *psl;
+    /* measurement: device time of the one-lane-per-interval kernel alone (part of kernel_ms; 0 when the batch did not use
+     * it) and the number of intervals it left to the one-warp-per-interval walk */
+    float fast_ms;
+    size_t n_complex;
+    void *owner;              /* private: the context whose buffer cache the device buffers return to */
 } halgpu_lift_result;
 
 enum {
@@ -79,6 +84,9 @@ enum {
                                  * result->recs (same size as halgpu_lift_rec; cast), in no particular order within an
                                  * interval.  For callers that refine and merge across intervals themselves (halSynteny lifts
                                  * whole chromosomes).  Not with HALGPU_PSL or HALGPU_COLUMN_LIFTOVER. */
+    HALGPU_NO_FAST = 64u,       /* walk every interval piece by piece (one warp per interval) even where the whole interval is one
+                                 * collinear run that the one-lane-per-interval kernel would map in one step per genome;
+                                 * same results, for measurements and tests */
     HALGPU_SEED_BOTTOM = 32u,   /* take the source segments from the genome's BOTTOM array even if it has a top array
                                  * (BlockMapper::map does so when the source genome is the MRCA, halBlockMapper.cpp:76-83) */
     HALGPU_COLUMN_LIFTOVER = 8u /* hal::ColumnLiftover::liftInterval semantics (liftover/impl/halColumnLiftover.cpp:21-92)
@@ -119,13 +127,16 @@ void *halgpu_stream(const halgpu_ctx *ctx);                         /* the cudaS
  *      api/impl/halSegmentMapper.cpp:525-576; ignored with HALGPU_NO_DUPES like in the reference, :619); a genome that
  *      is not the MRCA or one of its ancestors fails with the reference's "Hit root genome ..." message.
  *      Host buffers in, host result out;
- *      the host<->device copies are part of the call. ---- */
+ *      the host<->device copies are part of the call.
+ *      result->recs[i].n_frag counts the pieces THIS library merged into the line (a whole collinear run counts once); it is
+ *      a diagnostic, the reference has no such field. ---- */
 int halgpu_liftover(halgpu_ctx *ctx, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
                     size_t n, const int64_t *src_start, const int64_t *src_end_incl, const uint8_t *strand,
                     halgpu_lift_result **out, char **err);
 
 /* Same, with the three input arrays already resident in device memory of the context's GPU and the
- * result left in device memory (result->on_device == 1). */
+ * result left in device memory (result->on_device == 1).  The result's device buffers belong to the context: free the
+ * result (halgpu_free_result) before halgpu_close. */
 int halgpu_liftover_device(halgpu_ctx *ctx, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
                            size_t n, const int64_t *d_src_start, const int64_t *d_src_end_incl,
                            const uint8_t *d_strand, halgpu_lift_result **out, char **err);
