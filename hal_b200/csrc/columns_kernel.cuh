@@ -1,4 +1,4 @@
-// columns_kernel.cuh -- per-reference-base alignment column walk, one thread per column.
+// columns_kernel.cuh -- alignment column walk, one walk per PIECE of a reference segment.
 //
 // Replaces, for the default ColumnIterator flags (unique=false, maxInsertLength=0: every reference base is an
 // independent query, api/impl/halColumnIterator.cpp:785-787), the reference call chain
@@ -8,10 +8,12 @@
 //     colMapInsert (noAncestors / targets filters)   :766-819
 // and the per-column reduction of halAlignmentDepth (alignmentDepth/halAlignmentDepth.cpp:262-280).
 //
-// The reference re-derives every row by pointer-chasing linked iterators once per base (one full tree walk
-// per column).  Here every thread runs the same walk as an explicit-stack DFS in discovery order; the 32
-// threads of a warp hold 32 consecutive reference bases, which almost always sit in the same segments, so
-// each record fetch is one broadcast transaction per warp and the segment arrays stream through L2 once.
+// The reference re-derives every row by pointer-chasing linked iterators once per base (one full tree walk per column).
+// The walk of column p only looks at WHICH segment holds the current position in each genome it visits (the vertical
+// hops between homologous segments keep the offset), so all columns p .. p + room, where room is the smallest distance
+// from a visited position to the end of its segment in walking direction, run the identical walk with every position
+// shifted by the column offset: same rows, same discovery order, collinear.  walkColumn returns that room; the kernels
+// walk once per piece [p, p + room] and fill / emit the whole piece: one walk per ~segment instead of one per base.
 #pragma once
 #include "liftover_kernel.cuh"
 
@@ -23,6 +25,7 @@ struct DepthParams {
     const GenomeTab *genomes;
     int32_t numGenomes, ref;
     int64_t first, step, n; // column i is reference position first + i*step (forward genome coordinates)
+    int64_t seg0, nSegs;    // the reference segments (top array if the genome has one, else bottom) that hold the columns
     uint32_t flags;
     int32_t *depth;         // n entries
     uint32_t *error;        // set to 1 if a walk overflowed its stack
@@ -75,7 +78,7 @@ struct WalkStack {
     stack.sPos = hgPos; stack.sA = hgA; stack.sB = hgB; stack.sMeta = hgMeta; stack.spill = hgSpill; stack.tid = (int)threadIdx.x;
 
 struct NoRefHook {
-    __device__ __forceinline__ void operator()(int64_t) const {}
+    __device__ __forceinline__ void operator()(int64_t, bool) const {}
 };
 
 // ColumnIterator(unique = true) as used by MafExport (maf/impl/halMafExport.cpp:46-81): class of the column of reference
@@ -86,20 +89,37 @@ struct NoRefHook {
 //   1  walked, but its left-most reference-genome base lies left of the window: isCanonicalOnRef (:208-212) is false and
 //      MafExport does not write it (its sequences still became ColumnMap keys)
 //   0  written
+// Along a piece (columns p + j, rows at pos + j or pos - j) the two tests are monotone in j, so the class is constant up
+// to the first j at which one of them flips: `flip` collects that bound and the piece is cut there.
 struct UniqueClass {
     int64_t window, p;
     int cls;
-    __device__ __forceinline__ void operator()(int64_t pos) {
+    int64_t flip; // smallest j > 0 at which the class of column p + j may differ from cls (INT64_MAX: never)
+    __device__ __forceinline__ void bound(int64_t j) { if (j > 0 && j < flip) flip = j; }
+    __device__ __forceinline__ void operator()(int64_t pos, bool rev) {
         if (pos >= window && pos < p) cls = 2;
         else if (pos < window && cls == 0) cls = 1;
+        if (!rev) {
+            bound(window - pos);                  // pos + j reaches the window (both tests)
+        } else {
+            bound(pos - window + 1);              // pos - j drops below the window (both tests)
+            if (pos >= p) bound((pos - p) / 2 + 1); // pos - j < p + j from here on
+        }
     }
 };
 
 // Visitor: void emit(int g, int64_t pos, bool rev) for rows that pass the colMapInsert filters; refHook(pos) sees every
 // base of the reference genome the walk meets, filtered or not.
+// room (out): every column p .. p + room runs this same walk shifted by its offset (see the header comment)
 template <class Emit, class RefHook>
 __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, Emit &&emit,
-                                           RefHook &&refHook) {
+                                           RefHook &&refHook, int64_t &room) {
+    room = INT64_MAX;
+    // the position pos (walking direction rev) was located in the segment [s0, s1) of some array
+    auto located = [&](int64_t pos, bool rev, int64_t s0, int64_t s1) {
+        const int64_t r = rev ? pos - s0 : s1 - 1 - pos;
+        if (r < room) room = r;
+    };
     const bool noDupes = (flags & COL_NO_DUPES) != 0, noAnc = (flags & COL_NO_ANCESTORS) != 0,
                onlyOrtho = (flags & COL_ONLY_ORTHOLOGS) != 0;
     int sp = 0;
@@ -112,7 +132,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
     };
     auto report = [&](int g, int64_t pos, bool rev) {
         const GenomeTab &T = G[g];
-        if (g == ref) refHook(pos);
+        if (g == ref) refHook(pos, rev);
         if (noAnc && T.nc > 0) return;
         if (!T.isTarget) return;
         emit(g, pos, rev);
@@ -121,11 +141,13 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
     report(ref, p, false);
     if (R.numTop > 0) { // recursiveUpdate, reference with top segments (:254-303)
         const int64_t t = searchFrom<true>(R.top, (int64_t)__ldg(&R.topBucket[p >> R.topShift]), R.numTop, p);
+        located(p, false, topStart(R.top, t), topStart(R.top, t + 1));
         push(W_DOWN, ref, t, 0, p, false, 0);
         if (!onlyOrtho) push(W_RING, ref, t, 0, p, false, 0);
         push(W_UP, ref, t, 0, p, false, 0);
     } else { // root reference (:306-354)
         const int64_t b = searchFrom<false>(R.bot, (int64_t)__ldg(&R.botBucket[p >> R.botShift]), R.numBot, p);
+        located(p, false, botStart(R.bot, b), botStart(R.bot, b + 1));
         for (int k = R.nc - 1; k >= 0; --k) push(W_CHILD, ref, b, 0, p, false, k);
     }
     while (sp > 0 && ok) {
@@ -154,6 +176,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
             const int64_t tp = ldBot(&T.bot[w.a]).topParse;
             if (tp < 0) break;
             const int64_t t = searchFrom<true>(T.top, tp, T.numTop, w.pos);
+            located(w.pos, rev, topStart(T.top, t), topStart(T.top, t + 1));
             if (!onlyOrtho) push(W_RING, w.g, t, 0, w.pos, rev, 0);
             push(W_UP, w.g, t, 0, w.pos, rev, 0);
             break;
@@ -196,6 +219,7 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
             const int64_t bp = ldTop(&T.top[w.a]).botParse;
             if (bp < 0 || T.nc == 0) break;
             const int64_t b = searchFrom<false>(T.bot, bp, T.numBot, w.pos);
+            located(w.pos, rev, botStart(T.bot, b), botStart(T.bot, b + 1));
             for (int k = T.nc - 1; k >= 0; --k) push(W_CHILD, w.g, b, 0, w.pos, rev, k);
             break;
         }
@@ -205,28 +229,66 @@ __device__ __forceinline__ bool walkColumn(const GenomeTab *G, int ref, int64_t 
     return ok;
 }
 
+// start of reference segment i (top array if the genome has one, else bottom)
+__device__ __forceinline__ int64_t refSegStart(const GenomeTab &R, int64_t i) {
+    return R.numTop > 0 ? topStart(R.top, i) : botStart(R.bot, i);
+}
+
+// One thread per reference segment; the thread walks once per piece of its segment and the warp then fills the
+// pieces of its 32 lanes with coalesced stores.
 __global__ void __launch_bounds__(128) depthKernel(const DepthParams P) {
     HG_WALK_STACK_DECL
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        uint64_t seen[4] = {0, 0, 0, 0}; // distinct genomes (<= 256, checked on the host)
-        int rows = 0;
-        const bool ok = walkColumn(P.genomes, P.ref, P.first + i * P.step, P.flags, stack, [&](int g, int64_t, bool) {
-            seen[g >> 6] |= 1ull << (g & 63);
-            ++rows;
-        }, NoRefHook());
-        if (!ok) *P.error = 1u;
-        int d;
-        if (P.flags & COL_COUNT_DUPES) {
-            d = rows - 1;
-        } else {
-            d = -1;
-            for (int w = 0; w < 4; ++w) {
-                uint64_t x = seen[w];
-                while (x) { x &= x - 1; ++d; }
+    const GenomeTab R = P.genomes[P.ref];
+    const int64_t lastPos = P.first + (P.n - 1) * P.step;
+    const int64_t nRound = (P.nSegs + 31) & ~(int64_t)31; // whole warps stay in the loop together
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nRound; k += stride) {
+        int64_t col = 0, colEnd = -1; // this thread's columns [col, colEnd] (indices into depth[])
+        if (k < P.nSegs) {
+            const int64_t s = refSegStart(R, P.seg0 + k), e = refSegStart(R, P.seg0 + k + 1) - 1;
+            const int64_t lo = s > P.first ? s : P.first, hi = e < lastPos ? e : lastPos;
+            if (lo <= hi) {
+                col = (lo - P.first + P.step - 1) / P.step;
+                colEnd = (hi - P.first) / P.step;
             }
         }
-        P.depth[i] = d;
+        while (__any_sync(HG_FULL, col <= colEnd)) {
+            const bool active = col <= colEnd;
+            int d = 0;
+            int64_t pieceEnd = col;
+            if (active) {
+                uint64_t seen[4] = {0, 0, 0, 0}; // distinct genomes (<= 256, checked on the host)
+                int rows = 0;
+                int64_t room;
+                const int64_t p = P.first + col * P.step;
+                const bool ok = walkColumn(P.genomes, P.ref, p, P.flags, stack, [&](int g, int64_t, bool) {
+                    seen[g >> 6] |= 1ull << (g & 63);
+                    ++rows;
+                }, NoRefHook(), room);
+                if (!ok) *P.error = 1u;
+                if (P.flags & COL_COUNT_DUPES) {
+                    d = rows - 1;
+                } else {
+                    d = -1;
+                    for (int w = 0; w < 4; ++w) {
+                        uint64_t x = seen[w];
+                        while (x) { x &= x - 1; ++d; }
+                    }
+                }
+                const int64_t far = room / P.step; // columns col .. col + far share the walk
+                pieceEnd = far < colEnd - col ? col + far : colEnd;
+            }
+            unsigned am = __ballot_sync(HG_FULL, active);
+            while (am) {
+                const int j = __ffs((int)am) - 1;
+                am &= am - 1;
+                const int64_t c0 = __shfl_sync(HG_FULL, col, j), c1 = __shfl_sync(HG_FULL, pieceEnd, j);
+                const int dj = __shfl_sync(HG_FULL, d, j);
+                for (int64_t c = c0 + lane; c <= c1; c += 32) P.depth[c] = dj;
+            }
+            if (active) col = pieceEnd + 1;
+        }
     }
 }
 
@@ -235,41 +297,35 @@ __global__ void __launch_bounds__(128) depthKernel(const DepthParams P) {
 // columns whose rows are the same sequences/strands advancing collinearly -- what MafBlock::canAppendColumn
 // (maf/impl/halMafBlock.cpp:401-450) needs to know.  Rows of a column are kept in ColumnMap order: by
 // (genome name, sequence index), discovery order within a sequence (api/inc/halColumnIterator.h:45-54).
+// Pass 1 counts the pieces and rows of every reference segment, pass 2 (after two scans) walks again and stores
+// each piece's first column and rows; pieceMergeKernel then joins neighbouring pieces whose rows continue each
+// other exactly (same count, same genomes / sequences / strands, positions advanced by the piece length), so a
+// run is as long as the alignment is collinear, not as long as the shortest segment.
 // ---------------------------------------------------------------------------------------------------------
 #define HG_MAX_ROWS 128
 
-struct ColSigParams {
+struct ColPieceParams {
     const GenomeTab *genomes;
     int32_t ref;
     uint32_t flags;
-    int64_t first, n;
-    int64_t window;        // COL_UNIQUE: reference position the sweep started at (<= first)
-    uint64_t *sigA, *sigB; // n entries each: 128-bit signature of the column's normalised rows
-    uint32_t *nrows;       // n entries
-    uint32_t *error;
-};
-
-struct ColEmitParams {
-    const GenomeTab *genomes;
-    int32_t ref;
-    uint32_t flags;
-    int64_t first, n;         // n = number of runs
-    const int64_t *runCol;    // per run: column index (relative to first)
-    const uint64_t *runRowOff; // per run: first row
+    int64_t first, n;          // columns first .. first + n - 1
+    int64_t seg0, nSegs;       // reference segments holding them
+    int64_t window;            // COL_UNIQUE: reference position the sweep started at (<= first)
+    // pass 1 (pieceOff == NULL): per segment counts
+    uint32_t *segPieces, *segRows; // nSegs + 1 entries each (last = 0) for the scans
+    // pass 2: per segment offsets in, pieces out
+    const uint64_t *pieceOff, *rowOff;
+    int64_t *pieceCol;         // per piece: first column (relative to `first`)
+    uint64_t *pieceRowOff;     // per piece: first row
+    uint32_t *pieceRows;       // per piece: number of rows
+    uint8_t *pieceClass;       // per piece: UniqueClass (0 without COL_UNIQUE)
     ColRowRec *rows;
     uint32_t *error;
-    int64_t window;           // COL_UNIQUE
-    uint8_t *runClass;        // COL_UNIQUE: per run, UniqueClass of its columns
 };
-
-__device__ __forceinline__ uint64_t hgMix(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-    return x;
-}
 
 // walk column p and leave its rows sorted in ColumnMap order; returns the row count or -1 on overflow
 __device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t p, uint32_t flags, WalkStack &stack, ColRowRec *rows,
-                                            uint64_t *keys, UniqueClass &uc) {
+                                            uint64_t *keys, UniqueClass &uc, int64_t &room) {
     int n = 0;
     bool over = false;
     const bool ok = walkColumn(G, ref, p, flags, stack, [&](int g, int64_t pos, bool rev) {
@@ -283,85 +339,117 @@ __device__ __forceinline__ int sortedColumn(const GenomeTab *G, int ref, int64_t
         while (j > 0 && keys[j - 1] > key) { rows[j] = rows[j - 1]; keys[j] = keys[j - 1]; --j; }
         rows[j] = r; keys[j] = key;
         ++n;
-    }, uc);
+    }, uc, room);
     return (ok && !over) ? n : -1;
 }
 
-// Signature of a column = 128-bit hash of its rows IN DISCOVERY ORDER, each normalised by the column offset, so
-// that it is constant along a collinear run.  (Equal discovery order implies equal ColumnMap order; the converse
-// can only split a run, which the host state machine handles.)  Nothing but the walk stack is stored.
-__global__ void __launch_bounds__(128) colSigKernel(const ColSigParams P) {
+template <bool EMIT>
+__global__ void __launch_bounds__(128) colPieceKernel(const ColPieceParams P) {
     HG_WALK_STACK_DECL
+    ColRowRec rows[EMIT ? HG_MAX_ROWS : 1];
+    uint64_t keys[EMIT ? HG_MAX_ROWS : 1];
+    const GenomeTab *G = P.genomes;
+    const GenomeTab R = G[P.ref];
+    const bool unique = (P.flags & COL_UNIQUE) != 0;
+    const int64_t lastPos = P.first + P.n - 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xd1b54a32d192ed03ull;
-        int n = 0;
-        const GenomeTab *G = P.genomes;
-        UniqueClass uc;
-        uc.window = (P.flags & COL_UNIQUE) ? P.window : INT64_MIN; uc.p = (P.flags & COL_UNIQUE) ? P.first + i : INT64_MIN; uc.cls = 0;
-        const bool ok = walkColumn(G, P.ref, P.first + i, P.flags, stack, [&](int g, int64_t pos, bool rev) {
-            const GenomeTab &T = G[g];
-            const int sq = T.numSeq > 1 ? seqOf(T.seqStart, T.numSeq, pos) : 0;
-            const uint64_t norm = (uint64_t)(rev ? pos + i : pos - i);
-            const uint64_t id = ((((uint64_t)(uint32_t)g << 32) | (uint32_t)sq) << 1) | (rev ? 1u : 0u);
-            a = hgMix(a ^ norm) + hgMix(id + 0x632be59bd9b4e019ull * (uint64_t)(n + 1));
-            b = hgMix(b + id) ^ hgMix(norm * 0x9fb21c651e98df25ull + (uint64_t)n);
-            ++n;
-        }, uc);
-        if (!ok || n > HG_MAX_ROWS) { *P.error = 1u; P.nrows[i] = 0; P.sigA[i] = 0; P.sigB[i] = 0; continue; }
-        // the class is part of the signature: a run never mixes written and skipped columns
-        P.sigA[i] = a ^ (0x2545f4914f6cdd1dull * (uint64_t)uc.cls); P.sigB[i] = b; P.nrows[i] = (uint32_t)n;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P.nSegs; k += stride) {
+        const int64_t s = refSegStart(R, P.seg0 + k), e = refSegStart(R, P.seg0 + k + 1) - 1;
+        int64_t p = s > P.first ? s : P.first;
+        const int64_t hi = e < lastPos ? e : lastPos;
+        uint32_t nPieces = 0, nRows = 0;
+        uint64_t pieceAt = EMIT ? P.pieceOff[k] : 0, rowAt = EMIT ? P.rowOff[k] : 0;
+        while (p <= hi) {
+            UniqueClass uc;
+            uc.window = unique ? P.window : INT64_MIN; uc.p = unique ? p : INT64_MIN; uc.cls = 0; uc.flip = INT64_MAX;
+            int64_t room;
+            int n;
+            if (EMIT) {
+                n = sortedColumn(G, P.ref, p, P.flags, stack, rows, keys, uc, room);
+            } else {
+                n = 0;
+                const bool ok = walkColumn(G, P.ref, p, P.flags, stack, [&](int, int64_t, bool) { ++n; }, uc, room);
+                if (!ok || n > HG_MAX_ROWS) n = -1;
+            }
+            if (n < 0) { *P.error = 1u; n = 0; }
+            if (unique && uc.flip - 1 < room) room = uc.flip - 1;
+            if (EMIT) {
+                P.pieceCol[pieceAt] = p - P.first;
+                P.pieceRowOff[pieceAt] = rowAt;
+                P.pieceRows[pieceAt] = (uint32_t)n;
+                P.pieceClass[pieceAt] = (uint8_t)uc.cls;
+                for (int r = 0; r < n; ++r) P.rows[rowAt + r] = rows[r];
+                ++pieceAt; rowAt += (uint64_t)n;
+            }
+            ++nPieces; nRows += (uint32_t)n;
+            p = room >= hi - p ? hi + 1 : p + room + 1;
+        }
+        if (!EMIT) { P.segPieces[k] = nPieces; P.segRows[k] = nRows; }
     }
+    if (!EMIT && blockIdx.x == 0 && threadIdx.x == 0) { P.segPieces[P.nSegs] = 0; P.segRows[P.nSegs] = 0; }
 }
 
-struct RunFlagParams {
-    const uint64_t *sigA, *sigB;
-    const uint32_t *nrows;
-    uint32_t *isStart, *startRows; // n + 1 entries each (last = 0) for the scans
-    int64_t n;
+struct PieceMergeParams {
+    const int64_t *pieceCol;
+    const uint64_t *pieceRowOff;
+    const uint32_t *pieceRows;
+    const uint8_t *pieceClass;
+    const ColRowRec *rows;
+    uint32_t *isStart, *startRows; // nPieces + 1 entries each (last = 0) for the scans
+    int64_t nPieces;
 };
-__global__ void runFlagKernel(const RunFlagParams P) {
+// piece q opens a new run unless its rows continue piece q - 1's exactly
+__global__ void pieceMergeKernel(const PieceMergeParams P) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= P.n; i += stride) {
-        uint32_t s = 0;
-        if (i < P.n) s = (i == 0 || P.sigA[i] != P.sigA[i - 1] || P.sigB[i] != P.sigB[i - 1] || P.nrows[i] != P.nrows[i - 1]) ? 1u : 0u;
-        P.isStart[i] = s;
-        P.startRows[i] = s ? P.nrows[i] : 0u;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= P.nPieces; q += stride) {
+        uint32_t start = 0, nr = 0;
+        if (q < P.nPieces) {
+            nr = P.pieceRows[q];
+            start = 1;
+            if (q > 0 && P.pieceRows[q - 1] == nr && P.pieceClass[q - 1] == P.pieceClass[q]) {
+                const int64_t len = P.pieceCol[q] - P.pieceCol[q - 1];
+                const ColRowRec *a = P.rows + P.pieceRowOff[q - 1], *b = P.rows + P.pieceRowOff[q];
+                bool same = true;
+                for (uint32_t r = 0; r < nr && same; ++r) {
+                    same = a[r].genome == b[r].genome && a[r].seq == b[r].seq && a[r].rev == b[r].rev &&
+                           b[r].pos == (a[r].rev ? a[r].pos - len : a[r].pos + len);
+                }
+                if (same) start = 0;
+            }
+        }
+        P.isStart[q] = start;
+        P.startRows[q] = start ? nr : 0u;
     }
 }
 
 struct RunScatterParams {
     const uint32_t *isStart;
-    const uint64_t *runIndex, *rowOffset;
-    int64_t *runCol;     // nRuns + 1 (sentinel = n)
+    const uint64_t *runIndex, *runRowOffset; // exclusive scans of isStart / startRows
+    const int64_t *pieceCol;
+    const uint64_t *pieceRowOff;
+    const uint32_t *pieceRows;
+    const uint8_t *pieceClass;
+    const ColRowRec *rows;
+    int64_t *runCol;     // nRuns + 1 (sentinel = n columns)
     uint64_t *runRowOff; // nRuns + 1 (sentinel = total rows)
-    int64_t n;
+    uint8_t *runClass;   // nRuns (may be NULL)
+    ColRowRec *runRows;
+    int64_t nPieces, nCols;
 };
 __global__ void runScatterKernel(const RunScatterParams P) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= P.n; i += stride) {
-        if (i == P.n || P.isStart[i]) {
-            P.runCol[P.runIndex[i]] = i;
-            P.runRowOff[P.runIndex[i]] = P.rowOffset[i];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= P.nPieces; q += stride) {
+        if (q == P.nPieces) {
+            P.runCol[P.runIndex[q]] = P.nCols;
+            P.runRowOff[P.runIndex[q]] = P.runRowOffset[q];
+        } else if (P.isStart[q]) {
+            const uint64_t r = P.runIndex[q], to = P.runRowOffset[q], from = P.pieceRowOff[q];
+            P.runCol[r] = P.pieceCol[q];
+            P.runRowOff[r] = to;
+            if (P.runClass) P.runClass[r] = P.pieceClass[q];
+            const uint32_t nr = P.pieceRows[q];
+            for (uint32_t k = 0; k < nr; ++k) P.runRows[to + k] = P.rows[from + k];
         }
-    }
-}
-
-// one thread per run: re-walk the run's first column and store its rows
-__global__ void __launch_bounds__(128) colEmitKernel(const ColEmitParams P) {
-    HG_WALK_STACK_DECL
-    ColRowRec rows[HG_MAX_ROWS];
-    uint64_t keys[HG_MAX_ROWS];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += stride) {
-        const int64_t i = P.runCol[r];
-        UniqueClass uc;
-        uc.window = (P.flags & COL_UNIQUE) ? P.window : INT64_MIN; uc.p = (P.flags & COL_UNIQUE) ? P.first + i : INT64_MIN; uc.cls = 0;
-        const int n = sortedColumn(P.genomes, P.ref, P.first + i, P.flags, stack, rows, keys, uc);
-        if (n < 0) { *P.error = 1u; continue; }
-        if (P.runClass) P.runClass[r] = (uint8_t)uc.cls;
-        const uint64_t off = P.runRowOff[r];
-        for (int k = 0; k < n; ++k) P.rows[off + k] = rows[k];
     }
 }
 

@@ -15,6 +15,8 @@
 //              landing top segment carries a paralogy ring and stops before the first following segment whose landing
 //              top does (mapSelf fans out there, api/impl/halSegmentMapper.cpp:263-288).  Computed once at staging
 //              (stage_kernels.cuh: linkRunKernel); the file format has no such field.
+// Beside every link array sits an xlate array (topX / childX): the constant c of the affine map of that link's run,
+// position q -> q + c (forward) or c - q (reversed) in the other genome (stage_kernels.cuh: linkXlateKernel).
 // Both arrays keep the file's +1 sentinel record so that length(i) = start(i+1) - start(i)
 // (api/mmap_impl/mmapTopSegment.h:78-80).
 #pragma once
@@ -64,6 +66,10 @@ struct PathStep {
     // position -> segment index tables of this genome (fastLiftKernel re-locates a fragment after every hop)
     const uint32_t *topBucket, *botBucket;
     int32_t topShift, botShift;
+    // translation constants of the transition p -> p+1, one per segment of the array the hop leaves (tops for an up
+    // transition, this slot's bottoms for a down transition): a position q inside the segment's collinear run maps to
+    // q + xlate (forward link) or xlate - q (reversed link) without touching the other genome's records
+    const int64_t *xlate;
 };
 // halLiftover --coalescenceLimit (mapRecursiveParalogies, api/impl/halSegmentMapper.cpp:525-576): between the upward and the
 // downward part of the path sit the genomes from the MRCA up to the child of the limit (STEP_PARA entries, walked upward),
@@ -172,10 +178,7 @@ struct FastParams {
     const unsigned long long *sortedGs;   // optional: gs in visiting order ...
     const unsigned long long *sortedVal;  // ... with (interval id | min(length, 2^32 - 1) << 32)
     unsigned long long *tileCursor;       // next tile of 32 work items
-    unsigned long long *outLoc;
-    halgpu_lift_rec *pool;
-    unsigned long long *poolCursor;
-    uint64_t poolCap;
+    halgpu_lift_rec *pool;                // a finished interval's one line goes to pool[interval id] (outLoc is preset to that)
     uint32_t *complexList;                // interval ids left to liftoverKernel
     unsigned long long *complexCount;
 };

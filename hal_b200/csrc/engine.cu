@@ -257,11 +257,24 @@ void Context::stageLinkRuns(int gi) {
         lp.mark = next.as<uint32_t>();
         rt::launch(linkRunKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
     };
+    auto xlate = [&](const int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n,
+                     const int64_t *otherStarts, int64_t otherStride, int64_t *out) {
+        LinkXlateParams xp;
+        xp.links = links; xp.starts = starts; xp.otherStarts = otherStarts; xp.linkStride = linkStride; xp.startStride = startStride;
+        xp.otherStride = otherStride; xp.n = n; xp.xlate = out;
+        rt::launch(linkXlateKernel, gridFor(n, 256, _sms), 256, 0, _stream, xp);
+    };
+    const int64_t topStride = sizeof(TopRec) / 8, botStride = sizeof(BotCore) / 8;
     if (g.numTop > 0 && g.parent >= 0) {
-        run(&d.top[0].parentEnc, sizeof(TopRec) / 8, &d.top[0].start, sizeof(TopRec) / 8, g.numTop, nullptr);
+        run(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, nullptr);
+        d.topX = static_cast<int64_t *>(alloc((size_t)g.numTop * sizeof(int64_t)));
+        xlate(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, &_g[g.parent].bot[0].start, botStride, d.topX);
     }
+    if (!g.children.empty() && g.numBottom > 0) d.childX = static_cast<int64_t *>(alloc(g.children.size() * (size_t)g.numBottom * sizeof(int64_t)));
     for (size_t k = 0; k < g.children.size() && g.numBottom > 0; ++k) {
-        run(d.child + k * (size_t)g.numBottom, 1, &d.bot[0].start, sizeof(BotCore) / 8, g.numBottom, _g[g.children[k]].top);
+        int64_t *col = d.child + k * (size_t)g.numBottom;
+        run(col, 1, &d.bot[0].start, botStride, g.numBottom, _g[g.children[k]].top);
+        xlate(col, 1, &d.bot[0].start, botStride, g.numBottom, &_g[g.children[k]].top[0].start, topStride, d.childX + k * (size_t)g.numBottom);
     }
     rt::sync(_stream);
 }
@@ -315,10 +328,13 @@ const Plan &Context::plan(int src, int tgt, int coal) {
         s.topBucket = _g[g].topBucket; s.botBucket = _g[g].botBucket; s.topShift = _g[g].topShift; s.botShift = _g[g].botShift;
         if (i + 1 >= ent.size()) continue;
         const int nx = ent[i + 1].g;
+        s.xlate = nullptr;
         if (!s.up) { // this genome's childEnc column for the slot of the next genome down
             s.child = _g[g].child + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
+            s.xlate = _g[g].childX + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
         } else if (G[g].parent >= 0 && G[g].parent == nx) { // the parent's column for this genome's slot: canonical-paralog test
             s.child = _g[nx].child + (size_t)G[g].slotInParent * (size_t)G[nx].numBottom;
+            s.xlate = _g[g].topX;
         }
     }
     p.dSteps = static_cast<PathStep *>(rt::dmalloc(steps.size() * sizeof(PathStep)));
@@ -363,71 +379,115 @@ void Context::buildGenomeTab(int ref, const std::vector<int> &targets, std::vect
     }
 }
 
+// reference segments (top array if the genome has one, else bottom) holding the positions first..last: binary search
+// over the start fields of the mapped file
+static void refSegRange(const GenomeInfo &g, int64_t first, int64_t last, int64_t &seg0, int64_t &nSegs) {
+    const bool top = g.numTop > 0;
+    const int64_t N = top ? g.numTop : g.numBottom;
+    const uint8_t *base = top ? g.top : g.bottom;
+    const size_t stride = top ? 40 : g.bottomStride;
+    if (N <= 0) throw HalError("genome " + g.name + " has no segments");
+    auto startOf = [&](int64_t i) { int64_t v; std::memcpy(&v, base + (size_t)i * stride, 8); return v; };
+    auto find = [&](int64_t pos) { // largest i with start(i) <= pos
+        int64_t lo = 0, hi = N;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (startOf(mid) <= pos) lo = mid; else hi = mid; }
+        return lo;
+    };
+    seg0 = find(first);
+    nSegs = find(last) - seg0 + 1;
+}
+
 void Context::columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out,
                          int64_t windowFirst) {
     const auto &G = _file->genomes();
     const int ng = (int)G.size();
     if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
     if (ng > 32767) throw HalError("too many genomes for the column row record");
+    for (const GenomeInfo &g : G) { // WalkStack packs the child slot into 12 bits (columns_kernel.cuh)
+        if (g.children.size() > 4095) throw HalError("genome " + g.name + " has more than 4095 children; not supported by the column walk");
+    }
     if (first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
     const bool unique = (flags & COL_UNIQUE) != 0;
     if (windowFirst < 0) windowFirst = first;
     if (unique && windowFirst > first) throw HalError("the sweep start of a unique column range lies right of the range");
-    DevBuf::current() = _stream;
     std::vector<GenomeTab> tab;
     buildGenomeTab(ref, targets, tab);
     const int64_t n = last - first + 1;
-    DevBuf dTab(tab.size() * sizeof(GenomeTab)), dErr(sizeof(uint32_t));
-    rt::h2d(dTab.p, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
-    rt::dmemset(dErr.p, 0, sizeof(uint32_t), _stream);
-    DevBuf sigA(n * 8), sigB(n * 8), nrows((n + 1) * 4), isStart((n + 1) * 4), startRows((n + 1) * 4), runIndex((n + 2) * 8), rowOffset((n + 2) * 8);
-    rt::Event e0, e1, e2, e3;
-    ColSigParams sp;
-    sp.genomes = dTab.as<GenomeTab>(); sp.ref = ref; sp.flags = flags; sp.first = first; sp.n = n; sp.window = windowFirst;
-    sp.sigA = sigA.as<uint64_t>(); sp.sigB = sigB.as<uint64_t>(); sp.nrows = nrows.as<uint32_t>(); sp.error = dErr.as<uint32_t>();
-    e0.record(_stream);
-    rt::launch(colSigKernel, gridFor(n, 128, _sms), 128, 0, _stream, sp);
-    e1.record(_stream);
-    RunFlagParams fp;
-    fp.sigA = sp.sigA; fp.sigB = sp.sigB; fp.nrows = sp.nrows; fp.isStart = isStart.as<uint32_t>(); fp.startRows = startRows.as<uint32_t>(); fp.n = n;
-    rt::launch(runFlagKernel, gridFor(n + 1, 256, _sms), 256, 0, _stream, fp);
-    rt::exclusiveScanU32(fp.isStart, runIndex.as<uint64_t>(), (size_t)n, _stream);
-    rt::exclusiveScanU32(fp.startRows, rowOffset.as<uint64_t>(), (size_t)n, _stream);
-    uint64_t totals[2] = {0, 0};
-    rt::d2h(&totals[0], runIndex.as<uint64_t>() + n, 8, _stream);
-    rt::d2h(&totals[1], rowOffset.as<uint64_t>() + n, 8, _stream);
-    uint32_t err = 0;
-    rt::d2h(&err, dErr.p, sizeof(err), _stream);
-    rt::sync(_stream);
-    if (err) throw HalError("column walk exceeded its stack or " + std::to_string(HG_MAX_ROWS) + " rows per column");
-    const uint64_t nRuns = totals[0], nRows = totals[1];
-    DevBuf runCol((nRuns + 1) * 8), runRowOff((nRuns + 1) * 8), rows(std::max<uint64_t>(nRows, 1) * sizeof(ColRowRec));
-    RunScatterParams rp;
-    rp.isStart = fp.isStart; rp.runIndex = runIndex.as<uint64_t>(); rp.rowOffset = rowOffset.as<uint64_t>();
-    rp.runCol = runCol.as<int64_t>(); rp.runRowOff = runRowOff.as<uint64_t>(); rp.n = n;
-    rt::launch(runScatterKernel, gridFor(n + 1, 256, _sms), 256, 0, _stream, rp);
-    ColEmitParams ep;
-    ep.genomes = sp.genomes; ep.ref = ref; ep.flags = flags; ep.first = first; ep.n = (int64_t)nRuns;
-    ep.runCol = rp.runCol; ep.runRowOff = rp.runRowOff; ep.rows = rows.as<ColRowRec>(); ep.error = sp.error;
-    DevBuf runClass(std::max<uint64_t>(nRuns, 1));
-    ep.window = windowFirst; ep.runClass = unique ? runClass.as<uint8_t>() : nullptr;
-    e2.record(_stream);
-    rt::launch(colEmitKernel, gridFor((int64_t)nRuns, 128, _sms), 128, 0, _stream, ep);
-    e3.record(_stream);
-    out.n_cols = (size_t)n; out.n_runs = (size_t)nRuns; out.n_rows = (size_t)nRows;
-    out.run_col = static_cast<int64_t *>(rt::hostAlloc((nRuns + 1) * 8));
-    out.row_offset = static_cast<uint64_t *>(rt::hostAlloc((nRuns + 1) * 8));
-    out.rows = static_cast<halgpu_col_row *>(rt::hostAlloc(std::max<uint64_t>(nRows, 1) * sizeof(halgpu_col_row)));
-    rt::d2h(out.run_col, runCol.p, (nRuns + 1) * 8, _stream);
-    rt::d2h(out.row_offset, runRowOff.p, (nRuns + 1) * 8, _stream);
-    rt::d2h(out.rows, rows.p, nRows * sizeof(halgpu_col_row), _stream);
-    out.run_class = nullptr;
-    if (unique) {
-        out.run_class = static_cast<uint8_t *>(rt::hostAlloc(std::max<uint64_t>(nRuns, 1)));
-        rt::d2h(out.run_class, runClass.p, nRuns, _stream);
+    int64_t seg0 = 0, nSegs = 0;
+    refSegRange(G[ref], first, last, seg0, nSegs);
+    Lease L(_cache);
+    try {
+        GenomeTab *dTab = L.as<GenomeTab>(tab.size());
+        uint32_t *dErr = L.as<uint32_t>(1);
+        rt::h2d(dTab, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
+        rt::dmemset(dErr, 0, sizeof(uint32_t), _stream);
+        uint32_t *segPieces = L.as<uint32_t>((size_t)nSegs + 1), *segRows = L.as<uint32_t>((size_t)nSegs + 1);
+        uint64_t *pieceOff = L.as<uint64_t>((size_t)nSegs + 2), *rowOff = L.as<uint64_t>((size_t)nSegs + 2);
+        ColPieceParams cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.genomes = dTab; cp.ref = ref; cp.flags = flags; cp.first = first; cp.n = n; cp.seg0 = seg0; cp.nSegs = nSegs;
+        cp.window = windowFirst; cp.segPieces = segPieces; cp.segRows = segRows; cp.error = dErr;
+        _ev[0]->record(_stream);
+        rt::launch(colPieceKernel<false>, gridFor(nSegs, 128, _sms), 128, 0, _stream, cp);
+        rt::exclusiveScanU32(segPieces, pieceOff, (size_t)nSegs, _stream);
+        rt::exclusiveScanU32(segRows, rowOff, (size_t)nSegs, _stream);
+        uint64_t totals[2] = {0, 0};
+        uint32_t err = 0;
+        rt::d2h(&totals[0], pieceOff + nSegs, 8, _stream);
+        rt::d2h(&totals[1], rowOff + nSegs, 8, _stream);
+        rt::d2h(&err, dErr, sizeof(err), _stream);
+        rt::sync(_stream);
+        if (err) throw HalError("column walk exceeded its stack or " + std::to_string(HG_MAX_ROWS) + " rows per column");
+        const uint64_t nPieces = totals[0], nPieceRows = totals[1];
+        int64_t *pieceCol = L.as<int64_t>(nPieces + 1);
+        uint64_t *pieceRowOff = L.as<uint64_t>(nPieces + 1);
+        uint32_t *pieceRows = L.as<uint32_t>(nPieces + 1);
+        uint8_t *pieceClass = L.as<uint8_t>(nPieces + 1);
+        ColRowRec *rows = L.as<ColRowRec>(std::max<uint64_t>(nPieceRows, 1));
+        cp.pieceOff = pieceOff; cp.rowOff = rowOff; cp.pieceCol = pieceCol; cp.pieceRowOff = pieceRowOff; cp.pieceRows = pieceRows;
+        cp.pieceClass = pieceClass; cp.rows = rows;
+        rt::launch(colPieceKernel<true>, gridFor(nSegs, 128, _sms), 128, 0, _stream, cp);
+        // join pieces that continue each other
+        uint32_t *isStart = L.as<uint32_t>(nPieces + 1), *startRows = L.as<uint32_t>(nPieces + 1);
+        uint64_t *runIndex = L.as<uint64_t>(nPieces + 2), *runRowOffset = L.as<uint64_t>(nPieces + 2);
+        PieceMergeParams mp;
+        mp.pieceCol = pieceCol; mp.pieceRowOff = pieceRowOff; mp.pieceRows = pieceRows; mp.pieceClass = pieceClass; mp.rows = rows;
+        mp.isStart = isStart; mp.startRows = startRows; mp.nPieces = (int64_t)nPieces;
+        rt::launch(pieceMergeKernel, gridFor((int64_t)nPieces + 1, 256, _sms), 256, 0, _stream, mp);
+        rt::exclusiveScanU32(isStart, runIndex, (size_t)nPieces, _stream);
+        rt::exclusiveScanU32(startRows, runRowOffset, (size_t)nPieces, _stream);
+        rt::d2h(&totals[0], runIndex + nPieces, 8, _stream);
+        rt::d2h(&totals[1], runRowOffset + nPieces, 8, _stream);
+        rt::sync(_stream);
+        const uint64_t nRuns = totals[0], nRows = totals[1];
+        int64_t *runCol = L.as<int64_t>(nRuns + 1);
+        uint64_t *runRowOff = L.as<uint64_t>(nRuns + 1);
+        uint8_t *runClass = L.as<uint8_t>(nRuns + 1);
+        ColRowRec *runRows = L.as<ColRowRec>(std::max<uint64_t>(nRows, 1));
+        RunScatterParams rp;
+        rp.isStart = isStart; rp.runIndex = runIndex; rp.runRowOffset = runRowOffset; rp.pieceCol = pieceCol; rp.pieceRowOff = pieceRowOff;
+        rp.pieceRows = pieceRows; rp.pieceClass = pieceClass; rp.rows = rows; rp.runCol = runCol; rp.runRowOff = runRowOff;
+        rp.runClass = unique ? runClass : nullptr; rp.runRows = runRows; rp.nPieces = (int64_t)nPieces; rp.nCols = n;
+        rt::launch(runScatterKernel, gridFor((int64_t)nPieces + 1, 256, _sms), 256, 0, _stream, rp);
+        _ev[1]->record(_stream);
+        out.n_cols = (size_t)n; out.n_runs = (size_t)nRuns; out.n_rows = (size_t)nRows;
+        out.run_col = static_cast<int64_t *>(rt::hostAlloc((nRuns + 1) * 8));
+        out.row_offset = static_cast<uint64_t *>(rt::hostAlloc((nRuns + 1) * 8));
+        out.rows = static_cast<halgpu_col_row *>(rt::hostAlloc(std::max<uint64_t>(nRows, 1) * sizeof(halgpu_col_row)));
+        rt::d2h(out.run_col, runCol, (nRuns + 1) * 8, _stream);
+        rt::d2h(out.row_offset, runRowOff, (nRuns + 1) * 8, _stream);
+        rt::d2h(out.rows, runRows, nRows * sizeof(halgpu_col_row), _stream);
+        out.run_class = nullptr;
+        if (unique) {
+            out.run_class = static_cast<uint8_t *>(rt::hostAlloc(std::max<uint64_t>(nRuns, 1)));
+            rt::d2h(out.run_class, runClass, nRuns, _stream);
+        }
+        rt::sync(_stream);
+        out.kernel_ms = rt::Event::elapsedMs(*_ev[0], *_ev[1]); // both walks, the scans and the merge
+    } catch (...) {
+        try { rt::sync(_stream); } catch (...) {}
+        throw;
     }
-    rt::sync(_stream);
-    out.kernel_ms = rt::Event::elapsedMs(e0, e1) + rt::Event::elapsedMs(e2, e3);
 }
 
 void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
@@ -436,26 +496,35 @@ void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const st
     const int ng = (int)G.size();
     if (ref < 0 || ref >= ng) throw HalError("genome index out of range");
     if (ng > 256) throw HalError("alignment depth supports at most 256 genomes");
+    for (const GenomeInfo &g : G) {
+        if (g.children.size() > 4095) throw HalError("genome " + g.name + " has more than 4095 children; not supported by the column walk");
+    }
     if (step < 1 || first < 0 || last < first || last >= G[ref].length) throw HalError("column range out of bounds for genome " + G[ref].name);
-    DevBuf::current() = _stream;
     std::vector<GenomeTab> tab;
     buildGenomeTab(ref, targets, tab);
-    DevBuf dTab(tab.size() * sizeof(GenomeTab)), dErr(sizeof(uint32_t));
-    rt::h2d(dTab.p, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
-    rt::dmemset(dErr.p, 0, sizeof(uint32_t), _stream);
-    DepthParams P;
-    P.genomes = dTab.as<GenomeTab>(); P.numGenomes = ng; P.ref = ref;
-    P.first = first; P.step = step; P.n = (last - first) / step + 1;
-    P.flags = flags; P.depth = dOut; P.error = dErr.as<uint32_t>();
-    rt::Event e0, e1;
-    e0.record(_stream);
-    rt::launch(depthKernel, gridFor(P.n, 128, _sms), 128, 0, _stream, P);
-    e1.record(_stream);
-    uint32_t err = 0;
-    rt::d2h(&err, dErr.p, sizeof(err), _stream);
-    rt::sync(_stream);
-    if (kernelMs) *kernelMs = rt::Event::elapsedMs(e0, e1);
-    if (err) throw HalError("column walk exceeded its stack (more than " + std::to_string(HG_WALK_STACK) + " pending branches)");
+    Lease L(_cache);
+    try {
+        GenomeTab *dTab = L.as<GenomeTab>(tab.size());
+        uint32_t *dErr = L.as<uint32_t>(1);
+        rt::h2d(dTab, tab.data(), tab.size() * sizeof(GenomeTab), _stream);
+        rt::dmemset(dErr, 0, sizeof(uint32_t), _stream);
+        DepthParams P;
+        P.genomes = dTab; P.numGenomes = ng; P.ref = ref;
+        P.first = first; P.step = step; P.n = (last - first) / step + 1;
+        refSegRange(G[ref], first, first + (P.n - 1) * step, P.seg0, P.nSegs);
+        P.flags = flags; P.depth = dOut; P.error = dErr;
+        _ev[0]->record(_stream);
+        rt::launch(depthKernel, gridFor(P.nSegs, 128, _sms), 128, 0, _stream, P);
+        _ev[1]->record(_stream);
+        uint32_t err = 0;
+        rt::d2h(&err, dErr, sizeof(err), _stream);
+        rt::sync(_stream); // (tab is pageable host memory: the copy above has completed by now)
+        if (kernelMs) *kernelMs = rt::Event::elapsedMs(*_ev[0], *_ev[1]);
+        if (err) throw HalError("column walk exceeded its stack (more than " + std::to_string(HG_WALK_STACK) + " pending branches)");
+    } catch (...) {
+        try { rt::sync(_stream); } catch (...) {}
+        throw;
+    }
 }
 
 namespace {
@@ -511,37 +580,50 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         unsigned long long *outLoc = L.as<unsigned long long>(n + 2);
         uint32_t *status = L.as<uint32_t>(n + 1);
         unsigned long long *ctr = L.as<unsigned long long>(C_WORDS);
-        rt::dmemset(outLoc, 0, (n + 2) * sizeof(unsigned long long), _stream);
         rt::dmemset(status, 0, (n + 1) * sizeof(uint32_t), _stream);
         rt::dmemset(ctr, 0, C_WORDS * sizeof(unsigned long long), _stream);
+        // fastLiftKernel leaves a finished interval's line in pool slot <interval id>; outLoc is preset to say so
+        if (fast) rt::dmemset(outLoc + n, 0, 2 * sizeof(unsigned long long), _stream);
+        else rt::dmemset(outLoc, 0, (n + 2) * sizeof(unsigned long long), _stream);
         pt.mark("alloc0");
 
         // visit the batch in source order so that neighbouring lanes / warps walk neighbouring records (coalescing, L2 reuse).
         // Only the upper bits of the start decide the order: ~32 source segments per sort bucket are as good as an exact order.
         const unsigned long long *sortedGs = nullptr, *sortedVal = nullptr;
-        if (!(flags & HALGPU_NO_SORT) && n > 1) {
-            uint64_t *keysIn = L.as<uint64_t>(n), *valsIn = L.as<uint64_t>(n), *keysOut = L.as<uint64_t>(n), *valsOut = L.as<uint64_t>(n);
+        const bool sorting = !(flags & HALGPU_NO_SORT) && n > 1;
+        if (sorting || fast) {
             IotaParams ip;
-            ip.vals = valsIn; ip.keys = keysIn; ip.gs = dGs; ip.ge = dGe; ip.n = (int64_t)n;
+            std::memset(&ip, 0, sizeof(ip));
+            uint64_t *keysIn = nullptr, *valsIn = nullptr;
+            if (sorting) { keysIn = L.as<uint64_t>(n); valsIn = L.as<uint64_t>(n); }
+            ip.vals = valsIn; ip.keys = keysIn; ip.gs = dGs; ip.ge = dGe; ip.directLoc = fast ? outLoc : nullptr; ip.n = (int64_t)n;
             rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
-            int endBit = 1;
-            while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
-            const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
-            int bits = ((endBit - coarse) / 8) * 8;
-            if (bits < 8) bits = std::min(8, endBit);
-            const int beginBit = std::max(0, endBit - bits);
-            size_t tmpBytes = 0;
-            rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
-            void *tmp = L.take(tmpBytes);
-            rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
-            sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
-            sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
+            if (sorting) {
+                uint64_t *keysOut = L.as<uint64_t>(n), *valsOut = L.as<uint64_t>(n);
+                int endBit = 1;
+                while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
+                const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
+                int bits = ((endBit - coarse) / 8) * 8;
+                if (bits < 8) bits = std::min(8, endBit);
+                const int beginBit = std::max(0, endBit - bits);
+                size_t tmpBytes = 0;
+                rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                void *tmp = L.take(tmpBytes);
+                rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
+                sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
+            }
         }
         if (pt.on) rt::sync(_stream);
         pt.mark("sort");
 
-        uint64_t poolCap = wig ? 1 : (uint64_t)n + (uint64_t)n / 4 + 4096; // (the wiggle mode emits no records)
+        // record pool: slots [0, n) are the direct slots of fastLiftKernel, the walk allocates behind them.  Sized from the
+        // lines-per-interval ratio the last batches on this path produced, so a steady stream of batches does not re-walk
+        // intervals that found the pool full.
+        const uint64_t direct = fast ? (uint64_t)n : 0;
+        uint64_t poolCap = wig ? 1 : direct + (uint64_t)((double)n * std::max(1.25, pl.linesPerInterval * 1.125)) + 4096; // (the wiggle mode emits no records)
         halgpu_lift_rec *pool = L.as<halgpu_lift_rec>(poolCap);
+        if (direct) rt::h2d(ctr + C_POOL, &direct, sizeof(direct), _stream); // (pageable 8 bytes: copied before the call returns)
         uint32_t *pslPool = nullptr;
         if (wantPsl) {
             pslPool = L.as<uint32_t>(poolCap * 4);
@@ -582,7 +664,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             F.tgtSeqStart = P.tgtSeqStart; F.tgtNumSeq = P.tgtNumSeq;
             F.n = (int64_t)n; F.gs = dGs; F.ge = dGe; F.strand = dStrand;
             F.sortedGs = sortedGs; F.sortedVal = sortedVal;
-            F.tileCursor = ctr + C_TILE; F.outLoc = outLoc; F.pool = pool; F.poolCursor = ctr + C_POOL; F.poolCap = poolCap;
+            F.tileCursor = ctr + C_TILE; F.pool = pool;
             F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
             const int64_t tiles = ((int64_t)n + 31) / 32;
             const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)_sms * 8));
@@ -630,6 +712,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             GatherParams gp;
             gp.pslPool = P.pslPool; gp.psl = psl;
             gp.outLoc = outLoc; gp.csr = csr; gp.pool = P.pool; gp.recs = recs; gp.n = (int64_t)n;
+            gp.skipIfZero = fast ? ctr + C_COMPLEX : nullptr;
             rt::launch(gatherKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, gp);
             rt::d2d(ctr + C_TOTAL, csr + n, sizeof(uint64_t), _stream);
             if (offsetBase != 0) { // chunk-local offsets -> offsets of the whole batch (halgpu_liftover lifts chunk by chunk)
@@ -748,7 +831,13 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             out.launches = (int)rt::g_launches - launches0;
             return;
         }
+        if (!raw && !columnMerge && n > 0) { // what the pool has to hold next time (the cursor counts every request, granted or not)
+            const uint64_t directLines = fast ? (uint64_t)n - (uint64_t)_hostCtr[C_COMPLEX] : 0;
+            const double lpi = (double)(_hostCtr[C_TOTAL] - directLines) / (double)n;
+            if (lpi > pl.linesPerInterval) pl.linesPerInterval = lpi;
+        }
         out.offsets = static_cast<uint64_t *>(L.detach(csr));
+        if (fast && _hostCtr[C_COMPLEX] == 0) recs = pool; // every line sits in its direct slot: the pool is the result
         out.recs = static_cast<halgpu_lift_rec *>(L.detach(recs));
         out.psl = wantPsl ? static_cast<uint32_t *>(L.detach(psl)) : nullptr;
         out.nRec = (size_t)_hostCtr[C_TOTAL];

@@ -16,6 +16,8 @@ struct GenomeDev {
     TopRec *top = nullptr;     // numTop + 1
     BotCore *bot = nullptr;    // numBottom + 1
     int64_t *child = nullptr;  // nc columns x numBottom
+    int64_t *topX = nullptr;   // numTop: xlate constant of every parent link
+    int64_t *childX = nullptr; // nc columns x numBottom: xlate constant of every child link
     uint8_t *dna = nullptr;    // (length + 1) / 2
     int64_t *seqStart = nullptr; // numSeq + 1
     int32_t *childGenome = nullptr; // nc entries
@@ -30,6 +32,7 @@ struct Plan {
     std::vector<int> path; // src .. mrca [.. child of the limit .. mrca] .. tgt (genome of every path position)
     int upSteps = 0;
     PathStep *dSteps = nullptr;
+    mutable double linesPerInterval = 0; // largest output lines / interval ratio seen on this path: sizes the next batch's record pool
 };
 
 struct LiftOutput { // device-side result of one batch; the buffers belong to the context's cache (Context::release)

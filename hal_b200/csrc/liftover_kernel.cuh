@@ -895,33 +895,40 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
             const int np = P.P;
             for (int p = 0; p < np - 1; ++p) {
                 const PathStep &st = sSteps[p];
+                // One hop = the bucket entry, then the segment's start, link and xlate constant in parallel: two dependent
+                // memory round trips.  Bucket segment i0 starts at or before tLo; if [tLo, tLo + len) lies inside i0's
+                // collinear run the run's affine map applies even when tLo is past i0's own end.  Otherwise the exact
+                // segment is searched and tested before the interval is declared complex.
+                int64_t e, x, s0;
                 if (st.up) { // toParent (api/impl/halBottomSegmentIterator.cpp:40-49) over a whole run
-                    const int64_t idx = locateSeg<true>(st, tLo);
-                    const TopRec r = ldTop(&st.top[idx]);
-                    const int64_t off = tLo - r.start;
-                    if (r.parentEnc < 0 || off + len > linkRun(r.parentEnc)) { ok = false; break; }
-                    const int64_t ps = botStart(sSteps[p + 1].bot, linkIdx(r.parentEnc));
-                    if (linkRev(r.parentEnc)) {
-                        const int64_t L = topStart(st.top, idx + 1) - r.start;
-                        tLo = ps + L - off - len;
-                        rev = !rev;
-                    } else {
-                        tLo = ps + off;
+                    int64_t i = (int64_t)__ldg(&st.topBucket[tLo >> st.topShift]);
+                    longlong2 h = __ldg(reinterpret_cast<const longlong2 *>(&st.top[i])); // start, parent link
+                    x = ldS(&st.xlate[i]);
+                    s0 = h.x; e = h.y;
+                    if (e < 0 || tLo - s0 + len > linkRun(e)) {
+                        i = searchFrom<true>(st.top, i, st.numTop, tLo);
+                        h = __ldg(reinterpret_cast<const longlong2 *>(&st.top[i]));
+                        x = ldS(&st.xlate[i]);
+                        s0 = h.x; e = h.y;
                     }
                 } else { // toChild (api/impl/halTopSegmentIterator.cpp:36-45) over a whole run
-                    const int64_t idx = locateSeg<false>(st, tLo);
-                    const int64_t ce = ldS(&st.child[idx]);
-                    const int64_t b0 = botStart(st.bot, idx);
-                    const int64_t off = tLo - b0;
-                    if (ce < 0 || off + len > linkRun(ce)) { ok = false; break; }
-                    const int64_t cs = topStart(sSteps[p + 1].top, linkIdx(ce));
-                    if (linkRev(ce)) {
-                        const int64_t L = botStart(st.bot, idx + 1) - b0;
-                        tLo = cs + L - off - len;
-                        rev = !rev;
-                    } else {
-                        tLo = cs + off;
+                    int64_t i = (int64_t)__ldg(&st.botBucket[tLo >> st.botShift]);
+                    s0 = botStart(st.bot, i);
+                    e = ldS(&st.child[i]);
+                    x = ldS(&st.xlate[i]);
+                    if (e < 0 || tLo - s0 + len > linkRun(e)) {
+                        i = searchFrom<false>(st.bot, i, st.numBot, tLo);
+                        s0 = botStart(st.bot, i);
+                        e = ldS(&st.child[i]);
+                        x = ldS(&st.xlate[i]);
                     }
+                }
+                if (e < 0 || tLo - s0 + len > linkRun(e)) { ok = false; break; }
+                if (linkRev(e)) {
+                    tLo = x - tLo - (len - 1); // the image of the interval's last base is the lowest target position
+                    rev = !rev;
+                } else {
+                    tLo += x;
                 }
             }
         }
@@ -932,17 +939,13 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
             seqStart = ldS(&P.tgtSeqStart[seq]);
             if (tLo + len > ldS(&P.tgtSeqStart[seq + 1])) ok = false; // the pieces would not merge across sequences
         }
-        const unsigned okm = __ballot_sync(HG_FULL, ok);
         const unsigned cm = __ballot_sync(HG_FULL, have && !ok);
-        unsigned long long base = 0, cbase = 0;
-        if (lane == 0) {
-            if (okm) base = atomicAdd(P.poolCursor, (unsigned long long)__popc(okm));
-            if (cm) cbase = atomicAdd(P.complexCount, (unsigned long long)__popc(cm));
-        }
-        base = __shfl_sync(HG_FULL, base, 0);
+        unsigned long long cbase = 0;
+        if (lane == 0 && cm) cbase = atomicAdd(P.complexCount, (unsigned long long)__popc(cm));
         cbase = __shfl_sync(HG_FULL, cbase, 0);
-        if (ok) { // (the engine sizes the pool for at least one record per interval, so slot < poolCap)
-            const unsigned long long slot = base + (unsigned long long)lanePrefix(okm, lane);
+        if (ok) {
+            // the line goes straight to pool slot `item`, which is where outLoc[item] (initialised by the engine) already
+            // points: when the whole batch ends here the pool IS the result in input order and nothing is gathered
             const uint8_t bs = P.strand ? P.strand[item] : (uint8_t)'+';
             const bool flip = bs == '-';
             const unsigned long long st8 = bs == '.' ? (unsigned long long)'.' : (unsigned long long)((flip != rev) ? '-' : '+');
@@ -951,9 +954,8 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
             a.x = tLo - seqStart; a.y = tLo + len - seqStart;
             b.x = gs;
             b.y = (long long)((unsigned long long)(uint32_t)seq | (st8 << 32) | (ss8 << 40) | (1ull << 48));
-            longlong2 *dst = reinterpret_cast<longlong2 *>(&P.pool[slot]);
+            longlong2 *dst = reinterpret_cast<longlong2 *>(&P.pool[item]);
             dst[0] = a; dst[1] = b;
-            P.outLoc[item] = (slot << HG_LOC_COUNT_BITS) | 1ull;
         } else if (have) {
             P.complexList[cbase + (unsigned long long)lanePrefix(cm, lane)] = item;
         }

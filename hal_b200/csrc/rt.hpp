@@ -66,7 +66,8 @@ struct Event {
 };
 template <class K, class P> inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, Stream, const P &param) {
     ++g_launches;
-    if (grid > 4) grid = 4; // kernels are grid-stride; keep the emulated thread count small
+    const unsigned cap = block >= 256 ? 1u : (block >= 128 ? 2u : 4u); // kernels are grid-stride; keep the emulated thread count small
+    if (grid > cap) grid = cap;
     simt::launch(kernel, dim3(grid), dim3(block), smem, param);
 }
 template <class K> inline void allowSmem(K, size_t) {}

@@ -111,20 +111,45 @@ __global__ void linkRunKernel(const LinkRunParams p) {
     }
 }
 
+// xlate constant of every link (device_index.cuh): with s0 / L the start / length of segment i and t0 the start of the
+// segment it links to, forward q -> q + (t0 - s0); reversed q -> (t0 + L - 1) - (q - s0) = (t0 + L - 1 + s0) - q
+struct LinkXlateParams {
+    const int64_t *links, *starts, *otherStarts;
+    int64_t linkStride, startStride, otherStride, n;
+    int64_t *xlate;
+};
+__global__ void linkXlateKernel(const LinkXlateParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const int64_t e = p.links[i * p.linkStride];
+        int64_t x = 0;
+        if (e >= 0) {
+            const int64_t s0 = p.starts[i * p.startStride], L = p.starts[(i + 1) * p.startStride] - s0;
+            const int64_t t0 = p.otherStarts[linkIdx(e) * p.otherStride];
+            x = linkRev(e) ? t0 + L - 1 + s0 : t0 - s0;
+        }
+        p.xlate[i] = x;
+    }
+}
+
 // sort input: key = source start (sorted on its upper bits only), value = interval id | min(length, 2^32 - 1) << 32
 struct IotaParams {
-    uint64_t *vals;
+    uint64_t *vals;             // NULL: no sort input wanted (HALGPU_NO_SORT), only directLoc
     uint64_t *keys;
     const int64_t *gs, *ge;
+    unsigned long long *directLoc; // optional: outLoc[i] = "one record in pool slot i" (what fastLiftKernel leaves behind on success)
     int64_t n;
 };
 __global__ void iotaKeysKernel(const IotaParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const int64_t a = p.gs[i], len = p.ge[i] - a + 1;
-        const uint64_t l32 = (len <= 0 || len >= 0xffffffffll) ? 0xffffffffull : (uint64_t)len;
-        p.vals[i] = (uint64_t)i | (l32 << 32);
-        p.keys[i] = (uint64_t)a;
+        if (p.vals) {
+            const int64_t a = p.gs[i], len = p.ge[i] - a + 1;
+            const uint64_t l32 = (len <= 0 || len >= 0xffffffffll) ? 0xffffffffull : (uint64_t)len;
+            p.vals[i] = (uint64_t)i | (l32 << 32);
+            p.keys[i] = (uint64_t)a;
+        }
+        if (p.directLoc) p.directLoc[i] = ((unsigned long long)i << HG_LOC_COUNT_BITS) | 1ull;
     }
 }
 
@@ -158,7 +183,8 @@ __global__ void addBaseKernel(const AddBaseParams p) { // chunk-local CSR offset
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) p.v[i] += p.base;
 }
 
-// pool (allocation order) -> CSR (input order)
+// pool (allocation order) -> CSR (input order).  One warp per 32 intervals: when every interval of the tile has at most two
+// records each lane copies its own, otherwise the warp copies interval after interval with 16-byte units across the lanes.
 struct GatherParams {
     const unsigned long long *outLoc;
     const uint64_t *csr;
@@ -166,19 +192,46 @@ struct GatherParams {
     halgpu_lift_rec *recs;
     const uint32_t *pslPool; // optional
     uint32_t *psl;
+    const unsigned long long *skipIfZero; // optional: nothing to do when this device counter is 0 (every record already sits in
+                                          // its final slot: a batch fastLiftKernel finished alone)
     int64_t n;
 };
-__global__ void gatherKernel(const GatherParams p) {
+__global__ void __launch_bounds__(256) gatherKernel(const GatherParams p) {
+    if (p.skipIfZero != nullptr && *p.skipIfZero == 0ull) return;
+    const int lane = threadIdx.x & 31;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const unsigned long long loc = p.outLoc[i];
-        const uint32_t c = (uint32_t)(loc & ((1ull << HG_LOC_COUNT_BITS) - 1ull));
-        const uint64_t from = loc >> HG_LOC_COUNT_BITS, to = p.csr[i];
-        const longlong2 *src = reinterpret_cast<const longlong2 *>(p.pool + from);
-        longlong2 *dst = reinterpret_cast<longlong2 *>(p.recs + to);
-        for (uint32_t k = 0; k < 2 * c; ++k) dst[k] = src[k];
-        if (p.pslPool)
-            for (uint32_t k = 0; k < 4 * c; ++k) p.psl[4 * to + k] = p.pslPool[4 * from + k];
+    const int64_t nRound = (p.n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += step) {
+        uint32_t c = 0;
+        uint64_t from = 0, to = 0;
+        if (i < p.n) {
+            const unsigned long long loc = p.outLoc[i];
+            c = (uint32_t)(loc & ((1ull << HG_LOC_COUNT_BITS) - 1ull));
+            from = loc >> HG_LOC_COUNT_BITS; to = p.csr[i];
+        }
+        if (!__any_sync(0xffffffffu, c > 2u)) {
+            const longlong2 *src = reinterpret_cast<const longlong2 *>(p.pool + from);
+            longlong2 *dst = reinterpret_cast<longlong2 *>(p.recs + to);
+            for (uint32_t k = 0; k < 2 * c; ++k) dst[k] = src[k];
+            if (p.pslPool)
+                for (uint32_t k = 0; k < 4 * c; ++k) p.psl[4 * to + k] = p.pslPool[4 * from + k];
+            continue;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, c > 0u);
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const uint32_t cj = __shfl_sync(0xffffffffu, c, j);
+            const uint64_t fj = __shfl_sync(0xffffffffu, from, j), tj = __shfl_sync(0xffffffffu, to, j);
+            const longlong2 *src = reinterpret_cast<const longlong2 *>(p.pool + fj);
+            longlong2 *dst = reinterpret_cast<longlong2 *>(p.recs + tj);
+            for (uint32_t u = (uint32_t)lane; u < 2 * cj; u += 32) dst[u] = src[u];
+            if (p.pslPool) {
+                const longlong2 *ps = reinterpret_cast<const longlong2 *>(p.pslPool + 4 * fj);
+                longlong2 *pd = reinterpret_cast<longlong2 *>(p.psl + 4 * tj);
+                for (uint32_t u = (uint32_t)lane; u < cj; u += 32) pd[u] = ps[u];
+            }
+        }
     }
 }
 

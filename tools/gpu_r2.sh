@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 GPU session script (one gpurun call): gpurun -- 'bash tools/gpu_r2.sh <stage>'
+# Outputs land in gpurun_out/ (merged back); numbers quoted in profiles/ come from these files.
+mkdir -p gpurun_out
+stage=${1:-a}
+case $stage in
+a)  # parity of the liftover path + first bench with the one-lane-per-interval kernel + launch list + ncu of both kernels
+    timeout 900 python -m pytest tests/test_liftover_gpu.py -x -q -m gpu > gpurun_out/pytest_lift.log 2>&1; tail -3 gpurun_out/pytest_lift.log
+    ( time timeout 600 python bench.py --steps 10 --warmup 3 --no-cli --no-maf --no-wiggle ) > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err
+    tail -c 1500 gpurun_out/bench_a.json; tail -5 gpurun_out/bench_a.err
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_a.csv \
+        python bench.py --steps 2 --warmup 1 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth > gpurun_out/bench_ncu_a.json 2> gpurun_out/bench_ncu_a.err
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:fastLiftKernel -s 1 -c 1 -o gpurun_out/prof_fast -f \
+        python bench.py --steps 1 --warmup 1 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth --no-divergent > /dev/null 2> gpurun_out/prof_fast.err
+    ;;
+b)  # whole GPU test tier + bench + ncu of the fast kernel (2-level hops), the piece-walk depth kernel and the divergent walk
+    timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_b.log 2>&1; tail -5 gpurun_out/pytest_b.log
+    ( time timeout 900 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err
+    tail -c 600 gpurun_out/bench_b.json; tail -5 gpurun_out/bench_b.err
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_b.csv \
+        python bench.py --steps 2 --warmup 1 --no-cli --no-wiggle --no-cpu-baseline > gpurun_out/bench_ncu_b.json 2> gpurun_out/bench_ncu_b.err
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel|depthKernel' -s 2 -c 3 -o gpurun_out/prof_b -f \
+        python bench.py --steps 1 --warmup 1 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-divergent > /dev/null 2> gpurun_out/prof_b.err
+    ;;
+*)  echo "unknown stage $stage"; exit 2;;
+esac
