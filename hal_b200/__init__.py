@@ -60,6 +60,8 @@ ABI_SYMBOLS = [
     "halgpu_staged_bytes", "halgpu_stream", "halgpu_liftover", "halgpu_liftover_device", "halgpu_free_result",
     "halgpu_free_string", "halgpu_launch_count", "halgpu_columns_depth", "halgpu_columns_depth_device",
     "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna", "halgpu_host_alloc", "halgpu_host_free",
+    "halgpu_comm_unique_id", "halgpu_comm_init", "halgpu_comm_free", "halgpu_comm_rank", "halgpu_comm_size",
+    "halgpu_liftover_allgather_begin", "halgpu_liftover_allgather_end",
     "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_column_runs_in_sweep", "halgpu_genome_metadata", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
 ]
 
@@ -106,6 +108,13 @@ def load_library(path=None):
     L.halgpu_free_result.argtypes = [C.POINTER(_Result)]
     L.halgpu_free_string.argtypes = [C.c_void_p]
     L.halgpu_launch_count.restype = C.c_uint64
+    L.halgpu_comm_unique_id.argtypes = [vp, C.POINTER(C.c_char_p)]
+    L.halgpu_comm_init.argtypes = [vp, i32, i32, vp, C.POINTER(vp), C.POINTER(C.c_char_p)]
+    L.halgpu_comm_free.argtypes = [vp]
+    L.halgpu_comm_rank.argtypes = [vp]
+    L.halgpu_comm_size.argtypes = [vp]
+    L.halgpu_liftover_allgather_begin.argtypes = [vp, i32, i32, i32, C.c_uint32, C.c_size_t, vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_char_p)]
+    L.halgpu_liftover_allgather_end.argtypes = [vp, C.POINTER(C.POINTER(_Result)), vp, vp, C.POINTER(C.c_char_p)]
     return L
 
 
@@ -262,3 +271,54 @@ class Alignment:
         fn = self.L.halgpu_liftover_device if device else self.L.halgpu_liftover
         res = self._call(fn, src, tgt, flags, n, start_ptr, end_ptr, strand_ptr)
         return DeviceResult(self.L, res)
+
+
+class Comm:
+    """One rank of a multi-GPU communicator over an Alignment (include/halgpu.h: halgpu_comm_*).  The 128-byte id comes
+    from Comm.unique_id() on rank 0 and reaches the other ranks out of band (tests: shared between threads; bench.py:
+    torch.distributed broadcast)."""
+
+    def __init__(self, alignment, nranks, rank, uid):
+        self.a, self.L = alignment, alignment.L
+        h, errp = C.c_void_p(), C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        rc = self.L.halgpu_comm_init(alignment.h, nranks, rank, C.addressof(buf), C.byref(h), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            raise HalGpuError(_err_text(self.L, errp, "halgpu_comm_init failed"))
+        self.h, self.nranks, self.rank = h, nranks, rank
+
+    @staticmethod
+    def unique_id(lib):
+        buf, errp = (C.c_uint8 * 128)(), C.c_void_p()
+        if lib.halgpu_comm_unique_id(C.addressof(buf), C.cast(C.byref(errp), C.POINTER(C.c_char_p))) != 0:
+            raise HalGpuError(_err_text(lib, errp, "halgpu_comm_unique_id failed"))
+        return bytes(buf)
+
+    def begin(self, src, tgt, n, start_ptr, end_ptr, strand_ptr=None, flags=0, coalescence_limit=-1):
+        g, errp = C.c_void_p(), C.c_void_p()
+        rc = self.L.halgpu_liftover_allgather_begin(self.h, src, tgt, coalescence_limit, flags, n, start_ptr, end_ptr, strand_ptr, C.byref(g),
+                                                    C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            raise HalGpuError(_err_text(self.L, errp, "allgather_begin failed"))
+        return g
+
+    def end(self, g):
+        """-> (DeviceResult of the whole batch, intervals per rank, records per rank)"""
+        res, errp = C.POINTER(_Result)(), C.c_void_p()
+        npr, nrr = (C.c_size_t * self.nranks)(), (C.c_size_t * self.nranks)()
+        rc = self.L.halgpu_liftover_allgather_end(g, C.byref(res), C.addressof(npr), C.addressof(nrr), C.cast(C.byref(errp), C.POINTER(C.c_char_p)))
+        if rc != 0:
+            raise HalGpuError(_err_text(self.L, errp, "allgather_end failed"))
+        return DeviceResult(self.L, res), list(npr), list(nrr)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.halgpu_comm_free(self.h)
+            self.h = None
+
+
+def _err_text(lib, errp, default):
+    msg = C.cast(errp, C.c_char_p).value.decode() if errp.value else default
+    if errp.value:
+        lib.halgpu_free_string(errp)
+    return msg

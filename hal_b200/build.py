@@ -18,8 +18,8 @@ LIB = os.path.join(HERE, "libhalgpu.so")
 BIN = os.path.join(HERE, "bin")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-Wno-deprecated-declarations", "-shared"]
-LIB_SOURCES = ["capi.cu", "engine.cu", "halmmap.cpp"]
+              "-Xcompiler", "-Wno-deprecated-declarations", "-shared", "-ldl"]
+LIB_SOURCES = ["capi.cu", "engine.cu", "multi.cu", "halmmap.cpp"]
 
 
 def _newer(target, sources):

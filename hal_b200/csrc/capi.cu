@@ -7,11 +7,6 @@
 
 using namespace halgpu;
 
-struct halgpu_ctx {
-    std::unique_ptr<Context> impl;
-    std::vector<std::vector<halgpu_seq>> seqTables;
-};
-
 namespace {
 int fail(char **err, const std::string &msg) {
     if (err != nullptr) {

@@ -690,15 +690,12 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         halgpu_lift_rec *recs = nullptr;
         uint32_t *psl = nullptr;
         uint64_t recCap = 0;
-        void *scanTmp = nullptr;
-        size_t scanTmpBytes = 0;
-        const uint64_t countMask = (1ull << HG_LOC_COUNT_BITS) - 1ull;
+        uint64_t *blockSums = nullptr;
         auto assemble = [&]() {
             if (wig) return;
             if (csr == nullptr) {
                 csr = L.as<uint64_t>(n + 2);
-                rt::exclusiveScanMaskedTmp(nullptr, scanTmpBytes, outLoc, csr, n, countMask, _stream);
-                scanTmp = L.take(scanTmpBytes);
+                blockSums = L.as<uint64_t>(n / (HG_SCAN_BLOCK * HG_SCAN_ITEMS) + 2);
             }
             if (recs == nullptr || recCap < P.poolCap) {
                 if (recs) L.giveNow(recs);
@@ -707,8 +704,14 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 recs = L.as<halgpu_lift_rec>(recCap);
                 psl = wantPsl ? L.as<uint32_t>(recCap * 4) : nullptr;
             }
-            size_t tb = scanTmpBytes;
-            rt::exclusiveScanMaskedTmp(scanTmp, tb, outLoc, csr, n, countMask, _stream);
+            CsrScanParams sp;
+            sp.outLoc = outLoc; sp.csr = csr; sp.blockSums = blockSums; sp.n = (int64_t)n;
+            sp.skipIfZero = fast ? ctr + C_COMPLEX : nullptr; // all intervals finished by fastLiftKernel: offsets[i] = i
+            const unsigned sgrid = gridFor(((int64_t)n + HG_SCAN_BLOCK * HG_SCAN_ITEMS - 1) / (HG_SCAN_BLOCK * HG_SCAN_ITEMS), 1, _sms);
+            if (fast) rt::launch(csrIdentityKernel, gridFor((int64_t)n + 1, 256, _sms), 256, 0, _stream, sp);
+            rt::launch(csrScanKernel<0>, sgrid, HG_SCAN_BLOCK, 0, _stream, sp);
+            rt::launch(csrScanSumsKernel, 1, HG_SCAN_BLOCK, 0, _stream, sp);
+            rt::launch(csrScanKernel<2>, sgrid, HG_SCAN_BLOCK, 0, _stream, sp);
             GatherParams gp;
             gp.pslPool = P.pslPool; gp.psl = psl;
             gp.outLoc = outLoc; gp.csr = csr; gp.pool = P.pool; gp.recs = recs; gp.n = (int64_t)n;

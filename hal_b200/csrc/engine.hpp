@@ -128,3 +128,9 @@ class Context {
 };
 
 } // namespace halgpu
+
+// the opaque context of include/halgpu.h (shared by capi.cu and multi.cu)
+struct halgpu_ctx {
+    std::unique_ptr<halgpu::Context> impl;
+    std::vector<std::vector<halgpu_seq>> seqTables;
+};

@@ -183,6 +183,87 @@ __global__ void addBaseKernel(const AddBaseParams p) { // chunk-local CSR offset
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) p.v[i] += p.base;
 }
 
+// CSR offsets = exclusive scan of the per-interval record counts (low bits of outLoc), as three small kernels so that the
+// whole scan can be skipped on the device: when fastLiftKernel finished the batch alone (*skipIfZero == 0) every interval
+// has exactly one record and offsets[i] = i was already written by csrIdentityKernel.
+#define HG_SCAN_BLOCK 256
+#define HG_SCAN_ITEMS 8 // per thread: a block covers 2048 intervals
+struct CsrScanParams {
+    const unsigned long long *outLoc; // n entries
+    uint64_t *csr;                    // n + 1 entries
+    uint64_t *blockSums;              // ceil(n / 2048) + 1 entries
+    const unsigned long long *skipIfZero;
+    int64_t n;
+};
+__global__ void csrIdentityKernel(const CsrScanParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= p.n; i += step) p.csr[i] = (uint64_t)i;
+}
+__device__ __forceinline__ uint64_t csrBlockScan(uint64_t v, uint64_t *warpSums, uint64_t &blockTotal) { // exclusive, 256 threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warpSums[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0, total = 0;
+    for (int w = 0; w < HG_SCAN_BLOCK / 32; ++w) {
+        const uint64_t sW = warpSums[w];
+        if (w < warp) base += sW;
+        total += sW;
+    }
+    __syncthreads();
+    blockTotal = total;
+    return base + incl - v;
+}
+template <int PHASE> // 0: block sums, 2: final offsets
+__global__ void __launch_bounds__(HG_SCAN_BLOCK) csrScanKernel(const CsrScanParams p) {
+    if (p.skipIfZero != nullptr && *p.skipIfZero == 0ull) return;
+    __shared__ uint64_t warpSums[HG_SCAN_BLOCK / 32];
+    const uint64_t mask = (1ull << HG_LOC_COUNT_BITS) - 1ull;
+    const int64_t perBlock = (int64_t)HG_SCAN_BLOCK * HG_SCAN_ITEMS;
+    const int64_t nBlocks = (p.n + perBlock - 1) / perBlock;
+    for (int64_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const int64_t first = b * perBlock + (int64_t)threadIdx.x * HG_SCAN_ITEMS;
+        uint64_t c[HG_SCAN_ITEMS], mine = 0;
+        for (int k = 0; k < HG_SCAN_ITEMS; ++k) {
+            c[k] = first + k < p.n ? (uint64_t)p.outLoc[first + k] & mask : 0ull;
+            mine += c[k];
+        }
+        uint64_t total;
+        uint64_t at = csrBlockScan(mine, warpSums, total);
+        if (PHASE == 0) {
+            if (threadIdx.x == 0) p.blockSums[b] = total;
+        } else {
+            at += p.blockSums[b];
+            for (int k = 0; k < HG_SCAN_ITEMS; ++k) {
+                if (first + k < p.n) p.csr[first + k] = at;
+                at += c[k];
+            }
+            if (b == nBlocks - 1 && threadIdx.x == HG_SCAN_BLOCK - 1) p.csr[p.n] = at;
+        }
+    }
+}
+// phase 1: exclusive scan of the block sums by one block
+__global__ void __launch_bounds__(HG_SCAN_BLOCK) csrScanSumsKernel(const CsrScanParams p) {
+    if (p.skipIfZero != nullptr && *p.skipIfZero == 0ull) return;
+    __shared__ uint64_t warpSums[HG_SCAN_BLOCK / 32];
+    const int64_t perBlock = (int64_t)HG_SCAN_BLOCK * HG_SCAN_ITEMS;
+    const int64_t nBlocks = (p.n + perBlock - 1) / perBlock;
+    uint64_t carry = 0;
+    for (int64_t base = 0; base < nBlocks; base += HG_SCAN_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        const uint64_t v = i < nBlocks ? p.blockSums[i] : 0ull;
+        uint64_t total;
+        const uint64_t at = csrBlockScan(v, warpSums, total);
+        if (i < nBlocks) p.blockSums[i] = carry + at;
+        carry += total;
+    }
+    if (p.n == 0 && threadIdx.x == 0) p.csr[0] = 0;
+}
+
 // pool (allocation order) -> CSR (input order).  One warp per 32 intervals: when every interval of the tile has at most two
 // records each lane copies its own, otherwise the warp copies interval after interval with 16-byte units across the lanes.
 struct GatherParams {

@@ -247,6 +247,33 @@ void halgpu_free_string(char *s);
 void *halgpu_host_alloc(size_t bytes);
 void halgpu_host_free(void *p);
 
+/* ---- multi-GPU liftover (the reference's only parallel driver partitions work the same way across
+ *      processes: maf/hal2mafMP.py:63-79).  One process -- or host thread -- per GPU, each with its own context on the same
+ *      HAL file (the staged index is replicated).  Every rank lifts its own shard of the interval batch; ONE all-gather of
+ *      the output interval buffer over NCCL / NVLink then leaves the result of the WHOLE batch, shards in rank order, in the
+ *      device memory of every rank.  The communicator is bootstrapped like NCCL's: rank 0 creates a 128-byte id
+ *      (halgpu_comm_unique_id) and hands it to the other ranks by any out-of-band means (a file, MPI, torch.distributed);
+ *      all ranks then call halgpu_comm_init.  NCCL is resolved at run time (libnccl.so.2); without it these calls fail and
+ *      everything else works.
+ *      begin() returns once this rank's shard is lifted and the collectives are enqueued on the communicator's own stream;
+ *      end() waits for them and hands out the gathered result (device memory of the context; halgpu_free_result).  A
+ *      caller that begins batch k+1 before ending batch k overlaps the gather of k with the lift of k+1.  begin/end are
+ *      collective: every rank must issue them in the same order. ---- */
+typedef struct halgpu_comm halgpu_comm;
+typedef struct halgpu_gather halgpu_gather;
+int halgpu_comm_unique_id(uint8_t id[128], char **err);
+int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128], halgpu_comm **out, char **err);
+void halgpu_comm_free(halgpu_comm *comm); /* before halgpu_close of its context */
+int halgpu_comm_rank(const halgpu_comm *comm);
+int halgpu_comm_size(const halgpu_comm *comm);
+int halgpu_liftover_allgather_begin(halgpu_comm *comm, int src_genome, int tgt_genome, int coalescence_limit, uint32_t flags,
+                                    size_t n, const int64_t *d_src_start, const int64_t *d_src_end_incl, const uint8_t *d_strand,
+                                    halgpu_gather **out, char **err);
+/* n_per_rank / n_rec_per_rank (optional, halgpu_comm_size entries): intervals / records each rank contributed; the
+ * gather handle is consumed whether or not the call succeeds */
+int halgpu_liftover_allgather_end(halgpu_gather *gather, halgpu_lift_result **out, size_t *n_per_rank, size_t *n_rec_per_rank,
+                                  char **err);
+
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t halgpu_launch_count(void);
 

@@ -41,7 +41,7 @@ def emul_lib():
     """tests/simt/libhalgpu_emul.so: the SAME kernel/engine sources compiled for the host warp emulator."""
     out = os.path.join(ROOT, "tests", "simt", "libhalgpu_emul.so")
     csrc = os.path.join(ROOT, "hal_b200", "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("capi.cu", "engine.cu", "halmmap.cpp")]
+    srcs = [os.path.join(csrc, f) for f in ("capi.cu", "engine.cu", "multi.cu", "halmmap.cpp")]
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if os.path.isfile(os.path.join(csrc, f))] + \
            [os.path.join(ROOT, "tests", "simt", "simt_emul.h"), os.path.join(ROOT, "include", "halgpu.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):

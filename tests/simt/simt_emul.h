@@ -63,7 +63,17 @@ template <class T> inline T fromBits(uint64_t b) {
 }
 inline void warpBarrier() { pthread_barrier_wait(&ctx().warp->bar); }
 
+inline pthread_mutex_t &launchMutex() {
+    static pthread_mutex_t m = PTHREAD_MUTEX_INITIALIZER;
+    return m;
+}
 template <class K, class P> void launch(K kernel, dim3 grid, dim3 block, size_t smemBytes, const P &param) {
+    // one kernel at a time in the whole process: __shared__ variables are statics, and the multi-rank tests launch from
+    // several host threads
+    struct Guard {
+        Guard() { pthread_mutex_lock(&launchMutex()); }
+        ~Guard() { pthread_mutex_unlock(&launchMutex()); }
+    } guard;
     const unsigned nb = grid.x, nt = block.x, nw = (nt + 31) / 32;
     std::vector<Block> blocks(nb);
     std::vector<std::vector<uint8_t>> smems(nb);

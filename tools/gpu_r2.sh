@@ -22,5 +22,14 @@ b)  # whole GPU test tier + bench + ncu of the fast kernel (2-level hops), the p
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel|depthKernel' -s 2 -c 3 -o gpurun_out/prof_b -f \
         python bench.py --steps 1 --warmup 1 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-divergent > /dev/null 2> gpurun_out/prof_b.err
     ;;
+c)  # reworked bench (checks, in-run ncu traffic) at N=1; with 2 GPUs: NCCL tests of the C++ multi path + bench at N=2
+    timeout 600 python -m pytest tests/test_multi_gpu.py tests/test_liftover_gpu.py -x -q -m gpu > gpurun_out/pytest_c.log 2>&1; tail -5 gpurun_out/pytest_c.log
+    ( time timeout 900 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_c.json 2> gpurun_out/bench_c.err
+    tail -c 400 gpurun_out/bench_c.json; tail -5 gpurun_out/bench_c.err
+    if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+        ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline ) > gpurun_out/bench_c_n2.json 2> gpurun_out/bench_c_n2.err
+        tail -c 1500 gpurun_out/bench_c_n2.json; tail -5 gpurun_out/bench_c_n2.err
+    fi
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
