@@ -121,6 +121,8 @@ struct LiftParams {
     const int64_t *wigValOff;    // per interval: >= 0 index of its first per-base value in wigVals; < 0: ~index of its single value
     const double *wigVals;
     // scratch: lists live in dynamic shared memory unless gscratch != NULL
+    int32_t seedTile;  // 1: stage every interval's run of source top records into shared memory with one cp.async.bulk (TMA)
+    int32_t pad1;
     int32_t listCap;   // fragments per list (two lists per warp)
     int32_t frameCap;  // work-pool frames per warp
     uint8_t *gscratch;

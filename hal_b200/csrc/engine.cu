@@ -649,8 +649,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
         if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
+        // HALGPU_SEED_TILE=1 (measurement switch): TMA-staged seed tiles, see liftover_kernel.cuh and DESIGN.md
+        const char *tileEnv = std::getenv("HALGPU_SEED_TILE");
+        const bool seedTile = !wig && !raw && !coalPath && srcIsTop && tileEnv != nullptr && tileEnv[0] == '1';
         void (*const mapKernel)(const LiftParams) =
-            wig ? liftoverKernel<LIFT_WIG>
+            seedTile ? liftoverKernel<LIFT_BED | LIFT_TILE> : wig ? liftoverKernel<LIFT_WIG>
                 : (raw ? (coalPath ? liftoverKernel<LIFT_RAW_COAL> : liftoverKernel<LIFT_RAW>) : (coalPath ? liftoverKernel<LIFT_COAL> : liftoverKernel<LIFT_BED>));
         const unsigned block = 128, warpsPerBlock = block / 32;
         uint32_t *complexList = nullptr;
@@ -676,7 +679,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             P.n = (int64_t)n;
             if (fast) { P.work = complexList; P.nDev = ctr + C_COMPLEX; }
             else P.work64 = sortedVal;
-            const size_t smem = (size_t)liftScratchBytes(P.listCap, P.frameCap) * warpsPerBlock;
+            P.seedTile = seedTile ? 1 : 0;
+            const size_t smem = ((size_t)liftScratchBytes(P.listCap, P.frameCap) + (P.seedTile ? (size_t)seedTileBytes() : 0)) * warpsPerBlock;
             rt::allowSmem(mapKernel, smem);
             rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
             P.work = nullptr; P.work64 = nullptr; P.nDev = nullptr;
@@ -792,7 +796,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 else { scratch = L.take(per * (uint64_t)warps); P.gscratch = static_cast<uint8_t *>(scratch); P.gscratchPerWarp = per; }
                 const unsigned grid = inSmem ? gridFor((int64_t)nFull, warpsPerBlock, _sms * 2) : (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock);
                 r0.record(_stream);
-                rt::launch(mapKernel, grid, block, inSmem ? (size_t)per * warpsPerBlock : 0, _stream, P);
+                rt::launch(mapKernel, grid, block, (inSmem ? (size_t)per * warpsPerBlock : 0) + (seedTile ? (size_t)seedTileBytes() * warpsPerBlock : 0), _stream, P);
                 r1.record(_stream);
                 readBack();
                 out.kernelMs += rt::Event::elapsedMs(r0, r1);
@@ -818,7 +822,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             P.n = (int64_t)nOver; P.work = ids;
             P.listCap = listCap; P.frameCap = frameCap; P.gscratch = static_cast<uint8_t *>(scratch); P.gscratchPerWarp = per;
             r0.record(_stream);
-            rt::launch(mapKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, 0, _stream, P);
+            rt::launch(mapKernel, (unsigned)((warps + warpsPerBlock - 1) / warpsPerBlock), block, seedTile ? (size_t)seedTileBytes() * warpsPerBlock : 0, _stream, P);
             r1.record(_stream);
             readBack();
             out.kernelMs += rt::Event::elapsedMs(r0, r1);

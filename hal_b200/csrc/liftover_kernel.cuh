@@ -174,14 +174,40 @@ __device__ __forceinline__ void liftDone(const LiftParams &P, uint32_t item, uns
 struct WarpScratch {
     Frag *listA, *listB;
     Frame *frames;
+    // optional seed tile (LiftParams::seedTile): the interval's run of source top records, staged into shared memory by one
+    // cp.async.bulk (TMA, 1-D) per interval and completed through an mbarrier
+    TopRec *tile;
+    uint32_t tileBar, tilePhase;
 };
+
+#define HG_SEED_TILE 40 // records per tile: covers a 1.2 kb interval of 32-bp segments plus the successor record
+
+#if !defined(HALGPU_SIMT_EMUL)
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tileBarInit(uint32_t bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one lane: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void tileLoad(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tileWait(uint32_t bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    }
+}
+#endif
 
 // MODE: the wiggle mode, the coalescence-limit path and the raw-fragment mode are separate instantiations so that the
 // default BED path's code and register allocation are untouched by them
-enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 4, LIFT_RAW_COAL = 6 }; // COAL and RAW are bits
+enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 4, LIFT_RAW_COAL = 6, LIFT_TILE = 8 }; // COAL, RAW and TILE are bits
 template <int MODE>
-__device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpScratch &ws, uint32_t item, int lane) {
-    constexpr bool WIG = MODE == LIFT_WIG, COAL = (MODE & LIFT_COAL) != 0, RAW = (MODE & LIFT_RAW) != 0;
+__device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch &ws, uint32_t item, int lane) {
+    constexpr bool WIG = MODE == LIFT_WIG, COAL = (MODE & LIFT_COAL) != 0, RAW = (MODE & LIFT_RAW) != 0, TILE = (MODE & LIFT_TILE) != 0;
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';
@@ -205,6 +231,20 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
     }
     int64_t nextSeg = __shfl_sync(HG_FULL, mySeg, 0);
     const int64_t lastSeg = __shfl_sync(HG_FULL, mySeg, 1);
+    // seed tile: records [tileFirst, tileFirst + tileN) of the source top array in shared memory
+    const TopRec *tile = nullptr;
+    int64_t tileFirst = 0;
+    int tileN = 0;
+#if !defined(HALGPU_SIMT_EMUL)
+    if (TILE && ws.tile != nullptr && P.srcIsTop) {
+        int64_t cnt = lastSeg - nextSeg + 2;
+        if (cnt > HG_SEED_TILE) cnt = HG_SEED_TILE;
+        if (lane == 0) tileLoad(smemAddr(ws.tile), &steps[0].top[nextSeg], (uint32_t)cnt * (uint32_t)sizeof(TopRec), ws.tileBar);
+        tileWait(ws.tileBar, ws.tilePhase);
+        ws.tilePhase ^= 1u;
+        tile = ws.tile; tileFirst = nextSeg; tileN = (int)cnt;
+    }
+#endif
 
     // ---- phase 1 ----
     bool valid = false;
@@ -237,7 +277,9 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
             if (!valid && rank >= takePool && rank - takePool < takeSeeds) {
                 const int64_t seg = nextSeg + (rank - takePool);
                 int64_t s0, s1;
-                if (P.srcIsTop) {
+                if (TILE && tile != nullptr && seg + 1 - tileFirst < tileN) {
+                    s0 = tile[seg - tileFirst].start; s1 = tile[seg + 1 - tileFirst].start;
+                } else if (P.srcIsTop) {
                     s0 = topStart(steps[0].top, seg); s1 = topStart(steps[0].top, seg + 1);
                 } else {
                     s0 = botStart(steps[0].bot, seg); s1 = botStart(steps[0].bot, seg + 1);
@@ -344,13 +386,19 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
                     }
                     kindTop = true; idx = t; cursor = -1;
                 }
-                const TopRec r = ldTop(&st.top[idx]); // toParent, halBottomSegmentIterator.cpp:40-49
+                TopRec r; // toParent, halBottomSegmentIterator.cpp:40-49
+                int64_t rNext;
+                if (TILE && p == 0 && tile != nullptr && idx >= tileFirst && idx + 1 - tileFirst < tileN) {
+                    r = tile[idx - tileFirst]; rNext = tile[idx + 1 - tileFirst].start;
+                } else {
+                    r = ldTop(&st.top[idx]); rNext = r.parentEnc < 0 ? 0 : topStart(st.top, idx + 1);
+                }
                 if (r.parentEnc < 0) {
                     valid = false;
                 } else if (P.upCanonicalOnly && linkIdx(ldS(&st.child[linkIdx(r.parentEnc)])) != idx) {
                     valid = false; // ColumnIterator noDupes: only the canonical paralog goes up (halColumnIterator.cpp:559-560)
                 } else {
-                    const int64_t L = topStart(st.top, idx + 1) - r.start;
+                    const int64_t L = rNext - r.start;
                     const int64_t pi = linkIdx(r.parentEnc);
                     const bool fl = (r.parentEnc & 1) != 0;
                     const int64_t ps = botStart(steps[p + 1].bot, pi);
@@ -810,6 +858,8 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, const WarpS
 __host__ __device__ inline uint64_t liftScratchBytes(int listCap, int frameCap) {
     return (uint64_t)listCap * 2u * sizeof(Frag) + (uint64_t)frameCap * sizeof(Frame);
 }
+// shared memory per warp of the optional seed tile (records + its mbarrier, 16-byte aligned)
+__host__ __device__ inline uint64_t seedTileBytes() { return (uint64_t)HG_SEED_TILE * sizeof(TopRec) + 16u; }
 
 #if !defined(HALGPU_SIMT_EMUL)
 extern __shared__ __align__(16) uint8_t hg_dyn_smem[];
@@ -831,6 +881,16 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
     ws.listA = reinterpret_cast<Frag *>(basePtr);
     ws.listB = ws.listA + P.listCap;
     ws.frames = reinterpret_cast<Frame *>(ws.listB + P.listCap);
+    ws.tile = nullptr; ws.tileBar = 0; ws.tilePhase = 0;
+#if !defined(HALGPU_SIMT_EMUL)
+    if ((MODE & LIFT_TILE) != 0 && P.seedTile) { // behind the lists of all warps (the lists may live in global scratch; the tiles are always shared)
+        uint8_t *t = hg_dyn_smem + (P.gscratch ? 0 : (uint64_t)warpsPerBlock * per) + (uint64_t)warpInBlock * seedTileBytes();
+        ws.tile = reinterpret_cast<TopRec *>(t);
+        ws.tileBar = smemAddr(t + (uint64_t)HG_SEED_TILE * sizeof(TopRec));
+        if (lane == 0) tileBarInit(ws.tileBar);
+        __syncwarp();
+    }
+#endif
     const int64_t n = P.nDev ? (int64_t)*P.nDev : P.n; // the complex list's length is only known on the device
     for (int64_t w = gwarp; w < n; w += nwarps) {
         const uint32_t item = P.work64 ? (uint32_t)P.work64[w] : (P.work ? __ldg(&P.work[w]) : (uint32_t)w);

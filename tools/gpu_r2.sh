@@ -31,5 +31,10 @@ c)  # reworked bench (checks, in-run ncu traffic) at N=1; with 2 GPUs: NCCL test
         tail -c 1500 gpurun_out/bench_c_n2.json; tail -5 gpurun_out/bench_c_n2.err
     fi
     ;;
+d)  # TMA seed-tile A/B (tools/tile_ab.py) with and without ncu
+    timeout 900 python tools/tile_ab.py > gpurun_out/tile_ab.json 2> gpurun_out/tile_ab.err; cat gpurun_out/tile_ab.json | head -60; tail -3 gpurun_out/tile_ab.err
+    TILE_AB_REPS=1 TILE_AB_INTERVALS=2000000 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,dram__bytes_read.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
+        --clock-control none -k regex:liftoverKernel --csv --log-file gpurun_out/tile_ab_ncu.csv python tools/tile_ab.py > gpurun_out/tile_ab_under_ncu.json 2>> gpurun_out/tile_ab.err
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
