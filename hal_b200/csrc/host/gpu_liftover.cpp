@@ -154,7 +154,12 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                 linesIn += fast.linesSeen();
                 fastLines += fast.linesSeen();
                 if (fast.numIntervals() > 0) {
-                    halgpu_lift_result *res = lift(fast.numIntervals(), fast.starts(), fast.endsIncl(), fast.strands());
+                    halgpu_lift_result *res = nullptr;
+                    try {
+                        res = lift(fast.numIntervals(), fast.starts(), fast.endsIncl(), fast.strands());
+                    } catch (std::exception &e) { // the reference raises inside liftInterval of the first line it maps (halBedScanner.cpp:53-58)
+                        throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(lineNumber - fast.linesSeen() + 1)); // (first line of the block)
+                    }
                     t0 = std::chrono::steady_clock::now();
                     linesOut += fast.formatBlock(block, res, threads, fastText);
                     textSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -182,6 +187,9 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         std::vector<PendingLine> pending;
         std::vector<int64_t> gs, ge;
         std::vector<uint8_t> st;
+        std::string deferredError; // a malformed line ends the run, but only after the lines before it are lifted and written:
+                                   // the reference streams every line's result before it reads the next (halBedScanner.cpp:40-61)
+        size_t batchFirstLine = 0;
         // ---- read one batch (Liftover::visitLine up to the liftInterval call) ----
         while (pending.size() < batchLines && p < blockEnd) {
             ++lineNumber;
@@ -191,7 +199,8 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
             try {
                 cur.parse(lineBuf, bedType);
             } catch (std::exception &e) {
-                throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(lineNumber));
+                deferredError = std::string(e.what()) + " in input bed line " + std::to_string(lineNumber);
+                break;
             }
             skipWs();
             ++linesIn;
@@ -232,12 +241,21 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
             }
             p.numIntervals = gs.size() - p.firstInterval;
             p.bed = cur;
+            if (pending.empty()) batchFirstLine = lineNumber;
             pending.push_back(std::move(p));
         }
-        if (pending.empty()) continue;
+        if (pending.empty()) {
+            if (!deferredError.empty()) { out->flush(); throw std::runtime_error(deferredError); }
+            continue;
+        }
 
         // ---- one GPU call for the whole batch ----
-        halgpu_lift_result *res = lift(gs.size(), gs.data(), ge.data(), st.data());
+        halgpu_lift_result *res = nullptr;
+        try {
+            res = lift(gs.size(), gs.data(), ge.data(), st.data());
+        } catch (std::exception &e) { // the reference raises inside liftInterval of the first line it maps
+            throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(batchFirstLine));
+        }
 
         // ---- per-line post-processing and output ----
         outBuf.clear();
@@ -365,6 +383,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         }
         out->write(outBuf.data(), (std::streamsize)outBuf.size());
         halgpu_free_result(res);
+        if (!deferredError.empty()) { out->flush(); throw std::runtime_error(deferredError); }
         } // batches of the block
     }
 }

@@ -13,7 +13,7 @@
  *   merge          liftover/impl/halBlockMapper.cpp:331-394, api/impl/halMappedSegment.cpp:109-161
  *   output line    liftover/impl/halBlockLiftover.cpp:79-112, liftover/impl/halLiftover.cpp:90
  * Parity pinned against oracle/_ref (the reference compiled from /root/reference): see
- * tests/test_oracle_vs_ref.py and tests/golden/.
+ * tests/test_oracle.py and tests/golden/.
  */
 #include "liftover.h"
 #include <algorithm>

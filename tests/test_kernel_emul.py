@@ -159,3 +159,29 @@ def test_emulated_reference_coalescence_limit_kat(emul_lib):
     # extractSegment cannot merge them (source deltas differ), so three lines
     assert sorted((int(r["start"]), int(r["end"]), chr(r["strand"])) for r in recs) == [(0, 3, "-"), (3, 6, "-"), (6, 9, "-")]
     a.close()
+
+
+@pytest.mark.parametrize("branch", ["0", "0.02"])
+def test_emulated_config1_shape_and_fast_kernel(emul_lib, oracle_lib, tmp_path, branch):
+    """BASELINE.json configs[0] shape scaled down (3-genome linear tree, root -> leaf) through both mapping kernels: the
+    one-lane-per-interval kernel (collinear intervals) and the walk (HALGPU_NO_FAST) must agree with the oracle"""
+    import subprocess
+    import hal_b200
+    from conftest import ROOT
+    from hal_b200 import build
+    build.build()
+    hal = str(tmp_path / "c1.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", "((G2)G1)G0;", "--segs", "4000", "--segLen", "32",
+                           "--branch", branch, "--seed", "1", hal])
+    o = oracle_lib.Oracle(hal)
+    a = hal_b200.Alignment(hal, lib_path=emul_lib)
+    s, t = a.genome_id("G0"), a.genome_id("G2")
+    gs, ge, st = random_intervals(a.genome_length(s) - 64, 500, 900, seed=1)
+    exp = o.liftover(s, t, gs, ge, st)
+    off, recs, info = a.liftover(s, t, gs, ge, st)
+    assert_same_as_oracle(off, recs, exp)
+    assert info["n_complex"] < (5 if branch == "0" else 500)
+    off2, recs2, info2 = a.liftover(s, t, gs, ge, st, hal_b200.HALGPU_NO_FAST)
+    assert_same_as_oracle(off2, recs2, exp)
+    assert info2["n_complex"] == 0
+    a.close()

@@ -216,3 +216,45 @@ def test_cuda_column_liftover_cli_vs_reference_class(tmp_path):
             subprocess.check_call(["timeout", "120", drv, hal, src, str(bed), tgt, str(tmp_path / "ref.bed")] + extra)
             subprocess.check_call([cli, "--columnLiftover"] + extra + [hal, src, str(bed), tgt, str(tmp_path / "got.bed")])
             assert sorted(open(tmp_path / "ref.bed").read().splitlines()) == sorted(open(tmp_path / "got.bed").read().splitlines()), (src, tgt)
+
+
+def _config1(tmp_path, branch):
+    """BASELINE.json configs[0]: 3-genome linear tree, 1 Mbp per genome (31 250 x 32 bp), 10 k BED3 intervals of 50..2000 bp
+    (python random.seed(1)), root -> leaf; SURVEY.md 8(d) "C1" """
+    import random
+    hal = str(tmp_path / f"c1_{branch}.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", "((G2)G1)G0;", "--segs", "31250", "--segLen", "32",
+                           "--branch", branch, "--seed", "1", hal])
+    rng = random.Random(1)
+    glen = 31250 * 32
+    gs, ge = [], []
+    for _ in range(10000):
+        ln = rng.randint(50, 2000)
+        s = rng.randint(0, glen - ln)
+        gs.append(s)
+        ge.append(s + ln - 1)
+    return hal, np.array(gs, np.int64), np.array(ge, np.int64)
+
+
+@pytest.mark.parametrize("branch", ["0", "0.05"])
+def test_cuda_config1_root_to_leaf(hb, oracle_lib, tmp_path, branch):
+    from conftest import ref_bin
+    hal, gs, ge = _config1(tmp_path, branch)
+    o = oracle_lib.Oracle(hal)
+    with hb.Alignment(hal) as a:
+        s, t = a.genome_id("G0"), a.genome_id("G2")
+        off, recs, info = a.liftover(s, t, gs, ge)
+        assert_same_as_oracle(off, recs, o.liftover(s, t, gs, ge))
+        if branch == "0":
+            assert info["n_complex"] < 100  # collinear data: the one-lane-per-interval kernel does (nearly) all of it
+        off2, recs2, info2 = a.liftover(s, t, gs, ge, None, hb.HALGPU_NO_FAST)
+        assert info2["n_complex"] == 0 and np.array_equal(off, off2)
+        for k in ("start", "end", "src_start", "tgt_seq", "strand", "src_strand"):
+            assert np.array_equal(recs[k], recs2[k])
+    ref = ref_bin("halLiftover")
+    if ref is not None:  # the reference's own CLI on the same BED, byte for byte against the product CLI
+        bed = tmp_path / "c1.bed"
+        bed.write_text("".join(f"G0_seq\t{a}\t{b + 1}\n" for a, b in zip(gs.tolist(), ge.tolist())))
+        subprocess.check_call([ref, hal, "G0", str(bed), "G2", str(tmp_path / "ref.bed")])
+        subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), hal, "G0", str(bed), "G2", str(tmp_path / "got.bed")])
+        assert open(tmp_path / "ref.bed").read() == open(tmp_path / "got.bed").read()
