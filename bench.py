@@ -296,7 +296,7 @@ def cli_throughput(hal, src, tgt, gs, ge, seq_name):
             best = (dt, [l for l in r.stderr.splitlines() if l.startswith("[halLiftover]")])
     out_bytes = os.path.getsize(outp)
     res = {"metric": "halLiftover_cli_lines_per_sec", "value": len(gs) / best[0], "unit": "BED lines/s", "seconds": best[0],
-           "lines": len(gs), "in_bytes": os.path.getsize(inp), "out_bytes": out_bytes, "breakdown": best[1][0] if best[1] else None,
+           "lines": len(gs), "in_bytes": os.path.getsize(inp), "out_bytes": out_bytes, "breakdown": " | ".join(best[1]) if best[1] else None,
            "includes": "process start, CUDA context, open+stage, tokenise, halgpu_liftover (host buffers), format, file write"}
     os.remove(inp)
     os.remove(outp)

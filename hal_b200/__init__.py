@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "halgpu_column_runs", "halgpu_free_col_runs", "halgpu_genome_dna", "halgpu_host_alloc", "halgpu_host_free",
     "halgpu_comm_unique_id", "halgpu_comm_init", "halgpu_comm_free", "halgpu_comm_rank", "halgpu_comm_size",
     "halgpu_liftover_allgather_begin", "halgpu_liftover_allgather_end",
-    "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_column_runs_in_sweep", "halgpu_genome_metadata", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
+    "halgpu_maf_text", "halgpu_wiggle_liftover", "halgpu_free_wig_result", "halgpu_column_runs_in_sweep", "halgpu_genome_metadata", "halgpu_genome_top_segments", "halgpu_genome_bottom_segments",
 ]
 
 

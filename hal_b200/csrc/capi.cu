@@ -132,7 +132,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         }
         std::vector<size_t> lo(nChunks + 1);
         for (size_t k = 0; k <= nChunks; ++k) lo[k] = n * k / nChunks;
-        void *dS = rt::dmallocAsync(n * 8, cs), *dE = rt::dmallocAsync(n * 8, cs), *dT = strand ? rt::dmallocAsync(n, cs) : nullptr;
+        void *dS = nullptr, *dE = nullptr, *dT = nullptr;
         std::vector<rt::Event> inReady(nChunks);
         auto upload = [&](size_t k) {
             const size_t a = lo[k], c = lo[k + 1] - lo[k];
@@ -142,10 +142,13 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
             inReady[k].record(cs);
         };
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
+        if (r == nullptr) throw HalError("out of memory");
         std::vector<halgpu_lift_result *> parts;
         size_t recCap = n + n / 4 + 4096, nRec = 0;
         const bool wantPsl = (flags & HALGPU_PSL) != 0;
         try {
+            DeviceCache &cache = ctx->impl->cache();
+            dS = cache.take(n * 8); dE = cache.take(n * 8); dT = strand ? cache.take(n) : nullptr;
             r->n = n;
             r->offsets = static_cast<uint64_t *>(rt::hostAlloc((n + 1) * sizeof(uint64_t)));
             r->recs = static_cast<halgpu_lift_rec *>(rt::hostAlloc(recCap * sizeof(halgpu_lift_rec)));
@@ -193,12 +196,12 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         } catch (...) {
             rt::sync(cs);
             for (halgpu_lift_result *d : parts) halgpu_free_result(d);
-            rt::dfreeAsync(dS, cs); rt::dfreeAsync(dE, cs); rt::dfreeAsync(dT, cs);
+            ctx->impl->release(dS); ctx->impl->release(dE); ctx->impl->release(dT);
             halgpu_free_result(r);
             throw;
         }
         for (halgpu_lift_result *d : parts) halgpu_free_result(d);
-        rt::dfreeAsync(dS, cs); rt::dfreeAsync(dE, cs); rt::dfreeAsync(dT, cs);
+        ctx->impl->release(dS); ctx->impl->release(dE); ctx->impl->release(dT);
         *out = r;
     });
 }
@@ -276,6 +279,18 @@ int halgpu_wiggle_liftover(halgpu_ctx *ctx, int src, int tgt, uint32_t flags, si
         halgpu_wig_result *r = static_cast<halgpu_wig_result *>(std::calloc(1, sizeof(halgpu_wig_result)));
         r->n = wo.n; r->pos = wo.pos; r->val = wo.val; r->kernel_ms = wo.kernelMs; r->launches = wo.launches; r->n_retry = wo.nRetry;
         *out = r;
+    });
+}
+
+int halgpu_maf_text(halgpu_ctx *ctx, size_t nRows, const halgpu_maf_row *rows, size_t nPieces, const halgpu_maf_piece *pieces, const char *prefix,
+                    size_t prefixBytes, size_t outBytes, char *out, float *kernelMs, char **err) {
+    if (ctx == nullptr || (nRows > 0 && rows == nullptr) || (nPieces > 0 && pieces == nullptr) || (prefixBytes > 0 && prefix == nullptr) ||
+        (outBytes > 0 && out == nullptr)) {
+        return fail(err, "halgpu_maf_text: null argument");
+    }
+    return guarded(err, [&] {
+        rt::setDevice(ctx->impl->device());
+        ctx->impl->mafText(nRows, rows, nPieces, pieces, prefix, prefixBytes, outBytes, out, kernelMs);
     });
 }
 

@@ -3,12 +3,16 @@
 #include "liftover_kernel.cuh"
 #include "stage_kernels.cuh"
 #include "wiggle_kernels.cuh"
+#include "maf_kernels.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <fcntl.h>
+#include <unistd.h>
 
 namespace halgpu {
 namespace rt {
@@ -138,6 +142,65 @@ void *Context::alloc(size_t bytes) {
     return p;
 }
 
+// ---- staging: file -> pinned ring (several reader threads) -> HBM -> re-pack kernels -------------------------------------
+// The arrays are read with pread() straight into page-locked chunks by a few threads (no page faults on a mapping, and one
+// thread cannot keep PCIe busy), each chunk travels with an asynchronous copy while the next one is being read, and the
+// re-pack kernels run behind the copies on the same stream.  Genomes are staged on first use (a liftover touches the genomes
+// on its path only; the column sweeps and blockViz ask for all of them).
+struct Context::Stager {
+    static constexpr size_t CHUNK = 32u << 20;
+    int fd = -1;
+    uint8_t *pin[2] = {nullptr, nullptr};
+    std::unique_ptr<rt::Event> done[2];
+    bool used[2] = {false, false};
+    unsigned turn = 0, threads = 4;
+    explicit Stager(const std::string &path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw HalError(path + ": can't open HAL file for staging");
+        for (int i = 0; i < 2; ++i) { pin[i] = static_cast<uint8_t *>(rt::hostAlloc(CHUNK)); done[i].reset(new rt::Event); }
+        const unsigned hw = std::thread::hardware_concurrency();
+        threads = std::max(1u, std::min(hw ? hw : 1u, 6u));
+    }
+    ~Stager() {
+        if (fd >= 0) ::close(fd);
+        for (int i = 0; i < 2; ++i) rt::hostFree(pin[i]);
+    }
+    static void readAll(int fd, uint8_t *dst, uint64_t off, size_t n) {
+        while (n > 0) {
+            const ssize_t r = ::pread(fd, dst, n, (off_t)off);
+            if (r <= 0) throw HalError("short read while staging the HAL file");
+            dst += r; off += (uint64_t)r; n -= (size_t)r;
+        }
+    }
+    void copy(void *dst, uint64_t fileOff, size_t bytes, rt::Stream s) {
+        for (size_t at = 0; at < bytes; at += CHUNK) {
+            const size_t n = std::min(CHUNK, bytes - at);
+            const unsigned b = turn++ & 1u;
+            if (used[b]) done[b]->hostWait(); // the copy that last used this chunk has left it
+            const unsigned T = n >= (4u << 20) ? threads : 1u;
+            if (T == 1) {
+                readAll(fd, pin[b], fileOff + at, n);
+            } else {
+                std::vector<std::thread> th;
+                std::string failure;
+                std::mutex fm;
+                for (unsigned t = 0; t < T; ++t) {
+                    const size_t lo = n * t / T, hi = n * (t + 1) / T;
+                    th.emplace_back([&, lo, hi] {
+                        try { readAll(fd, pin[b] + lo, fileOff + at + lo, hi - lo); }
+                        catch (const std::exception &e) { std::lock_guard<std::mutex> g(fm); failure = e.what(); }
+                    });
+                }
+                for (auto &x : th) x.join();
+                if (!failure.empty()) throw HalError(failure);
+            }
+            rt::h2d(static_cast<uint8_t *>(dst) + at, pin[b], n, s);
+            done[b]->record(s);
+            used[b] = true;
+        }
+    }
+};
+
 Context::Context(const std::string &path, int device) : _file(new HalFile(path)), _device(device) {
     rt::setDevice(device);
     rt::retainPool(device);
@@ -146,11 +209,10 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     _sms = rt::smCount();
     _g.resize(_file->genomes().size());
     try {
-        for (size_t g = 0; g < _g.size(); ++g) stageGenome((int)g);
-        for (size_t g = 0; g < _g.size(); ++g) stageLinkRuns((int)g); // needs every genome's arrays in place
-        rt::sync(_stream);
+        _stager.reset(new Stager(path));
         _hostCtr = static_cast<unsigned long long *>(rt::hostAlloc(32 * sizeof(unsigned long long)));
         for (auto &e : _ev) e.reset(new rt::Event);
+        if (std::getenv("HALGPU_EAGER_STAGE") != nullptr) ensureAll(true);
     } catch (...) {
         for (void *p : _owned) rt::dfree(p);
         rt::destroyStream(_stream);
@@ -160,6 +222,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
 }
 
 Context::~Context() {
+    try { rt::sync(_stream); } catch (...) {}
     rt::hostFree(_hostCtr);
     for (auto &kv : _plans) rt::dfree(kv.second.dSteps);
     for (void *p : _owned) rt::dfree(p);
@@ -178,105 +241,119 @@ void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, u
     rt::launch(bucketKernel, gridFor(nb, 256, _sms), 256, 0, _stream, bp);
 }
 
-void Context::stageGenome(int gi) {
-    DevBuf::current() = _stream;
-    const GenomeInfo &g = _file->genomes()[gi];
+void Context::ensureGenome(int gi) {
     GenomeDev &d = _g[gi];
+    if (d.staged) return;
+    const GenomeInfo &g = _file->genomes()[gi];
     if (g.numTop >= (int64_t)0xffffffffll || g.numBottom >= (int64_t)0xffffffffll) {
         throw HalError("genome " + g.name + " has more than 2^32 segments; not supported by the bucket index");
     }
     const int nc = (int)g.children.size();
+    Lease L(_cache);
     // top records
     {
         const size_t rawBytes = (size_t)(g.numTop + 1) * 40;
-        DevBuf raw(rawBytes);
-        rt::h2d(raw.p, g.top, rawBytes, _stream);
+        uint8_t *raw = L.as<uint8_t>(rawBytes);
+        _stager->copy(raw, _file->offsetOf(g.top), rawBytes, _stream);
         d.top = static_cast<TopRec *>(alloc((size_t)(g.numTop + 1) * sizeof(TopRec)));
         PackTopParams pp;
-        pp.raw = raw.as<uint8_t>(); pp.out = d.top; pp.n = g.numTop + 1;
+        pp.raw = raw; pp.out = d.top; pp.n = g.numTop + 1;
         rt::launch(packTopKernel, gridFor(pp.n, 256, _sms), 256, 0, _stream, pp);
-        rt::sync(_stream);
     }
     // bottom records
     {
         const size_t rawBytes = (size_t)(g.numBottom + 1) * g.bottomStride;
-        DevBuf raw(rawBytes);
-        rt::h2d(raw.p, g.bottom, rawBytes, _stream);
+        uint8_t *raw = L.as<uint8_t>(rawBytes);
+        _stager->copy(raw, _file->offsetOf(g.bottom), rawBytes, _stream);
         d.bot = static_cast<BotCore *>(alloc((size_t)(g.numBottom + 1) * sizeof(BotCore)));
         d.child = static_cast<int64_t *>(alloc(std::max<size_t>(8, (size_t)nc * (size_t)g.numBottom * sizeof(int64_t))));
         PackBotParams pp;
-        pp.raw = raw.as<uint8_t>(); pp.core = d.bot; pp.child = d.child;
+        pp.raw = raw; pp.core = d.bot; pp.child = d.child;
         pp.n = g.numBottom + 1; pp.numBot = g.numBottom; pp.nc = nc; pp.stride = (int32_t)g.bottomStride;
         rt::launch(packBotKernel, gridFor(pp.n, 256, _sms), 256, 0, _stream, pp);
-        rt::sync(_stream);
     }
-    // DNA (packed nibbles, used by the column / MAF path)
-    {
-        const size_t bytes = (size_t)((g.length + 1) / 2);
-        d.dna = static_cast<uint8_t *>(alloc(std::max<size_t>(bytes, 1)));
-        rt::h2d(d.dna, g.dna, bytes, _stream);
-    }
-    // sequence start table (+ sentinel)
-    {
-        std::vector<int64_t> ss;
-        for (const SequenceInfo &s : g.sequences) ss.push_back(s.start);
-        ss.push_back(g.length);
-        d.seqStart = static_cast<int64_t *>(alloc(ss.size() * sizeof(int64_t)));
-        rt::h2d(d.seqStart, ss.data(), ss.size() * sizeof(int64_t), _stream);
-        rt::sync(_stream); // ss goes out of scope
-    }
-    {
-        std::vector<int32_t> kids(g.children.begin(), g.children.end());
-        kids.push_back(-1);
-        d.childGenome = static_cast<int32_t *>(alloc(kids.size() * sizeof(int32_t)));
-        rt::h2d(d.childGenome, kids.data(), kids.size() * sizeof(int32_t), _stream);
-        rt::sync(_stream);
-    }
+    // sequence start table (+ sentinel) and the child genome ids
+    std::vector<int64_t> ss;
+    for (const SequenceInfo &q : g.sequences) ss.push_back(q.start);
+    ss.push_back(g.length);
+    d.seqStart = static_cast<int64_t *>(alloc(ss.size() * sizeof(int64_t)));
+    rt::h2d(d.seqStart, ss.data(), ss.size() * sizeof(int64_t), _stream);
+    std::vector<int32_t> kids(g.children.begin(), g.children.end());
+    kids.push_back(-1);
+    d.childGenome = static_cast<int32_t *>(alloc(kids.size() * sizeof(int32_t)));
+    rt::h2d(d.childGenome, kids.data(), kids.size() * sizeof(int32_t), _stream);
     if (g.numTop > 0) buildBucket(d.top, true, g.numTop, g.length, d.topBucket, d.topShift, d.topBuckets);
     if (g.numBottom > 0) buildBucket(d.bot, false, g.numBottom, g.length, d.botBucket, d.botShift, d.botBuckets);
+    rt::sync(_stream); // the raw copies return to the cache, ss / kids leave scope
+    d.staged = true;
 }
 
-void Context::stageLinkRuns(int gi) {
-    // the run field of every vertical link (device_index.cuh): parent links of this genome's tops, child links of its bottoms
+void Context::ensureDna(int gi) {
+    GenomeDev &d = _g[gi];
+    if (d.dna != nullptr) return;
+    const GenomeInfo &g = _file->genomes()[gi];
+    const size_t bytes = (size_t)((g.length + 1) / 2);
+    d.dna = static_cast<uint8_t *>(alloc(std::max<size_t>(bytes, 1)));
+    if (bytes > 0) _stager->copy(d.dna, _file->offsetOf(g.dna), bytes, _stream);
+    rt::sync(_stream);
+}
+
+void Context::ensureAll(bool dna) {
+    for (size_t g = 0; g < _g.size(); ++g) ensureGenome((int)g);
+    if (dna)
+        for (size_t g = 0; g < _g.size(); ++g) ensureDna((int)g);
+}
+
+// the run and xlate fields of a vertical link array (device_index.cuh)
+void Context::linkFields(int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n, const TopRec *landTop,
+                         const int64_t *otherStarts, int64_t otherStride, int64_t *xlateOut) {
+    Lease L(_cache);
+    uint32_t *mark = L.as<uint32_t>((size_t)n), *next = L.as<uint32_t>((size_t)n);
+    size_t tmpBytes = 0;
+    rt::suffixMinU32Tmp(nullptr, tmpBytes, mark, next, (size_t)n, _stream);
+    void *tmp = L.take(tmpBytes);
+    LinkRunParams lp;
+    lp.links = links; lp.starts = starts; lp.linkStride = linkStride; lp.startStride = startStride; lp.n = n;
+    lp.landTop = landTop; lp.mark = mark;
+    rt::launch(linkBreakKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
+    rt::suffixMinU32Tmp(tmp, tmpBytes, mark, next, (size_t)n, _stream);
+    lp.mark = next;
+    rt::launch(linkRunKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
+    LinkXlateParams xp;
+    xp.links = links; xp.starts = starts; xp.otherStarts = otherStarts; xp.linkStride = linkStride; xp.startStride = startStride;
+    xp.otherStride = otherStride; xp.n = n; xp.xlate = xlateOut;
+    rt::launch(linkXlateKernel, gridFor(n, 256, _sms), 256, 0, _stream, xp);
+    rt::sync(_stream);
+}
+
+void Context::ensureUpLinks(int gi) { // parent links of genome gi's tops
     const GenomeInfo &g = _file->genomes()[gi];
     GenomeDev &d = _g[gi];
-    const int64_t nMax = std::max(g.numTop, g.numBottom);
-    if (nMax == 0) return;
-    DevBuf::current() = _stream;
-    DevBuf mark((size_t)nMax * 4), next((size_t)nMax * 4);
-    size_t tmpBytes = 0;
-    rt::suffixMinU32Tmp(nullptr, tmpBytes, mark.as<uint32_t>(), next.as<uint32_t>(), (size_t)nMax, _stream);
-    DevBuf tmp(tmpBytes);
-    auto run = [&](int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n, const TopRec *landTop) {
-        LinkRunParams lp;
-        lp.links = links; lp.starts = starts; lp.linkStride = linkStride; lp.startStride = startStride; lp.n = n;
-        lp.landTop = landTop; lp.mark = mark.as<uint32_t>();
-        rt::launch(linkBreakKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
-        size_t tb = tmpBytes;
-        rt::suffixMinU32Tmp(tmp.p, tb, mark.as<uint32_t>(), next.as<uint32_t>(), (size_t)n, _stream);
-        lp.mark = next.as<uint32_t>();
-        rt::launch(linkRunKernel, gridFor(n, 256, _sms), 256, 0, _stream, lp);
-    };
-    auto xlate = [&](const int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n,
-                     const int64_t *otherStarts, int64_t otherStride, int64_t *out) {
-        LinkXlateParams xp;
-        xp.links = links; xp.starts = starts; xp.otherStarts = otherStarts; xp.linkStride = linkStride; xp.startStride = startStride;
-        xp.otherStride = otherStride; xp.n = n; xp.xlate = out;
-        rt::launch(linkXlateKernel, gridFor(n, 256, _sms), 256, 0, _stream, xp);
-    };
+    if (d.topX != nullptr || g.parent < 0 || g.numTop == 0) return;
+    ensureGenome(gi);
+    ensureGenome(g.parent);
     const int64_t topStride = sizeof(TopRec) / 8, botStride = sizeof(BotCore) / 8;
-    if (g.numTop > 0 && g.parent >= 0) {
-        run(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, nullptr);
-        d.topX = static_cast<int64_t *>(alloc((size_t)g.numTop * sizeof(int64_t)));
-        xlate(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, &_g[g.parent].bot[0].start, botStride, d.topX);
+    int64_t *x = static_cast<int64_t *>(alloc((size_t)g.numTop * sizeof(int64_t)));
+    linkFields(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, nullptr, &_g[g.parent].bot[0].start, botStride, x);
+    d.topX = x;
+}
+
+void Context::ensureDownLinks(int gi, int slot) { // child links of genome gi's bottoms, one child slot
+    const GenomeInfo &g = _file->genomes()[gi];
+    GenomeDev &d = _g[gi];
+    ensureGenome(gi);
+    if (g.numBottom == 0 || slot < 0 || slot >= (int)g.children.size()) return;
+    if (d.childX == nullptr) {
+        d.childX = static_cast<int64_t *>(alloc(g.children.size() * (size_t)g.numBottom * sizeof(int64_t)));
+        d.childLinked.assign(g.children.size(), 0);
     }
-    if (!g.children.empty() && g.numBottom > 0) d.childX = static_cast<int64_t *>(alloc(g.children.size() * (size_t)g.numBottom * sizeof(int64_t)));
-    for (size_t k = 0; k < g.children.size() && g.numBottom > 0; ++k) {
-        int64_t *col = d.child + k * (size_t)g.numBottom;
-        run(col, 1, &d.bot[0].start, botStride, g.numBottom, _g[g.children[k]].top);
-        xlate(col, 1, &d.bot[0].start, botStride, g.numBottom, &_g[g.children[k]].top[0].start, topStride, d.childX + k * (size_t)g.numBottom);
-    }
-    rt::sync(_stream);
+    if (d.childLinked[(size_t)slot]) return;
+    const int c = g.children[(size_t)slot];
+    ensureGenome(c);
+    const int64_t topStride = sizeof(TopRec) / 8, botStride = sizeof(BotCore) / 8;
+    int64_t *col = d.child + (size_t)slot * (size_t)g.numBottom;
+    linkFields(col, 1, &d.bot[0].start, botStride, g.numBottom, _g[c].top, &_g[c].top[0].start, topStride, d.childX + (size_t)slot * (size_t)g.numBottom);
+    d.childLinked[(size_t)slot] = 1;
 }
 
 const Plan &Context::plan(int src, int tgt, int coal) {
@@ -318,6 +395,11 @@ const Plan &Context::plan(int src, int tgt, int coal) {
     for (int g : down) ent.push_back(Entry{g, 0, 0, 0});
     p.path.clear();
     for (const Entry &e : ent) p.path.push_back(e.g);
+    for (const Entry &e : ent) ensureGenome(e.g); // stage what this path touches (first use of a genome)
+    for (size_t i = 0; i + 1 < ent.size(); ++i) {
+        if (ent[i].up) { if (G[ent[i].g].parent == ent[i + 1].g) ensureUpLinks(ent[i].g); }
+        else ensureDownLinks(ent[i].g, G[ent[i + 1].g].slotInParent);
+    }
     std::vector<PathStep> steps(ent.size());
     for (size_t i = 0; i < ent.size(); ++i) {
         const int g = ent[i].g;
@@ -331,7 +413,7 @@ const Plan &Context::plan(int src, int tgt, int coal) {
         s.xlate = nullptr;
         if (!s.up) { // this genome's childEnc column for the slot of the next genome down
             s.child = _g[g].child + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
-            s.xlate = _g[g].childX + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
+            s.xlate = _g[g].childX ? _g[g].childX + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom : nullptr;
         } else if (G[g].parent >= 0 && G[g].parent == nx) { // the parent's column for this genome's slot: canonical-paralog test
             s.child = _g[nx].child + (size_t)G[g].slotInParent * (size_t)G[nx].numBottom;
             s.xlate = _g[g].topX;
@@ -365,6 +447,10 @@ void Context::buildGenomeTab(int ref, const std::vector<int> &targets, std::vect
     std::sort(order.begin(), order.end(), [&](int a, int b) { return G[a].name < G[b].name; });
     std::vector<int> rank(ng);
     for (int i = 0; i < ng; ++i) rank[order[i]] = i;
+    for (int g = 0; g < ng; ++g) {
+        if (!inScope[g]) continue;
+        ensureGenome(g); // (the walk tests a genome's scope flag before it touches its arrays)
+    }
     tab.resize(ng);
     for (int g = 0; g < ng; ++g) {
         GenomeTab &t = tab[g];
@@ -527,6 +613,59 @@ void Context::depth(int ref, int64_t first, int64_t last, int64_t step, const st
     }
 }
 
+void Context::mafText(size_t nRows, const halgpu_maf_row *rows, size_t nPieces, const halgpu_maf_piece *pieces, const char *prefix,
+                      size_t prefixBytes, size_t outBytes, char *out, float *kernelMs) {
+    const auto &G = _file->genomes();
+    std::vector<char> needDna(G.size(), 0);
+    for (size_t r = 0; r < nRows; ++r) { // nothing the kernel derives an address from goes unchecked
+        const halgpu_maf_row &w = rows[r];
+        if (w.genome < 0 || w.genome >= (int)G.size()) throw HalError("MAF row " + std::to_string(r) + ": genome index out of range");
+        if ((uint64_t)w.first_piece + w.num_pieces > nPieces || (uint64_t)w.prefix_offset + w.prefix_len > prefixBytes) {
+            throw HalError("MAF row " + std::to_string(r) + " refers to pieces / prefix bytes outside the arrays");
+        }
+        uint64_t bytes = (uint64_t)w.prefix_len + w.tail_newlines;
+        for (uint32_t k = 0; k < w.num_pieces; ++k) {
+            const halgpu_maf_piece &pc = pieces[w.first_piece + k];
+            const int64_t count = pc.count_kind >> 2;
+            const int kind = (int)(pc.count_kind & 3);
+            if (count < 0 || kind > 2) throw HalError("MAF row " + std::to_string(r) + ": malformed piece");
+            if (kind != 0 && count > 0) {
+                const int64_t lo = kind == 1 ? pc.pos : pc.pos - count + 1, hi = kind == 1 ? pc.pos + count - 1 : pc.pos;
+                if (lo < 0 || hi >= G[(size_t)w.genome].length) throw HalError("MAF row " + std::to_string(r) + ": bases outside genome " + G[(size_t)w.genome].name);
+                needDna[(size_t)w.genome] = 1;
+            }
+            bytes += (uint64_t)count;
+        }
+        if (w.tail_newlines > 2 || w.out_offset > outBytes || bytes > outBytes - w.out_offset) throw HalError("MAF row " + std::to_string(r) + " does not fit the output");
+    }
+    std::vector<const uint8_t *> dnaTab(G.size(), nullptr);
+    for (size_t g = 0; g < G.size(); ++g)
+        if (needDna[g]) { ensureDna((int)g); dnaTab[g] = _g[g].dna; }
+    Lease L(_cache);
+    try {
+        halgpu_maf_row *dRows = L.as<halgpu_maf_row>(std::max<size_t>(nRows, 1));
+        halgpu_maf_piece *dPieces = L.as<halgpu_maf_piece>(std::max<size_t>(nPieces, 1));
+        char *dPrefix = L.as<char>(std::max<size_t>(prefixBytes, 1));
+        const uint8_t **dDna = L.as<const uint8_t *>(G.size());
+        char *dOut = L.as<char>(std::max<size_t>(outBytes, 1));
+        rt::h2d(dRows, rows, nRows * sizeof(halgpu_maf_row), _stream);
+        rt::h2d(dPieces, pieces, nPieces * sizeof(halgpu_maf_piece), _stream);
+        rt::h2d(dPrefix, prefix, prefixBytes, _stream);
+        rt::h2d(dDna, dnaTab.data(), G.size() * sizeof(const uint8_t *), _stream);
+        MafTextParams P;
+        P.rows = dRows; P.pieces = dPieces; P.prefix = dPrefix; P.dna = dDna; P.out = dOut; P.nRows = (int64_t)nRows;
+        _ev[0]->record(_stream);
+        if (nRows > 0) rt::launch(mafTextKernel, gridFor((int64_t)nRows * 32, 256, _sms), 256, 0, _stream, P);
+        _ev[1]->record(_stream);
+        rt::d2h(out, dOut, outBytes, _stream);
+        rt::sync(_stream);
+        if (kernelMs) *kernelMs = rt::Event::elapsedMs(*_ev[0], *_ev[1]);
+    } catch (...) {
+        try { rt::sync(_stream); } catch (...) {}
+        throw;
+    }
+}
+
 namespace {
 struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch (diagnostics only)
     bool on;
@@ -646,6 +785,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         P.outLoc = outLoc; P.status = status; P.failCount = ctr + C_FAIL;
         P.pool = pool; P.poolCursor = ctr + C_POOL; P.poolCap = poolCap;
         P.pslPool = pslPool;
+        if (wantPsl) { ensureDna(src); ensureDna(tgt); }
         P.srcDna = _g[src].dna; P.tgtDna = _g[tgt].dna;
         if (wig) { P.wigKeys = wig->keys; P.wigValOff = wig->valOff; P.wigVals = wig->vals; }
 
@@ -811,6 +951,12 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             listCap *= (listCap == 64 ? 64 : 16); // 64 -> 4096 -> 65536 -> 1M
             frameCap = listCap / 4;
             if (listCap > (1 << 24)) throw HalError("an interval maps to more than 16M fragments; not supported");
+            // the per-warp refinement / merge of one interval sorts and cuts its fragments with quadratic work (fine for the tens of
+            // fragments of a BED interval, seconds at 64 K): beyond that the caller has to lift pieces, or take the fragments
+            // themselves (HALGPU_RAW_FRAGMENTS) and refine them with an n log n pass as halSynteny's host layer does
+            if (!raw && !wig && listCap > (1 << 16)) {
+                throw HalError("an interval maps to more than 65536 fragments; lift it in pieces (or use HALGPU_RAW_FRAGMENTS and refine on the caller's side, as halSynteny does)");
+            }
             const uint64_t per = liftScratchBytes(listCap, frameCap);
             int64_t warps = std::min<int64_t>((int64_t)nOver, (int64_t)_sms * 8);
             const uint64_t budget = 8ull << 30; // scratch budget

@@ -24,6 +24,8 @@ struct GenomeDev {
     uint32_t *topBucket = nullptr, *botBucket = nullptr;
     int topShift = 0, botShift = 0;
     int64_t topBuckets = 0, botBuckets = 0;
+    bool staged = false;              // top / bot / child / seqStart / buckets are resident
+    std::vector<char> childLinked;    // per child slot: run + xlate fields of that column are filled in
 };
 
 struct Plan {
@@ -98,6 +100,10 @@ class Context {
     void depth(int ref, int64_t first, int64_t last, int64_t step, const std::vector<int> &targets, uint32_t flags,
                int32_t *dOut, float *kernelMs);
 
+    // text of MAF rows (maf_kernels.cuh); every piece must lie inside its genome (checked here)
+    void mafText(size_t nRows, const halgpu_maf_row *rows, size_t nPieces, const halgpu_maf_piece *pieces, const char *prefix,
+                 size_t prefixBytes, size_t outBytes, char *out, float *kernelMs);
+
     // column runs of reference positions first..last; host (pinned) output owned by the caller
     // windowFirst (COL_UNIQUE only): where the ColumnIterator sweep this range belongs to started (-1: at `first`)
     void columnRuns(int ref, int64_t first, int64_t last, const std::vector<int> &targets, uint32_t flags, halgpu_col_runs &out,
@@ -106,10 +112,19 @@ class Context {
     void release(void *deviceBuffer) { _cache.give(deviceBuffer); } // result buffers of liftover()
     DeviceCache &cache() { return _cache; }
 
+    // genomes are staged on first use; these make one genome (its DNA / all of them) resident now
+    void ensureGenome(int g);
+    void ensureDna(int g);
+    void ensureAll(bool dna);
+    const uint8_t *deviceDna(int g) { ensureDna(g); return _g[(size_t)g].dna; }
+
   private:
-    void stageLinkRuns(int g);
+    struct Stager;
+    void ensureUpLinks(int g);
+    void ensureDownLinks(int g, int slot);
+    void linkFields(int64_t *links, int64_t linkStride, const int64_t *starts, int64_t startStride, int64_t n, const TopRec *landTop,
+                    const int64_t *otherStarts, int64_t otherStride, int64_t *xlateOut);
     void buildGenomeTab(int ref, const std::vector<int> &targets, std::vector<GenomeTab> &tab);
-    void stageGenome(int g);
     void buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb);
     const Plan &plan(int src, int tgt, int coal = -1);
     void *alloc(size_t bytes);
@@ -123,6 +138,7 @@ class Context {
     size_t _staged = 0;
     int _sms = 0;
     DeviceCache _cache;
+    std::unique_ptr<Stager> _stager;
     unsigned long long *_hostCtr = nullptr; // pinned: the counters of one batch, read back with its single synchronisation
     std::unique_ptr<rt::Event> _ev[4];
 };

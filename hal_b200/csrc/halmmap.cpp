@@ -38,6 +38,15 @@ Newick parseNewick(const std::string &s, size_t &i) {
 }
 } // namespace
 
+// record count x record size of an array named by a (possibly corrupt) file: a product that wraps around must not slip
+// through the bounds check of at()
+static uint64_t arrayBytes(uint64_t count, uint64_t each, const std::string &path, const char *what) {
+    if (each != 0 && count > UINT64_MAX / each) {
+        throw HalError(path + ": " + what + " out of file bounds, probably file corruption");
+    }
+    return count * each;
+}
+
 const uint8_t *HalFile::at(uint64_t off, uint64_t len, const char *what) const {
     if (off > _size || len > _size - off) {
         throw HalError(_path + ": " + what + " out of file bounds, probably file corruption");
@@ -73,6 +82,7 @@ HalFile::HalFile(const std::string &path) : _path(path) {
         _map = nullptr;
         throw HalError(path + ": mmap failed: " + std::strerror(errno));
     }
+    try { // a constructor that throws never runs its destructor: give the mapping back here
     const char *hdr = reinterpret_cast<const char *>(_map);
     if (std::string(hdr, strnlen(hdr, 32)) != "HAL-MMAP") {
         throw HalError(path + ": invalid file header, expected format name of 'HAL-MMAP'");
@@ -96,7 +106,7 @@ HalFile::HalFile(const std::string &path) : _path(path) {
     }
     const char *nw = reinterpret_cast<const char *>(at(nwOff, nwLen, "newick string"));
     _newick.assign(nw, strnlen(nw, nwLen));
-    at(gaOff, numGenomes * GENOME_BYTES, "genome array");
+    at(gaOff, arrayBytes(numGenomes, GENOME_BYTES, _path, "genome array"), "genome array");
     _genomes.resize(numGenomes);
     for (uint64_t g = 0; g < numGenomes; ++g) {
         const uint64_t b = gaOff + g * GENOME_BYTES;
@@ -109,7 +119,7 @@ HalFile::HalFile(const std::string &path) : _path(path) {
         const uint64_t nameLen = u64(nameOff + 16); // MMapArrayData::_length, includes the NUL
         const char *nm = reinterpret_cast<const char *>(at(nameOff + ARRAY_HEADER_BYTES, nameLen, "genome name"));
         gi.name.assign(nm, strnlen(nm, nameLen));
-        at(seqOff, nseq * SEQUENCE_BYTES, "sequence array");
+        at(seqOff, arrayBytes(nseq, SEQUENCE_BYTES, _path, "sequence array"), "sequence array");
         gi.sequences.resize(nseq);
         int64_t expectStart = 0;
         for (uint64_t s = 0; s < nseq; ++s) {
@@ -178,8 +188,13 @@ HalFile::HalFile(const std::string &path) : _path(path) {
         const uint64_t nc = gi.children.size();
         gi.bottomStride = 8 * (2 + nc) + ((nc + 7) / 8) * 8;
         gi.dna = at(u64(b + 72), static_cast<uint64_t>((gi.length + 1) / 2), "dna array");
-        gi.top = at(u64(b + 80), static_cast<uint64_t>(gi.numTop + 1) * TOP_BYTES, "top segment array");
-        gi.bottom = at(u64(b + 88), static_cast<uint64_t>(gi.numBottom + 1) * gi.bottomStride, "bottom segment array");
+        gi.top = at(u64(b + 80), arrayBytes(static_cast<uint64_t>(gi.numTop) + 1, TOP_BYTES, _path, "top segment array"), "top segment array");
+        gi.bottom = at(u64(b + 88), arrayBytes(static_cast<uint64_t>(gi.numBottom) + 1, gi.bottomStride, _path, "bottom segment array"), "bottom segment array");
+    }
+    } catch (...) {
+        munmap(_map, _size);
+        _map = nullptr;
+        throw;
     }
 }
 

@@ -57,6 +57,8 @@ class HalFile {
     int root() const { return _root; }
     const std::vector<GenomeInfo> &genomes() const { return _genomes; }
     int genomeId(const std::string &name) const;
+    // file offset of a pointer handed out by this object (GenomeInfo::top / bottom / dna)
+    uint64_t offsetOf(const void *p) const { return (uint64_t)(static_cast<const uint8_t *>(p) - static_cast<const uint8_t *>(_map)); }
     // lowest common ancestor (api/impl/halCommon.cpp:123-152)
     int mrca(int a, int b) const;
 

@@ -3,7 +3,10 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <chrono>
 #include <cstring>
@@ -39,38 +42,139 @@ bool compatible(const BedLine &tgtBed, const BedLine &newBlock, char inputStrand
 
 // Hands the input stream out in blocks of whole lines: about `target` bytes, extended to the end of the line the
 // cut falls into.  The final block may lack a trailing newline (as the final line of a BED file may).
+struct BlockBuf { // text of one block, owned by a pipeline slot
+    std::unique_ptr<char[]> buf;
+    size_t cap = 0;
+};
 class BlockReader {
   public:
     BlockReader(std::istream &in, size_t target) : _in(in), _target(std::max<size_t>(target, 1)) {}
-    bool next(const char *&p, size_t &n) {
+    bool next(BlockBuf &b, const char *&p, size_t &n) {
         if (!_in.good()) return false;
-        if (_cap < _target) {
-            _buf.reset(new char[_target]); // uninitialised on purpose: pages are touched only as far as the input reaches
-            _cap = _target;
+        if (b.cap < _target) {
+            b.buf.reset(new char[_target]); // uninitialised on purpose: pages are touched only as far as the input reaches
+            b.cap = _target;
         }
-        _in.read(_buf.get(), (std::streamsize)_target);
+        _in.read(b.buf.get(), (std::streamsize)_target);
         size_t got = (size_t)_in.gcount();
-        if (got == _target && _in.good() && _buf[got - 1] != '\n') {
+        if (got == _target && _in.good() && b.buf[got - 1] != '\n') {
             std::string tail;
             std::getline(_in, tail); // consumes the newline; it only separated lines
-            if (got + tail.size() > _cap) {
+            if (got + tail.size() > b.cap) {
                 std::unique_ptr<char[]> bigger(new char[got + tail.size()]);
-                std::memcpy(bigger.get(), _buf.get(), got);
-                _buf = std::move(bigger);
-                _cap = got + tail.size();
+                std::memcpy(bigger.get(), b.buf.get(), got);
+                b.buf = std::move(bigger);
+                b.cap = got + tail.size();
             }
-            std::memcpy(_buf.get() + got, tail.data(), tail.size());
+            std::memcpy(b.buf.get() + got, tail.data(), tail.size());
             got += tail.size();
         }
-        p = _buf.get();
+        p = b.buf.get();
         n = got;
         return got > 0;
     }
 
   private:
     std::istream &_in;
-    size_t _target, _cap = 0;
-    std::unique_ptr<char[]> _buf;
+    size_t _target;
+};
+
+// The fast text path as a three-stage pipeline over blocks: the calling thread reads and tokenises block k+2 while one
+// worker lifts block k+1 (halgpu_liftover: PCIe + GPU) and another formats and writes block k.  Blocks leave in input order.
+struct FastSlot {
+    BlockBuf text;
+    const char *block = nullptr;
+    size_t blockLen = 0;
+    std::unique_ptr<FastBedBlock> fast;
+    std::vector<TextBuf> out;
+    halgpu_lift_result *res = nullptr;
+    size_t firstLine = 0; // input line number of the block's first line
+    int state = 0; // 0 free, 1 parsed (waits for the lift), 2 lifted (waits for format + write)
+};
+class FastPipeline {
+  public:
+    FastPipeline(size_t nSlots, std::function<halgpu_lift_result *(FastSlot &)> lift, std::function<void(FastSlot &)> emit)
+        : _slots(nSlots), _lift(std::move(lift)), _emit(std::move(emit)) {
+        _lifter = std::thread([this] { run(1, 2, _lift2); });
+        _writer = std::thread([this] { run(2, 0, _emit2); });
+    }
+    ~FastPipeline() {
+        {
+            std::lock_guard<std::mutex> g(_m);
+            _stop = true;
+        }
+        _cv.notify_all();
+        _lifter.join();
+        _writer.join();
+        for (FastSlot &s : _slots) if (s.res) halgpu_free_result(s.res);
+    }
+    FastSlot &acquire() { // the next slot in ring order, once it is free again
+        std::unique_lock<std::mutex> g(_m);
+        FastSlot &s = _slots[_head % _slots.size()];
+        _cv.wait(g, [&] { return s.state == 0 || !_error.empty(); });
+        rethrow();
+        return s;
+    }
+    void submit() { // the slot handed out by the last acquire() is parsed
+        {
+            std::lock_guard<std::mutex> g(_m);
+            _slots[_head % _slots.size()].state = 1;
+            ++_head;
+        }
+        _cv.notify_all();
+    }
+    void drain() { // everything submitted so far has been written
+        std::unique_lock<std::mutex> g(_m);
+        _cv.wait(g, [&] {
+            if (!_error.empty()) return true;
+            for (const FastSlot &s : _slots) if (s.state != 0) return false;
+            return true;
+        });
+        rethrow();
+    }
+
+  private:
+    void rethrow() {
+        if (!_error.empty()) throw std::runtime_error(_error);
+    }
+    void run(int from, int to, const std::function<void(FastSlot &)> &work) {
+        size_t next = 0;
+        while (true) {
+            FastSlot *s;
+            {
+                std::unique_lock<std::mutex> g(_m);
+                s = &_slots[next % _slots.size()];
+                _cv.wait(g, [&] { return _stop || s->state == from; });
+                if (s->state != from) return; // stop requested and nothing left for this stage
+            }
+            try {
+                work(*s);
+            } catch (const std::exception &e) {
+                std::lock_guard<std::mutex> g(_m);
+                if (_error.empty()) _error = e.what();
+                _stop = true;
+                _cv.notify_all();
+                return;
+            }
+            {
+                std::lock_guard<std::mutex> g(_m);
+                s->state = to;
+            }
+            _cv.notify_all();
+            ++next;
+        }
+    }
+    std::vector<FastSlot> _slots;
+    std::function<halgpu_lift_result *(FastSlot &)> _lift;
+    std::function<void(FastSlot &)> _emit;
+    std::function<void(FastSlot &)> _lift2 = [this](FastSlot &s) { s.res = _lift(s); };
+    std::function<void(FastSlot &)> _emit2 = [this](FastSlot &s) { _emit(s); };
+    std::mutex _m;
+    std::condition_variable _cv;
+    std::thread _lifter, _writer;
+    size_t _head = 0;
+    bool _stop = false;
+    std::string _error;
 };
 
 } // namespace
@@ -103,8 +207,6 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
     size_t lineNumber = 0;
     unsigned threads = textThreads;
     if (const char *tt = std::getenv("HALGPU_TEXT_THREADS")) threads = (unsigned)std::max(0L, std::atol(tt));
-    FastBedBlock fast(sseq, ns, tseq, nt);
-    std::vector<TextBuf> fastText;
     size_t blockTarget = blockBytes;
     if (const char *bb = std::getenv("HALGPU_BLOCK_BYTES")) blockTarget = (size_t)std::max(1L, std::atol(bb)); // test hook
     BlockReader reader(*in, blockTarget);
@@ -112,33 +214,77 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
     size_t blockLen = 0;
     const uint32_t liftFlags = (traverseDupes ? 0u : (uint32_t)HALGPU_NO_DUPES) | (outPSL ? (uint32_t)HALGPU_PSL : 0u) |
                                (columnLiftover ? (uint32_t)HALGPU_COLUMN_LIFTOVER : 0u);
+    std::mutex statMutex; // the pipeline's workers add to the totals too
     auto lift = [&](size_t n, const int64_t *gs, const int64_t *ge, const uint8_t *st) {
         halgpu_lift_result *res = nullptr;
         char *err = nullptr;
         auto t0 = std::chrono::steady_clock::now();
         const int rc = halgpu_liftover(_ctx, srcGenome, tgtGenome, coalescenceLimit, liftFlags, n, gs, ge, st, &res, &err);
-        gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        {
+            std::lock_guard<std::mutex> g(statMutex);
+            gpuSeconds += dt;
+            if (rc == 0) intervalsLifted += n;
+        }
         if (rc != 0) {
             std::string m = err ? err : "halgpu_liftover failed";
             halgpu_free_string(err);
             throw std::runtime_error(m);
         }
-        intervalsLifted += n;
         return res;
     };
+    // the fast text path runs as a pipeline over blocks (FastPipeline); its two workers
+    std::unique_ptr<FastPipeline> pipe;
+    BlockBuf serialText; // block buffer of the serial path (and of the fast path's look-ahead read)
+    auto liftSlot = [&](FastSlot &sl) -> halgpu_lift_result * {
+        if (sl.fast->numIntervals() == 0) return nullptr;
+        try {
+            return lift(sl.fast->numIntervals(), sl.fast->starts(), sl.fast->endsIncl(), sl.fast->strands());
+        } catch (std::exception &e) { // the reference raises inside liftInterval of the first line it maps (halBedScanner.cpp:53-58)
+            throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(sl.firstLine));
+        }
+    };
+    auto emitSlot = [&](FastSlot &sl) {
+        if (sl.res == nullptr) return;
+        auto t0 = std::chrono::steady_clock::now();
+        const size_t lines = sl.fast->formatBlock(sl.block, sl.res, threads, sl.out);
+        const double tf = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        halgpu_free_result(sl.res);
+        sl.res = nullptr;
+        t0 = std::chrono::steady_clock::now();
+        for (const TextBuf &tb : sl.out) out->write(tb.data(), (std::streamsize)tb.size());
+        const double tw = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> g(statMutex);
+        linesOut += lines; textSeconds += tf; writeSeconds += tw;
+    };
+    const bool fastEligible = threads > 0 && !outPSL;
+    if (fastEligible) {
+        pipe.reset(new FastPipeline(3, liftSlot, emitSlot));
+    }
     while (true) {
+        FastSlot *sl = nullptr;
+        if (fastEligible) {
+            sl = &pipe->acquire();
+        }
+        BlockBuf &textBuf = sl ? sl->text : serialText;
         {
             auto tr = std::chrono::steady_clock::now();
-            const bool more = reader.next(block, blockLen);
+            const bool more = reader.next(textBuf, block, blockLen);
             readSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr).count();
             if (!more) break;
         }
         // ---- fast path: the whole block tokenised and formatted by `threads` threads (bed_fast.hpp) ----
-        if (threads > 0 && !outPSL) {
+        if (sl != nullptr) {
+            if (!sl->fast) sl->fast.reset(new FastBedBlock(sseq, ns, tseq, nt));
+            FastBedBlock &fast = *sl->fast;
             auto t0 = std::chrono::steady_clock::now();
             const bool ok = fast.parseBlock(block, blockLen, bedType, cur, threads);
-            textSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            parseSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double tp = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            {
+                std::lock_guard<std::mutex> g(statMutex);
+                textSeconds += tp;
+            }
+            parseSeconds += tp;
             if (ok) {
                 for (const FastEvent &ev : fast.events()) { // Liftover::visitLine's messages (halLiftover.cpp:53-69), in input order
                     if (ev.kind == FastEvent::MISSING_SEQUENCE) {
@@ -150,32 +296,21 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
                                   << ev.seqLength << std::endl;
                     }
                 }
+                sl->firstLine = lineNumber + 1;
                 lineNumber += fast.linesSeen();
                 linesIn += fast.linesSeen();
                 fastLines += fast.linesSeen();
-                if (fast.numIntervals() > 0) {
-                    halgpu_lift_result *res = nullptr;
-                    try {
-                        res = lift(fast.numIntervals(), fast.starts(), fast.endsIncl(), fast.strands());
-                    } catch (std::exception &e) { // the reference raises inside liftInterval of the first line it maps (halBedScanner.cpp:53-58)
-                        throw std::runtime_error(std::string(e.what()) + " in input bed line " + std::to_string(lineNumber - fast.linesSeen() + 1)); // (first line of the block)
-                    }
-                    t0 = std::chrono::steady_clock::now();
-                    linesOut += fast.formatBlock(block, res, threads, fastText);
-                    textSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                    halgpu_free_result(res);
-                    t0 = std::chrono::steady_clock::now();
-                    for (const TextBuf &s : fastText) out->write(s.data(), (std::streamsize)s.size());
-                    writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                }
                 uint64_t lo = 0;
                 uint32_t ll = 0;
-                if (fast.lastLine(lo, ll)) { // carry the scanner's sticky BedLine on for a later serial block
+                if (fast.lastLine(lo, ll)) { // carry the scanner's sticky BedLine on for the next block
                     lineBuf.assign(block + lo, ll);
                     cur.parse(lineBuf, bedType);
                 }
+                sl->block = block; sl->blockLen = blockLen;
+                pipe->submit();
                 continue;
             }
+            pipe->drain(); // the serial path below writes to the same stream: everything before this block goes out first
         }
         // ---- serial path over the block: BedLine::parse per line, every BED flavour, the reference's messages ----
         const char *p = block, *const blockEnd = block + blockLen;
@@ -386,6 +521,7 @@ void GpuBlockLiftover::convert(int srcGenome, std::istream *in, int tgtGenome, s
         if (!deferredError.empty()) { out->flush(); throw std::runtime_error(deferredError); }
         } // batches of the block
     }
+    if (pipe) pipe->drain();
 }
 
 } // namespace halgpu

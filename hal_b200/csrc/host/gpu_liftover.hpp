@@ -27,7 +27,7 @@ class GpuBlockLiftover {
     // of one width goes through the multi-threaded text layer (bed_fast.hpp) and one GPU call; any other block through
     // the serial BedLine code in batches of batchLines.  textThreads == 0 disables the fast path (env HALGPU_TEXT_THREADS
     // overrides it).
-    size_t blockBytes = 128u << 20;
+    size_t blockBytes = 24u << 20; // (small enough for the read / lift / write pipeline of the fast path to overlap)
     unsigned textThreads = defaultTextThreads();
     static unsigned defaultTextThreads();
     // lift with hal::ColumnLiftover::liftInterval semantics (liftover/inc/halColumnLiftover.h:19-26) instead of

@@ -211,6 +211,10 @@ int main(int argc, char **argv) {
             for (size_t i = 0; i < nseq; ++i) ex.convertSequence(maf, ref, (int)i, start, length, targets);
         }
         maf.flush();
+        if (getenv("HALGPU_TIMING") != nullptr) {
+            cerr << "[hal2maf] columns " << ex.columns << ", runs " << ex.runs << ", blocks " << ex.blocks << "; column runs (GPU) " << ex.gpuSeconds
+                 << " s, block state machine " << ex.blockerSeconds << " s, row text " << ex.textSeconds() << " s, write " << ex.writeSeconds() << " s" << endl;
+        }
         if (mafPath != "stdout" && mafFile.tellp() == (streampos)0) std::remove(mafPath.c_str()); // hal2maf.cpp:206-215
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;

@@ -108,9 +108,11 @@ int main(int argc, char **argv) {
         }
         halgpu::GpuBlockLiftover lift(ctx);
         lift.columnLiftover = flag["columnLiftover"];
+        const auto tConvert = chrono::steady_clock::now();
         lift.convert(src, in, tgt, out, bedType, !flag["noDupes"], outPSL, outPSLWithName, coal);
         out->flush();
         if (getenv("HALGPU_TIMING")) {
+            cerr << "[halLiftover] convert() wall " << since(tConvert) << " s (read / tokenise, lift and format / write overlap in a pipeline)" << endl;
             cerr << "[halLiftover] lines in " << lift.linesIn << " (" << lift.fastLines << " on the multi-threaded text path), intervals "
                  << lift.intervalsLifted << ", lines out " << lift.linesOut << "; text " << lift.textSeconds << " s (parse " << lift.parseSeconds << "), halgpu_liftover "
                  << lift.gpuSeconds << " s, read " << lift.readSeconds << " s, write " << lift.writeSeconds << " s, " << lift.textThreads
@@ -120,6 +122,8 @@ int main(int argc, char **argv) {
         cerr << "hal exception caught: " << e.what() << endl;
         rc = 1;
     }
+    const auto tClose = chrono::steady_clock::now();
     halgpu_close(ctx);
+    if (getenv("HALGPU_TIMING")) cerr << "[halLiftover] close " << since(tClose) << " s, main() " << since(tMain) << " s" << endl;
     return rc;
 }

@@ -300,9 +300,79 @@ struct GpuMafExport::Impl {
     }
     // Writes every queued block ("a\n" + rows + blank line) except that the LAST one gets no blank line when `last` is set
     // (MafExport::convertSequence ends with `mafStream << _mafBlock << endl`).
+    // The same bytes produced on the device (halgpu_maf_text, csrc/maf_kernels.cuh): the host formats only the row prefixes
+    // and says where every row goes; bases and gap runs are written by the GPU straight from the staged packed DNA.
+    bool deviceText = true;
+    double deviceTextSeconds = 0, prefixSeconds = 0, writeSeconds = 0, hostTextSeconds = 0;
+    void formatQueuedOnDevice(std::ostream &os, bool last) {
+        const size_t nb = jobBlocks.size();
+        auto t0 = std::chrono::steady_clock::now();
+        std::string prefix;
+        prefix.reserve(jobRows.size() * 48 + nb * 2);
+        std::vector<halgpu_maf_row> rows;
+        rows.reserve(jobRows.size() + 1);
+        std::vector<halgpu_maf_piece> pieces(jobPieces.size());
+        for (size_t i = 0; i < jobPieces.size(); ++i) {
+            pieces[i].pos = jobPieces[i].pos;
+            pieces[i].count_kind = (jobPieces[i].count << 2) | (int64_t)jobPieces[i].kind;
+        }
+        uint64_t at = 0;
+        char buf[24];
+        for (size_t b = 0; b < nb; ++b) {
+            const BlockJob &B = jobBlocks[b];
+            const bool blank = !(last && b + 1 == nb);
+            if (B.numRows == 0) { // (does not happen: a block always has its reference row) "a\n" and the blank line alone
+                halgpu_maf_row w{at, (uint32_t)prefix.size(), 2u, 0u, 0u, 0, blank ? 1u : 0u};
+                prefix += "a\n";
+                rows.push_back(w);
+                at += 2 + (blank ? 1 : 0);
+                continue;
+            }
+            for (size_t r = B.firstRow; r < B.firstRow + B.numRows; ++r) {
+                const RowJob &R = jobRows[r];
+                halgpu_maf_row w;
+                w.out_offset = at; w.prefix_offset = (uint32_t)prefix.size();
+                if (r == B.firstRow) prefix += "a\n";
+                prefix += "s\t"; prefix += *R.name; prefix += '\t';
+                auto c = std::to_chars(buf, buf + sizeof buf, R.start); prefix.append(buf, c.ptr); prefix += '\t';
+                c = std::to_chars(buf, buf + sizeof buf, R.length); prefix.append(buf, c.ptr); prefix += '\t';
+                prefix += R.strand; prefix += '\t';
+                c = std::to_chars(buf, buf + sizeof buf, R.srcLength); prefix.append(buf, c.ptr); prefix += '\t';
+                w.prefix_len = (uint32_t)(prefix.size() - w.prefix_offset);
+                w.first_piece = (uint32_t)R.firstPiece; w.num_pieces = (uint32_t)R.numPieces; w.genome = R.genome;
+                w.tail_newlines = (r + 1 == B.firstRow + B.numRows && blank) ? 2u : 1u;
+                uint64_t text = 0;
+                for (size_t i = 0; i < R.numPieces; ++i) text += (uint64_t)jobPieces[R.firstPiece + i].count;
+                at += w.prefix_len + text + w.tail_newlines;
+                rows.push_back(w);
+            }
+        }
+        if (prefix.size() >= 0xffffffffull || jobPieces.size() >= 0xffffffffull) throw std::runtime_error("too much queued MAF text for one device call");
+        prefixSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        t0 = std::chrono::steady_clock::now();
+        char *out = static_cast<char *>(halgpu_host_alloc(std::max<uint64_t>(at, 1)));
+        if (out == nullptr) throw std::runtime_error("out of page-locked memory for the MAF text");
+        char *err = nullptr;
+        const int rc = halgpu_maf_text(ctx, rows.size(), rows.data(), pieces.size(), pieces.data(), prefix.data(), prefix.size(), at, out, nullptr, &err);
+        deviceTextSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != 0) {
+            std::string msg = err ? err : "halgpu_maf_text failed";
+            halgpu_free_string(err);
+            halgpu_host_free(out);
+            throw std::runtime_error(msg);
+        }
+        t0 = std::chrono::steady_clock::now();
+        os.write(out, (std::streamsize)at);
+        writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        halgpu_host_free(out);
+        jobPieces.clear(); jobRows.clear(); jobBlocks.clear();
+        queuedBytes = 0;
+    }
     void formatQueued(std::ostream &os, bool last) {
         const size_t nb = jobBlocks.size();
         if (nb == 0) return;
+        if (deviceText) { formatQueuedOnDevice(os, last); return; }
+        const auto tHost0 = std::chrono::steady_clock::now();
         unsigned T = std::max(1u, std::min<unsigned>(formatThreads, (unsigned)(queuedBytes >> 20) + 1));
         std::vector<size_t> cut(T + 1, nb); // contiguous groups of blocks with about equal text
         cut[0] = 0;
@@ -331,7 +401,10 @@ struct GpuMafExport::Impl {
             for (unsigned k = 0; k < T; ++k) th.emplace_back(work, k);
             for (auto &x : th) x.join();
         }
+        hostTextSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tHost0).count();
+        const auto tw0 = std::chrono::steady_clock::now();
         for (const std::string &o : outs) os.write(o.data(), (std::streamsize)o.size());
+        writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
         jobPieces.clear(); jobRows.clear(); jobBlocks.clear();
         queuedBytes = 0;
     }
@@ -373,6 +446,8 @@ GpuMafExport::GpuMafExport(halgpu_ctx *ctx) : _impl(new Impl), _ctx(ctx) {
 }
 
 GpuMafExport::~GpuMafExport() {}
+double GpuMafExport::textSeconds() const { return _impl->deviceTextSeconds + _impl->prefixSeconds + _impl->hostTextSeconds; }
+double GpuMafExport::writeSeconds() const { return _impl->writeSeconds; }
 
 unsigned GpuMafExport::defaultFormatThreads() {
     const unsigned hw = std::thread::hardware_concurrency();
@@ -405,6 +480,7 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
     uint64_t appendCount = 0;
     size_t numBlocks = 0;
     m.formatThreads = formatThreads;
+    m.deviceText = std::getenv("HALGPU_MAF_HOST_TEXT") == nullptr; // measurement / test switch: format on host threads instead
     auto flush = [&]() {
         if (appendCount > 0 && (_keepEmptyRefBlocks || !m.referenceIsAllGaps())) {
             m.queueBlock();
@@ -425,6 +501,8 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
             throw std::runtime_error(msg);
         }
         gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const auto tb0 = std::chrono::steady_clock::now();
+        const double textBefore = textSeconds() + writeSeconds();
         for (size_t r = 0; r < cr->n_runs; ++r) {
             const int64_t col0 = cr->run_col[r], runLen = cr->run_col[r + 1] - col0;
             const int cls = cr->run_class ? cr->run_class[r] : 0;
@@ -460,6 +538,7 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
                 for (Row &d : m.rows) d.pos += d.rev ? -take : take;
             }
         }
+        blockerSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count() - (textSeconds() + writeSeconds() - textBefore);
         columns += cr->n_cols;
         runs += cr->n_runs;
         halgpu_free_col_runs(cr);

@@ -41,7 +41,10 @@ class GpuMafExport {
     size_t queueBytes = (size_t)256 << 20;           // finished blocks are formatted and written once about this much text is queued
     // totals
     uint64_t columns = 0, runs = 0, blocks = 0;
-    double gpuSeconds = 0;
+    double gpuSeconds = 0;          // halgpu_column_runs calls
+    double blockerSeconds = 0;      // the sequential block state machine over the runs
+    double textSeconds() const;     // halgpu_maf_text calls (row prefixes, device text, copy back) or the host formatter
+    double writeSeconds() const;    // ostream writes of the finished text
 
   private:
     struct Impl;

@@ -62,6 +62,7 @@ struct Event {
     std::chrono::steady_clock::time_point t;
     void record(Stream) { t = std::chrono::steady_clock::now(); }
     void wait(Stream) const {}
+    void hostWait() const {}
     static float elapsedMs(const Event &a, const Event &b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
 };
 template <class K, class P> inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, Stream, const P &param) {
@@ -153,6 +154,7 @@ struct Event {
     Event &operator=(const Event &) = delete;
     void record(Stream s) { check(cudaEventRecord(e, s), "cudaEventRecord"); }
     void wait(Stream s) const { check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); } // s waits for this event
+    void hostWait() const { check(cudaEventSynchronize(e), "cudaEventSynchronize"); }
     static float elapsedMs(const Event &a, const Event &b) { float ms = 0; check(cudaEventElapsedTime(&ms, a.e, b.e), "cudaEventElapsedTime"); return ms; }
 };
 template <class K, class P> inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, Stream s, const P &param) {

@@ -213,6 +213,27 @@ int halgpu_genome_metadata(const halgpu_ctx *ctx, int genome, size_t index, cons
 const void *halgpu_genome_top_segments(const halgpu_ctx *ctx, int genome);
 const void *halgpu_genome_bottom_segments(const halgpu_ctx *ctx, int genome, size_t *stride);
 
+/* ---- MAF row text (replaces the per-base appendColumn / DnaIterator::getBase loop and the row printer of MafBlock,
+ *      maf/impl/halMafBlock.cpp:370-395,452-456,499-519; api/inc/halDnaIterator.h:131-138).  The caller (the block state
+ *      machine of csrc/host/maf_export.cpp) describes every row of the finished blocks: where its bytes go in the output,
+ *      its formatted prefix, and its text as pieces -- runs of gaps or of consecutive bases of one genome, read forward or
+ *      reverse-complemented from the staged packed DNA.  The whole text is produced on the device and copied to `out`
+ *      (host memory; page-locked memory from halgpu_host_alloc makes the copy run at full PCIe rate). ---- */
+typedef struct halgpu_maf_row {
+    uint64_t out_offset;     /* first byte of the row in the output */
+    uint32_t prefix_offset;  /* the row's prefix inside `prefix` ("a\n" of a block's first row included) */
+    uint32_t prefix_len;
+    uint32_t first_piece, num_pieces;
+    int32_t genome;
+    uint32_t tail_newlines;  /* '\n' characters after the text: 1, or 2 for the last row of a block that is followed by a blank line */
+} halgpu_maf_row;
+typedef struct halgpu_maf_piece {
+    int64_t pos;         /* forward genome coordinate of the first base (walks DOWN for reverse-complemented pieces) */
+    int64_t count_kind;  /* (characters << 2) | kind: 0 gap run, 1 bases forward, 2 bases reverse-complemented */
+} halgpu_maf_piece;
+int halgpu_maf_text(halgpu_ctx *ctx, size_t n_rows, const halgpu_maf_row *rows, size_t n_pieces, const halgpu_maf_piece *pieces,
+                    const char *prefix, size_t prefix_bytes, size_t out_bytes, char *out, float *kernel_ms, char **err);
+
 /* ---- wiggle liftover (replaces the mapping core of hal::WiggleLiftover -- mapSegment / mapFragments and the
  *      WiggleTiles<double> accumulator, liftover/impl/halWiggleLiftover.cpp:98-158, liftover/inc/halWiggleTiles.h; the
  *      --append preload of WiggleLoader::visitLine, halWiggleLoader.cpp:37-48).

@@ -15,6 +15,7 @@
 #define __device__
 #define __host__
 #define __global__
+#define __constant__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
