@@ -36,5 +36,27 @@ d)  # TMA seed-tile A/B (tools/tile_ab.py) with and without ncu
     TILE_AB_REPS=1 TILE_AB_INTERVALS=2000000 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,dram__bytes_read.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
         --clock-control none -k regex:liftoverKernel --csv --log-file gpurun_out/tile_ab_ncu.csv python tools/tile_ab.py > gpurun_out/tile_ab_under_ncu.json 2>> gpurun_out/tile_ab.err
     ;;
+e)  # CLI wall-clock breakdowns (halLiftover pipeline, hal2maf with device text vs host text) on the bench files
+    python - <<'PY' > gpurun_out/cli_e.log 2>&1
+import os, subprocess, sys, time
+sys.path.insert(0, os.getcwd())
+import bench
+W = bench.WORKLOADS["C2"]
+hal = bench.ensure_hal("C2", W["segs"])
+gs, ge = bench.make_intervals(10_000_000, W["segs"] * 32, 2)
+bench.write_bed3("/tmp/in.bed", "L0_seq", gs, ge)
+env = dict(os.environ, HALGPU_TIMING="1")
+for i in range(3):
+    t = time.time(); r = subprocess.run(["hal_b200/bin/halLiftover", hal, "L0", "/tmp/in.bed", "L7", "/tmp/out.bed"], env=env, capture_output=True, text=True)
+    print("halLiftover wall %.3f s" % (time.time() - t)); print(r.stderr[-1500:])
+for name, extra in (("device text", {}), ("host text", {"HALGPU_MAF_HOST_TEXT": "1"})):
+    for i in range(2):
+        t = time.time(); r = subprocess.run(["hal_b200/bin/hal2maf", hal, "/tmp/out.maf", "--refGenome", "R", "--refSequence", "R_seq"], env=dict(env, **extra), capture_output=True, text=True)
+        print("hal2maf (%s) wall %.3f s, %d bytes" % (name, time.time() - t, os.path.getsize("/tmp/out.maf"))); print(r.stderr[-800:])
+    os.rename("/tmp/out.maf", "/tmp/out_%s.maf" % name.split()[0])
+print("maf outputs identical:", open("/tmp/out_device.maf", "rb").read() == open("/tmp/out_host.maf", "rb").read())
+PY
+    cat gpurun_out/cli_e.log
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
