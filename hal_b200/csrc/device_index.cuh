@@ -52,6 +52,16 @@ struct alignas(16) BotCore {
     int64_t topParse; // topParseIndex (-1 for the root)
 };
 
+// fastLiftKernel's index of one vertical transition: per position bucket (the buckets of topBucket / botBucket) everything
+// a hop needs from the segment that holds the bucket's first base, in ONE 32-byte sector -- so a hop whose interval lies in
+// that segment's collinear run costs a single memory round trip.
+struct alignas(32) FastRec {
+    int64_t start; // start of that segment
+    int64_t link;  // its vertical link (reversed flag, index, run)
+    int64_t xlate; // the run's translation constant
+    int64_t idx;   // the segment's index (where the exact search resumes when the run does not cover the interval)
+};
+
 // One genome on the src -> mrca -> tgt path.  Entry p describes genome path[p] and the transition p -> p+1.
 struct PathStep {
     const TopRec *top;
@@ -70,6 +80,7 @@ struct PathStep {
     // transition, this slot's bottoms for a down transition): a position q inside the segment's collinear run maps to
     // q + xlate (forward link) or xlate - q (reversed link) without touching the other genome's records
     const int64_t *xlate;
+    const FastRec *fast; // the transition's bucket-indexed hop records (same buckets as topBucket / botBucket)
 };
 // halLiftover --coalescenceLimit (mapRecursiveParalogies, api/impl/halSegmentMapper.cpp:525-576): between the upward and the
 // downward part of the path sit the genomes from the MRCA up to the child of the limit (STEP_PARA entries, walked upward),
@@ -179,6 +190,7 @@ struct FastParams {
     const uint8_t *strand;                // may be NULL
     const unsigned long long *sortedGs;   // optional: gs in visiting order ...
     const unsigned long long *sortedVal;  // ... with (interval id | min(length, 2^32 - 1) << 32)
+    const unsigned long long *sortedKey;  // or (source genomes shorter than 2^32): source start << 32 | interval id, in visiting order
     unsigned long long *tileCursor;       // next tile of 32 work items
     halgpu_lift_rec *pool;                // a finished interval's one line goes to pool[interval id] (outLoc is preset to that)
     uint32_t *complexList;                // interval ids left to liftoverKernel

@@ -336,6 +336,12 @@ void Context::ensureUpLinks(int gi) { // parent links of genome gi's tops
     int64_t *x = static_cast<int64_t *>(alloc((size_t)g.numTop * sizeof(int64_t)));
     linkFields(&d.top[0].parentEnc, topStride, &d.top[0].start, topStride, g.numTop, nullptr, &_g[g.parent].bot[0].start, botStride, x);
     d.topX = x;
+    d.topFast = static_cast<FastRec *>(alloc((size_t)d.topBuckets * sizeof(FastRec)));
+    FastIndexParams fp;
+    fp.bucket = d.topBucket; fp.links = &d.top[0].parentEnc; fp.starts = &d.top[0].start; fp.xlate = x; fp.linkStride = topStride;
+    fp.startStride = topStride; fp.numBuckets = d.topBuckets; fp.out = d.topFast;
+    rt::launch(fastIndexKernel, gridFor(d.topBuckets, 256, _sms), 256, 0, _stream, fp);
+    rt::sync(_stream);
 }
 
 void Context::ensureDownLinks(int gi, int slot) { // child links of genome gi's bottoms, one child slot
@@ -346,13 +352,21 @@ void Context::ensureDownLinks(int gi, int slot) { // child links of genome gi's 
     if (d.childX == nullptr) {
         d.childX = static_cast<int64_t *>(alloc(g.children.size() * (size_t)g.numBottom * sizeof(int64_t)));
         d.childLinked.assign(g.children.size(), 0);
+        d.childFast.assign(g.children.size(), nullptr);
     }
     if (d.childLinked[(size_t)slot]) return;
     const int c = g.children[(size_t)slot];
     ensureGenome(c);
     const int64_t topStride = sizeof(TopRec) / 8, botStride = sizeof(BotCore) / 8;
     int64_t *col = d.child + (size_t)slot * (size_t)g.numBottom;
-    linkFields(col, 1, &d.bot[0].start, botStride, g.numBottom, _g[c].top, &_g[c].top[0].start, topStride, d.childX + (size_t)slot * (size_t)g.numBottom);
+    int64_t *xcol = d.childX + (size_t)slot * (size_t)g.numBottom;
+    linkFields(col, 1, &d.bot[0].start, botStride, g.numBottom, _g[c].top, &_g[c].top[0].start, topStride, xcol);
+    d.childFast[(size_t)slot] = static_cast<FastRec *>(alloc((size_t)d.botBuckets * sizeof(FastRec)));
+    FastIndexParams fp;
+    fp.bucket = d.botBucket; fp.links = col; fp.starts = &d.bot[0].start; fp.xlate = xcol; fp.linkStride = 1; fp.startStride = botStride;
+    fp.numBuckets = d.botBuckets; fp.out = d.childFast[(size_t)slot];
+    rt::launch(fastIndexKernel, gridFor(d.botBuckets, 256, _sms), 256, 0, _stream, fp);
+    rt::sync(_stream);
     d.childLinked[(size_t)slot] = 1;
 }
 
@@ -410,15 +424,19 @@ const Plan &Context::plan(int src, int tgt, int coal) {
         s.topBucket = _g[g].topBucket; s.botBucket = _g[g].botBucket; s.topShift = _g[g].topShift; s.botShift = _g[g].botShift;
         if (i + 1 >= ent.size()) continue;
         const int nx = ent[i + 1].g;
-        s.xlate = nullptr;
+        s.xlate = nullptr; s.fast = nullptr;
         if (!s.up) { // this genome's childEnc column for the slot of the next genome down
             s.child = _g[g].child + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom;
             s.xlate = _g[g].childX ? _g[g].childX + (size_t)G[nx].slotInParent * (size_t)G[g].numBottom : nullptr;
+            s.fast = _g[g].childFast.empty() ? nullptr : _g[g].childFast[(size_t)G[nx].slotInParent];
         } else if (G[g].parent >= 0 && G[g].parent == nx) { // the parent's column for this genome's slot: canonical-paralog test
             s.child = _g[nx].child + (size_t)G[g].slotInParent * (size_t)G[nx].numBottom;
             s.xlate = _g[g].topX;
+            s.fast = _g[g].topFast;
         }
     }
+    p.fastOk = coal < 0;
+    for (size_t i = 0; i + 1 < steps.size(); ++i) p.fastOk = p.fastOk && steps[i].fast != nullptr;
     p.dSteps = static_cast<PathStep *>(rt::dmalloc(steps.size() * sizeof(PathStep)));
     rt::h2d(p.dSteps, steps.data(), steps.size() * sizeof(PathStep), _stream);
     rt::sync(_stream);
@@ -710,7 +728,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
     out.n = n;
     const int launches0 = (int)rt::g_launches;
     // the one-lane-per-interval kernel computes BlockLiftover lines only (no PSL base counts, no raw fragments, ...)
-    const bool fast = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !(flags & HALGPU_NO_FAST) && n > 0 &&
+    const bool fast = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !(flags & HALGPU_NO_FAST) && n > 0 && pl.fastOk &&
                       pl.path.size() <= (size_t)HG_FAST_MAX_PATH && std::getenv("HALGPU_NO_FAST") == nullptr;
 
     Lease L(_cache);
@@ -728,17 +746,19 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
         // visit the batch in source order so that neighbouring lanes / warps walk neighbouring records (coalescing, L2 reuse).
         // Only the upper bits of the start decide the order: ~32 source segments per sort bucket are as good as an exact order.
-        const unsigned long long *sortedGs = nullptr, *sortedVal = nullptr;
+        const unsigned long long *sortedGs = nullptr, *sortedVal = nullptr, *sortedKey = nullptr;
         const bool sorting = !(flags & HALGPU_NO_SORT) && n > 1;
+        const bool packed = sorting && S.length < 0xffffffffll; // one 64-bit word per interval instead of a (key, value) pair
         if (sorting || fast) {
             IotaParams ip;
             std::memset(&ip, 0, sizeof(ip));
             uint64_t *keysIn = nullptr, *valsIn = nullptr;
-            if (sorting) { keysIn = L.as<uint64_t>(n); valsIn = L.as<uint64_t>(n); }
-            ip.vals = valsIn; ip.keys = keysIn; ip.gs = dGs; ip.ge = dGe; ip.directLoc = fast ? outLoc : nullptr; ip.n = (int64_t)n;
+            if (sorting) { keysIn = L.as<uint64_t>(n); if (!packed) valsIn = L.as<uint64_t>(n); }
+            ip.vals = valsIn; ip.keys = packed ? nullptr : keysIn; ip.packed = packed ? keysIn : nullptr;
+            ip.gs = dGs; ip.ge = dGe; ip.directLoc = fast ? outLoc : nullptr; ip.n = (int64_t)n;
             rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
             if (sorting) {
-                uint64_t *keysOut = L.as<uint64_t>(n), *valsOut = L.as<uint64_t>(n);
+                uint64_t *keysOut = L.as<uint64_t>(n), *valsOut = packed ? nullptr : L.as<uint64_t>(n);
                 int endBit = 1;
                 while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
                 const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
@@ -746,11 +766,18 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 if (bits < 8) bits = std::min(8, endBit);
                 const int beginBit = std::max(0, endBit - bits);
                 size_t tmpBytes = 0;
-                rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
-                void *tmp = L.take(tmpBytes);
-                rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
-                sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
-                sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
+                if (packed) {
+                    rt::sortKeysU64Tmp(nullptr, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, _stream);
+                    void *tmp = L.take(tmpBytes);
+                    rt::sortKeysU64Tmp(tmp, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, _stream);
+                    sortedKey = reinterpret_cast<const unsigned long long *>(keysOut);
+                } else {
+                    rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                    void *tmp = L.take(tmpBytes);
+                    rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                    sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
+                    sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
+                }
             }
         }
         if (pt.on) rt::sync(_stream);
@@ -806,7 +833,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             F.steps = pl.dSteps; F.P = P.P; F.srcIsTop = P.srcIsTop; F.srcLen = S.length;
             F.tgtSeqStart = P.tgtSeqStart; F.tgtNumSeq = P.tgtNumSeq;
             F.n = (int64_t)n; F.gs = dGs; F.ge = dGe; F.strand = dStrand;
-            F.sortedGs = sortedGs; F.sortedVal = sortedVal;
+            F.sortedGs = sortedGs; F.sortedVal = sortedVal; F.sortedKey = sortedKey;
             F.tileCursor = ctr + C_TILE; F.pool = pool;
             F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
             const int64_t tiles = ((int64_t)n + 31) / 32;
@@ -818,7 +845,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             P.listCap = 64; P.frameCap = 32; P.gscratch = nullptr; P.gscratchPerWarp = 0;
             P.n = (int64_t)n;
             if (fast) { P.work = complexList; P.nDev = ctr + C_COMPLEX; }
-            else P.work64 = sortedVal;
+            else P.work64 = sortedKey ? sortedKey : sortedVal; // (the interval id sits in the low 32 bits of either)
             P.seedTile = seedTile ? 1 : 0;
             const size_t smem = ((size_t)liftScratchBytes(P.listCap, P.frameCap) + (P.seedTile ? (size_t)seedTileBytes() : 0)) * warpsPerBlock;
             rt::allowSmem(mapKernel, smem);

@@ -16,6 +16,8 @@ struct GenomeDev {
     TopRec *top = nullptr;     // numTop + 1
     BotCore *bot = nullptr;    // numBottom + 1
     int64_t *child = nullptr;  // nc columns x numBottom
+    FastRec *topFast = nullptr;            // topBuckets: fastLiftKernel's records of the transition to the parent
+    std::vector<FastRec *> childFast;      // per child slot: botBuckets records of the transition to that child
     int64_t *topX = nullptr;   // numTop: xlate constant of every parent link
     int64_t *childX = nullptr; // nc columns x numBottom: xlate constant of every child link
     uint8_t *dna = nullptr;    // (length + 1) / 2
@@ -34,6 +36,7 @@ struct Plan {
     std::vector<int> path; // src .. mrca [.. child of the limit .. mrca] .. tgt (genome of every path position)
     int upSteps = 0;
     PathStep *dSteps = nullptr;
+    bool fastOk = false;   // every transition has its FastRec table: fastLiftKernel can run this path
     mutable double linesPerInterval = 0; // largest output lines / interval ratio seen on this path: sizes the next batch's record pool
 };
 

@@ -111,12 +111,13 @@ int main(int argc, char **argv) {
         const auto tConvert = chrono::steady_clock::now();
         lift.convert(src, in, tgt, out, bedType, !flag["noDupes"], outPSL, outPSLWithName, coal);
         out->flush();
+        const double convertSeconds = since(tConvert);
         if (getenv("HALGPU_TIMING")) {
-            cerr << "[halLiftover] convert() wall " << since(tConvert) << " s (read / tokenise, lift and format / write overlap in a pipeline)" << endl;
             cerr << "[halLiftover] lines in " << lift.linesIn << " (" << lift.fastLines << " on the multi-threaded text path), intervals "
                  << lift.intervalsLifted << ", lines out " << lift.linesOut << "; text " << lift.textSeconds << " s (parse " << lift.parseSeconds << "), halgpu_liftover "
                  << lift.gpuSeconds << " s, read " << lift.readSeconds << " s, write " << lift.writeSeconds << " s, " << lift.textThreads
-                 << " text threads; open+stage (incl. CUDA context) " << openSeconds << " s, total so far " << since(tMain) << " s" << endl;
+                 << " text threads; open (CUDA context; genomes are staged by the first lift) " << openSeconds << " s, total so far " << since(tMain) << " s" << endl;
+            cerr << "[halLiftover] convert() wall " << convertSeconds << " s (read / tokenise, lift and format / write overlap in a pipeline)" << endl;
         }
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;

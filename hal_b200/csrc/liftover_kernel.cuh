@@ -936,7 +936,12 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
         uint32_t item = 0;
         int64_t gs = 0, ge = -1;
         if (have) {
-            if (P.sortedGs) {
+            if (P.sortedKey) {
+                const unsigned long long k = P.sortedKey[w];
+                item = (uint32_t)k;
+                gs = (int64_t)(k >> 32);
+                ge = ldS(&P.ge[item]);
+            } else if (P.sortedGs) {
                 const unsigned long long v = P.sortedVal[w];
                 item = (uint32_t)v;
                 gs = (int64_t)P.sortedGs[w];
@@ -955,32 +960,28 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
             const int np = P.P;
             for (int p = 0; p < np - 1; ++p) {
                 const PathStep &st = sSteps[p];
-                // One hop = the bucket entry, then the segment's start, link and xlate constant in parallel: two dependent
-                // memory round trips.  Bucket segment i0 starts at or before tLo; if [tLo, tLo + len) lies inside i0's
-                // collinear run the run's affine map applies even when tLo is past i0's own end.  Otherwise the exact
-                // segment is searched and tested before the interval is declared complex.
+                // One hop = ONE 32-byte read: the transition's FastRec of the bucket tLo falls into (start, link and translation
+                // constant of the segment i0 holding the bucket's first base).  i0 starts at or before tLo; if [tLo, tLo + len)
+                // lies inside i0's collinear run the run's affine map applies even when tLo is past i0's own end.  Otherwise
+                // the exact segment is searched and tested before the interval is declared complex.
                 int64_t e, x, s0;
-                if (st.up) { // toParent (api/impl/halBottomSegmentIterator.cpp:40-49) over a whole run
-                    int64_t i = (int64_t)__ldg(&st.topBucket[tLo >> st.topShift]);
-                    longlong2 h = __ldg(reinterpret_cast<const longlong2 *>(&st.top[i])); // start, parent link
-                    x = ldS(&st.xlate[i]);
-                    s0 = h.x; e = h.y;
+                {
+                    const FastRec *fr = &st.fast[tLo >> (st.up ? st.topShift : st.botShift)];
+                    const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(fr));
+                    const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(fr) + 1);
+                    s0 = a.x; e = a.y; x = b.x;
                     if (e < 0 || tLo - s0 + len > linkRun(e)) {
-                        i = searchFrom<true>(st.top, i, st.numTop, tLo);
-                        h = __ldg(reinterpret_cast<const longlong2 *>(&st.top[i]));
-                        x = ldS(&st.xlate[i]);
-                        s0 = h.x; e = h.y;
-                    }
-                } else { // toChild (api/impl/halTopSegmentIterator.cpp:36-45) over a whole run
-                    int64_t i = (int64_t)__ldg(&st.botBucket[tLo >> st.botShift]);
-                    s0 = botStart(st.bot, i);
-                    e = ldS(&st.child[i]);
-                    x = ldS(&st.xlate[i]);
-                    if (e < 0 || tLo - s0 + len > linkRun(e)) {
-                        i = searchFrom<false>(st.bot, i, st.numBot, tLo);
-                        s0 = botStart(st.bot, i);
-                        e = ldS(&st.child[i]);
-                        x = ldS(&st.xlate[i]);
+                        if (st.up) { // toParent (api/impl/halBottomSegmentIterator.cpp:40-49)
+                            const int64_t i = searchFrom<true>(st.top, b.y, st.numTop, tLo);
+                            const longlong2 h = __ldg(reinterpret_cast<const longlong2 *>(&st.top[i])); // start, parent link
+                            x = ldS(&st.xlate[i]);
+                            s0 = h.x; e = h.y;
+                        } else { // toChild (api/impl/halTopSegmentIterator.cpp:36-45)
+                            const int64_t i = searchFrom<false>(st.bot, b.y, st.numBot, tLo);
+                            s0 = botStart(st.bot, i);
+                            e = ldS(&st.child[i]);
+                            x = ldS(&st.xlate[i]);
+                        }
                     }
                 }
                 if (e < 0 || tLo - s0 + len > linkRun(e)) { ok = false; break; }

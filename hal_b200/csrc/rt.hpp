@@ -99,6 +99,13 @@ inline void sortPairsU64U64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keys
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (keysIn[a] & mask) < (keysIn[b] & mask); });
     for (size_t i = 0; i < n; ++i) { keysOut[i] = keysIn[idx[i]]; valsOut[i] = valsIn[idx[i]]; }
 }
+inline void sortKeysU64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keysIn, uint64_t *keysOut, size_t n, int beginBit, int endBit, Stream) {
+    if (tmp == nullptr) { tmpBytes = 1; return; }
+    const uint64_t mask = (endBit >= 64 ? ~0ull : ((1ull << endBit) - 1ull)) & ~((1ull << beginBit) - 1ull);
+    std::vector<uint64_t> v(keysIn, keysIn + n);
+    std::stable_sort(v.begin(), v.end(), [&](uint64_t a, uint64_t b) { return (a & mask) < (b & mask); });
+    std::copy(v.begin(), v.end(), keysOut);
+}
 // out[i] = sum of (in[j] & mask) for j < i, i in [0, n]  (n + 1 entries are read and written)
 inline void exclusiveScanMaskedTmp(void *tmp, size_t &tmpBytes, const unsigned long long *in, uint64_t *out, size_t n, uint64_t mask, Stream) {
     if (tmp == nullptr) { tmpBytes = 1; return; }
@@ -203,6 +210,10 @@ inline void selectFlagged(const uint8_t *flag, int64_t *out, unsigned long long 
 inline void sortPairsU64U64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keysIn, uint64_t *keysOut, const uint64_t *valsIn, uint64_t *valsOut,
                                size_t n, int beginBit, int endBit, Stream s) {
     check(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, (int64_t)n, beginBit, endBit, s), "radix sort");
+    if (tmp != nullptr) g_launches += 1;
+}
+inline void sortKeysU64Tmp(void *tmp, size_t &tmpBytes, const uint64_t *keysIn, uint64_t *keysOut, size_t n, int beginBit, int endBit, Stream s) {
+    check(cub::DeviceRadixSort::SortKeys(tmp, tmpBytes, keysIn, keysOut, (int64_t)n, beginBit, endBit, s), "radix sort (keys)");
     if (tmp != nullptr) g_launches += 1;
 }
 struct MaskU64 {

@@ -132,10 +132,29 @@ __global__ void linkXlateKernel(const LinkXlateParams p) {
     }
 }
 
+// FastRec table of one vertical transition (device_index.cuh)
+struct FastIndexParams {
+    const uint32_t *bucket;
+    const int64_t *links, *starts, *xlate;
+    int64_t linkStride, startStride, numBuckets;
+    FastRec *out;
+};
+__global__ void fastIndexKernel(const FastIndexParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < p.numBuckets; b += step) {
+        const int64_t i = (int64_t)p.bucket[b];
+        FastRec r;
+        r.start = p.starts[i * p.startStride]; r.link = p.links[i * p.linkStride]; r.xlate = p.xlate[i]; r.idx = i;
+        p.out[b] = r;
+    }
+}
+
 // sort input: key = source start (sorted on its upper bits only), value = interval id | min(length, 2^32 - 1) << 32
 struct IotaParams {
-    uint64_t *vals;             // NULL: no sort input wanted (HALGPU_NO_SORT), only directLoc
+    uint64_t *vals;             // NULL: no (key, value) sort input wanted
     uint64_t *keys;
+    uint64_t *packed;           // optional, instead of vals/keys: one 64-bit word per interval, source start << 32 | interval id
+                                // (source genomes shorter than 2^32: half the sort traffic; the kernels re-read the end)
     const int64_t *gs, *ge;
     unsigned long long *directLoc; // optional: outLoc[i] = "one record in pool slot i" (what fastLiftKernel leaves behind on success)
     int64_t n;
@@ -148,6 +167,11 @@ __global__ void iotaKeysKernel(const IotaParams p) {
             const uint64_t l32 = (len <= 0 || len >= 0xffffffffll) ? 0xffffffffull : (uint64_t)len;
             p.vals[i] = (uint64_t)i | (l32 << 32);
             p.keys[i] = (uint64_t)a;
+        }
+        if (p.packed) {
+            const int64_t a = p.gs[i];
+            // an out-of-range start becomes 2^32 - 1, beyond any such genome: the interval fails the range test like the original
+            p.packed[i] = ((a < 0 || a >= 0xffffffffll ? 0xffffffffull : (uint64_t)a) << 32) | (uint64_t)i;
         }
         if (p.directLoc) p.directLoc[i] = ((unsigned long long)i << HG_LOC_COUNT_BITS) | 1ull;
     }

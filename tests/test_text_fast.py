@@ -38,7 +38,7 @@ def run(cli, hal, src, bed_path, tgt, out_path, args=(), threads=None, block=Non
     if block is not None:
         env["HALGPU_BLOCK_BYTES"] = str(block)
     r = subprocess.run([cli] + list(args) + [hal, src, bed_path, tgt, out_path], capture_output=True, text=True, env=env)
-    timing = [l for l in r.stderr.splitlines() if l.startswith("[halLiftover]")]
+    timing = [l for l in r.stderr.splitlines() if l.startswith("[halLiftover] lines in")]
     stderr = "\n".join(l for l in r.stderr.splitlines() if not l.startswith(("[halLiftover]", "[halgpu timing]")))
     fast = int(timing[0].split("(")[1].split()[0]) if timing else -1
     return r.returncode, stderr, fast

@@ -58,5 +58,24 @@ print("maf outputs identical:", open("/tmp/out_device.maf", "rb").read() == open
 PY
     cat gpurun_out/cli_e.log
     ;;
+f)  # whole GPU tier + bench at N=1 (FastRec hops, packed sort) + launch list + ncu of the fast kernel on the full batch
+    timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_f.log 2>&1; tail -5 gpurun_out/pytest_f.log
+    ( time timeout 900 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err
+    tail -c 300 gpurun_out/bench_f.json; tail -5 gpurun_out/bench_f.err
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_f.csv \
+        python bench.py --steps 2 --warmup 1 --no-cli --no-wiggle --no-cpu-baseline --no-traffic > gpurun_out/bench_ncu_f.json 2> gpurun_out/bench_ncu_f.err
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel' -s 1 -c 1 -o gpurun_out/prof_f_fast -f \
+        python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/prof_f.err
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:'depthKernel' -c 1 -o gpurun_out/prof_f_depth -f \
+        python bench.py --probe --no-divergent > /dev/null 2>> gpurun_out/prof_f.err
+    ;;
+g)  # multi-GPU: NCCL tests of the C++ path + bench at N = number of GPUs on the box
+    N=$(nvidia-smi -L | wc -l)
+    timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu > gpurun_out/pytest_g.log 2>&1; tail -5 gpurun_out/pytest_g.log
+    ( time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline ) > gpurun_out/bench_g_n$N.json 2> gpurun_out/bench_g_n$N.err
+    tail -c 2500 gpurun_out/bench_g_n$N.json; tail -8 gpurun_out/bench_g_n$N.err
+    ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-gather --no-depth --no-c4 ) > gpurun_out/bench_g_n${N}_nogather.json 2> gpurun_out/bench_g_n${N}_nogather.err
+    tail -c 600 gpurun_out/bench_g_n${N}_nogather.json
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
