@@ -2,6 +2,9 @@
 #include <algorithm>
 #include <charconv>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -304,48 +307,125 @@ struct GpuMafExport::Impl {
     // and says where every row goes; bases and gap runs are written by the GPU straight from the staged packed DNA.
     bool deviceText = true;
     double deviceTextSeconds = 0, prefixSeconds = 0, writeSeconds = 0, hostTextSeconds = 0;
+    // finished text leaves through one writer thread, so the next batch of blocks is assembled while this one is written
+    struct WriteJob { char *buf; size_t n; };
+    std::thread writer;
+    std::mutex wm;
+    std::condition_variable wcv;
+    std::deque<WriteJob> wq;
+    bool wstop = false, wbusy = false;
+    std::string werror;
+    std::ostream *wos = nullptr;
+    void writerLoop() {
+        while (true) {
+            WriteJob j;
+            {
+                std::unique_lock<std::mutex> g(wm);
+                wcv.wait(g, [&] { return wstop || !wq.empty(); });
+                if (wq.empty()) return;
+                j = wq.front(); wq.pop_front();
+                wbusy = true;
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            wos->write(j.buf, (std::streamsize)j.n);
+            halgpu_host_free(j.buf);
+            {
+                std::lock_guard<std::mutex> g(wm);
+                writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                wbusy = false;
+            }
+            wcv.notify_all();
+        }
+    }
+    void enqueueWrite(std::ostream &os, char *buf, size_t n) {
+        {
+            std::unique_lock<std::mutex> g(wm);
+            wcv.wait(g, [&] { return wq.size() < 2; }); // at most two finished buffers wait for the disk
+            wos = &os;
+            wq.push_back(WriteJob{buf, n});
+        }
+        if (!writer.joinable()) writer = std::thread([this] { writerLoop(); });
+        wcv.notify_all();
+    }
+    void drainWriter() { // everything handed to the writer is in the stream
+        std::unique_lock<std::mutex> g(wm);
+        wcv.wait(g, [&] { return wq.empty() && !wbusy; });
+    }
+    ~Impl() {
+        {
+            std::lock_guard<std::mutex> g(wm);
+            wstop = true;
+        }
+        wcv.notify_all();
+        if (writer.joinable()) writer.join();
+    }
     void formatQueuedOnDevice(std::ostream &os, bool last) {
         const size_t nb = jobBlocks.size();
         auto t0 = std::chrono::steady_clock::now();
+        // rows in output order; (block, row) -> descriptor.  The prefixes are formatted by several threads, each into its own
+        // string; offsets follow from two prefix sums.
+        struct RowRef { size_t row; bool first, lastOfBlock, blank; };
+        std::vector<RowRef> refs;
+        refs.reserve(jobRows.size());
+        for (size_t b = 0; b < nb; ++b) {
+            const BlockJob &B = jobBlocks[b];
+            const bool blank = !(last && b + 1 == nb);
+            for (size_t r = B.firstRow; r < B.firstRow + B.numRows; ++r) refs.push_back(RowRef{r, r == B.firstRow, r + 1 == B.firstRow + B.numRows, blank});
+        }
+        const size_t nr = refs.size();
+        std::vector<halgpu_maf_row> rows(nr);
+        std::vector<uint64_t> textLen(nr);
+        const unsigned T = std::max(1u, std::min<unsigned>(formatThreads, (unsigned)(nr >> 12) + 1));
+        std::vector<std::string> parts(T);
+        auto work = [&](unsigned k) {
+            const size_t lo = nr * k / T, hi = nr * (k + 1) / T;
+            std::string &px = parts[k];
+            px.reserve((hi - lo) * 48);
+            char buf[24];
+            for (size_t i = lo; i < hi; ++i) {
+                const RowJob &R = jobRows[refs[i].row];
+                halgpu_maf_row &w = rows[i];
+                const size_t at0 = px.size();
+                if (refs[i].first) px += "a\n";
+                px += "s\t"; px += *R.name; px += '\t';
+                auto c = std::to_chars(buf, buf + sizeof buf, R.start); px.append(buf, c.ptr); px += '\t';
+                c = std::to_chars(buf, buf + sizeof buf, R.length); px.append(buf, c.ptr); px += '\t';
+                px += R.strand; px += '\t';
+                c = std::to_chars(buf, buf + sizeof buf, R.srcLength); px.append(buf, c.ptr); px += '\t';
+                w.prefix_offset = (uint32_t)at0; // relative to this thread's string for now
+                w.prefix_len = (uint32_t)(px.size() - at0);
+                w.first_piece = (uint32_t)R.firstPiece; w.num_pieces = (uint32_t)R.numPieces; w.genome = R.genome;
+                w.tail_newlines = (refs[i].lastOfBlock && refs[i].blank) ? 2u : 1u;
+                uint64_t text = 0;
+                for (size_t q = 0; q < R.numPieces; ++q) text += (uint64_t)jobPieces[R.firstPiece + q].count;
+                textLen[i] = text;
+            }
+        };
+        if (T == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < T; ++k) th.emplace_back(work, k);
+            for (auto &x : th) x.join();
+        }
         std::string prefix;
-        prefix.reserve(jobRows.size() * 48 + nb * 2);
-        std::vector<halgpu_maf_row> rows;
-        rows.reserve(jobRows.size() + 1);
+        size_t total = 0;
+        for (const std::string &px : parts) total += px.size();
+        prefix.reserve(total);
+        uint64_t at = 0;
+        for (unsigned k = 0; k < T; ++k) {
+            const size_t lo = nr * k / T, hi = nr * (k + 1) / T, base = prefix.size();
+            prefix += parts[k];
+            for (size_t i = lo; i < hi; ++i) {
+                rows[i].prefix_offset += (uint32_t)base;
+                rows[i].out_offset = at;
+                at += rows[i].prefix_len + textLen[i] + rows[i].tail_newlines;
+            }
+        }
         std::vector<halgpu_maf_piece> pieces(jobPieces.size());
         for (size_t i = 0; i < jobPieces.size(); ++i) {
             pieces[i].pos = jobPieces[i].pos;
             pieces[i].count_kind = (jobPieces[i].count << 2) | (int64_t)jobPieces[i].kind;
-        }
-        uint64_t at = 0;
-        char buf[24];
-        for (size_t b = 0; b < nb; ++b) {
-            const BlockJob &B = jobBlocks[b];
-            const bool blank = !(last && b + 1 == nb);
-            if (B.numRows == 0) { // (does not happen: a block always has its reference row) "a\n" and the blank line alone
-                halgpu_maf_row w{at, (uint32_t)prefix.size(), 2u, 0u, 0u, 0, blank ? 1u : 0u};
-                prefix += "a\n";
-                rows.push_back(w);
-                at += 2 + (blank ? 1 : 0);
-                continue;
-            }
-            for (size_t r = B.firstRow; r < B.firstRow + B.numRows; ++r) {
-                const RowJob &R = jobRows[r];
-                halgpu_maf_row w;
-                w.out_offset = at; w.prefix_offset = (uint32_t)prefix.size();
-                if (r == B.firstRow) prefix += "a\n";
-                prefix += "s\t"; prefix += *R.name; prefix += '\t';
-                auto c = std::to_chars(buf, buf + sizeof buf, R.start); prefix.append(buf, c.ptr); prefix += '\t';
-                c = std::to_chars(buf, buf + sizeof buf, R.length); prefix.append(buf, c.ptr); prefix += '\t';
-                prefix += R.strand; prefix += '\t';
-                c = std::to_chars(buf, buf + sizeof buf, R.srcLength); prefix.append(buf, c.ptr); prefix += '\t';
-                w.prefix_len = (uint32_t)(prefix.size() - w.prefix_offset);
-                w.first_piece = (uint32_t)R.firstPiece; w.num_pieces = (uint32_t)R.numPieces; w.genome = R.genome;
-                w.tail_newlines = (r + 1 == B.firstRow + B.numRows && blank) ? 2u : 1u;
-                uint64_t text = 0;
-                for (size_t i = 0; i < R.numPieces; ++i) text += (uint64_t)jobPieces[R.firstPiece + i].count;
-                at += w.prefix_len + text + w.tail_newlines;
-                rows.push_back(w);
-            }
         }
         if (prefix.size() >= 0xffffffffull || jobPieces.size() >= 0xffffffffull) throw std::runtime_error("too much queued MAF text for one device call");
         prefixSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -361,10 +441,7 @@ struct GpuMafExport::Impl {
             halgpu_host_free(out);
             throw std::runtime_error(msg);
         }
-        t0 = std::chrono::steady_clock::now();
-        os.write(out, (std::streamsize)at);
-        writeSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        halgpu_host_free(out);
+        enqueueWrite(os, out, (size_t)at);
         jobPieces.clear(); jobRows.clear(); jobBlocks.clear();
         queuedBytes = 0;
     }
@@ -372,6 +449,7 @@ struct GpuMafExport::Impl {
         const size_t nb = jobBlocks.size();
         if (nb == 0) return;
         if (deviceText) { formatQueuedOnDevice(os, last); return; }
+        drainWriter();
         const auto tHost0 = std::chrono::steady_clock::now();
         unsigned T = std::max(1u, std::min<unsigned>(formatThreads, (unsigned)(queuedBytes >> 20) + 1));
         std::vector<size_t> cut(T + 1, nb); // contiguous groups of blocks with about equal text
@@ -502,7 +580,7 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         }
         gpuSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const auto tb0 = std::chrono::steady_clock::now();
-        const double textBefore = textSeconds() + writeSeconds();
+        const double textBefore = textSeconds();
         for (size_t r = 0; r < cr->n_runs; ++r) {
             const int64_t col0 = cr->run_col[r], runLen = cr->run_col[r + 1] - col0;
             const int cls = cr->run_class ? cr->run_class[r] : 0;
@@ -538,7 +616,7 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
                 for (Row &d : m.rows) d.pos += d.rev ? -take : take;
             }
         }
-        blockerSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count() - (textSeconds() + writeSeconds() - textBefore);
+        blockerSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count() - (textSeconds() - textBefore);
         columns += cr->n_cols;
         runs += cr->n_runs;
         halgpu_free_col_runs(cr);
@@ -548,9 +626,11 @@ void GpuMafExport::convertSequence(std::ostream &mafStream, int refGenome, int r
         m.queueBlock();
         ++blocks;
         m.formatQueued(mafStream, true);
+        m.drainWriter();
         mafStream << std::endl;
     } else {
         m.formatQueued(mafStream, false);
+        m.drainWriter();
     }
 }
 

@@ -38,7 +38,7 @@ class GpuMafExport {
     size_t chunkColumns = 8u << 20; // columns per halgpu_column_runs call
     unsigned formatThreads = defaultFormatThreads(); // threads that decode and print the rows of finished blocks
     static unsigned defaultFormatThreads();
-    size_t queueBytes = (size_t)256 << 20;           // finished blocks are formatted and written once about this much text is queued
+    size_t queueBytes = (size_t)64 << 20;            // finished blocks are formatted and written once about this much text is queued
     // totals
     uint64_t columns = 0, runs = 0, blocks = 0;
     double gpuSeconds = 0;          // halgpu_column_runs calls

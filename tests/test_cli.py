@@ -141,6 +141,19 @@ def test_maf_cli_emulated_whole_genome_live(emul_maf_cli, tmp_path):
         assert open(a, "rb").read() == open(b, "rb").read(), args
 
 
+def test_maf_cli_emulated_device_text_equals_host_text(emul_maf_cli, tmp_path):
+    """the row text written by mafTextKernel (halgpu_maf_text) against the host formatter, with a queue small enough for
+    many device calls and hand-offs to the writer thread"""
+    hal = os.path.join(GOLDEN, "varlen8.hal")
+    for args in (["--refGenome", "L1"], ["--refGenome", "R", "--maxBlockLen", "37"], ["--refGenome", "L2", "--noAncestors"]):
+        outs = []
+        for env in ({}, {"HALGPU_MAF_HOST_TEXT": "1"}, {"HALGPU_MAF_QUEUE_BYTES": "20000", "HALGPU_TEXT_THREADS": "3"}):
+            o = str(tmp_path / "o.maf")
+            subprocess.check_call([emul_maf_cli, hal, o] + args, env=dict(os.environ, **env))
+            outs.append(open(o, "rb").read())
+        assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 1000, args
+
+
 @pytest.mark.skipif(ref_bin("hal2maf") is None, reason="oracle/_ref not built")
 def test_maf_cli_emulated_unique_across_chunks(emul_maf_cli, tmp_path):
     """--unique keeps one visit cache per convertSequence sweep: the column range is processed in chunks, every chunk must

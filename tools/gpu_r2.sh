@@ -77,5 +77,9 @@ g)  # multi-GPU: NCCL tests of the C++ path + bench at N = number of GPUs on the
     ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-gather --no-depth --no-c4 ) > gpurun_out/bench_g_n${N}_nogather.json 2> gpurun_out/bench_g_n${N}_nogather.err
     tail -c 600 gpurun_out/bench_g_n${N}_nogather.json
     ;;
+h)  # source-level profile of the warp-per-interval walk on the divergent file (2 M intervals)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:'liftoverKernel' -s 3 -c 1 -o gpurun_out/prof_h_walk -f \
+        python tools/walk_profile.py > gpurun_out/prof_h.log 2> gpurun_out/prof_h.err
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
