@@ -124,7 +124,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
         // (interval bounds are validated by the kernel itself: an out-of-range interval makes the call fail)
         // Pipeline: the batch is cut into chunks; while chunk k is being lifted on the engine's stream, chunk k+1's inputs
         // travel host->device and chunk k-1's records travel device->host on the copy stream.
-        rt::Stream cs = ctx->impl->copyStream();
+        rt::Stream cs = ctx->impl->copyStream(), cb = ctx->impl->copyBackStream();
         size_t nChunks = n >= (4u << 20) ? 8 : (n >= (1u << 20) ? 4 : 1);
         if (const char *forced = std::getenv("HALGPU_HOST_CHUNKS")) { // test hook
             const long f = std::atol(forced);
@@ -169,7 +169,7 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                 }
                 parts.push_back(dev);
                 if (nRec + dev->n_rec > recCap) { // grow the pinned result (rare: more than 1.25 lines per interval)
-                    rt::sync(cs);
+                    rt::sync(cb);
                     const size_t newCap = std::max(recCap * 2, nRec + dev->n_rec + (n - lo[k + 1]) * 2);
                     halgpu_lift_rec *nr = static_cast<halgpu_lift_rec *>(rt::hostAlloc(newCap * sizeof(halgpu_lift_rec)));
                     std::memcpy(nr, r->recs, nRec * sizeof(halgpu_lift_rec));
@@ -184,17 +184,18 @@ int halgpu_liftover(halgpu_ctx *ctx, int src, int tgt, int coalescenceLimit, uin
                     recCap = newCap;
                 }
                 // halgpu_liftover_device returns with the engine's stream idle, so the copy stream may read the result now
-                rt::d2h(r->offsets + a, dev->offsets, (c + (k + 1 == nChunks ? 1 : 0)) * sizeof(uint64_t), cs);
-                rt::d2h(r->recs + nRec, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), cs);
-                if (wantPsl) rt::d2h(r->psl + 4 * nRec, dev->psl, dev->n_rec * 16, cs);
+                rt::d2h(r->offsets + a, dev->offsets, (c + (k + 1 == nChunks ? 1 : 0)) * sizeof(uint64_t), cb);
+                rt::d2h(r->recs + nRec, dev->recs, dev->n_rec * sizeof(halgpu_lift_rec), cb);
+                if (wantPsl) rt::d2h(r->psl + 4 * nRec, dev->psl, dev->n_rec * 16, cb);
                 nRec += dev->n_rec;
                 r->kernel_ms += dev->kernel_ms; r->launches += dev->launches; r->n_retry += dev->n_retry;
                 r->fast_ms += dev->fast_ms; r->n_complex += dev->n_complex;
             }
             rt::sync(cs);
+            rt::sync(cb);
             r->n_rec = nRec; // (offsets already carry each chunk's base: added on the device)
         } catch (...) {
-            rt::sync(cs);
+            try { rt::sync(cs); rt::sync(cb); } catch (...) {}
             for (halgpu_lift_result *d : parts) halgpu_free_result(d);
             ctx->impl->release(dS); ctx->impl->release(dE); ctx->impl->release(dT);
             halgpu_free_result(r);

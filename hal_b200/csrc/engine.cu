@@ -206,6 +206,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     rt::retainPool(device);
     _stream = rt::createStream();
     _copy = rt::createStream();
+    _copyBack = rt::createStream();
     _sms = rt::smCount();
     _g.resize(_file->genomes().size());
     try {
@@ -217,6 +218,7 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
         for (void *p : _owned) rt::dfree(p);
         rt::destroyStream(_stream);
         rt::destroyStream(_copy);
+        rt::destroyStream(_copyBack);
         throw;
     }
 }
@@ -228,6 +230,7 @@ Context::~Context() {
     for (void *p : _owned) rt::dfree(p);
     rt::destroyStream(_stream);
     rt::destroyStream(_copy);
+    rt::destroyStream(_copyBack);
 }
 
 void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb) {

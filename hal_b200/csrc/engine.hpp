@@ -86,7 +86,8 @@ class Context {
     ~Context();
     const HalFile &file() const { return *_file; }
     rt::Stream stream() const { return _stream; }
-    rt::Stream copyStream() const { return _copy; } // host<->device traffic of the pipelined host-buffer entry point
+    rt::Stream copyStream() const { return _copy; }     // host->device traffic of the pipelined host-buffer entry point
+    rt::Stream copyBackStream() const { return _copyBack; } // device->host traffic (its own stream: PCIe is full duplex)
     size_t stagedBytes() const { return _staged; }
     int device() const { return _device; }
     // device pointers in, device result out (the caller hands offsets/recs/psl back with release())
@@ -134,7 +135,7 @@ class Context {
 
     std::unique_ptr<HalFile> _file;
     int _device;
-    rt::Stream _stream, _copy;
+    rt::Stream _stream, _copy, _copyBack;
     std::vector<GenomeDev> _g;
     std::map<std::tuple<int, int, int>, Plan> _plans; // (src, tgt, coalescence limit or -1)
     std::vector<void *> _owned;
