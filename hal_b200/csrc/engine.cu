@@ -751,7 +751,10 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // Only the upper bits of the start decide the order: ~32 source segments per sort bucket are as good as an exact order.
         const unsigned long long *sortedGs = nullptr, *sortedVal = nullptr, *sortedKey = nullptr;
         const bool sorting = !(flags & HALGPU_NO_SORT) && n > 1;
-        const bool packed = sorting && S.length < 0xffffffffll; // one 64-bit word per interval instead of a (key, value) pair
+        // HALGPU_PACKED_SORT=1: one 64-bit word per interval (start << 32 | id) instead of a (key, value) pair.  Measured (profiles/
+        // r02_bench_n1_f.json): CUB's onesweep pass takes ~100 us for 10 M elements either way, while the lane kernel then has to
+        // fetch every interval's end with a scattered read (+50 us): off by default.
+        const bool packed = sorting && S.length < 0xffffffffll && std::getenv("HALGPU_PACKED_SORT") != nullptr;
         if (sorting || fast) {
             IotaParams ip;
             std::memset(&ip, 0, sizeof(ip));
@@ -766,7 +769,9 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
                 const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
                 int bits = ((endBit - coarse) / 8) * 8;
+                if (const char *sb = std::getenv("HALGPU_SORT_BITS")) bits = std::atoi(sb); // measurement switch
                 if (bits < 8) bits = std::min(8, endBit);
+                if (bits > endBit) bits = endBit;
                 const int beginBit = std::max(0, endBit - bits);
                 size_t tmpBytes = 0;
                 if (packed) {

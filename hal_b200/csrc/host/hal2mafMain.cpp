@@ -4,6 +4,7 @@
 // Not implemented (rejected with an error): --maxRefGap > 0, --global, --printTree.
 #include "bed.hpp"
 #include "maf_export.hpp"
+#include <chrono>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -92,6 +93,9 @@ static void refTargets(halgpu::GpuMafExport &ex, ostream &maf, halgpu_ctx *ctx, 
 }
 
 int main(int argc, char **argv) {
+    const auto tMain = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+    double openSeconds = 0;
     string halPath, mafPath, refGenomeName, rootGenomeName, targetGenomes, refSequenceName, refTargetsPath;
     int64_t start = 0, maxBlockLen = 1000;
     uint64_t length = 0;
@@ -145,7 +149,10 @@ int main(int argc, char **argv) {
     int rc = 0;
     try {
         char *err = nullptr;
-        if (halgpu_open(halPath.c_str(), device, &ctx, &err) != 0) {
+        const auto tOpen = std::chrono::steady_clock::now();
+        const int openRc = halgpu_open(halPath.c_str(), device, &ctx, &err);
+        openSeconds = since(tOpen);
+        if (openRc != 0) {
             string m = err ? err : "cannot open";
             halgpu_free_string(err);
             throw runtime_error(m);
@@ -213,13 +220,16 @@ int main(int argc, char **argv) {
         maf.flush();
         if (getenv("HALGPU_TIMING") != nullptr) {
             cerr << "[hal2maf] columns " << ex.columns << ", runs " << ex.runs << ", blocks " << ex.blocks << "; column runs (GPU) " << ex.gpuSeconds
-                 << " s, block state machine " << ex.blockerSeconds << " s, row text " << ex.textSeconds() << " s, write " << ex.writeSeconds() << " s" << endl;
+                 << " s, block state machine " << ex.blockerSeconds << " s, row text " << ex.textSeconds() << " s, write (own thread) " << ex.writeSeconds()
+                 << " s; open (CUDA context) " << openSeconds << " s, total so far " << since(tMain) << " s" << endl;
         }
         if (mafPath != "stdout" && mafFile.tellp() == (streampos)0) std::remove(mafPath.c_str()); // hal2maf.cpp:206-215
     } catch (exception &e) {
         cerr << "hal exception caught: " << e.what() << endl;
         rc = 1;
     }
+    const auto tClose = std::chrono::steady_clock::now();
     halgpu_close(ctx);
+    if (getenv("HALGPU_TIMING") != nullptr) cerr << "[hal2maf] close " << since(tClose) << " s, main() " << since(tMain) << " s" << endl;
     return rc;
 }

@@ -13,6 +13,7 @@
 #include "../../include/halgpu.h"
 #include "comm.hpp"
 #include "engine.hpp"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -28,6 +29,63 @@ struct PackOffParams {
 __global__ void packOffKernel(const PackOffParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) p.off32[i] = (uint32_t)p.off64[i];
+}
+
+// Compact wire form of an output record, 16 bytes instead of 32 (the all-gather is NVLink-bound: bytes are time):
+//   word 0: start (40 bits) | end - start (24 bits)
+//   word 1: src_start (40) | tgt_seq (16) | n_frag (4) | strand (2) | src_strand (2)      strands: '+' 0, '-' 1, '.' 2
+// A batch travels compact only if EVERY record of EVERY rank fits (fitsKernel clears this rank's flag in the header that is
+// exchanged before the gather); otherwise the 32-byte records travel as they are.
+__device__ __forceinline__ bool recFits(const halgpu_lift_rec &r) {
+    return r.start >= 0 && r.start < (1ll << 40) && r.end >= r.start && r.end - r.start < (1ll << 24) && r.src_start >= 0 && r.src_start < (1ll << 40) &&
+           r.tgt_seq >= 0 && r.tgt_seq < (1 << 16) && r.n_frag < 16;
+}
+__device__ __forceinline__ unsigned long long strandCode(uint8_t c) { return c == '+' ? 0ull : (c == '-' ? 1ull : 2ull); }
+__device__ __forceinline__ uint8_t strandChar(unsigned long long c) { return c == 0 ? '+' : (c == 1 ? '-' : '.'); }
+struct WireParams {
+    const halgpu_lift_rec *recs;   // fits / pack: this rank's records
+    unsigned long long *wire;      // pack: 2 words per record; unpack: all ranks' words
+    halgpu_lift_rec *out;          // unpack
+    unsigned long long *fitFlag;   // fits: cleared when a record does not fit
+    int64_t n;
+};
+__global__ void fitsKernel(const WireParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    bool ok = true;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const halgpu_lift_rec r = p.recs[i];
+        ok = ok && recFits(r) && (r.strand == '+' || r.strand == '-' || r.strand == '.') && (r.src_strand == '+' || r.src_strand == '-' || r.src_strand == '.');
+    }
+    if (!ok) *p.fitFlag = 0ull;
+}
+__global__ void packRecKernel(const WireParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const halgpu_lift_rec r = p.recs[i];
+        p.wire[2 * i] = (unsigned long long)r.start | ((unsigned long long)(r.end - r.start) << 40);
+        p.wire[2 * i + 1] = (unsigned long long)r.src_start | ((unsigned long long)(uint32_t)r.tgt_seq << 40) | ((unsigned long long)r.n_frag << 56) |
+                            (strandCode(r.strand) << 60) | (strandCode(r.src_strand) << 62);
+    }
+}
+__global__ void unpackRecKernel(const WireParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const unsigned long long m40 = (1ull << 40) - 1ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const unsigned long long a = p.wire[2 * i], b = p.wire[2 * i + 1];
+        halgpu_lift_rec r;
+        r.start = (int64_t)(a & m40); r.end = r.start + (int64_t)(a >> 40);
+        r.src_start = (int64_t)(b & m40); r.tgt_seq = (int32_t)((b >> 40) & 0xffffull); r.n_frag = (uint16_t)((b >> 56) & 0xfull);
+        r.strand = strandChar((b >> 60) & 3ull); r.src_strand = strandChar(b >> 62);
+        p.out[i] = r;
+    }
+}
+struct IdentityOffParams {
+    uint64_t *off64;
+    int64_t n; // writes n + 1 entries
+};
+__global__ void identityOffKernel(const IdentityOffParams p) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= p.n; i += step) p.off64[i] = (uint64_t)i;
 }
 
 #define HG_MAX_RANKS 64
@@ -64,6 +122,8 @@ struct halgpu_gather {
     std::vector<uint64_t> n, nRec; // per rank
     uint32_t *wireOff = nullptr;   // all ranks' 32-bit offsets
     uint32_t *sendOff = nullptr;
+    unsigned long long *sendWire = nullptr, *recvWire = nullptr; // compact records (16 bytes each), when every rank's fit
+    bool compact = false, identity = false;
     uint64_t *offsets = nullptr;   // global CSR
     halgpu_lift_rec *recs = nullptr;
     std::unique_ptr<rt::Event> ready, done;
@@ -149,8 +209,17 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             if (g->local.nRec >= 0xffffffffull) throw HalError("a shard produced 2^32 or more records; use smaller batches");
             // 1. every rank learns every shard's size (one 32-byte header per rank; the only host round trip of the gather)
             uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * 32));
-            uint64_t mine[4] = {(uint64_t)n, (uint64_t)g->local.nRec, 0, 0};
+            // header: intervals, records, "all my records fit the compact wire form", "my offsets are the identity"
+            const bool myIdentity = g->local.fastMs > 0 && g->local.nComplex == 0 && g->local.nRec == n;
+            const bool wantCompact = std::getenv("HALGPU_GATHER_WIRE32") == nullptr; // measurement switch: always send 32-byte records
+            uint64_t mine[4] = {(uint64_t)n, (uint64_t)g->local.nRec, wantCompact ? 1u : 0u, myIdentity ? 1u : 0u};
             rt::h2d(dHdr + (size_t)W * 4, mine, 32, cm->stream);
+            if (wantCompact && g->local.nRec > 0) {
+                WireParams fp;
+                std::memset(&fp, 0, sizeof(fp));
+                fp.recs = g->local.recs; fp.n = (int64_t)g->local.nRec; fp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * 4 + 2);
+                rt::launch(fitsKernel, gridOf(fp.n, 256), 256, 0, cm->stream, fp);
+            }
             rt::commAllGather(cm->comm, dHdr + (size_t)W * 4, dHdr, 32, cm->stream);
             rt::d2h(cm->hostHdr, dHdr, (size_t)W * 32, cm->stream);
             rt::sync(cm->stream);
@@ -158,32 +227,49 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             g->n.resize((size_t)W); g->nRec.resize((size_t)W);
             uint64_t nTotal = 0, recTotal = 0, maxN = 0;
             bool uniform = true;
+            g->compact = true; g->identity = true;
             for (int r = 0; r < W; ++r) {
                 g->n[(size_t)r] = cm->hostHdr[4 * r]; g->nRec[(size_t)r] = cm->hostHdr[4 * r + 1];
+                g->compact = g->compact && cm->hostHdr[4 * r + 2] == 1;
+                g->identity = g->identity && cm->hostHdr[4 * r + 3] == 1;
                 nTotal += g->n[(size_t)r]; recTotal += g->nRec[(size_t)r];
                 maxN = std::max(maxN, g->n[(size_t)r]);
                 uniform = uniform && g->n[(size_t)r] == g->n[0] && g->nRec[(size_t)r] == g->nRec[0];
             }
-            // 2. this rank's offsets in wire form
-            g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4));
-            g->wireOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4 * (size_t)W));
+            if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] gather rank %d: compact %d identity %d uniform %d records %llu\n", me, (int)g->compact, (int)g->identity, (int)uniform, (unsigned long long)recTotal);
+            // 2. this rank's offsets (unless every rank's are the identity) and records in wire form
             g->offsets = static_cast<uint64_t *>(cache.take((size_t)(nTotal + 2) * 8));
             g->recs = static_cast<halgpu_lift_rec *>(cache.take(std::max<uint64_t>(recTotal, 1) * sizeof(halgpu_lift_rec)));
-            PackOffParams pp;
-            pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
-            rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+            if (!g->identity) {
+                g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4));
+                g->wireOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4 * (size_t)W));
+                PackOffParams pp;
+                pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
+                rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+            }
+            if (g->compact) {
+                g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
+                g->recvWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(recTotal, 1) * 16));
+                WireParams wp;
+                std::memset(&wp, 0, sizeof(wp));
+                wp.recs = g->local.recs; wp.wire = g->sendWire; wp.n = (int64_t)g->local.nRec;
+                rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
+            }
             g->ready.reset(new rt::Event);
             g->done.reset(new rt::Event);
             g->ready->record(C.stream());
             g->ready->wait(cm->stream);
             // 3. the gather: offsets and records, fused into one NCCL group
+            const void *sendRecs = g->compact ? (const void *)g->sendWire : (const void *)g->local.recs;
+            void *recvRecs = g->compact ? (void *)g->recvWire : (void *)g->recs;
+            const size_t recBytes = g->compact ? 16 : sizeof(halgpu_lift_rec);
             rt::commGroupStart();
             if (uniform) {
-                rt::commAllGather(cm->comm, g->sendOff, g->wireOff, (size_t)g->n[0] * 4, cm->stream);
-                rt::commAllGather(cm->comm, g->local.recs, g->recs, (size_t)g->nRec[0] * sizeof(halgpu_lift_rec), cm->stream);
+                if (!g->identity) rt::commAllGather(cm->comm, g->sendOff, g->wireOff, (size_t)g->n[0] * 4, cm->stream);
+                rt::commAllGather(cm->comm, sendRecs, recvRecs, (size_t)g->nRec[0] * recBytes, cm->stream);
             } else {
-                rt::commAllGatherV(cm->comm, g->sendOff, g->wireOff, g->n, 4, (maxN + 1), cm->stream);
-                rt::commAllGatherV(cm->comm, g->local.recs, g->recs, g->nRec, sizeof(halgpu_lift_rec), 0, cm->stream);
+                if (!g->identity) rt::commAllGatherV(cm->comm, g->sendOff, g->wireOff, g->n, 4, (maxN + 1), cm->stream);
+                rt::commAllGatherV(cm->comm, sendRecs, recvRecs, g->nRec, recBytes, 0, cm->stream);
             }
             rt::commGroupEnd();
             g->done->record(cm->stream);
@@ -192,6 +278,7 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             try { rt::sync(cm->stream); } catch (...) {}
             C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
             cache.give(g->sendOff); cache.give(g->wireOff); cache.give(g->offsets); cache.give(g->recs);
+            cache.give(g->sendWire); cache.give(g->recvWire);
             throw;
         }
         *out = g.release();
@@ -218,7 +305,19 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
             up.wireBase[r] = uniform ? up.ivBase[r] : (int64_t)r * (int64_t)(maxN + 1);
         }
         g->done->wait(C.stream()); // the engine's stream continues once the gather has landed
-        rt::launch(unpackOffKernel, gridOf(up.ivBase[W] + 1, 256), 256, 0, C.stream(), up);
+        if (g->identity) {
+            IdentityOffParams ip;
+            ip.off64 = g->offsets; ip.n = up.ivBase[W];
+            rt::launch(identityOffKernel, gridOf(ip.n + 1, 256), 256, 0, C.stream(), ip);
+        } else {
+            rt::launch(unpackOffKernel, gridOf(up.ivBase[W] + 1, 256), 256, 0, C.stream(), up);
+        }
+        if (g->compact) {
+            WireParams wp;
+            std::memset(&wp, 0, sizeof(wp));
+            wp.wire = g->recvWire; wp.out = g->recs; wp.n = (int64_t)up.recBase[W];
+            if (wp.n > 0) rt::launch(unpackRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
+        }
         rt::sync(C.stream());
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = (size_t)up.ivBase[W]; r->n_rec = (size_t)up.recBase[W]; r->offsets = g->offsets; r->recs = g->recs; r->on_device = 1;
@@ -234,6 +333,7 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
     if (rc != 0) { try { rt::sync(cm->stream); } catch (...) {} }
     C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
     C.cache().give(g->sendOff); C.cache().give(g->wireOff); C.cache().give(g->offsets); C.cache().give(g->recs);
+    C.cache().give(g->sendWire); C.cache().give(g->recvWire);
     delete g;
     return rc;
 }

@@ -66,3 +66,30 @@ def test_emulated_allgather_equals_single_lift(emul_lib, sizes, maxlen):
             assert np.array_equal(goff, off), f"rank {r}: gathered offsets differ"
             assert np.array_equal(grecs, recs), f"rank {r}: gathered records differ"
             assert sum(nrr) == len(recs)
+
+
+@pytest.mark.parametrize("wire32", [False, True])
+def test_emulated_allgather_collinear_uniform_shards(emul_lib, tmp_path, monkeypatch, wire32):
+    """equal shards of a collinear alignment: every interval ends in the one-lane-per-interval kernel, the offsets are the
+    identity on every rank (not sent) and the records travel in compact 16-byte form -- or, with HALGPU_GATHER_WIRE32, as
+    they are"""
+    import subprocess
+    import hal_b200
+    from conftest import ROOT
+    from hal_b200 import build
+    build.build()
+    if wire32:
+        monkeypatch.setenv("HALGPU_GATHER_WIRE32", "1")
+    hal = str(tmp_path / "flat.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", "((L0,L1)A0,(L2)A1)R;", "--segs", "3000", "--segLen", "16", hal])
+    a = hal_b200.Alignment(hal, lib_path=emul_lib)
+    s, t = a.genome_id("L0"), a.genome_id("L2")
+    shards = [random_intervals(a.genome_length(s) - 32, 200, 300, seed=3 + r, strands=b"+-") for r in range(2)]
+    gs, ge, st = (np.concatenate([sh[k] for sh in shards]) for k in range(3))
+    off, recs, info = a.liftover(s, t, gs, ge, st)
+    a.close()
+    assert info["n_complex"] == 0 and np.array_equal(off, np.arange(401, dtype=np.uint64))
+    out = _run_ranks(emul_lib, hal, "L0", "L2", shards)
+    for r in range(2):
+        goff, grecs, npr, nrr = out[r][0]
+        assert np.array_equal(goff, off) and np.array_equal(grecs, recs)

@@ -81,5 +81,19 @@ h)  # source-level profile of the warp-per-interval walk on the divergent file (
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:'liftoverKernel' -s 3 -c 1 -o gpurun_out/prof_h_walk -f \
         python tools/walk_profile.py > gpurun_out/prof_h.log 2> gpurun_out/prof_h.err
     ;;
+i)  # 1-GPU experiments: sort granularity, CLI / hal2maf breakdowns after the text pipeline changes
+    Q="--steps 20 --warmup 5 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth --no-divergent --no-traffic"
+    python bench.py $Q > gpurun_out/bench_i_default.json 2> gpurun_out/bench_i.err
+    HALGPU_SORT_BITS=8 python bench.py $Q > gpurun_out/bench_i_sort8.json 2>> gpurun_out/bench_i.err
+    HALGPU_SORT_BITS=24 python bench.py $Q > gpurun_out/bench_i_sort24.json 2>> gpurun_out/bench_i.err
+    HALGPU_PACKED_SORT=1 python bench.py $Q > gpurun_out/bench_i_packed.json 2>> gpurun_out/bench_i.err
+    for f in default sort8 sort24 packed; do python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_i_$f.json').read().strip().splitlines()[-1])
+print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'fast_ms %.4f' % d['detail']['fast_kernel_ms'], 'e2e %.4g' % d['e2e']['value'], d['check'])
+"; done
+    bash tools/gpu_r2.sh e
+    bash tools/gpu_r2.sh h
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
