@@ -207,18 +207,21 @@ Context::Context(const std::string &path, int device) : _file(new HalFile(path))
     _stream = rt::createStream();
     _copy = rt::createStream();
     _copyBack = rt::createStream();
+    _aux = rt::createStream();
     _sms = rt::smCount();
     _g.resize(_file->genomes().size());
     try {
         _stager.reset(new Stager(path));
         _hostCtr = static_cast<unsigned long long *>(rt::hostAlloc(32 * sizeof(unsigned long long)));
         for (auto &e : _ev) e.reset(new rt::Event);
+        for (auto &e : _sliceEv) e.reset(new rt::Event);
         if (std::getenv("HALGPU_EAGER_STAGE") != nullptr) ensureAll(true);
     } catch (...) {
         for (void *p : _owned) rt::dfree(p);
         rt::destroyStream(_stream);
         rt::destroyStream(_copy);
         rt::destroyStream(_copyBack);
+        rt::destroyStream(_aux);
         throw;
     }
 }
@@ -231,6 +234,7 @@ Context::~Context() {
     rt::destroyStream(_stream);
     rt::destroyStream(_copy);
     rt::destroyStream(_copyBack);
+    rt::destroyStream(_aux);
 }
 
 void Context::buildBucket(const void *arr, bool isTop, int64_t N, int64_t len, uint32_t *&table, int &shift, int64_t &nb) {
@@ -736,7 +740,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
     Lease L(_cache);
     try {
-        enum { C_POOL = 0, C_COLLECT = 1, C_TILE = 2, C_COMPLEX = 3, C_FAIL = 4, C_TOTAL = 8, C_WORDS = 16 };
+        enum { C_POOL = 0, C_COLLECT = 1, C_TILE = 2, C_COMPLEX = 3, C_FAIL = 4, C_TOTAL = 8, C_TILE_CHUNK = 9 /* .. 12 */, C_WORDS = 16 };
         unsigned long long *outLoc = L.as<unsigned long long>(n + 2);
         uint32_t *status = L.as<uint32_t>(n + 1);
         unsigned long long *ctr = L.as<unsigned long long>(C_WORDS);
@@ -755,14 +759,25 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // r02_bench_n1_f.json): CUB's onesweep pass takes ~100 us for 10 M elements either way, while the lane kernel then has to
         // fetch every interval's end with a scattered read (+50 us): off by default.
         const bool packed = sorting && S.length < 0xffffffffll && std::getenv("HALGPU_PACKED_SORT") != nullptr;
+        // A large batch is sorted in up to four slices on a second stream, so that the lane kernel of slice c (main stream) runs
+        // while slice c+1 is being sorted; slices only bound the sort and the kernel launches, everything else sees one batch.
+        int nSlices = (fast && sorting && !packed) ? (n >= (4u << 20) ? 4 : (n >= (2u << 20) ? 2 : 1)) : 1;
+        if (const char *fs = std::getenv("HALGPU_SLICES")) { // test hook
+            if (fast && sorting && !packed) nSlices = std::max(1, std::min(4, std::atoi(fs)));
+        }
+        if ((size_t)nSlices > n) nSlices = 1;
+        size_t sliceLo[5];
+        for (int c = 0; c <= nSlices; ++c) sliceLo[c] = n * (size_t)c / (size_t)nSlices;
         if (sorting || fast) {
+            const rt::Stream ss = nSlices > 1 ? _aux : _stream;
+            if (nSlices > 1) { _sliceEv[4]->record(_stream); _sliceEv[4]->wait(_aux); } // behind the memsets above
             IotaParams ip;
             std::memset(&ip, 0, sizeof(ip));
             uint64_t *keysIn = nullptr, *valsIn = nullptr;
             if (sorting) { keysIn = L.as<uint64_t>(n); if (!packed) valsIn = L.as<uint64_t>(n); }
             ip.vals = valsIn; ip.keys = packed ? nullptr : keysIn; ip.packed = packed ? keysIn : nullptr;
             ip.gs = dGs; ip.ge = dGe; ip.directLoc = fast ? outLoc : nullptr; ip.n = (int64_t)n;
-            rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, ip);
+            rt::launch(iotaKeysKernel, gridFor((int64_t)n, 256, _sms), 256, 0, ss, ip);
             if (sorting) {
                 uint64_t *keysOut = L.as<uint64_t>(n), *valsOut = packed ? nullptr : L.as<uint64_t>(n);
                 int endBit = 1;
@@ -775,14 +790,20 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 const int beginBit = std::max(0, endBit - bits);
                 size_t tmpBytes = 0;
                 if (packed) {
-                    rt::sortKeysU64Tmp(nullptr, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, _stream);
+                    rt::sortKeysU64Tmp(nullptr, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, ss);
                     void *tmp = L.take(tmpBytes);
-                    rt::sortKeysU64Tmp(tmp, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, _stream);
+                    rt::sortKeysU64Tmp(tmp, tmpBytes, keysIn, keysOut, n, 32 + beginBit, 32 + endBit, ss);
                     sortedKey = reinterpret_cast<const unsigned long long *>(keysOut);
                 } else {
-                    rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                    const size_t widest = sliceLo[1] - sliceLo[0] + 1;
+                    rt::sortPairsU64U64Tmp(nullptr, tmpBytes, keysIn, keysOut, valsIn, valsOut, widest, beginBit, endBit, ss);
                     void *tmp = L.take(tmpBytes);
-                    rt::sortPairsU64U64Tmp(tmp, tmpBytes, keysIn, keysOut, valsIn, valsOut, n, beginBit, endBit, _stream);
+                    for (int c = 0; c < nSlices; ++c) { // (the slices' sorts run one after the other: one temporary buffer)
+                        const size_t lo = sliceLo[c], cnt = sliceLo[c + 1] - lo;
+                        size_t tb = tmpBytes;
+                        rt::sortPairsU64U64Tmp(tmp, tb, keysIn + lo, keysOut + lo, valsIn + lo, valsOut + lo, cnt, beginBit, endBit, ss);
+                        if (nSlices > 1) _sliceEv[c]->record(ss);
+                    }
                     sortedGs = reinterpret_cast<const unsigned long long *>(keysOut);
                     sortedVal = reinterpret_cast<const unsigned long long *>(valsOut);
                 }
@@ -844,9 +865,19 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             F.sortedGs = sortedGs; F.sortedVal = sortedVal; F.sortedKey = sortedKey;
             F.tileCursor = ctr + C_TILE; F.pool = pool;
             F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
-            const int64_t tiles = ((int64_t)n + 31) / 32;
-            const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)_sms * 8));
-            rt::launch(fastLiftKernel, fgrid, 256, 0, _stream, F);
+            for (int c = 0; c < nSlices; ++c) {
+                const size_t lo = sliceLo[c], cnt = sliceLo[c + 1] - lo;
+                if (cnt == 0) continue;
+                if (nSlices > 1) _sliceEv[c]->wait(_stream); // this slice is sorted
+                FastParams Fc = F;
+                Fc.n = (int64_t)cnt;
+                if (sortedGs) { Fc.sortedGs = sortedGs + lo; Fc.sortedVal = sortedVal + lo; }
+                if (sortedKey) Fc.sortedKey = sortedKey + lo;
+                Fc.tileCursor = nSlices > 1 ? ctr + C_TILE_CHUNK + c : ctr + C_TILE;
+                const int64_t tiles = ((int64_t)cnt + 31) / 32;
+                const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)_sms * 8));
+                rt::launch(fastLiftKernel, fgrid, 256, 0, _stream, Fc);
+            }
             _ev[1]->record(_stream);
         }
         {
@@ -1031,7 +1062,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         out.nRec = (size_t)_hostCtr[C_TOTAL];
         out.launches = (int)rt::g_launches - launches0;
     } catch (...) {
-        try { rt::sync(_stream); } catch (...) {} // nothing of this batch may still run when its buffers return to the cache
+        try { rt::sync(_aux); rt::sync(_stream); } catch (...) {} // nothing of this batch may still run when its buffers return to the cache
         throw;
     }
 }

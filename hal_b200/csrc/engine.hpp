@@ -135,7 +135,7 @@ class Context {
 
     std::unique_ptr<HalFile> _file;
     int _device;
-    rt::Stream _stream, _copy, _copyBack;
+    rt::Stream _stream, _copy, _copyBack, _aux; // _aux: sorts slice c+1 of a batch while the lane kernel runs slice c
     std::vector<GenomeDev> _g;
     std::map<std::tuple<int, int, int>, Plan> _plans; // (src, tgt, coalescence limit or -1)
     std::vector<void *> _owned;
@@ -144,7 +144,7 @@ class Context {
     DeviceCache _cache;
     std::unique_ptr<Stager> _stager;
     unsigned long long *_hostCtr = nullptr; // pinned: the counters of one batch, read back with its single synchronisation
-    std::unique_ptr<rt::Event> _ev[4];
+    std::unique_ptr<rt::Event> _ev[4], _sliceEv[5];
 };
 
 } // namespace halgpu

@@ -146,14 +146,22 @@ __device__ __forceinline__ bool canMergeRight(const Frag &p, const Frag &q) {
     return p.sLo - (q.sLo + q.len - 1) == 1;
 }
 
-// stable rank sort of src[0..m) into dst by fragLess (ties keep list order)
+// stable rank sort of src[0..m) into dst by fragLess (ties keep list order).  The rank of an element is the number of
+// elements before it in that order; nearly all pairs are decided by the target start alone, so the inner loop reads just
+// that field (one shared-memory broadcast) and falls back to the full comparison only on equal starts.
 __device__ __forceinline__ void warpRankSort(const Frag *src, Frag *dst, int m, int lane) {
     for (int i = lane; i < m; i += 32) {
         const Frag me = src[i];
+        const int64_t myT = me.tLo;
         int r = 0;
         for (int j = 0; j < m; ++j) {
-            const Frag o = src[j];
-            r += (fragLess(o, me) || (!fragLess(me, o) && j < i)) ? 1 : 0;
+            const int64_t ot = src[j].tLo;
+            if (ot < myT) {
+                ++r;
+            } else if (ot == myT) {
+                const Frag o = src[j];
+                r += (fragLess(o, me) || (!fragLess(me, o) && j < i)) ? 1 : 0;
+            }
         }
         dst[r] = me;
     }
@@ -796,13 +804,19 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
         if (lane == 0) liftFail(P, item, ST_POOL_FULL);
         return;
     }
+    // source start of every line first (qcut's slots are free after the merge scan: 8 bytes per line), then rank on those
+    int64_t *lineSrc = qcut;
+    for (int r = lane; r < nLines; r += 32) {
+        const int64_t a = cur[runHead[r]].sLo, b = cur[runTail[r]].sLo;
+        lineSrc[r] = a < b ? a : b;
+    }
+    __syncwarp();
     for (int r = lane; r < nLines; r += 32) {
         const Frag h = cur[runHead[r]], t = cur[runTail[r]];
-        const int64_t src = h.sLo < t.sLo ? h.sLo : t.sLo;
+        const int64_t src = lineSrc[r];
         int rank = 0;
         for (int j = 0; j < nLines; ++j) {
-            const Frag hj = cur[runHead[j]], tj = cur[runTail[j]];
-            const int64_t sj = hj.sLo < tj.sLo ? hj.sLo : tj.sLo;
+            const int64_t sj = lineSrc[j];
             rank += (sj < src || (sj == src && j < r)) ? 1 : 0;
         }
         const int seq = (int)(h.meta >> 3);
