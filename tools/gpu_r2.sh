@@ -95,5 +95,17 @@ print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'f
     bash tools/gpu_r2.sh e
     bash tools/gpu_r2.sh h
     ;;
+j)  # quick N=1 bench variants (sliced sort on/off) + liftover GPU tests + divergent walk timing
+    timeout 900 python -m pytest tests/test_liftover_gpu.py -x -q -m gpu > gpurun_out/pytest_j.log 2>&1; tail -3 gpurun_out/pytest_j.log
+    Q="--steps 20 --warmup 5 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth --no-traffic"
+    python bench.py $Q > gpurun_out/bench_j_default.json 2> gpurun_out/bench_j.err
+    HALGPU_SLICES=1 python bench.py $Q --no-divergent > gpurun_out/bench_j_slices1.json 2>> gpurun_out/bench_j.err
+    HALGPU_SLICES=2 python bench.py $Q --no-divergent > gpurun_out/bench_j_slices2.json 2>> gpurun_out/bench_j.err
+    for f in default slices1 slices2; do python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_j_$f.json').read().strip().splitlines()[-1])
+print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'fast_ms %.4f' % d['detail']['fast_kernel_ms'], 'e2e %.4g' % d['e2e']['value'], d['check'], (d.get('secondary_divergent') or {}).get('value'), (d.get('secondary_divergent') or {}).get('kernel_ms'), (d.get('secondary_divergent') or {}).get('check'))
+"; done
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
