@@ -595,6 +595,14 @@ def main():
         step_e2e()
     barrier()
     e2e_s = (time.perf_counter() - w0) / args.steps
+    # latency of the smallest call (what a one-interval-per-liftInterval binding pays): n = 1, host buffers
+    one_s, one_e = np.array([gs[0]], np.int64), np.array([ge[0]], np.int64)
+    for _ in range(50):
+        a.liftover(src, tgt, one_s, one_e)
+    w0 = time.perf_counter()
+    for _ in range(500):
+        a.liftover_ptrs(src, tgt, 1, one_s.ctypes.data, one_e.ctypes.data, None, 0, device=False).close()
+    call_us = (time.perf_counter() - w0) / 500 * 1e6
 
     # BASELINE.json configs[4] on N > 1 GPUs: the halAlignmentDepth sweep of the whole reference genome, one window per rank,
     # ONE all-gather of the per-column values (hal_b200/parallel.py); strong scaling: the sweep is the same 50 M columns
@@ -693,7 +701,7 @@ def main():
         "check": check,
         "detail": {"output_lines_per_step": int(n_rec_last), "retry_intervals": int(last_info.get("n_retry") or 0), "wall_s_per_step": wall / args.steps,
                    "stage_seconds": stage_s, "staged_bytes": staged_bytes, "mapping_kernels_ms": kmean, "kernel_share_of_step": kmean / ms_step,
-                   "fast_kernel_ms": fast_ms, "complex_intervals": n_complex,
+                   "fast_kernel_ms": fast_ms, "complex_intervals": n_complex, "single_interval_call_us": call_us,
                    "step_wall_ms": {"median": sw[len(sw) // 2], "p95": sw[min(len(sw) - 1, int(0.95 * len(sw)))], "max": sw[-1], "all": [round(x, 3) for x in step_wall]},
                    "oracle_sample_stats": ostats},
     }

@@ -759,10 +759,12 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // r02_bench_n1_f.json): CUB's onesweep pass takes ~100 us for 10 M elements either way, while the lane kernel then has to
         // fetch every interval's end with a scattered read (+50 us): off by default.
         const bool packed = sorting && S.length < 0xffffffffll && std::getenv("HALGPU_PACKED_SORT") != nullptr;
-        // A large batch is sorted in up to four slices on a second stream, so that the lane kernel of slice c (main stream) runs
-        // while slice c+1 is being sorted; slices only bound the sort and the kernel launches, everything else sees one batch.
-        int nSlices = (fast && sorting && !packed) ? (n >= (4u << 20) ? 4 : (n >= (2u << 20) ? 2 : 1)) : 1;
-        if (const char *fs = std::getenv("HALGPU_SLICES")) { // test hook
+        // HALGPU_SLICES=k (measurement switch, default 1): sort the batch in k slices on a second stream so that the lane kernel of
+        // slice c runs while slice c+1 is being sorted.  Measured on 10 M intervals (profiles/r02_bench_n1_slices*.json): one
+        // slice 0.776 ms per step, two 0.862 ms, four 1.052 ms -- the two kernels compete for the same L2 / DRAM queues and the
+        // shorter launches lose more at their tails than the overlap wins, so the product path keeps one slice.
+        int nSlices = 1;
+        if (const char *fs = std::getenv("HALGPU_SLICES")) {
             if (fast && sorting && !packed) nSlices = std::max(1, std::min(4, std::atoi(fs)));
         }
         if ((size_t)nSlices > n) nSlices = 1;
