@@ -120,7 +120,7 @@ struct LiftParams {
     // outputs
     unsigned long long *outLoc; // per interval: (first record in pool << LOC_COUNT_BITS) | number of records; 0 until written
     uint32_t *status;        // per interval: ST_* (zeroed == ST_OK by the engine; only failures are written)
-    unsigned long long *failCount; // 4 counters indexed by ST_*: intervals that ended in that state (ST_OK is not counted)
+    unsigned long long *failCount; // 5 counters indexed by ST_*: intervals that ended in that state (ST_OK is not counted)
     halgpu_lift_rec *pool;
     uint32_t *pslPool;        // optional (HALGPU_PSL): 4 counters per pool record (matches, misMatches, repMatches, nCount), zeroed
     const uint8_t *srcDna, *tgtDna; // packed nibbles of the source / target genome (PSL only)
@@ -171,7 +171,7 @@ struct ColRowRec { // 16 B
 static const unsigned long long WIG_UNSET = 0x7fffffffffffffffull;
 static const unsigned long long WIG_ZERO = 0x8000000000000000ull;
 
-enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2, ST_BAD_INPUT = 3 };
+enum : uint32_t { ST_OK = 0, ST_SCRATCH_OVERFLOW = 1, ST_POOL_FULL = 2, ST_BAD_INPUT = 3, ST_REDO_EXACT = 4 /* fused walk (LIFT_FUSE) only */ };
 #define HG_LOC_COUNT_BITS 25 // an interval yields at most 2^24 records (engine.cu: listCap ladder)
 
 // fastLiftKernel (liftover_kernel.cuh): one LANE per interval.  An interval whose whole source range maps through every

@@ -740,7 +740,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
 
     Lease L(_cache);
     try {
-        enum { C_POOL = 0, C_COLLECT = 1, C_TILE = 2, C_COMPLEX = 3, C_FAIL = 4, C_TOTAL = 8, C_TILE_CHUNK = 9 /* .. 12 */, C_WORDS = 16 };
+        enum { C_POOL = 0, C_COLLECT = 1, C_TILE = 2, C_COMPLEX = 3, C_FAIL = 4 /* .. 8, indexed by ST_* */, C_TOTAL = 9, C_TILE_CHUNK = 10 /* .. 13 */, C_WORDS = 16 };
         unsigned long long *outLoc = L.as<unsigned long long>(n + 2);
         uint32_t *status = L.as<uint32_t>(n + 1);
         unsigned long long *ctr = L.as<unsigned long long>(C_WORDS);
@@ -850,6 +850,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // HALGPU_SEED_TILE=1 (measurement switch): TMA-staged seed tiles, see liftover_kernel.cuh and DESIGN.md
         const char *tileEnv = std::getenv("HALGPU_SEED_TILE");
         const bool seedTile = !wig && !raw && !coalPath && srcIsTop && tileEnv != nullptr && tileEnv[0] == '1';
+        // the fused walk (whole collinear runs per fragment, liftover_kernel.cuh) runs the first pass over plain BED batches; what
+        // it flags ST_REDO_EXACT, and every retry rung, is walked piece by piece by the plain instantiation
+        const bool fuse = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !seedTile && !(flags & HALGPU_NO_FAST) && pl.fastOk &&
+                          std::getenv("HALGPU_NO_FUSE") == nullptr;
+        void (*const firstKernel)(const LiftParams) = fuse ? liftoverKernel<LIFT_BED | LIFT_FUSE> : nullptr;
         void (*const mapKernel)(const LiftParams) =
             seedTile ? liftoverKernel<LIFT_BED | LIFT_TILE> : wig ? liftoverKernel<LIFT_WIG>
                 : (raw ? (coalPath ? liftoverKernel<LIFT_RAW_COAL> : liftoverKernel<LIFT_RAW>) : (coalPath ? liftoverKernel<LIFT_COAL> : liftoverKernel<LIFT_BED>));
@@ -890,7 +895,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             P.seedTile = seedTile ? 1 : 0;
             const size_t smem = ((size_t)liftScratchBytes(P.listCap, P.frameCap) + (P.seedTile ? (size_t)seedTileBytes() : 0)) * warpsPerBlock;
             rt::allowSmem(mapKernel, smem);
-            rt::launch(mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
+            if (firstKernel) rt::allowSmem(firstKernel, smem);
+            rt::launch(firstKernel ? firstKernel : mapKernel, gridFor((int64_t)n, warpsPerBlock, _sms * 2), block, smem, _stream, P);
             P.work = nullptr; P.work64 = nullptr; P.nDev = nullptr;
         }
         _ev[2]->record(_stream);
@@ -967,14 +973,18 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             if (fails[ST_BAD_INPUT] > 0) {
                 throw HalError(std::to_string(fails[ST_BAD_INPUT]) + " interval(s) lie outside genome " + S.name + " (length " + std::to_string(S.length) + ")");
             }
-            if (fails[ST_POOL_FULL] == 0 && fails[ST_SCRATCH_OVERFLOW] == 0) break;
+            if (fails[ST_POOL_FULL] == 0 && fails[ST_SCRATCH_OVERFLOW] == 0 && fails[ST_REDO_EXACT] == 0) break;
             redo = true;
             rt::Event r0, r1;
-            // (a) intervals that found the output pool full: grow it (old records stay valid) and redo them
-            const uint64_t nFull = fails[ST_POOL_FULL] ? collect(ST_POOL_FULL) : 0;
+            // (a) intervals the fused walk handed back, and intervals that found the output pool full (grow it: old records stay
+            //     valid): redo them with the plain walk
+            const uint32_t want = fails[ST_REDO_EXACT] ? (uint32_t)ST_REDO_EXACT : (uint32_t)ST_POOL_FULL;
+            const uint64_t nFull = (fails[ST_REDO_EXACT] || fails[ST_POOL_FULL]) ? collect(want) : 0;
             if (nFull > 0) {
+                if (want == ST_REDO_EXACT) out.nRedo += nFull;
                 const uint64_t used = _hostCtr[C_POOL];
-                const uint64_t newCap = std::max<uint64_t>(poolCap * 2, used * 2);
+                const uint64_t newCap = want == ST_REDO_EXACT ? poolCap : std::max<uint64_t>(poolCap * 2, used * 2);
+                if (newCap != poolCap) {
                 halgpu_lift_rec *np = L.as<halgpu_lift_rec>(newCap);
                 rt::d2d(np, pool, poolCap * sizeof(halgpu_lift_rec), _stream);
                 if (wantPsl) { // counters of the records already written move along; the new tail starts at zero
@@ -991,9 +1001,10 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
                 pool = np;
                 poolCap = newCap;
                 P.pool = pool; P.poolCap = poolCap;
+                }
                 uint32_t *ids = L.as<uint32_t>(nFull);
                 rt::d2d(ids, list, nFull * sizeof(uint32_t), _stream);
-                rt::dmemset(ctr + C_FAIL + ST_POOL_FULL, 0, sizeof(unsigned long long), _stream); // all of them run again
+                rt::dmemset(ctr + C_FAIL + want, 0, sizeof(unsigned long long), _stream); // all of them run again
                 P.n = (int64_t)nFull; P.work = ids;
                 const bool inSmem = listCap == 64;
                 const uint64_t per = liftScratchBytes(listCap, frameCap);

@@ -46,6 +46,7 @@ struct LiftOutput { // device-side result of one batch; the buffers belong to th
     uint32_t *psl = nullptr;     // 4 per record when HALGPU_PSL
     size_t n = 0, nRec = 0, nRetry = 0;
     size_t nComplex = 0;         // intervals the one-lane-per-interval kernel handed to the warp-per-interval walk
+    size_t nRedo = 0;            // intervals the fused walk handed back to the piece-by-piece walk
     float kernelMs = 0;          // mapping kernels of the batch (fast + walk + retries)
     float fastMs = 0;            // fastLiftKernel alone (0 when the batch did not use it)
     int launches = 0;

@@ -210,12 +210,25 @@ __device__ __forceinline__ void tileWait(uint32_t bar, uint32_t phase) {
 }
 #endif
 
+// index of the segment of genome st that holds position pos: bucket table + gallop
+template <bool TOP> __device__ __forceinline__ int64_t locateSeg(const PathStep &st, int64_t pos) {
+    if (TOP) return searchFrom<true>(st.top, (int64_t)__ldg(&st.topBucket[pos >> st.topShift]), st.numTop, pos);
+    return searchFrom<false>(st.bot, (int64_t)__ldg(&st.botBucket[pos >> st.botShift]), st.numBot, pos);
+}
+
 // MODE: the wiggle mode, the coalescence-limit path and the raw-fragment mode are separate instantiations so that the
 // default BED path's code and register allocation are untouched by them
-enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 4, LIFT_RAW_COAL = 6, LIFT_TILE = 8 }; // COAL, RAW and TILE are bits
+enum : int { LIFT_BED = 0, LIFT_WIG = 1, LIFT_COAL = 2, LIFT_RAW = 4, LIFT_RAW_COAL = 6, LIFT_TILE = 8, LIFT_FUSE = 16 }; // COAL, RAW, TILE and FUSE are bits
 template <int MODE>
 __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch &ws, uint32_t item, int lane) {
     constexpr bool WIG = MODE == LIFT_WIG, COAL = (MODE & LIFT_COAL) != 0, RAW = (MODE & LIFT_RAW) != 0, TILE = (MODE & LIFT_TILE) != 0;
+    // FUSE: fragments follow whole collinear runs of the vertical links (device_index.cuh) instead of being cut at every segment
+    // boundary.  A fused fragment is the union of reference fragments that are images of one affine map and adjacent on both
+    // sides; if the interval's fused fragments are pairwise disjoint in the target (and none crosses a target sequence
+    // boundary) so are the reference's, extractSegment merges exactly the chains of neighbours that merge here, and the output
+    // lines are identical.  Phase 2 checks that; an interval that fails the check is flagged ST_REDO_EXACT and re-walked piece by
+    // piece by the plain instantiation.
+    constexpr bool FUSE = (MODE & LIFT_FUSE) != 0;
     const int64_t gs = ldS(&P.gs[item]), ge = ldS(&P.ge[item]);
     const uint8_t bedStrand = P.strand ? P.strand[item] : (uint8_t)'+';
     const bool flip = bedStrand == '-';
@@ -254,6 +267,11 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
     }
 #endif
 
+    // FUSE: seeds are whole runs of the source genome's first transition (parent links of its tops when the path starts
+    // upward, child links of its bottoms when it starts downward from a genome without tops)
+    const bool seedFuse = FUSE && np > 1 && ((P.srcIsTop != 0) == (steps[0].up != 0));
+    int64_t seedCovered = -1; // FUSE: last base covered by the runs of the seeds handed out so far
+
     // ---- phase 1 ----
     bool valid = false;
     int64_t sLo = 0, tLo = 0, len = 0, idx = 0, cursor = -1, ringFirst = -1;
@@ -282,7 +300,39 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
             if (avail < 0) avail = 0;
             const int want = nIdle - takePool;
             const int takeSeeds = (int64_t)want < avail ? want : (int)avail;
-            if (!valid && rank >= takePool && rank - takePool < takeSeeds) {
+            if (seedFuse) {
+                const bool cand = !valid && rank >= takePool && rank - takePool < takeSeeds;
+                const int64_t seg = nextSeg + (rank - takePool);
+                int64_t s0 = 0, runEnd = -1;
+                if (cand) {
+                    int64_t s1, link;
+                    if (P.srcIsTop) {
+                        const longlong2 h = __ldg(reinterpret_cast<const longlong2 *>(&steps[0].top[seg]));
+                        s0 = h.x; link = h.y; s1 = topStart(steps[0].top, seg + 1);
+                    } else {
+                        s0 = botStart(steps[0].bot, seg); s1 = botStart(steps[0].bot, seg + 1); link = ldS(&steps[0].child[seg]);
+                    }
+                    runEnd = s1 - 1;
+                    if (link >= 0 && s0 + linkRun(link) - 1 > runEnd) runEnd = s0 + linkRun(link) - 1;
+                }
+                // a segment opens a seed unless an earlier segment's run already covers it: running maximum of the run ends
+                int64_t mx = runEnd;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int64_t v = __shfl_up_sync(HG_FULL, mx, d);
+                    if (lane >= d && v > mx) mx = v;
+                }
+                int64_t before = __shfl_up_sync(HG_FULL, mx, 1);
+                if (lane == 0 || before < seedCovered) before = seedCovered;
+                const int64_t all = __shfl_sync(HG_FULL, mx, 31);
+                if (all > seedCovered) seedCovered = all;
+                if (cand && s0 > before) {
+                    const int64_t a = gs > s0 ? gs : s0, b = ge < runEnd ? ge : runEnd;
+                    sLo = a; tLo = a; len = b - a + 1;
+                    sRev = flip; tRev = flip; kindTop = P.srcIsTop != 0; idx = seg;
+                    p = 0; cursor = -1; ringFirst = -1;
+                    valid = true;
+                }
+            } else if (!valid && rank >= takePool && rank - takePool < takeSeeds) {
                 const int64_t seg = nextSeg + (rank - takePool);
                 int64_t s0, s1;
                 if (TILE && tile != nullptr && seg + 1 - tileFirst < tileN) {
@@ -378,6 +428,77 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
                     // (a) mapSelf: this top and every member of its paralogy ring head back down to the MRCA
                     landedDown = r.nextPara >= 0;
                     p = st.jump;
+                }
+            } else if (FUSE && st.up) {
+                // the top segment holding tLo, then as far as its parent link's run reaches
+                int64_t t;
+                if (kindTop) t = idx >= 0 ? idx : locateSeg<true>(st, tLo);
+                else if (cursor >= 0) t = cursor;
+                else if (idx >= 0) t = searchFrom<true>(st.top, ldBot(&st.bot[idx]).topParse, st.numTop, tLo);
+                else t = locateSeg<true>(st, tLo);
+                cursor = -1;
+                const TopRec r = ldTop(&st.top[t]);
+                const int64_t tNext = topStart(st.top, t + 1);
+                int64_t covEnd = tNext - 1;
+                if (r.parentEnc >= 0 && r.start + linkRun(r.parentEnc) - 1 > covEnd) covEnd = r.start + linkRun(r.parentEnc) - 1;
+                if (covEnd < tHi) {
+                    push.sLo = sLo; push.tLo = tLo; push.len = len;
+                    subRange(push.sLo, push.tLo, push.len, sRev, tRev, covEnd + 1, tHi);
+                    push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1) | (1ll << 2) | (int64_t)(~7ull); // a top piece, segment unknown (-1)
+                    push.aux = -1; push.p = p; push.type = 0;
+                    doPush = true;
+                    subRange(sLo, tLo, len, sRev, tRev, tLo, covEnd);
+                }
+                if (r.parentEnc < 0) {
+                    valid = false;
+                } else {
+                    const int64_t L = tNext - r.start;
+                    const int64_t pi = linkIdx(r.parentEnc);
+                    const bool fl = (r.parentEnc & 1) != 0;
+                    const int64_t ps = botStart(steps[p + 1].bot, pi);
+                    const int64_t off = tLo - r.start;
+                    tLo = fl ? ps + L - off - len : ps + off;
+                    tRev = tRev != fl;
+                    kindTop = false; idx = (!fl || off + len <= L) ? pi : -1; ++p; // (a reversed run lands in earlier segments)
+                }
+            } else if (FUSE) {
+                // the bottom segment holding tLo, then as far as its child link's run reaches (0 when the landing top has a ring)
+                int64_t b;
+                if (!kindTop) b = idx >= 0 ? idx : locateSeg<false>(st, tLo);
+                else if (cursor >= 0) b = cursor;
+                else if (idx >= 0) b = searchFrom<false>(st.bot, ldTop(&st.top[idx]).botParse, st.numBot, tLo);
+                else b = locateSeg<false>(st, tLo);
+                cursor = -1;
+                const int64_t ce = ldS(&st.child[b]);
+                const int64_t b0 = botStart(st.bot, b), bNext = botStart(st.bot, b + 1);
+                int64_t covEnd = bNext - 1;
+                if (ce >= 0 && b0 + linkRun(ce) - 1 > covEnd) covEnd = b0 + linkRun(ce) - 1;
+                if (covEnd < tHi) {
+                    push.sLo = sLo; push.tLo = tLo; push.len = len;
+                    subRange(push.sLo, push.tLo, push.len, sRev, tRev, covEnd + 1, tHi);
+                    push.meta = (int64_t)(sRev ? 1 : 0) | ((int64_t)(tRev ? 1 : 0) << 1) | (int64_t)(~7ull); // a bottom piece, segment unknown (-1)
+                    push.aux = -1; push.p = p; push.type = 0;
+                    doPush = true;
+                    subRange(sLo, tLo, len, sRev, tRev, tLo, covEnd);
+                }
+                if (ce < 0) {
+                    valid = false;
+                } else {
+                    const int64_t L = bNext - b0;
+                    const int64_t ci = linkIdx(ce);
+                    const bool fl = (ce & 1) != 0;
+                    int64_t cs;
+                    if (P.dupes) {
+                        const TopRec rc = ldTop(&steps[p + 1].top[ci]);
+                        cs = rc.start;
+                        landedDown = rc.nextPara >= 0; // (then the run is 0 and the piece lies inside this one segment)
+                    } else {
+                        cs = topStart(steps[p + 1].top, ci);
+                    }
+                    const int64_t off = tLo - b0;
+                    tLo = fl ? cs + L - off - len : cs + off;
+                    tRev = tRev != fl;
+                    kindTop = true; idx = (!fl || off + len <= L) ? ci : -1; ++p;
                 }
             } else if (st.up) {
                 if (!kindTop) { // bottom fragment: cut at the top-segment boundary (toParseUp, halTopSegmentIterator.cpp:55-81)
@@ -535,9 +656,12 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
         return;
     }
     // target sequence of every fragment (MappedSegment::getSequence)
+    bool redoExact = false; // FUSE: this interval needs the piece-by-piece walk
     if (P.tgtNumSeq > 1) {
         for (int i = lane; i < m; i += 32) {
-            listA[i].meta |= (int64_t)seqOf(P.tgtSeqStart, P.tgtNumSeq, listA[i].tLo) << 3;
+            const int sq = seqOf(P.tgtSeqStart, P.tgtNumSeq, listA[i].tLo);
+            listA[i].meta |= (int64_t)sq << 3;
+            if (FUSE && listA[i].tLo + listA[i].len > ldS(&P.tgtSeqStart[sq + 1])) redoExact = true; // pieces would not merge across sequences
         }
     }
     __syncwarp();
@@ -628,6 +752,12 @@ __device__ __forceinline__ void liftOneInterval(const LiftParams &P, WarpScratch
             clash |= !(same || b.tLo > a.tLo + a.len - 1) || (COAL && fragSameCoords(a, b));
             classes |= a.tLo == b.tLo;
         }
+    }
+    if (FUSE && __any_sync(HG_FULL, clash || classes || redoExact)) {
+        // fused fragments that overlap in the target (paralogous source pieces hit the same target bases): the reference cuts
+        // them against each other at its own piece boundaries -- walk this interval piece by piece instead
+        if (lane == 0) liftFail(P, item, ST_REDO_EXACT);
+        return;
     }
     bool refined = false;
     if (__any_sync(HG_FULL, clash)) {
@@ -928,11 +1058,6 @@ __global__ void __launch_bounds__(128, 8) liftoverKernel(const LiftParams P) {
 // input) goes to the complex list and is walked piece by piece by liftoverKernel.
 // ---------------------------------------------------------------------------------------------------------------
 #define HG_FAST_MAX_PATH 24
-
-template <bool TOP> __device__ __forceinline__ int64_t locateSeg(const PathStep &st, int64_t pos) {
-    if (TOP) return searchFrom<true>(st.top, (int64_t)__ldg(&st.topBucket[pos >> st.topShift]), st.numTop, pos);
-    return searchFrom<false>(st.bot, (int64_t)__ldg(&st.botBucket[pos >> st.botShift]), st.numBot, pos);
-}
 
 __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
     __shared__ PathStep sSteps[HG_FAST_MAX_PATH];
