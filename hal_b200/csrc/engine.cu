@@ -1059,6 +1059,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             readBack();
         }
         pt.mark("retries");
+        if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] batch of %zu: complex %llu, re-walked exactly %zu, scratch retries %zu, fused walk %d\n", n, _hostCtr[C_COMPLEX], out.nRedo, out.nRetry, (int)fuse);
         if (wig) { // values went straight into wig->keys; there is no record list to assemble
             out.launches = (int)rt::g_launches - launches0;
             return;
