@@ -850,10 +850,13 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // HALGPU_SEED_TILE=1 (measurement switch): TMA-staged seed tiles, see liftover_kernel.cuh and DESIGN.md
         const char *tileEnv = std::getenv("HALGPU_SEED_TILE");
         const bool seedTile = !wig && !raw && !coalPath && srcIsTop && tileEnv != nullptr && tileEnv[0] == '1';
-        // the fused walk (whole collinear runs per fragment, liftover_kernel.cuh) runs the first pass over plain BED batches; what
-        // it flags ST_REDO_EXACT, and every retry rung, is walked piece by piece by the plain instantiation
+        // HALGPU_FUSE=1 (measurement switch): the fused walk (whole collinear runs per fragment, liftover_kernel.cuh) runs the first
+        // pass over plain BED batches; what it flags ST_REDO_EXACT, and every retry rung, is walked piece by piece by the plain
+        // instantiation.  Measured on the divergent C2 (gpurun_out/bench_j_default.json): nearly every interval has paralogous
+        // pieces that clash in the target and is walked twice, 87 -> 138 ms per 9.94 M intervals -- off by default.
+        const char *fuseEnv = std::getenv("HALGPU_FUSE");
         const bool fuse = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !seedTile && !(flags & HALGPU_NO_FAST) && pl.fastOk &&
-                          std::getenv("HALGPU_NO_FUSE") == nullptr;
+                          fuseEnv != nullptr && fuseEnv[0] == '1';
         void (*const firstKernel)(const LiftParams) = fuse ? liftoverKernel<LIFT_BED | LIFT_FUSE> : nullptr;
         void (*const mapKernel)(const LiftParams) =
             seedTile ? liftoverKernel<LIFT_BED | LIFT_TILE> : wig ? liftoverKernel<LIFT_WIG>

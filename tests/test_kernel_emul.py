@@ -204,3 +204,25 @@ def test_emulated_sliced_sort_equals_unsliced(emul_lib, oracle_lib, monkeypatch)
         assert_same_as_oracle(off, recs, exp)
         assert np.array_equal(recs, recs1) and info["n_complex"] == info1["n_complex"] and info["n_complex"] < 333
     a.close()
+
+
+@pytest.mark.parametrize("hal,src,tgt,n,maxlen", [
+    ("varlen8.hal", "L0", "L3", 250, 300),
+    ("varlen8.hal", "A0", "L2", 150, 500),
+    ("randgenSmallSeed0.hal", "Genome_3", "Genome_2", 100, 900),
+])
+def test_emulated_fused_walk_equals_oracle(emul_lib, oracle_lib, monkeypatch, hal, src, tgt, n, maxlen):
+    """HALGPU_FUSE=1 (measurement switch, engine.cu): fragments follow whole collinear runs; intervals whose fused fragments
+    clash in the target are walked again piece by piece -- the lines are the oracle's either way (n_frag, a diagnostic, is not)"""
+    import hal_b200
+    path = os.path.join(GOLDEN, hal)
+    o = oracle_lib.Oracle(path)
+    a = hal_b200.Alignment(path, lib_path=emul_lib)
+    s, t = a.genome_id(src), a.genome_id(tgt)
+    gs, ge, st = random_intervals(a.genome_length(s), n, maxlen, seed=n)
+    exp = o.liftover(s, t, gs, ge, st)
+    monkeypatch.setenv("HALGPU_FUSE", "1")
+    for _ in range(2):  # (the second call sizes its record pool from the first one's history)
+        off, recs, _ = a.liftover(s, t, gs, ge, st)
+        assert_same_as_oracle(off, recs, exp)
+    a.close()

@@ -258,3 +258,23 @@ def test_cuda_config1_root_to_leaf(hb, oracle_lib, tmp_path, branch):
         subprocess.check_call([ref, hal, "G0", str(bed), "G2", str(tmp_path / "ref.bed")])
         subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), hal, "G0", str(bed), "G2", str(tmp_path / "got.bed")])
         assert open(tmp_path / "ref.bed").read() == open(tmp_path / "got.bed").read()
+
+
+@pytest.mark.parametrize("hal,src,tgt,n,maxlen", [
+    ("varlen8.hal", "L0", "L3", 20000, 400),
+    ("varlen8.hal", "A0", "L2", 10000, 500),
+    ("randgenSmallSeed0.hal", "Genome_3", "Genome_2", 5000, 900),
+])
+def test_cuda_fused_walk_equals_oracle(hb, oracle_lib, monkeypatch, hal, src, tgt, n, maxlen):
+    """HALGPU_FUSE=1 (measurement switch, engine.cu): whole collinear runs per fragment, clashing intervals re-walked piece by
+    piece; the lines equal the oracle's (n_frag, a diagnostic, counts fused pieces and is not compared)"""
+    path = os.path.join(GOLDEN, hal)
+    o = oracle_lib.Oracle(path)
+    with hb.Alignment(path) as a:
+        s, t = a.genome_id(src), a.genome_id(tgt)
+        gs, ge, st = random_intervals(a.genome_length(s), n, maxlen, seed=n + len(src))
+        exp = o.liftover(s, t, gs, ge, st)
+        monkeypatch.setenv("HALGPU_FUSE", "1")
+        for _ in range(2):
+            off, recs, _ = a.liftover(s, t, gs, ge, st)
+            assert_same_as_oracle(off, recs, exp)
