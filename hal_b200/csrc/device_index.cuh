@@ -184,7 +184,7 @@ struct FastParams {
     int64_t srcLen;
     const int64_t *tgtSeqStart;
     int32_t tgtNumSeq;
-    int32_t pad0;
+    int32_t tileGrab;                     // 0: a warp's tiles are warp id, warp id + warps of the grid, ...; k > 0: k tiles per atomicAdd on tileCursor
     int64_t n;
     const int64_t *gs, *ge;               // input order
     const uint8_t *strand;                // may be NULL

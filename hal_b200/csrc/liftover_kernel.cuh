@@ -1065,12 +1065,20 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t nTiles = (P.n + 31) >> 5;
+    const int64_t warpsInGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t tile = P.tileGrab == 0 ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) - warpsInGrid : -1;
+    int64_t grabEnd = 0; // (atomic cursor: end of the tiles this warp holds)
     while (true) {
-        unsigned long long tile = 0;
-        if (lane == 0) tile = atomicAdd(P.tileCursor, 1ull);
-        tile = __shfl_sync(HG_FULL, tile, 0);
-        if ((int64_t)tile >= nTiles) break;
-        const int64_t w = (int64_t)tile * 32 + lane;
+        if (P.tileGrab == 0) {
+            tile += warpsInGrid;
+        } else if (++tile >= grabEnd) {
+            unsigned long long t0 = 0;
+            if (lane == 0) t0 = atomicAdd(P.tileCursor, (unsigned long long)P.tileGrab);
+            tile = (int64_t)__shfl_sync(HG_FULL, t0, 0);
+            grabEnd = tile + P.tileGrab;
+        }
+        if (tile >= nTiles) break;
+        const int64_t w = tile * 32 + lane;
         const bool have = w < P.n;
         uint32_t item = 0;
         int64_t gs = 0, ge = -1;

@@ -226,3 +226,23 @@ def test_emulated_fused_walk_equals_oracle(emul_lib, oracle_lib, monkeypatch, ha
         off, recs, _ = a.liftover(s, t, gs, ge, st)
         assert_same_as_oracle(off, recs, exp)
     a.close()
+
+
+@pytest.mark.parametrize("env", [{"HALGPU_RADIX_SORT": "1"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "4"}, {"HALGPU_SORT_BITS": "3"}])
+def test_emulated_order_switches_equal_default(emul_lib, oracle_lib, monkeypatch, env):
+    """the visiting order (bucket sort by default, CUB radix sort behind HALGPU_RADIX_SORT) and the way the lane kernel's warps
+    take their tiles (fixed stride by default, atomic cursor behind HALGPU_TILE_GRAB) never change a result"""
+    import hal_b200
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    a = hal_b200.Alignment(path, lib_path=emul_lib)
+    s, t = a.genome_id("L2"), a.genome_id("A1")
+    gs, ge, st = random_intervals(a.genome_length(s), 700, 40, seed=5)
+    exp = o.liftover(s, t, gs, ge, st)
+    off1, recs1, info1 = a.liftover(s, t, gs, ge, st)
+    assert_same_as_oracle(off1, recs1, exp)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    off, recs, info = a.liftover(s, t, gs, ge, st)
+    assert np.array_equal(off, off1) and np.array_equal(recs, recs1) and info["n_complex"] == info1["n_complex"]
+    a.close()

@@ -278,3 +278,19 @@ def test_cuda_fused_walk_equals_oracle(hb, oracle_lib, monkeypatch, hal, src, tg
         for _ in range(2):
             off, recs, _ = a.liftover(s, t, gs, ge, st)
             assert_same_as_oracle(off, recs, exp)
+
+
+@pytest.mark.parametrize("env", [{"HALGPU_RADIX_SORT": "1"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "4"}, {"HALGPU_SORT_BITS": "3"}])
+def test_cuda_order_switches_equal_default(hb, oracle_lib, monkeypatch, env):
+    """bucket sort (default) vs CUB radix sort, fixed-stride tiles (default) vs the atomic tile cursor: identical results"""
+    path = os.path.join(GOLDEN, "varlen8.hal")
+    o = oracle_lib.Oracle(path)
+    with hb.Alignment(path) as a:
+        s, t = a.genome_id("L2"), a.genome_id("A1")
+        gs, ge, st = random_intervals(a.genome_length(s), 50000, 40, seed=5)
+        off1, recs1, info1 = a.liftover(s, t, gs, ge, st)
+        assert_same_as_oracle(off1, recs1, o.liftover(s, t, gs, ge, st))
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        off, recs, info = a.liftover(s, t, gs, ge, st)
+        assert np.array_equal(off, off1) and np.array_equal(recs, recs1) and info["n_complex"] == info1["n_complex"]

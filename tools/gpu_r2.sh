@@ -107,5 +107,21 @@ d=json.loads(open('gpurun_out/bench_j_$f.json').read().strip().splitlines()[-1])
 print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'fast_ms %.4f' % d['detail']['fast_kernel_ms'], 'e2e %.4g' % d['e2e']['value'], d['check'], (d.get('secondary_divergent') or {}).get('value'), (d.get('secondary_divergent') or {}).get('kernel_ms'), (d.get('secondary_divergent') or {}).get('check'))
 "; done
     ;;
+k)  # bucket sort / tile scheduling A/B at N=1 + liftover GPU tests + launch list of the default step
+    timeout 900 python -m pytest tests/test_liftover_gpu.py -x -q -m gpu > gpurun_out/pytest_k.log 2>&1; tail -3 gpurun_out/pytest_k.log
+    Q="--steps 20 --warmup 5 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth --no-traffic"
+    python bench.py $Q > gpurun_out/bench_k_default.json 2> gpurun_out/bench_k.err
+    HALGPU_RADIX_SORT=1 python bench.py $Q --no-divergent > gpurun_out/bench_k_radix.json 2>> gpurun_out/bench_k.err
+    HALGPU_TILE_GRAB=1 python bench.py $Q --no-divergent > gpurun_out/bench_k_grab1.json 2>> gpurun_out/bench_k.err
+    HALGPU_TILE_GRAB=4 python bench.py $Q --no-divergent > gpurun_out/bench_k_grab4.json 2>> gpurun_out/bench_k.err
+    HALGPU_SORT_BITS=14 python bench.py $Q --no-divergent > gpurun_out/bench_k_bits14.json 2>> gpurun_out/bench_k.err
+    for f in default radix grab1 grab4 bits14; do python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_k_$f.json').read().strip().splitlines()[-1])
+print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'fast_ms %.4f' % d['detail']['fast_kernel_ms'], 'e2e %.4g' % d['e2e']['value'], d['check'], (d.get('secondary_divergent') or {}).get('value'), (d.get('secondary_divergent') or {}).get('kernel_ms'), (d.get('secondary_divergent') or {}).get('check'))
+"; done
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_k.csv \
+        python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/bench_ncu_k.err
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
