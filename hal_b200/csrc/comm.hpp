@@ -7,6 +7,7 @@
 // multi-GPU path is covered by the CPU-only test tier (world size 2).
 #pragma once
 #include "rt.hpp"
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -66,6 +67,8 @@ inline void commAllGather(Comm *c, const void *send, void *recv, size_t bytesPer
     c->group->barrier();
 }
 
+inline void commAllGatherSmall(Comm *c, const void *send, void *recv, size_t bytesPerRank, Stream s) { commAllGather(c, send, recv, bytesPerRank, s); }
+
 // ragged all-gather: rank r contributes count[r] elements of elemBytes; they land at recv + r * slotElems * elemBytes
 // (slotElems > 0) or packed back to back in rank order (slotElems == 0)
 inline void commAllGatherV(Comm *c, const void *send, void *recv, const std::vector<uint64_t> &count, size_t elemBytes, uint64_t slotElems, Stream) {
@@ -87,6 +90,7 @@ struct NcclApi {
     ncclResult_t (*getUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*commInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*commSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr; // optional (NCCL >= 2.18)
     ncclResult_t (*allGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*groupStart)() = nullptr;
@@ -106,6 +110,7 @@ struct NcclApi {
             api.getUniqueId = reinterpret_cast<decltype(api.getUniqueId)>(sym("ncclGetUniqueId"));
             api.commInitRank = reinterpret_cast<decltype(api.commInitRank)>(sym("ncclCommInitRank"));
             api.commDestroy = reinterpret_cast<decltype(api.commDestroy)>(sym("ncclCommDestroy"));
+            api.commSplit = reinterpret_cast<decltype(api.commSplit)>(sym("ncclCommSplit"));
             api.allGather = reinterpret_cast<decltype(api.allGather)>(sym("ncclAllGather"));
             api.broadcast = reinterpret_cast<decltype(api.broadcast)>(sym("ncclBroadcast"));
             api.groupStart = reinterpret_cast<decltype(api.groupStart)>(sym("ncclGroupStart"));
@@ -124,6 +129,10 @@ struct NcclApi {
 struct Comm {
     ncclComm_t c;
     int nranks, rank;
+    // a second communicator over the same ranks for the per-batch 32-byte headers: NCCL runs the operations of ONE communicator
+    // in issue order, so on `c` the header of batch k+1 would wait behind the record gather of batch k.  Equal to c when
+    // ncclCommSplit is unavailable.
+    ncclComm_t small;
 };
 static_assert(NCCL_UNIQUE_ID_BYTES == 128, "halgpu_comm_unique_id hands out 128-byte ids");
 inline void commUniqueId(uint8_t id[128]) {
@@ -138,10 +147,16 @@ inline Comm *commInit(int nranks, int rank, const uint8_t id[128]) {
     std::memcpy(u.internal, id, 128);
     ncclComm_t c;
     a.check(a.commInitRank(&c, nranks, u, rank), "ncclCommInitRank");
-    return new Comm{c, nranks, rank};
+    ncclComm_t small = c;
+    if (a.commSplit != nullptr && nranks > 1 && std::getenv("HALGPU_ONE_COMM") == nullptr) {
+        ncclComm_t c2 = nullptr;
+        if (a.commSplit(c, 0, rank, &c2, nullptr) == ncclSuccess && c2 != nullptr) small = c2;
+    }
+    return new Comm{c, nranks, rank, small};
 }
 inline void commDestroy(Comm *c) {
     if (c == nullptr) return;
+    if (c->small != c->c) NcclApi::get().commDestroy(c->small);
     NcclApi::get().commDestroy(c->c);
     delete c;
 }
@@ -150,6 +165,11 @@ inline void commGroupEnd() { NcclApi &a = NcclApi::get(); a.check(a.groupEnd(), 
 inline void commAllGather(Comm *c, const void *send, void *recv, size_t bytesPerRank, Stream s) {
     NcclApi &a = NcclApi::get();
     a.check(a.allGather(send, recv, bytesPerRank, ncclUint8, c->c, s), "ncclAllGather");
+}
+
+inline void commAllGatherSmall(Comm *c, const void *send, void *recv, size_t bytesPerRank, Stream s) {
+    NcclApi &a = NcclApi::get();
+    a.check(a.allGather(send, recv, bytesPerRank, ncclUint8, c->small, s), "ncclAllGather (header)");
 }
 
 // ragged all-gather (see the harness version above): one broadcast per rank with its exact size; inside an ncclGroup NCCL

@@ -770,31 +770,10 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         if ((size_t)nSlices > n) nSlices = 1;
         size_t sliceLo[5];
         for (int c = 0; c <= nSlices; ++c) sliceLo[c] = n * (size_t)c / (size_t)nSlices;
-        // Default order: ONE counting pass into <= 2^16 position buckets + one scatter (stage_kernels.cuh: bucket*Kernel).
-        // HALGPU_RADIX_SORT=1 (measurement switch) keeps CUB's radix sort of the same bits; the packed and sliced variants
-        // below are radix-sort variants.
-        const bool bucketSort = sorting && !packed && nSlices == 1 && n < 0xffffffffull && std::getenv("HALGPU_RADIX_SORT") == nullptr;
-        if (bucketSort) {
-            int endBit = 1;
-            while (endBit < 64 && (S.length >> endBit) != 0) ++endBit;
-            const int coarse = (srcIsTop ? _g[src].topShift : _g[src].botShift) + 5;
-            int bits = std::min(HG_BUCKET_SORT_MAX_BITS, std::max(1, endBit - coarse));
-            if (const char *sb = std::getenv("HALGPU_SORT_BITS")) bits = std::max(1, std::min(HG_BUCKET_SORT_MAX_BITS, std::atoi(sb))); // measurement switch
-            if (bits > endBit) bits = endBit;
-            BucketSortParams bp;
-            std::memset(&bp, 0, sizeof(bp));
-            bp.gs = dGs; bp.ge = dGe; bp.n = (int64_t)n;
-            bp.shift = endBit - bits; bp.nBins = 1 << bits;
-            bp.bins = L.as<uint32_t>((size_t)bp.nBins);
-            bp.keysOut = L.as<uint64_t>(n); bp.valsOut = L.as<uint64_t>(n);
-            bp.directLoc = fast ? outLoc : nullptr;
-            rt::dmemset(bp.bins, 0, (size_t)bp.nBins * sizeof(uint32_t), _stream);
-            rt::launch(bucketCountKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, bp);
-            rt::launch(bucketScanKernel, 1, 1024, 0, _stream, bp);
-            rt::launch(bucketScatterKernel, gridFor((int64_t)n, 256, _sms), 256, 0, _stream, bp);
-            sortedGs = reinterpret_cast<const unsigned long long *>(bp.keysOut);
-            sortedVal = reinterpret_cast<const unsigned long long *>(bp.valsOut);
-        } else if (sorting || fast) {
+        // (A single-pass bucket sort -- count into 2^16 position buckets, scan, scatter with one atomic per interval -- was
+        // measured against CUB's two onesweep passes on 10 M intervals: 467 us (count 89, scan 112, scatter 266: scattered
+        // 8-byte stores) against 285 us, gpurun_out/launches_k.csv; the radix sort stays.)
+        if (sorting || fast) {
             const rt::Stream ss = nSlices > 1 ? _aux : _stream;
             if (nSlices > 1) { _sliceEv[4]->record(_stream); _sliceEv[4]->wait(_aux); } // behind the memsets above
             IotaParams ip;
@@ -898,11 +877,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             F.n = (int64_t)n; F.gs = dGs; F.ge = dGe; F.strand = dStrand;
             F.sortedGs = sortedGs; F.sortedVal = sortedVal; F.sortedKey = sortedKey;
             F.tileCursor = ctr + C_TILE; F.pool = pool;
-            // tiles of 32 work items: by default every warp takes its tiles at a fixed stride (the grid is one resident wave, so
-            // at any time the running warps cover one stretch of the sorted batch); HALGPU_TILE_GRAB=k (measurement switch)
-            // hands them out k at a time from an atomic cursor instead
-            int tileGrab = 0;
-            if (const char *tg = std::getenv("HALGPU_TILE_GRAB")) tileGrab = std::max(0, std::min(64, std::atoi(tg)));
+            // tiles of 32 work items are handed out 4 at a time from an atomic cursor, so the resident warps sweep the sorted batch
+            // together.  Measured on 10 M intervals (gpurun_out/bench_k_*.json): 1 tile per atomicAdd 0.354 ms, 4 tiles 0.304 ms,
+            // fixed stride per warp (HALGPU_TILE_GRAB=0) 0.426 ms.
+            int tileGrab = 4;
+            if (const char *tg = std::getenv("HALGPU_TILE_GRAB")) tileGrab = std::max(0, std::min(64, std::atoi(tg))); // measurement switch
             F.tileGrab = tileGrab;
             F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
             for (int c = 0; c < nSlices; ++c) {

@@ -49,23 +49,21 @@ struct WireParams {
     unsigned long long *fitFlag;   // fits: cleared when a record does not fit
     int64_t n;
 };
-__global__ void fitsKernel(const WireParams p) {
+// pack + "does every record fit": one pass over this rank's records.  Runs BEFORE the header exchange (the header carries the
+// flag); when some rank's records do not fit the wire words are simply not used.
+__global__ void packRecKernel(const WireParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     bool ok = true;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
         const halgpu_lift_rec r = p.recs[i];
         ok = ok && recFits(r) && (r.strand == '+' || r.strand == '-' || r.strand == '.') && (r.src_strand == '+' || r.src_strand == '-' || r.src_strand == '.');
+        ulonglong2 w;
+        w.x = (unsigned long long)r.start | ((unsigned long long)(r.end - r.start) << 40);
+        w.y = (unsigned long long)r.src_start | ((unsigned long long)(uint32_t)r.tgt_seq << 40) | ((unsigned long long)r.n_frag << 56) |
+              (strandCode(r.strand) << 60) | (strandCode(r.src_strand) << 62);
+        reinterpret_cast<ulonglong2 *>(p.wire)[i] = w;
     }
     if (!ok) *p.fitFlag = 0ull;
-}
-__global__ void packRecKernel(const WireParams p) {
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const halgpu_lift_rec r = p.recs[i];
-        p.wire[2 * i] = (unsigned long long)r.start | ((unsigned long long)(r.end - r.start) << 40);
-        p.wire[2 * i + 1] = (unsigned long long)r.src_start | ((unsigned long long)(uint32_t)r.tgt_seq << 40) | ((unsigned long long)r.n_frag << 56) |
-                            (strandCode(r.strand) << 60) | (strandCode(r.src_strand) << 62);
-    }
 }
 __global__ void unpackRecKernel(const WireParams p) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -112,8 +110,11 @@ __global__ void unpackOffKernel(const UnpackOffParams p) {
 struct halgpu_comm {
     halgpu_ctx *ctx = nullptr;
     rt::Comm *comm = nullptr;
-    rt::Stream stream{};
+    rt::Stream stream{};         // record gathers
+    rt::Stream hdrStream{};      // per-batch headers (own communicator: comm.hpp)
     uint64_t *hostHdr = nullptr; // pinned: 4 words per rank
+    bool timeline = false;       // HALGPU_GATHER_TIMELINE=1: end() prints when each phase of the batch ran on the device
+    std::unique_ptr<rt::Event> origin;
 };
 
 struct halgpu_gather {
@@ -127,6 +128,7 @@ struct halgpu_gather {
     uint64_t *offsets = nullptr;   // global CSR
     halgpu_lift_rec *recs = nullptr;
     std::unique_ptr<rt::Event> ready, done;
+    std::unique_ptr<rt::Event> tl[3]; // timeline: lift done / gather starts / unpack done
     float kernelMs = 0, fastMs = 0;
     size_t nComplex = 0, nRetry = 0;
     int launches = 0;
@@ -174,6 +176,9 @@ int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128
         c->ctx = ctx;
         c->comm = rt::commInit(nranks, rank, id);
         c->stream = rt::createStream();
+        c->hdrStream = rt::createStream();
+        c->timeline = std::getenv("HALGPU_GATHER_TIMELINE") != nullptr;
+        if (c->timeline) { c->origin.reset(new rt::Event); c->origin->record(ctx->impl->stream()); }
         c->hostHdr = static_cast<uint64_t *>(rt::hostAlloc((size_t)nranks * 4 * sizeof(uint64_t)));
         *out = c.release();
     });
@@ -183,6 +188,7 @@ void halgpu_comm_free(halgpu_comm *c) {
     if (c == nullptr) return;
     rt::commDestroy(c->comm);
     rt::destroyStream(c->stream);
+    rt::destroyStream(c->hdrStream);
     rt::hostFree(c->hostHdr);
     delete c;
 }
@@ -207,22 +213,45 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             g->kernelMs = g->local.kernelMs; g->fastMs = g->local.fastMs; g->nComplex = g->local.nComplex; g->nRetry = g->local.nRetry;
             g->launches = g->local.launches;
             if (g->local.nRec >= 0xffffffffull) throw HalError("a shard produced 2^32 or more records; use smaller batches");
-            // 1. every rank learns every shard's size (one 32-byte header per rank; the only host round trip of the gather)
+            // 1. this rank's records in compact wire form (packRecKernel also decides whether they all fit), on the engine's
+            //    stream.  The compact form halves the link bytes and costs one pack pass here and one unpack pass over ALL
+            //    ranks' records in end(): worth it from 4 ranks up (every rank receives (W - 1) / W of the result), while 2
+            //    ranks are faster with the 32-byte records gathered in place.  HALGPU_GATHER_WIRE32 / HALGPU_GATHER_WIRE16
+            //    force either form (measurement switches).
             uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * 32));
-            // header: intervals, records, "all my records fit the compact wire form", "my offsets are the identity"
             const bool myIdentity = g->local.fastMs > 0 && g->local.nComplex == 0 && g->local.nRec == n;
-            const bool wantCompact = std::getenv("HALGPU_GATHER_WIRE32") == nullptr; // measurement switch: always send 32-byte records
+            bool wantCompact = W >= 4;
+            if (std::getenv("HALGPU_GATHER_WIRE32") != nullptr) wantCompact = false;
+            if (std::getenv("HALGPU_GATHER_WIRE16") != nullptr) wantCompact = true;
+            // header: intervals, records, "all my records fit the compact wire form", "my offsets are the identity"
             uint64_t mine[4] = {(uint64_t)n, (uint64_t)g->local.nRec, wantCompact ? 1u : 0u, myIdentity ? 1u : 0u};
-            rt::h2d(dHdr + (size_t)W * 4, mine, 32, cm->stream);
-            if (wantCompact && g->local.nRec > 0) {
-                WireParams fp;
-                std::memset(&fp, 0, sizeof(fp));
-                fp.recs = g->local.recs; fp.n = (int64_t)g->local.nRec; fp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * 4 + 2);
-                rt::launch(fitsKernel, gridOf(fp.n, 256), 256, 0, cm->stream, fp);
+            rt::h2d(dHdr + (size_t)W * 4, mine, 32, C.stream());
+            if (cm->timeline) { g->tl[0].reset(new rt::Event); g->tl[0]->record(C.stream()); }
+            if (wantCompact) {
+                g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
+                if (g->local.nRec > 0) {
+                    WireParams wp;
+                    std::memset(&wp, 0, sizeof(wp));
+                    wp.recs = g->local.recs; wp.wire = g->sendWire; wp.n = (int64_t)g->local.nRec;
+                    wp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * 4 + 2);
+                    rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
+                }
             }
-            rt::commAllGather(cm->comm, dHdr + (size_t)W * 4, dHdr, 32, cm->stream);
-            rt::d2h(cm->hostHdr, dHdr, (size_t)W * 32, cm->stream);
-            rt::sync(cm->stream);
+            if (!myIdentity) { // (32-bit offsets on the wire; not needed when every rank's offsets turn out to be the identity)
+                g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4));
+                PackOffParams pp;
+                pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
+                rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+            }
+            g->ready.reset(new rt::Event);
+            g->done.reset(new rt::Event);
+            g->ready->record(C.stream());
+            // 2. every rank learns every shard's size: one 32-byte header per rank over the header communicator on its own
+            //    stream -- the only host round trip of the gather, and not queued behind the previous batch's records
+            g->ready->wait(cm->hdrStream);
+            rt::commAllGatherSmall(cm->comm, dHdr + (size_t)W * 4, dHdr, 32, cm->hdrStream);
+            rt::d2h(cm->hostHdr, dHdr, (size_t)W * 32, cm->hdrStream);
+            rt::sync(cm->hdrStream);
             cache.give(dHdr);
             g->n.resize((size_t)W); g->nRec.resize((size_t)W);
             uint64_t nTotal = 0, recTotal = 0, maxN = 0;
@@ -237,29 +266,22 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                 uniform = uniform && g->n[(size_t)r] == g->n[0] && g->nRec[(size_t)r] == g->nRec[0];
             }
             if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] gather rank %d: compact %d identity %d uniform %d records %llu\n", me, (int)g->compact, (int)g->identity, (int)uniform, (unsigned long long)recTotal);
-            // 2. this rank's offsets (unless every rank's are the identity) and records in wire form
             g->offsets = static_cast<uint64_t *>(cache.take((size_t)(nTotal + 2) * 8));
             g->recs = static_cast<halgpu_lift_rec *>(cache.take(std::max<uint64_t>(recTotal, 1) * sizeof(halgpu_lift_rec)));
             if (!g->identity) {
-                g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4));
                 g->wireOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4 * (size_t)W));
-                PackOffParams pp;
-                pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
-                rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+                if (g->sendOff == nullptr) { // my offsets are the identity, some other rank's are not
+                    g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4));
+                    PackOffParams pp;
+                    pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
+                    rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+                    g->ready->record(C.stream());
+                }
             }
-            if (g->compact) {
-                g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
-                g->recvWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(recTotal, 1) * 16));
-                WireParams wp;
-                std::memset(&wp, 0, sizeof(wp));
-                wp.recs = g->local.recs; wp.wire = g->sendWire; wp.n = (int64_t)g->local.nRec;
-                rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
-            }
-            g->ready.reset(new rt::Event);
-            g->done.reset(new rt::Event);
-            g->ready->record(C.stream());
+            if (g->compact) g->recvWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(recTotal, 1) * 16));
+            // 3. the gather on the communicator's stream: offsets and records, fused into one NCCL group
             g->ready->wait(cm->stream);
-            // 3. the gather: offsets and records, fused into one NCCL group
+            if (cm->timeline) { g->tl[1].reset(new rt::Event); g->tl[1]->record(cm->stream); }
             const void *sendRecs = g->compact ? (const void *)g->sendWire : (const void *)g->local.recs;
             void *recvRecs = g->compact ? (void *)g->recvWire : (void *)g->recs;
             const size_t recBytes = g->compact ? 16 : sizeof(halgpu_lift_rec);
@@ -275,7 +297,7 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             g->done->record(cm->stream);
             (void)me;
         } catch (...) {
-            try { rt::sync(cm->stream); } catch (...) {}
+            try { rt::sync(cm->stream); rt::sync(cm->hdrStream); } catch (...) {}
             C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
             cache.give(g->sendOff); cache.give(g->wireOff); cache.give(g->offsets); cache.give(g->recs);
             cache.give(g->sendWire); cache.give(g->recvWire);
@@ -318,7 +340,14 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
             wp.wire = g->recvWire; wp.out = g->recs; wp.n = (int64_t)up.recBase[W];
             if (wp.n > 0) rt::launch(unpackRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
         }
+        if (cm->timeline) { g->tl[2].reset(new rt::Event); g->tl[2]->record(C.stream()); }
         rt::sync(C.stream());
+        if (cm->timeline && g->tl[0] && g->tl[1] && g->tl[2]) {
+            const rt::Event &o = *cm->origin;
+            fprintf(stderr, "[halgpu] gather timeline rank %d (ms since the communicator was made): lift done %.3f | gather %.3f .. %.3f | unpack done %.3f | lift kernels %.3f ms, compact %d\n",
+                    cm->comm->rank, rt::Event::elapsedMs(o, *g->tl[0]), rt::Event::elapsedMs(o, *g->tl[1]), rt::Event::elapsedMs(o, *g->done),
+                    rt::Event::elapsedMs(o, *g->tl[2]), g->kernelMs, (int)g->compact);
+        }
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
         r->n = (size_t)up.ivBase[W]; r->n_rec = (size_t)up.recBase[W]; r->offsets = g->offsets; r->recs = g->recs; r->on_device = 1;
         r->kernel_ms = g->kernelMs; r->fast_ms = g->fastMs; r->n_complex = g->nComplex; r->n_retry = g->nRetry; r->launches = g->launches + 2;

@@ -177,74 +177,6 @@ __global__ void iotaKeysKernel(const IotaParams p) {
     }
 }
 
-// ---- bucket sort of the batch by source position (engine.cu: the default visiting order) -----------------------------
-// The kernels only need the batch in COARSE source order (about 32 source segments per bucket: neighbouring lanes and warps
-// then read neighbouring index records), so instead of a general radix sort the batch is counted into at most 2^16 position
-// buckets and scattered once: count (one 8-byte read + one RED per interval) -> exclusive scan of the bucket counters (one
-// block) -> scatter (one ATOM per interval hands out the slot).  10 M intervals: ~0.5 GB of traffic against the ~1 GB of
-// the two-pass radix sort it replaces.  The order inside a bucket is whatever the atomics give; results do not depend on it
-// (every interval's output location is a function of its id).
-#define HG_BUCKET_SORT_MAX_BITS 16
-struct BucketSortParams {
-    const int64_t *gs, *ge;
-    uint32_t *bins;                // 2^bits counters, zeroed; count: histogram; after the scan: running cursor of every bucket
-    uint64_t *keysOut, *valsOut;   // scatter: source start / (interval id | min(length, 2^32 - 1) << 32) in visiting order
-    unsigned long long *directLoc; // optional (count pass): outLoc[i] = "one record in pool slot i"
-    int64_t n;
-    int32_t shift, nBins;
-};
-__device__ __forceinline__ int32_t bucketOf(const BucketSortParams &p, int64_t a) {
-    if (a < 0) return 0; // (bad input: fails the kernels' own range test wherever it is visited)
-    const int64_t b = a >> p.shift;
-    return b >= (int64_t)p.nBins ? p.nBins - 1 : (int32_t)b;
-}
-__global__ void __launch_bounds__(256) bucketCountKernel(const BucketSortParams p) {
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        atomicAdd(&p.bins[bucketOf(p, p.gs[i])], 1u);
-        if (p.directLoc) p.directLoc[i] = ((unsigned long long)i << HG_LOC_COUNT_BITS) | 1ull;
-    }
-}
-// exclusive scan of the (at most 2^16) bucket counters in place, one block of 1024 threads
-__global__ void __launch_bounds__(1024) bucketScanKernel(const BucketSortParams p) {
-    __shared__ uint32_t warpSums[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (p.nBins + 1023) / 1024; // consecutive counters per thread
-    const int first = (int)threadIdx.x * per;
-    uint32_t mine = 0;
-    for (int k = 0; k < per; ++k) if (first + k < p.nBins) mine += p.bins[first + k];
-    uint32_t incl = mine;
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    if (lane == 31) warpSums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warpSums[lane], wi = w;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += v;
-        }
-        warpSums[lane] = wi - w;
-    }
-    __syncthreads();
-    uint32_t at = warpSums[warp] + incl - mine;
-    for (int k = 0; k < per; ++k) {
-        if (first + k < p.nBins) { const uint32_t c = p.bins[first + k]; p.bins[first + k] = at; at += c; }
-    }
-}
-__global__ void __launch_bounds__(256) bucketScatterKernel(const BucketSortParams p) {
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const int64_t a = p.gs[i], len = p.ge[i] - a + 1;
-        const uint64_t l32 = (len <= 0 || len >= 0xffffffffll) ? 0xffffffffull : (uint64_t)len;
-        const uint32_t slot = atomicAdd(&p.bins[bucketOf(p, a)], 1u);
-        p.keysOut[slot] = (uint64_t)a;
-        p.valsOut[slot] = (uint64_t)i | (l32 << 32);
-    }
-}
-
 // compact the ids of intervals whose status == want into list (order irrelevant)
 struct CollectParams {
     const uint32_t *status;

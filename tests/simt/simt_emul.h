@@ -28,6 +28,9 @@ struct dim3 {
 struct longlong2 {
     long long x, y;
 };
+struct ulonglong2 {
+    unsigned long long x, y;
+};
 
 namespace simt {
 struct Warp {

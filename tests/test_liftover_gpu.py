@@ -280,9 +280,9 @@ def test_cuda_fused_walk_equals_oracle(hb, oracle_lib, monkeypatch, hal, src, tg
             assert_same_as_oracle(off, recs, exp)
 
 
-@pytest.mark.parametrize("env", [{"HALGPU_RADIX_SORT": "1"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "4"}, {"HALGPU_SORT_BITS": "3"}])
+@pytest.mark.parametrize("env", [{"HALGPU_TILE_GRAB": "0"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "16"}, {"HALGPU_SORT_BITS": "8"}])
 def test_cuda_order_switches_equal_default(hb, oracle_lib, monkeypatch, env):
-    """bucket sort (default) vs CUB radix sort, fixed-stride tiles (default) vs the atomic tile cursor: identical results"""
+    """sort granularity and tile hand-out of the lane kernel (HALGPU_SORT_BITS, HALGPU_TILE_GRAB): identical results"""
     path = os.path.join(GOLDEN, "varlen8.hal")
     o = oracle_lib.Oracle(path)
     with hb.Alignment(path) as a:

@@ -49,9 +49,13 @@ def _run_ranks(emul_lib, hal, src, tgt, shards, flags=0, batches=1):
     return out
 
 
-@pytest.mark.parametrize("sizes,maxlen", [((120, 120), 12), ((150, 40), 200), ((0, 60), 100), ((70, 70, 70), 8)])
-def test_emulated_allgather_equals_single_lift(emul_lib, sizes, maxlen):
+@pytest.mark.parametrize("wire", ["default", "HALGPU_GATHER_WIRE16"])
+@pytest.mark.parametrize("sizes,maxlen", [((120, 120), 12), ((150, 40), 200), ((0, 60), 100), ((70, 70, 70), 8), ((40, 50, 0, 60), 30)])
+def test_emulated_allgather_equals_single_lift(emul_lib, monkeypatch, sizes, maxlen, wire):
+    """(the records travel as they are below 4 ranks, in compact 16-byte form from 4 ranks up; the switch forces the latter)"""
     import hal_b200
+    if wire != "default":
+        monkeypatch.setenv(wire, "1")
     hal = os.path.join(GOLDEN, "varlen8.hal")
     a = hal_b200.Alignment(hal, lib_path=emul_lib)
     s, t = a.genome_id("L0"), a.genome_id("L3")
@@ -70,6 +74,7 @@ def test_emulated_allgather_equals_single_lift(emul_lib, sizes, maxlen):
 
 @pytest.mark.parametrize("wire32", [False, True])
 def test_emulated_allgather_collinear_uniform_shards(emul_lib, tmp_path, monkeypatch, wire32):
+    monkeypatch.setenv("HALGPU_GATHER_WIRE32" if wire32 else "HALGPU_GATHER_WIRE16", "1")
     """equal shards of a collinear alignment: every interval ends in the one-lane-per-interval kernel, the offsets are the
     identity on every rank (not sent) and the records travel in compact 16-byte form -- or, with HALGPU_GATHER_WIRE32, as
     they are"""
@@ -78,8 +83,6 @@ def test_emulated_allgather_collinear_uniform_shards(emul_lib, tmp_path, monkeyp
     from conftest import ROOT
     from hal_b200 import build
     build.build()
-    if wire32:
-        monkeypatch.setenv("HALGPU_GATHER_WIRE32", "1")
     hal = str(tmp_path / "flat.hal")
     subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", "((L0,L1)A0,(L2)A1)R;", "--segs", "3000", "--segLen", "16", hal])
     a = hal_b200.Alignment(hal, lib_path=emul_lib)

@@ -56,10 +56,13 @@ def _gather(world, shards, hal, src, tgt, batches=2):
     return out
 
 
+@pytest.mark.parametrize("wire", ["default", "HALGPU_GATHER_WIRE16", "HALGPU_GATHER_WIRE32"])
 @pytest.mark.parametrize("ragged", [False, True])
-def test_nccl_allgather_equals_single_lift(ragged):
+def test_nccl_allgather_equals_single_lift(monkeypatch, ragged, wire):
     import torch
     import hal_b200
+    if wire != "default":
+        monkeypatch.setenv(wire, "1")
     world = min(torch.cuda.device_count(), 4)
     hal = os.path.join(GOLDEN, "varlen8.hal")
     with hal_b200.Alignment(hal) as a:

@@ -123,5 +123,34 @@ print('$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'f
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_k.csv \
         python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/bench_ncu_k.err
     ;;
+l)  # lane-kernel tile hand-out A/B at N=1 (HALGPU_TILE_GRAB) with the radix sort
+    Q="--steps 20 --warmup 5 --no-cli --no-maf --no-wiggle --no-cpu-baseline --no-depth --no-traffic --no-divergent"
+    for g in 4 2 8 16 32; do
+        HALGPU_TILE_GRAB=$g python bench.py $Q > gpurun_out/bench_l_grab$g.json 2>> gpurun_out/bench_l.err
+        python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_l_grab$g.json').read().strip().splitlines()[-1])
+print('grab$g', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'fast_ms %.4f' % d['detail']['fast_kernel_ms'], 'e2e %.4g' % d['e2e']['value'], d['check'])
+"
+    done
+    ;;
+m)  # multi-GPU (gpurun --gpus N): NCCL tests of the C++ path, the gather timeline, bench at N with the default / forced wire forms
+    N=$(nvidia-smi -L | wc -l)
+    T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+    Q="--gpus $N --no-cpu-baseline --no-depth --no-c4"
+    timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu > gpurun_out/pytest_m.log 2>&1; tail -3 gpurun_out/pytest_m.log
+    HALGPU_GATHER_TIMELINE=1 timeout 600 $T --master-port 29611 bench.py $Q --steps 6 --warmup 3 > gpurun_out/bench_m_n${N}_timeline.json 2> gpurun_out/bench_m_n${N}_timeline.err
+    grep "timeline rank 0" gpurun_out/bench_m_n${N}_timeline.err | tail -8
+    timeout 600 $T --master-port 29612 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}.json 2> gpurun_out/bench_m_n${N}.err
+    HALGPU_GATHER_WIRE16=1 timeout 600 $T --master-port 29613 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_wire16.json 2> gpurun_out/bench_m_n${N}_wire16.err
+    HALGPU_GATHER_WIRE32=1 timeout 600 $T --master-port 29614 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_wire32.json 2> gpurun_out/bench_m_n${N}_wire32.err
+    HALGPU_ONE_COMM=1 timeout 600 $T --master-port 29615 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_onecomm.json 2> gpurun_out/bench_m_n${N}_onecomm.err
+    timeout 600 $T --master-port 29616 bench.py $Q --steps 20 --warmup 5 --no-gather > gpurun_out/bench_m_n${N}_nogather.json 2> gpurun_out/bench_m_n${N}_nogather.err
+    for f in "" _wire16 _wire32 _onecomm _nogather; do python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_m_n${N}$f.json').read().strip().splitlines()[-1])
+print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
+"; done
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac

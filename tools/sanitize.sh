@@ -18,7 +18,7 @@ g++ $F -fPIC -shared -o libhalBlockVizGpu_emul.so $H/blockviz.cpp $H/maf_export.
 g++ $F -DHALGPU_BLOCKVIZ_HEADER -I$R/include -o blockVizCli_emul $R/tests/cpp/blockviz_cli.cpp -L. -lhalBlockVizGpu_emul $L
 g++ $F -o halAlignmentDepth_emul $H/halAlignmentDepthMain.cpp $L
 g++ $F -o hal2maf_emul $H/hal2mafMain.cpp $H/maf_export.cpp $H/bed.cpp $L
-export ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 HALGPU_TEXT_THREADS=4 HALGPU_WIG_GRAIN=50
+export ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 HALGPU_CLEAN_EXIT=1 HALGPU_TEXT_THREADS=4 HALGPU_WIG_GRAIN=50
 cd "$R"
 for hal in tests/golden/refBedLiftoverTest.hal tests/golden/varlen8.hal; do
     python tools/wig_cli_vs_ref.py $A/halWiggleLiftover_emul $hal 1 | tail -n 1
