@@ -855,8 +855,11 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         const bool seedTile = !wig && !raw && !coalPath && srcIsTop && tileEnv != nullptr && tileEnv[0] == '1';
         // HALGPU_FUSE=1 (measurement switch): the fused walk (whole collinear runs per fragment, liftover_kernel.cuh) runs the first
         // pass over plain BED batches; what it flags ST_REDO_EXACT, and every retry rung, is walked piece by piece by the plain
-        // instantiation.  Measured on the divergent C2 (gpurun_out/bench_j_default.json): nearly every interval has paralogous
-        // pieces that clash in the target and is walked twice, 87 -> 138 ms per 9.94 M intervals -- off by default.
+        // instantiation.  Measured on the divergent C2 (gpurun_out/bench_j_default.json): 87 -> 138 ms per 9.94 M intervals although only
+        // ~1 % of the intervals are handed back (and the scratch-overflow retries all but vanish): the plain walk moves the 32 equally
+        // cut pieces of a synthetic interval in lock step, one hop per iteration, while a fused fragment is cut at every run end into a
+        // chain of remainders that are pushed, popped and re-located (bucket search) one after the other with few lanes busy -- off by
+        // default; it is the better walk only where segment boundaries do not line up across genomes.
         const char *fuseEnv = std::getenv("HALGPU_FUSE");
         const bool fuse = !wig && !raw && !coalPath && !wantPsl && !columnMerge && !seedTile && !(flags & HALGPU_NO_FAST) && pl.fastOk &&
                           fuseEnv != nullptr && fuseEnv[0] == '1';
