@@ -13,9 +13,13 @@
 #include "../../include/halgpu.h"
 #include "comm.hpp"
 #include "engine.hpp"
+#include <array>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <unistd.h>
 
 using namespace halgpu;
 
@@ -107,24 +111,42 @@ __global__ void unpackOffKernel(const UnpackOffParams p) {
 
 } // namespace halgpu
 
+// per-batch header of one rank (32 words), all-gathered before the records move
+enum { H_N = 0, H_NREC = 1, H_FITS = 2 /* cleared on the device by packRecKernel */, H_IDENTITY = 3, H_PTR_WIRE = 4, H_PTR_RECS = 5, H_PTR_OFF = 6,
+       H_IPC_WIRE = 8, H_IPC_RECS = 16, H_IPC_OFF = 24, H_WORDS = 32 };
+
+struct PeerInfo { // exchanged once, when the communicator is made
+    uint64_t pid, token; // same pid + token: a rank of this very process (its pointers are used as they are)
+    uint8_t uuid[16];    // the GPU it runs on
+};
+
 struct halgpu_comm {
     halgpu_ctx *ctx = nullptr;
     rt::Comm *comm = nullptr;
-    rt::Stream stream{};         // record gathers
+    rt::Stream stream{};         // record transfers
     rt::Stream hdrStream{};      // per-batch headers (own communicator: comm.hpp)
-    uint64_t *hostHdr = nullptr; // pinned: 4 words per rank
+    uint64_t *hostHdr = nullptr; // pinned: H_WORDS per rank
     bool timeline = false;       // HALGPU_GATHER_TIMELINE=1: end() prints when each phase of the batch ran on the device
     std::unique_ptr<rt::Event> origin;
+    // peer-memory gather: every rank reads the other ranks' result buffers straight over NVLink with the copy engines
+    bool pull = false;
+    std::vector<PeerInfo> peers;
+    std::vector<uint8_t> sameProcess;
+    std::map<std::pair<int, std::array<uint8_t, 64>>, void *> opened; // (rank, IPC handle) -> mapping in this process
+    std::map<void *, rt::IpcHandle> exported;                            // this rank's buffers -> their handles
+    uint64_t exchanges = 0; // header exchanges completed
+    struct Zombie { uint64_t tag; void *buf[5]; };
+    std::vector<Zombie> zombies; // buffers the peers may still be reading: released after the next header exchange
 };
 
 struct halgpu_gather {
     halgpu_comm *cm = nullptr;
-    LiftOutput local;              // this rank's result, alive until the collectives have read it
+    LiftOutput local;              // this rank's result, alive until every rank has read it
     std::vector<uint64_t> n, nRec; // per rank
     uint32_t *wireOff = nullptr;   // all ranks' 32-bit offsets
     uint32_t *sendOff = nullptr;
     unsigned long long *sendWire = nullptr, *recvWire = nullptr; // compact records (16 bytes each), when every rank's fit
-    bool compact = false, identity = false;
+    bool compact = false, identity = false, pulled = false;
     uint64_t *offsets = nullptr;   // global CSR
     halgpu_lift_rec *recs = nullptr;
     std::unique_ptr<rt::Event> ready, done;
@@ -159,12 +181,40 @@ unsigned gridOf(int64_t n, unsigned block) {
 }
 } // namespace
 
+namespace {
+uint64_t processToken() {
+    static const uint64_t t = (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() ^ ((uint64_t)getpid() << 32);
+    return t;
+}
+// all ranks exchange `bytes` bytes each over the header communicator (host in, host out)
+void exchangeSmall(halgpu_comm *c, const void *mine, void *all, size_t bytes) {
+    DeviceCache &cache = c->ctx->impl->cache();
+    const int W = c->comm->nranks;
+    uint8_t *d = static_cast<uint8_t *>(cache.take((size_t)(W + 1) * bytes));
+    rt::h2d(d + (size_t)W * bytes, mine, bytes, c->hdrStream);
+    rt::commAllGatherSmall(c->comm, d + (size_t)W * bytes, d, bytes, c->hdrStream);
+    rt::d2h(all, d, (size_t)W * bytes, c->hdrStream);
+    rt::sync(c->hdrStream);
+    cache.give(d);
+}
+void releaseZombies(halgpu_comm *c, bool all) {
+    DeviceCache &cache = c->ctx->impl->cache();
+    size_t keep = 0;
+    for (halgpu_comm::Zombie &z : c->zombies) {
+        if (all || z.tag < c->exchanges) { for (void *b : z.buf) cache.give(b); }
+        else c->zombies[keep++] = z;
+    }
+    c->zombies.resize(keep);
+}
+} // namespace
+
 extern "C" {
 
 int halgpu_comm_unique_id(uint8_t id[128], char **err) {
     if (id == nullptr) return failMsg(err, "halgpu_comm_unique_id: null argument");
     return guardedCall(err, [&] { rt::commUniqueId(id); });
 }
+
 
 int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128], halgpu_comm **out, char **err) {
     if (ctx == nullptr || id == nullptr || out == nullptr) return failMsg(err, "halgpu_comm_init: null argument");
@@ -179,13 +229,48 @@ int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128
         c->hdrStream = rt::createStream();
         c->timeline = std::getenv("HALGPU_GATHER_TIMELINE") != nullptr;
         if (c->timeline) { c->origin.reset(new rt::Event); c->origin->record(ctx->impl->stream()); }
-        c->hostHdr = static_cast<uint64_t *>(rt::hostAlloc((size_t)nranks * 4 * sizeof(uint64_t)));
+        c->hostHdr = static_cast<uint64_t *>(rt::hostAlloc((size_t)nranks * H_WORDS * sizeof(uint64_t)));
+        // who the other ranks are, and whether every rank can read every other rank's memory (NVLink / PCIe peer access);
+        // HALGPU_GATHER_NCCL=1 (measurement switch) keeps the records on ncclAllGather
+        c->peers.resize((size_t)nranks);
+        c->sameProcess.assign((size_t)nranks, 0);
+        PeerInfo me;
+        std::memset(&me, 0, sizeof(me));
+        me.pid = (uint64_t)getpid(); me.token = processToken();
+        rt::deviceUuid(ctx->impl->device(), me.uuid);
+        if (nranks > 1) exchangeSmall(c.get(), &me, c->peers.data(), sizeof(PeerInfo));
+        else c->peers[0] = me;
+        uint64_t capable = std::getenv("HALGPU_GATHER_NCCL") == nullptr ? 1 : 0;
+        for (int r = 0; r < nranks; ++r) {
+            const PeerInfo &p = c->peers[(size_t)r];
+            c->sameProcess[(size_t)r] = p.pid == me.pid && p.token == me.token;
+            if (r == rank) continue;
+            const int dev = rt::deviceByUuid(p.uuid);
+            if (dev < 0 || !rt::enablePeerAccess(ctx->impl->device(), dev)) capable = 0;
+        }
+        std::vector<uint64_t> caps((size_t)nranks, capable);
+        if (nranks > 1) exchangeSmall(c.get(), &capable, caps.data(), sizeof(uint64_t));
+        c->pull = nranks > 1;
+        for (uint64_t v : caps) c->pull = c->pull && v == 1;
+        if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] communicator rank %d of %d: peer-memory gather %s\n", rank, nranks, c->pull ? "on" : "off (NCCL all-gather)");
         *out = c.release();
     });
 }
 
 void halgpu_comm_free(halgpu_comm *c) {
     if (c == nullptr) return;
+    try {
+        rt::setDevice(c->ctx->impl->device());
+        if (c->pull) { // nobody reads anybody's buffers any more once every rank is here (the call is collective)
+            uint64_t mine = 0;
+            std::vector<uint64_t> all((size_t)c->comm->nranks);
+            exchangeSmall(c, &mine, all.data(), sizeof(uint64_t));
+            for (auto &kv : c->opened) rt::ipcClose(kv.second);
+            c->opened.clear();
+            exchangeSmall(c, &mine, all.data(), sizeof(uint64_t)); // (every mapping is closed before any owner frees its memory)
+        }
+    } catch (...) {}
+    releaseZombies(c, true);
     rt::commDestroy(c->comm);
     rt::destroyStream(c->stream);
     rt::destroyStream(c->hdrStream);
@@ -216,84 +301,143 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             // 1. this rank's records in compact wire form (packRecKernel also decides whether they all fit), on the engine's
             //    stream.  The compact form halves the link bytes and costs one pack pass here and one unpack pass over ALL
             //    ranks' records in end(): worth it from 4 ranks up (every rank receives (W - 1) / W of the result), while 2
-            //    ranks are faster with the 32-byte records gathered in place.  HALGPU_GATHER_WIRE32 / HALGPU_GATHER_WIRE16
+            //    ranks are faster with the 32-byte records moved as they are.  HALGPU_GATHER_WIRE32 / HALGPU_GATHER_WIRE16
             //    force either form (measurement switches).
-            uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * 32));
+            uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * H_WORDS * 8));
             const bool myIdentity = g->local.fastMs > 0 && g->local.nComplex == 0 && g->local.nRec == n;
             bool wantCompact = W >= 4;
             if (std::getenv("HALGPU_GATHER_WIRE32") != nullptr) wantCompact = false;
             if (std::getenv("HALGPU_GATHER_WIRE16") != nullptr) wantCompact = true;
-            // header: intervals, records, "all my records fit the compact wire form", "my offsets are the identity"
-            uint64_t mine[4] = {(uint64_t)n, (uint64_t)g->local.nRec, wantCompact ? 1u : 0u, myIdentity ? 1u : 0u};
-            rt::h2d(dHdr + (size_t)W * 4, mine, 32, C.stream());
-            if (cm->timeline) { g->tl[0].reset(new rt::Event); g->tl[0]->record(C.stream()); }
-            if (wantCompact) {
-                g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
-                if (g->local.nRec > 0) {
-                    WireParams wp;
-                    std::memset(&wp, 0, sizeof(wp));
-                    wp.recs = g->local.recs; wp.wire = g->sendWire; wp.n = (int64_t)g->local.nRec;
-                    wp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * 4 + 2);
-                    rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
-                }
+            if (wantCompact) g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
+            if (!myIdentity) g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4)); // (32-bit offsets on the wire)
+            uint64_t mine[H_WORDS];
+            std::memset(mine, 0, sizeof(mine));
+            mine[H_N] = (uint64_t)n; mine[H_NREC] = (uint64_t)g->local.nRec; mine[H_FITS] = wantCompact ? 1u : 0u; mine[H_IDENTITY] = myIdentity ? 1u : 0u;
+            if (cm->pull) { // where the other ranks find this rank's buffers
+                auto put = [&](void *buf, int ptrWord, int ipcWord) {
+                    if (buf == nullptr) return;
+                    mine[ptrWord] = (uint64_t)(uintptr_t)buf;
+                    auto it = cm->exported.find(buf);
+                    if (it == cm->exported.end()) {
+                        rt::IpcHandle h;
+                        uint64_t off = 0;
+                        rt::ipcExport(buf, h, off);
+                        it = cm->exported.emplace(buf, h).first;
+                    }
+                    std::memcpy(&mine[ipcWord], it->second.b, 64);
+                };
+                put(g->sendWire, H_PTR_WIRE, H_IPC_WIRE);
+                put(g->local.recs, H_PTR_RECS, H_IPC_RECS);
+                put(g->sendOff, H_PTR_OFF, H_IPC_OFF);
             }
-            if (!myIdentity) { // (32-bit offsets on the wire; not needed when every rank's offsets turn out to be the identity)
-                g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4));
+            rt::h2d(dHdr + (size_t)W * H_WORDS, mine, sizeof(mine), C.stream());
+            if (cm->timeline) { g->tl[0].reset(new rt::Event); g->tl[0]->record(C.stream()); }
+            if (wantCompact && g->local.nRec > 0) {
+                WireParams wp;
+                std::memset(&wp, 0, sizeof(wp));
+                wp.recs = g->local.recs; wp.wire = g->sendWire; wp.n = (int64_t)g->local.nRec;
+                wp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * H_WORDS + H_FITS);
+                rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
+            }
+            auto packOffsets = [&] {
                 PackOffParams pp;
                 pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
                 rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
-            }
+            };
+            if (!myIdentity) packOffsets();
             g->ready.reset(new rt::Event);
             g->done.reset(new rt::Event);
             g->ready->record(C.stream());
-            // 2. every rank learns every shard's size: one 32-byte header per rank over the header communicator on its own
-            //    stream -- the only host round trip of the gather, and not queued behind the previous batch's records
+            // 2. every rank learns every shard's size (and buffers): one 256-byte header per rank over the header communicator
+            //    on its own stream -- the only host round trip of the gather, and not queued behind the previous batch's
+            //    records.  With the peer-memory gather a rank's header also says "my buffers are complete": the engine's
+            //    stream is drained first.
+            if (cm->pull) rt::sync(C.stream());
             g->ready->wait(cm->hdrStream);
-            rt::commAllGatherSmall(cm->comm, dHdr + (size_t)W * 4, dHdr, 32, cm->hdrStream);
-            rt::d2h(cm->hostHdr, dHdr, (size_t)W * 32, cm->hdrStream);
+            rt::commAllGatherSmall(cm->comm, dHdr + (size_t)W * H_WORDS, dHdr, H_WORDS * 8, cm->hdrStream);
+            rt::d2h(cm->hostHdr, dHdr, (size_t)W * H_WORDS * 8, cm->hdrStream);
             rt::sync(cm->hdrStream);
             cache.give(dHdr);
+            ++cm->exchanges;
+            releaseZombies(cm, false); // every rank has finished the batches it ended before this exchange
+            const uint64_t *H = cm->hostHdr;
             g->n.resize((size_t)W); g->nRec.resize((size_t)W);
             uint64_t nTotal = 0, recTotal = 0, maxN = 0;
-            bool uniform = true;
+            bool uniform = true, anyIdentity = false;
             g->compact = true; g->identity = true;
             for (int r = 0; r < W; ++r) {
-                g->n[(size_t)r] = cm->hostHdr[4 * r]; g->nRec[(size_t)r] = cm->hostHdr[4 * r + 1];
-                g->compact = g->compact && cm->hostHdr[4 * r + 2] == 1;
-                g->identity = g->identity && cm->hostHdr[4 * r + 3] == 1;
+                const uint64_t *h = H + (size_t)r * H_WORDS;
+                g->n[(size_t)r] = h[H_N]; g->nRec[(size_t)r] = h[H_NREC];
+                g->compact = g->compact && h[H_FITS] == 1;
+                g->identity = g->identity && h[H_IDENTITY] == 1;
+                anyIdentity = anyIdentity || h[H_IDENTITY] == 1;
                 nTotal += g->n[(size_t)r]; recTotal += g->nRec[(size_t)r];
                 maxN = std::max(maxN, g->n[(size_t)r]);
                 uniform = uniform && g->n[(size_t)r] == g->n[0] && g->nRec[(size_t)r] == g->nRec[0];
             }
-            if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] gather rank %d: compact %d identity %d uniform %d records %llu\n", me, (int)g->compact, (int)g->identity, (int)uniform, (unsigned long long)recTotal);
+            // (a rank whose offsets are the identity has packed none: in the rare mixed batch they are packed now and travel by NCCL)
+            g->pulled = cm->pull && !(anyIdentity && !g->identity);
+            if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] gather rank %d: compact %d identity %d uniform %d records %llu, %s\n", me, (int)g->compact, (int)g->identity, (int)uniform, (unsigned long long)recTotal, g->pulled ? "peer copies" : "NCCL");
             g->offsets = static_cast<uint64_t *>(cache.take((size_t)(nTotal + 2) * 8));
             g->recs = static_cast<halgpu_lift_rec *>(cache.take(std::max<uint64_t>(recTotal, 1) * sizeof(halgpu_lift_rec)));
             if (!g->identity) {
                 g->wireOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4 * (size_t)W));
                 if (g->sendOff == nullptr) { // my offsets are the identity, some other rank's are not
                     g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4));
-                    PackOffParams pp;
-                    pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
-                    rt::launch(packOffKernel, gridOf((int64_t)n, 256), 256, 0, C.stream(), pp);
+                    packOffsets();
                     g->ready->record(C.stream());
                 }
             }
             if (g->compact) g->recvWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(recTotal, 1) * 16));
-            // 3. the gather on the communicator's stream: offsets and records, fused into one NCCL group
+            // 3. the records (and offsets) of every rank, on the communicator's stream
             g->ready->wait(cm->stream);
             if (cm->timeline) { g->tl[1].reset(new rt::Event); g->tl[1]->record(cm->stream); }
             const void *sendRecs = g->compact ? (const void *)g->sendWire : (const void *)g->local.recs;
-            void *recvRecs = g->compact ? (void *)g->recvWire : (void *)g->recs;
+            uint8_t *recvRecs = g->compact ? reinterpret_cast<uint8_t *>(g->recvWire) : reinterpret_cast<uint8_t *>(g->recs);
             const size_t recBytes = g->compact ? 16 : sizeof(halgpu_lift_rec);
-            rt::commGroupStart();
-            if (uniform) {
-                if (!g->identity) rt::commAllGather(cm->comm, g->sendOff, g->wireOff, (size_t)g->n[0] * 4, cm->stream);
-                rt::commAllGather(cm->comm, sendRecs, recvRecs, (size_t)g->nRec[0] * recBytes, cm->stream);
+            if (g->pulled) {
+                // Peer-memory gather: this rank copies every other rank's shard out of that rank's own buffer, straight to its
+                // final place, with the copy engines over NVLink (no SMs, no staging, no NCCL kernel competing with the next
+                // batch's lift).  Rank me starts with rank me + 1 and goes round, so that at any time every rank serves one reader.
+                uint64_t recAt[HG_MAX_RANKS + 1];
+                recAt[0] = 0;
+                for (int r = 0; r < W; ++r) recAt[r + 1] = recAt[r] + g->nRec[(size_t)r];
+                auto peerBuf = [&](int r, int ptrWord, int ipcWord) -> const void * {
+                    const uint64_t *h = H + (size_t)r * H_WORDS;
+                    if (r == me || cm->sameProcess[(size_t)r]) return reinterpret_cast<const void *>((uintptr_t)h[ptrWord]);
+                    std::array<uint8_t, 64> key;
+                    std::memcpy(key.data(), &h[ipcWord], 64);
+                    auto it = cm->opened.find(std::make_pair(r, key));
+                    if (it == cm->opened.end()) {
+                        rt::IpcHandle ih;
+                        std::memcpy(ih.b, key.data(), 64);
+                        it = cm->opened.emplace(std::make_pair(r, key), rt::ipcOpen(ih)).first;
+                    }
+                    return it->second;
+                };
+                for (int k = 0; k < W; ++k) {
+                    const int r = (me + 1 + k) % W; // (my own shard last: a local copy)
+                    if (g->nRec[(size_t)r] > 0) {
+                        const void *src = r == me ? sendRecs : peerBuf(r, g->compact ? H_PTR_WIRE : H_PTR_RECS, g->compact ? H_IPC_WIRE : H_IPC_RECS);
+                        rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cm->stream);
+                    }
+                    if (!g->identity && g->n[(size_t)r] > 0) {
+                        const void *src = r == me ? (const void *)g->sendOff : peerBuf(r, H_PTR_OFF, H_IPC_OFF);
+                        const uint64_t at = uniform ? (uint64_t)r * g->n[0] : (uint64_t)r * (maxN + 1);
+                        rt::copyFromPeer(g->wireOff + at, src, (size_t)g->n[(size_t)r] * 4, cm->stream);
+                    }
+                }
             } else {
-                if (!g->identity) rt::commAllGatherV(cm->comm, g->sendOff, g->wireOff, g->n, 4, (maxN + 1), cm->stream);
-                rt::commAllGatherV(cm->comm, sendRecs, recvRecs, g->nRec, recBytes, 0, cm->stream);
+                rt::commGroupStart();
+                if (uniform) {
+                    if (!g->identity) rt::commAllGather(cm->comm, g->sendOff, g->wireOff, (size_t)g->n[0] * 4, cm->stream);
+                    rt::commAllGather(cm->comm, sendRecs, recvRecs, (size_t)g->nRec[0] * recBytes, cm->stream);
+                } else {
+                    if (!g->identity) rt::commAllGatherV(cm->comm, g->sendOff, g->wireOff, g->n, 4, (maxN + 1), cm->stream);
+                    rt::commAllGatherV(cm->comm, sendRecs, recvRecs, g->nRec, recBytes, 0, cm->stream);
+                }
+                rt::commGroupEnd();
             }
-            rt::commGroupEnd();
             g->done->record(cm->stream);
             (void)me;
         } catch (...) {
@@ -360,9 +504,18 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
         *out = r;
     });
     if (rc != 0) { try { rt::sync(cm->stream); } catch (...) {} }
-    C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
-    C.cache().give(g->sendOff); C.cache().give(g->wireOff); C.cache().give(g->offsets); C.cache().give(g->recs);
-    C.cache().give(g->sendWire); C.cache().give(g->recvWire);
+    if (g->pulled) {
+        // the other ranks may still be copying out of this rank's buffers: they go back to the cache after the next header
+        // exchange (every rank gets there only after it has ended this batch), or when the communicator is freed
+        halgpu_comm::Zombie z;
+        z.tag = cm->exchanges;
+        z.buf[0] = g->local.offsets; z.buf[1] = g->local.recs; z.buf[2] = g->local.psl; z.buf[3] = g->sendOff; z.buf[4] = g->sendWire;
+        cm->zombies.push_back(z);
+    } else {
+        C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
+        C.cache().give(g->sendOff); C.cache().give(g->sendWire);
+    }
+    C.cache().give(g->wireOff); C.cache().give(g->offsets); C.cache().give(g->recs); C.cache().give(g->recvWire);
     delete g;
     return rc;
 }

@@ -22,6 +22,7 @@
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/iterator/reverse_iterator.h>
 #include <cuda_runtime.h>
+#include <cstring>
 #endif
 
 namespace halgpu {
@@ -58,6 +59,15 @@ inline void dmemset(void *d, int v, size_t n, Stream) { if (n) std::memset(d, v,
 inline void sync(Stream) {}
 inline int smCount() { return 2; }
 inline void retainPool(int) {}
+// peer memory (multi.cu): the harness's ranks are threads of one process, "device" memory is host memory
+struct IpcHandle { uint8_t b[64]; };
+inline void ipcExport(void *p, IpcHandle &h, uint64_t &offset) { std::memset(&h, 0, sizeof(h)); std::memcpy(h.b, &p, sizeof(p)); offset = 0; }
+inline void *ipcOpen(const IpcHandle &h) { void *p; std::memcpy(&p, h.b, sizeof(p)); return p; }
+inline void ipcClose(void *) {}
+inline void deviceUuid(int, uint8_t out[16]) { std::memset(out, 0, 16); }
+inline int deviceByUuid(const uint8_t[16]) { return 0; }
+inline bool enablePeerAccess(int, int) { return true; }
+inline void copyFromPeer(void *dst, const void *src, size_t n, Stream) { if (n) std::memcpy(dst, src, n); }
 struct Event {
     std::chrono::steady_clock::time_point t;
     void record(Stream) { t = std::chrono::steady_clock::now(); }
@@ -152,6 +162,50 @@ inline void retainPool(int device) { // keep freed stream-ordered memory in the 
     check(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
     uint64_t keep = ~0ull;
     check(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+}
+// ---- peer memory (multi.cu): the other ranks' result buffers are read straight over NVLink ----
+struct IpcHandle { uint8_t b[64]; };
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IpcHandle carries a cudaIpcMemHandle_t");
+// handle of the cudaMalloc allocation that starts at p
+inline void ipcExport(void *p, IpcHandle &h, uint64_t &offset) {
+    cudaIpcMemHandle_t ch;
+    check(cudaIpcGetMemHandle(&ch, p), "cudaIpcGetMemHandle");
+    std::memcpy(h.b, &ch, 64);
+    offset = 0; // (callers export whole cudaMalloc allocations: the DeviceCache's buffers)
+}
+inline void *ipcOpen(const IpcHandle &h) { // (another process's allocation; peer access is enabled as needed)
+    cudaIpcMemHandle_t ch;
+    std::memcpy(&ch, h.b, 64);
+    void *p = nullptr;
+    check(cudaIpcOpenMemHandle(&p, ch, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return p;
+}
+inline void ipcClose(void *p) { if (p) cudaIpcCloseMemHandle(p); }
+inline void deviceUuid(int dev, uint8_t out[16]) {
+    cudaDeviceProp prop;
+    check(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+    std::memcpy(out, prop.uuid.bytes, 16);
+}
+inline int deviceByUuid(const uint8_t uuid[16]) { // ordinal among this process's visible devices, -1: not visible
+    int n = 0;
+    check(cudaGetDeviceCount(&n), "cudaGetDeviceCount");
+    for (int d = 0; d < n; ++d) {
+        uint8_t u[16];
+        deviceUuid(d, u);
+        if (std::memcmp(u, uuid, 16) == 0) return d;
+    }
+    return -1;
+}
+inline bool enablePeerAccess(int myDev, int peerDev) { // the current device is myDev
+    if (myDev == peerDev) return true;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, myDev, peerDev) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peerDev, 0);
+    cudaGetLastError();
+    return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+}
+inline void copyFromPeer(void *dst, const void *src, size_t n, Stream s) { // copy engines, no SMs
+    if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, s), "peer copy");
 }
 struct Event {
     cudaEvent_t e = nullptr;

@@ -144,9 +144,9 @@ m)  # multi-GPU (gpurun --gpus N): NCCL tests of the C++ path, the gather timeli
     timeout 600 $T --master-port 29612 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}.json 2> gpurun_out/bench_m_n${N}.err
     HALGPU_GATHER_WIRE16=1 timeout 600 $T --master-port 29613 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_wire16.json 2> gpurun_out/bench_m_n${N}_wire16.err
     HALGPU_GATHER_WIRE32=1 timeout 600 $T --master-port 29614 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_wire32.json 2> gpurun_out/bench_m_n${N}_wire32.err
-    HALGPU_ONE_COMM=1 timeout 600 $T --master-port 29615 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_onecomm.json 2> gpurun_out/bench_m_n${N}_onecomm.err
+    HALGPU_GATHER_NCCL=1 timeout 600 $T --master-port 29615 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_m_n${N}_nccl.json 2> gpurun_out/bench_m_n${N}_nccl.err
     timeout 600 $T --master-port 29616 bench.py $Q --steps 20 --warmup 5 --no-gather > gpurun_out/bench_m_n${N}_nogather.json 2> gpurun_out/bench_m_n${N}_nogather.err
-    for f in "" _wire16 _wire32 _onecomm _nogather; do python -c "
+    for f in "" _wire16 _wire32 _nccl _nogather; do python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_m_n${N}$f.json').read().strip().splitlines()[-1])
 print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
