@@ -531,6 +531,10 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local, enabled=(rank == 0))  # NVML initialised here, before the warm-up
+    if comm is not None:
+        # communicator priming, before the W warm-up steps: the first batches create the send slots and every rank maps the
+        # other ranks' slots (CUDA IPC), which costs milliseconds per mapping, once
+        run_steps(a, comm, src, tgt, n, d_gs, d_ge, 4)
     run_steps(a, comm, src, tgt, n, d_gs, d_ge, args.warmup)
     with sampler as clocks:
         barrier()
@@ -908,7 +912,7 @@ def run_c4(dist, rank, local, world):
         d_gs, d_ge = torch.from_numpy(gs).cuda(), torch.from_numpy(ge).cuda()
         comm = new_comm(a, dist, rank, world)
         stream = torch.cuda.ExternalStream(a.stream)
-        run_steps(a, comm, src, tgt, n, d_gs, d_ge, 3)
+        run_steps(a, comm, src, tgt, n, d_gs, d_ge, 4 + 3)  # (communicator priming + warm-up)
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

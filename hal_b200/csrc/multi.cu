@@ -111,9 +111,10 @@ __global__ void unpackOffKernel(const UnpackOffParams p) {
 
 } // namespace halgpu
 
-// per-batch header of one rank (32 words), all-gathered before the records move
-enum { H_N = 0, H_NREC = 1, H_FITS = 2 /* cleared on the device by packRecKernel */, H_IDENTITY = 3, H_PTR_WIRE = 4, H_PTR_RECS = 5, H_PTR_OFF = 6,
-       H_IPC_WIRE = 8, H_IPC_RECS = 16, H_IPC_OFF = 24, H_WORDS = 32 };
+// per-batch header of one rank (16 words), all-gathered before the records move
+enum { H_N = 0, H_NREC = 1, H_FITS = 2 /* cleared on the device by packRecKernel */, H_IDENTITY = 3,
+       H_PTR_SLOT = 4 /* this rank's send slot: records at its start ... */, H_OFF_OFFS = 5 /* ... 32-bit offsets at this byte offset */,
+       H_IPC_SLOT = 8 /* .. 15: the slot's IPC handle */, H_WORDS = 16 };
 
 struct PeerInfo { // exchanged once, when the communicator is made
     uint64_t pid, token; // same pid + token: a rank of this very process (its pointers are used as they are)
@@ -133,10 +134,14 @@ struct halgpu_comm {
     std::vector<PeerInfo> peers;
     std::vector<uint8_t> sameProcess;
     std::map<std::pair<int, std::array<uint8_t, 64>>, void *> opened; // (rank, IPC handle) -> mapping in this process
-    std::map<void *, rt::IpcHandle> exported;                            // this rank's buffers -> their handles
+    // What the other ranks read is a SEND SLOT owned by the communicator, not whatever buffer the engine's cache handed out:
+    // few allocations, exported once, so the peers map each of them once (the first copy out of a newly mapped allocation
+    // costs milliseconds).  A slot stays busy until the header exchange after the batch's end().
+    struct SendSlot { uint8_t *buf; size_t cap; bool busy; rt::IpcHandle ipc; };
+    std::vector<SendSlot> slots;
     uint64_t exchanges = 0; // header exchanges completed
-    struct Zombie { uint64_t tag; void *buf[5]; };
-    std::vector<Zombie> zombies; // buffers the peers may still be reading: released after the next header exchange
+    struct Zombie { uint64_t tag; int slot; };
+    std::vector<Zombie> zombies;
 };
 
 struct halgpu_gather {
@@ -144,8 +149,10 @@ struct halgpu_gather {
     LiftOutput local;              // this rank's result, alive until every rank has read it
     std::vector<uint64_t> n, nRec; // per rank
     uint32_t *wireOff = nullptr;   // all ranks' 32-bit offsets
-    uint32_t *sendOff = nullptr;
+    uint32_t *sendOff = nullptr;                                 // NCCL path: from the cache; peer-memory path: inside the send slot
     unsigned long long *sendWire = nullptr, *recvWire = nullptr; // compact records (16 bytes each), when every rank's fit
+    int slot = -1;                                               // peer-memory path: this batch's send slot
+    bool sendOffFromCache = false;
     bool compact = false, identity = false, pulled = false;
     uint64_t *offsets = nullptr;   // global CSR
     halgpu_lift_rec *recs = nullptr;
@@ -198,13 +205,41 @@ void exchangeSmall(halgpu_comm *c, const void *mine, void *all, size_t bytes) {
     cache.give(d);
 }
 void releaseZombies(halgpu_comm *c, bool all) {
-    DeviceCache &cache = c->ctx->impl->cache();
     size_t keep = 0;
     for (halgpu_comm::Zombie &z : c->zombies) {
-        if (all || z.tag < c->exchanges) { for (void *b : z.buf) cache.give(b); }
+        if (all || z.tag < c->exchanges) c->slots[(size_t)z.slot].busy = false;
         else c->zombies[keep++] = z;
     }
     c->zombies.resize(keep);
+}
+// the send side of a batch goes back: cache buffers at once, a send slot after the next header exchange (the other ranks
+// may still be copying out of it; every rank gets to that exchange only after it has ended this batch)
+void releaseSendSide(halgpu_gather *g) {
+    halgpu_comm *c = g->cm;
+    DeviceCache &cache = c->ctx->impl->cache();
+    if (g->slot >= 0) {
+        halgpu_comm::Zombie z;
+        z.tag = c->exchanges; z.slot = g->slot;
+        c->zombies.push_back(z);
+        if (g->sendOffFromCache) cache.give(g->sendOff);
+    } else {
+        cache.give(g->sendOff); cache.give(g->sendWire);
+    }
+    g->slot = -1; g->sendOff = nullptr; g->sendWire = nullptr;
+}
+int acquireSlot(halgpu_comm *c, size_t bytes) {
+    for (size_t i = 0; i < c->slots.size(); ++i) {
+        if (!c->slots[i].busy && c->slots[i].cap >= bytes) { c->slots[i].busy = true; return (int)i; }
+    }
+    // (smaller idle slots stay allocated until the communicator is freed: a peer may still have them mapped)
+    halgpu_comm::SendSlot sl;
+    sl.cap = (bytes + bytes / 4 + 4095) & ~(size_t)4095;
+    sl.buf = static_cast<uint8_t *>(rt::dmalloc(sl.cap));
+    sl.busy = true;
+    uint64_t off = 0;
+    rt::ipcExport(sl.buf, sl.ipc, off);
+    c->slots.push_back(sl);
+    return (int)c->slots.size() - 1;
 }
 } // namespace
 
@@ -271,6 +306,7 @@ void halgpu_comm_free(halgpu_comm *c) {
         }
     } catch (...) {}
     releaseZombies(c, true);
+    for (halgpu_comm::SendSlot &sl : c->slots) rt::dfree(sl.buf);
     rt::commDestroy(c->comm);
     rt::destroyStream(c->stream);
     rt::destroyStream(c->hdrStream);
@@ -308,27 +344,25 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             bool wantCompact = W >= 4;
             if (std::getenv("HALGPU_GATHER_WIRE32") != nullptr) wantCompact = false;
             if (std::getenv("HALGPU_GATHER_WIRE16") != nullptr) wantCompact = true;
-            if (wantCompact) g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
-            if (!myIdentity) g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4)); // (32-bit offsets on the wire)
+            const size_t recRegion = (std::max<uint64_t>(g->local.nRec, 1) * (wantCompact ? 16 : sizeof(halgpu_lift_rec)) + 255) & ~(size_t)255;
+            uint8_t *slotRecs = nullptr; // peer-memory path, 32-byte form: a copy of the records the other ranks read
+            if (cm->pull) {
+                g->slot = acquireSlot(cm, recRegion + (myIdentity ? 0 : (size_t)(n + 1) * 4));
+                uint8_t *sb = cm->slots[(size_t)g->slot].buf;
+                if (wantCompact) g->sendWire = reinterpret_cast<unsigned long long *>(sb);
+                else slotRecs = sb;
+                if (!myIdentity) g->sendOff = reinterpret_cast<uint32_t *>(sb + recRegion);
+            } else {
+                if (wantCompact) g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
+                if (!myIdentity) g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4)); // (32-bit offsets on the wire)
+            }
             uint64_t mine[H_WORDS];
             std::memset(mine, 0, sizeof(mine));
             mine[H_N] = (uint64_t)n; mine[H_NREC] = (uint64_t)g->local.nRec; mine[H_FITS] = wantCompact ? 1u : 0u; mine[H_IDENTITY] = myIdentity ? 1u : 0u;
-            if (cm->pull) { // where the other ranks find this rank's buffers
-                auto put = [&](void *buf, int ptrWord, int ipcWord) {
-                    if (buf == nullptr) return;
-                    mine[ptrWord] = (uint64_t)(uintptr_t)buf;
-                    auto it = cm->exported.find(buf);
-                    if (it == cm->exported.end()) {
-                        rt::IpcHandle h;
-                        uint64_t off = 0;
-                        rt::ipcExport(buf, h, off);
-                        it = cm->exported.emplace(buf, h).first;
-                    }
-                    std::memcpy(&mine[ipcWord], it->second.b, 64);
-                };
-                put(g->sendWire, H_PTR_WIRE, H_IPC_WIRE);
-                put(g->local.recs, H_PTR_RECS, H_IPC_RECS);
-                put(g->sendOff, H_PTR_OFF, H_IPC_OFF);
+            if (cm->pull) { // where the other ranks find this rank's shard
+                mine[H_PTR_SLOT] = (uint64_t)(uintptr_t)cm->slots[(size_t)g->slot].buf;
+                mine[H_OFF_OFFS] = (uint64_t)recRegion;
+                std::memcpy(&mine[H_IPC_SLOT], cm->slots[(size_t)g->slot].ipc.b, 64);
             }
             rt::h2d(dHdr + (size_t)W * H_WORDS, mine, sizeof(mine), C.stream());
             if (cm->timeline) { g->tl[0].reset(new rt::Event); g->tl[0]->record(C.stream()); }
@@ -339,6 +373,7 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                 wp.fitFlag = reinterpret_cast<unsigned long long *>(dHdr + (size_t)W * H_WORDS + H_FITS);
                 rt::launch(packRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
             }
+            if (slotRecs != nullptr && g->local.nRec > 0) rt::d2d(slotRecs, g->local.recs, (size_t)g->local.nRec * sizeof(halgpu_lift_rec), C.stream());
             auto packOffsets = [&] {
                 PackOffParams pp;
                 pp.off64 = g->local.offsets; pp.off32 = g->sendOff; pp.n = (int64_t)n;
@@ -376,14 +411,16 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                 uniform = uniform && g->n[(size_t)r] == g->n[0] && g->nRec[(size_t)r] == g->nRec[0];
             }
             // (a rank whose offsets are the identity has packed none: in the rare mixed batch they are packed now and travel by NCCL)
-            g->pulled = cm->pull && !(anyIdentity && !g->identity);
+            // (likewise a batch that wanted the compact form while some rank's records do not fit it)
+            g->pulled = cm->pull && !(anyIdentity && !g->identity) && g->compact == wantCompact;
             if (std::getenv("HALGPU_DEBUG")) fprintf(stderr, "[halgpu] gather rank %d: compact %d identity %d uniform %d records %llu, %s\n", me, (int)g->compact, (int)g->identity, (int)uniform, (unsigned long long)recTotal, g->pulled ? "peer copies" : "NCCL");
             g->offsets = static_cast<uint64_t *>(cache.take((size_t)(nTotal + 2) * 8));
             g->recs = static_cast<halgpu_lift_rec *>(cache.take(std::max<uint64_t>(recTotal, 1) * sizeof(halgpu_lift_rec)));
             if (!g->identity) {
                 g->wireOff = static_cast<uint32_t *>(cache.take((size_t)(maxN + 1) * 4 * (size_t)W));
-                if (g->sendOff == nullptr) { // my offsets are the identity, some other rank's are not
+                if (g->sendOff == nullptr) { // my offsets are the identity, some other rank's are not (NCCL path)
                     g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4));
+                    g->sendOffFromCache = true;
                     packOffsets();
                     g->ready->record(C.stream());
                 }
@@ -402,27 +439,27 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                 uint64_t recAt[HG_MAX_RANKS + 1];
                 recAt[0] = 0;
                 for (int r = 0; r < W; ++r) recAt[r + 1] = recAt[r] + g->nRec[(size_t)r];
-                auto peerBuf = [&](int r, int ptrWord, int ipcWord) -> const void * {
+                auto peerSlot = [&](int r) -> const uint8_t * {
                     const uint64_t *h = H + (size_t)r * H_WORDS;
-                    if (r == me || cm->sameProcess[(size_t)r]) return reinterpret_cast<const void *>((uintptr_t)h[ptrWord]);
+                    if (cm->sameProcess[(size_t)r]) return reinterpret_cast<const uint8_t *>((uintptr_t)h[H_PTR_SLOT]);
                     std::array<uint8_t, 64> key;
-                    std::memcpy(key.data(), &h[ipcWord], 64);
+                    std::memcpy(key.data(), &h[H_IPC_SLOT], 64);
                     auto it = cm->opened.find(std::make_pair(r, key));
                     if (it == cm->opened.end()) {
                         rt::IpcHandle ih;
                         std::memcpy(ih.b, key.data(), 64);
                         it = cm->opened.emplace(std::make_pair(r, key), rt::ipcOpen(ih)).first;
                     }
-                    return it->second;
+                    return static_cast<const uint8_t *>(it->second);
                 };
                 for (int k = 0; k < W; ++k) {
                     const int r = (me + 1 + k) % W; // (my own shard last: a local copy)
                     if (g->nRec[(size_t)r] > 0) {
-                        const void *src = r == me ? sendRecs : peerBuf(r, g->compact ? H_PTR_WIRE : H_PTR_RECS, g->compact ? H_IPC_WIRE : H_IPC_RECS);
+                        const void *src = r == me ? sendRecs : (const void *)peerSlot(r);
                         rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cm->stream);
                     }
                     if (!g->identity && g->n[(size_t)r] > 0) {
-                        const void *src = r == me ? (const void *)g->sendOff : peerBuf(r, H_PTR_OFF, H_IPC_OFF);
+                        const void *src = r == me ? (const void *)g->sendOff : (const void *)(peerSlot(r) + H[(size_t)r * H_WORDS + H_OFF_OFFS]);
                         const uint64_t at = uniform ? (uint64_t)r * g->n[0] : (uint64_t)r * (maxN + 1);
                         rt::copyFromPeer(g->wireOff + at, src, (size_t)g->n[(size_t)r] * 4, cm->stream);
                     }
@@ -443,8 +480,8 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
         } catch (...) {
             try { rt::sync(cm->stream); rt::sync(cm->hdrStream); } catch (...) {}
             C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
-            cache.give(g->sendOff); cache.give(g->wireOff); cache.give(g->offsets); cache.give(g->recs);
-            cache.give(g->sendWire); cache.give(g->recvWire);
+            releaseSendSide(g.get());
+            cache.give(g->wireOff); cache.give(g->offsets); cache.give(g->recs); cache.give(g->recvWire);
             throw;
         }
         *out = g.release();
@@ -504,17 +541,8 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
         *out = r;
     });
     if (rc != 0) { try { rt::sync(cm->stream); } catch (...) {} }
-    if (g->pulled) {
-        // the other ranks may still be copying out of this rank's buffers: they go back to the cache after the next header
-        // exchange (every rank gets there only after it has ended this batch), or when the communicator is freed
-        halgpu_comm::Zombie z;
-        z.tag = cm->exchanges;
-        z.buf[0] = g->local.offsets; z.buf[1] = g->local.recs; z.buf[2] = g->local.psl; z.buf[3] = g->sendOff; z.buf[4] = g->sendWire;
-        cm->zombies.push_back(z);
-    } else {
-        C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
-        C.cache().give(g->sendOff); C.cache().give(g->sendWire);
-    }
+    C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
+    releaseSendSide(g);
     C.cache().give(g->wireOff); C.cache().give(g->offsets); C.cache().give(g->recs); C.cache().give(g->recvWire);
     delete g;
     return rc;
