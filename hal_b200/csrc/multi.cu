@@ -275,7 +275,13 @@ int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128
         rt::deviceUuid(ctx->impl->device(), me.uuid);
         if (nranks > 1) exchangeSmall(c.get(), &me, c->peers.data(), sizeof(PeerInfo));
         else c->peers[0] = me;
-        uint64_t capable = std::getenv("HALGPU_GATHER_NCCL") == nullptr ? 1 : 0;
+        // Measured at 2 ranks (gpurun_out/bench_m_n2*.json): the copy-engine gather of 32-byte records 1.135 ms per step against
+        // 1.048 ms through ncclAllGather (one more copy of the shard into the send slot), so the peer-memory gather is the
+        // default from 4 ranks up, where the records travel in compact form and the pack pass writes the slot anyway;
+        // HALGPU_GATHER_PULL=1 / HALGPU_GATHER_NCCL=1 force either.
+        uint64_t capable = nranks >= 4 ? 1 : 0;
+        if (std::getenv("HALGPU_GATHER_PULL") != nullptr) capable = 1;
+        if (std::getenv("HALGPU_GATHER_NCCL") != nullptr) capable = 0;
         for (int r = 0; r < nranks; ++r) {
             const PeerInfo &p = c->peers[(size_t)r];
             c->sameProcess[(size_t)r] = p.pid == me.pid && p.token == me.token;

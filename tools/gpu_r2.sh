@@ -152,5 +152,20 @@ d=json.loads(open('gpurun_out/bench_m_n${N}$f.json').read().strip().splitlines()
 print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
 "; done
     ;;
+n)  # multi-GPU at N >= 4 (gpurun --gpus N): default gather (peer copies, compact wire) against NCCL and the sharded lift alone
+    N=$(nvidia-smi -L | wc -l)
+    T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+    Q="--gpus $N --no-cpu-baseline --no-depth --no-c4"
+    HALGPU_GATHER_TIMELINE=1 timeout 600 $T --master-port 29611 bench.py $Q --steps 6 --warmup 3 > gpurun_out/bench_n_n${N}_timeline.json 2> gpurun_out/bench_n_n${N}_timeline.err
+    grep "timeline rank 0" gpurun_out/bench_n_n${N}_timeline.err | tail -4
+    timeout 600 $T --master-port 29612 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_n_n${N}.json 2> gpurun_out/bench_n_n${N}.err
+    HALGPU_GATHER_NCCL=1 timeout 600 $T --master-port 29613 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_n_n${N}_nccl.json 2> gpurun_out/bench_n_n${N}_nccl.err
+    HALGPU_GATHER_WIRE32=1 timeout 600 $T --master-port 29614 bench.py $Q --steps 20 --warmup 5 > gpurun_out/bench_n_n${N}_wire32.json 2> gpurun_out/bench_n_n${N}_wire32.err
+    for f in "" _nccl _wire32; do python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_n_n${N}$f.json').read().strip().splitlines()[-1])
+print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
+"; done
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
