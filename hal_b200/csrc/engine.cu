@@ -707,8 +707,15 @@ struct PhaseTimer { // HALGPU_TIMING=1: host wall-clock of each phase of a batch
 };
 } // namespace
 
+size_t Context::poolBytesFor(int src, int tgt, size_t n, int coal) {
+    const auto &G = _file->genomes();
+    if (src < 0 || tgt < 0 || src >= (int)G.size() || tgt >= (int)G.size()) throw HalError("genome index out of range");
+    const Plan &pl = plan(src, tgt, coal);
+    return ((size_t)n + (size_t)((double)n * std::max(1.25, pl.linesPerInterval * 1.125)) + 4096) * sizeof(halgpu_lift_rec); // (liftover(): poolCap)
+}
+
 void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig, int coal) {
+                       const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase, const WigScatter *wig, int coal, const ExternalPool *ext) {
     // One batch == one pass of the hot path.  Everything up to the single stream synchronisation is enqueued without
     // waiting: sort -> fastLiftKernel (one lane per interval) -> liftoverKernel over the complex list (one warp per
     // interval) -> scan -> gather -> read-back of the counters.  Buffers come from the context's cache, so a warm batch
@@ -822,7 +829,8 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         // intervals that found the pool full.
         const uint64_t direct = fast ? (uint64_t)n : 0;
         uint64_t poolCap = wig ? 1 : direct + (uint64_t)((double)n * std::max(1.25, pl.linesPerInterval * 1.125)) + 4096; // (the wiggle mode emits no records)
-        halgpu_lift_rec *pool = L.as<halgpu_lift_rec>(poolCap);
+        const bool poolExternal = ext != nullptr && ext->buf != nullptr && ext->bytes >= poolCap * sizeof(halgpu_lift_rec) && !wig;
+        halgpu_lift_rec *pool = poolExternal ? static_cast<halgpu_lift_rec *>(ext->buf) : L.as<halgpu_lift_rec>(poolCap);
         if (direct) rt::h2d(ctr + C_POOL, &direct, sizeof(direct), _stream); // (pageable 8 bytes: copied before the call returns)
         uint32_t *pslPool = nullptr;
         if (wantPsl) {
@@ -1087,6 +1095,7 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
         out.offsets = static_cast<uint64_t *>(L.detach(csr));
         if (fast && _hostCtr[C_COMPLEX] == 0) recs = pool; // every line sits in its direct slot: the pool is the result
         out.recs = static_cast<halgpu_lift_rec *>(L.detach(recs));
+        out.recsExternal = poolExternal && recs == static_cast<halgpu_lift_rec *>(ext->buf);
         out.psl = wantPsl ? static_cast<uint32_t *>(L.detach(psl)) : nullptr;
         out.nRec = (size_t)_hostCtr[C_TOTAL];
         out.launches = (int)rt::g_launches - launches0;

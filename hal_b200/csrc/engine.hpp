@@ -47,6 +47,7 @@ struct LiftOutput { // device-side result of one batch; the buffers belong to th
     size_t n = 0, nRec = 0, nRetry = 0;
     size_t nComplex = 0;         // intervals the one-lane-per-interval kernel handed to the warp-per-interval walk
     size_t nRedo = 0;            // intervals the fused walk handed back to the piece-by-piece walk
+    bool recsExternal = false;   // recs is the caller's ExternalPool buffer (not to be handed back to the cache)
     float kernelMs = 0;          // mapping kernels of the batch (fast + walk + retries)
     float fastMs = 0;            // fastLiftKernel alone (0 when the batch did not use it)
     int launches = 0;
@@ -65,6 +66,13 @@ class DeviceCache {
     std::multimap<size_t, void *> _idle;
     std::map<void *, size_t> _sizeOf;
     size_t _held = 0;
+};
+
+// A caller-owned buffer for the record pool of one batch (multi.cu: the communicator's send slot).  Used when it is large
+// enough; a batch that the one-lane-per-interval kernel finishes alone then leaves its result right there.
+struct ExternalPool {
+    void *buf = nullptr;
+    size_t bytes = 0;
 };
 
 struct WigScatter { // wiggle mode of the mapping kernel (device pointers)
@@ -94,7 +102,10 @@ class Context {
     // device pointers in, device result out (the caller hands offsets/recs/psl back with release())
     // offsetBase is added to every CSR offset (the pipelined host entry point lifts a batch chunk by chunk)
     void liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t *dGs, const int64_t *dGe,
-                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr, int coal = -1);
+                  const uint8_t *dStrand, LiftOutput &out, uint64_t offsetBase = 0, const WigScatter *wig = nullptr, int coal = -1,
+                  const ExternalPool *ext = nullptr);
+    // bytes of record pool the next batch of n intervals on this path will ask for (what an ExternalPool has to hold)
+    size_t poolBytesFor(int src, int tgt, size_t n, int coal = -1);
 
     // wiggle liftover of nRuns source ranges [first, last] (genome coordinates) carrying per-base values (valOff >= 0) or
     // one value (valOff < 0: ~index), onto the target genome preloaded with nPre (position, value) pairs; host in, host out

@@ -69,16 +69,23 @@ __global__ void packRecKernel(const WireParams p) {
     }
     if (!ok) *p.fitFlag = 0ull;
 }
-__global__ void unpackRecKernel(const WireParams p) {
+__global__ void unpackRecKernel(const WireParams p) { // one 16-byte load and two 16-byte stores per record
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     const unsigned long long m40 = (1ull << 40) - 1ull;
+    static_assert(sizeof(halgpu_lift_rec) == 32, "record layout");
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
-        const unsigned long long a = p.wire[2 * i], b = p.wire[2 * i + 1];
-        halgpu_lift_rec r;
-        r.start = (int64_t)(a & m40); r.end = r.start + (int64_t)(a >> 40);
-        r.src_start = (int64_t)(b & m40); r.tgt_seq = (int32_t)((b >> 40) & 0xffffull); r.n_frag = (uint16_t)((b >> 56) & 0xfull);
-        r.strand = strandChar((b >> 60) & 3ull); r.src_strand = strandChar(b >> 62);
-        p.out[i] = r;
+        const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(p.wire)[i];
+        const unsigned long long a = w.x, b = w.y;
+        ulonglong2 lo, hi;
+        lo.x = a & m40;                 // start
+        lo.y = lo.x + (a >> 40);        // end
+        hi.x = b & m40;                 // src_start
+        hi.y = ((b >> 40) & 0xffffull)                                   // tgt_seq (32 bits)
+               | ((unsigned long long)strandChar((b >> 60) & 3ull) << 32) // strand
+               | ((unsigned long long)strandChar(b >> 62) << 40)          // src_strand
+               | (((b >> 56) & 0xfull) << 48);                            // n_frag (16 bits)
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(p.out + i);
+        dst[0] = lo; dst[1] = hi;
     }
 }
 struct IdentityOffParams {
@@ -125,6 +132,8 @@ struct halgpu_comm {
     halgpu_ctx *ctx = nullptr;
     rt::Comm *comm = nullptr;
     rt::Stream stream{};         // record transfers
+    std::vector<rt::Stream> pullStreams; // peer-memory gather: copies from several peers in flight at once (one copy engine
+                                         // stream moved 0.45 TB/s at 8 ranks, gpurun_out/bench_n_n8_timeline.err)
     rt::Stream hdrStream{};      // per-batch headers (own communicator: comm.hpp)
     uint64_t *hostHdr = nullptr; // pinned: H_WORDS per rank
     bool timeline = false;       // HALGPU_GATHER_TIMELINE=1: end() prints when each phase of the batch ran on the device
@@ -158,6 +167,7 @@ struct halgpu_gather {
     halgpu_lift_rec *recs = nullptr;
     std::unique_ptr<rt::Event> ready, done;
     std::unique_ptr<rt::Event> tl[3]; // timeline: lift done / gather starts / unpack done
+    std::unique_ptr<rt::Event> pullDone[3];
     float kernelMs = 0, fastMs = 0;
     size_t nComplex = 0, nRetry = 0;
     int launches = 0;
@@ -262,6 +272,7 @@ int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128
         c->comm = rt::commInit(nranks, rank, id);
         c->stream = rt::createStream();
         c->hdrStream = rt::createStream();
+        for (int i = 0; i < std::min(3, nranks - 1); ++i) c->pullStreams.push_back(rt::createStream());
         c->timeline = std::getenv("HALGPU_GATHER_TIMELINE") != nullptr;
         if (c->timeline) { c->origin.reset(new rt::Event); c->origin->record(ctx->impl->stream()); }
         c->hostHdr = static_cast<uint64_t *>(rt::hostAlloc((size_t)nranks * H_WORDS * sizeof(uint64_t)));
@@ -316,6 +327,7 @@ void halgpu_comm_free(halgpu_comm *c) {
     rt::commDestroy(c->comm);
     rt::destroyStream(c->stream);
     rt::destroyStream(c->hdrStream);
+    for (rt::Stream ps : c->pullStreams) rt::destroyStream(ps);
     rt::hostFree(c->hostHdr);
     delete c;
 }
@@ -336,7 +348,20 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
         g->cm = cm;
         DeviceCache &cache = C.cache();
         try {
-            C.liftover(src, tgt, flags, n, dStart, dEnd, dStrand, g->local, 0, nullptr, coalescenceLimit); // returns with the engine's stream idle
+            // the wire form of this batch's records, decided before the lift: with the peer-memory gather of 32-byte records the
+            // lift's record pool IS the send slot, so a batch the lane kernel finishes alone is read by the peers where it lies
+            bool wantCompact = W >= 4;
+            if (std::getenv("HALGPU_GATHER_WIRE32") != nullptr) wantCompact = false;
+            if (std::getenv("HALGPU_GATHER_WIRE16") != nullptr) wantCompact = true;
+            ExternalPool ext;
+            size_t slotOffRegion = 0; // where the 32-bit offsets go inside the slot
+            if (cm->pull && !wantCompact) {
+                const int coalForPlan = (flags & (HALGPU_NO_DUPES | HALGPU_COLUMN_LIFTOVER)) != 0 ? -1 : coalescenceLimit;
+                slotOffRegion = (C.poolBytesFor(src, tgt, n, coalForPlan) + 255) & ~(size_t)255;
+                g->slot = acquireSlot(cm, slotOffRegion + (size_t)(n + 1) * 4);
+                ext.buf = cm->slots[(size_t)g->slot].buf; ext.bytes = slotOffRegion;
+            }
+            C.liftover(src, tgt, flags, n, dStart, dEnd, dStrand, g->local, 0, nullptr, coalescenceLimit, ext.buf ? &ext : nullptr); // returns with the engine's stream idle
             g->kernelMs = g->local.kernelMs; g->fastMs = g->local.fastMs; g->nComplex = g->local.nComplex; g->nRetry = g->local.nRetry;
             g->launches = g->local.launches;
             if (g->local.nRec >= 0xffffffffull) throw HalError("a shard produced 2^32 or more records; use smaller batches");
@@ -347,17 +372,23 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             //    force either form (measurement switches).
             uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * H_WORDS * 8));
             const bool myIdentity = g->local.fastMs > 0 && g->local.nComplex == 0 && g->local.nRec == n;
-            bool wantCompact = W >= 4;
-            if (std::getenv("HALGPU_GATHER_WIRE32") != nullptr) wantCompact = false;
-            if (std::getenv("HALGPU_GATHER_WIRE16") != nullptr) wantCompact = true;
-            const size_t recRegion = (std::max<uint64_t>(g->local.nRec, 1) * (wantCompact ? 16 : sizeof(halgpu_lift_rec)) + 255) & ~(size_t)255;
-            uint8_t *slotRecs = nullptr; // peer-memory path, 32-byte form: a copy of the records the other ranks read
+            size_t recRegion = (std::max<uint64_t>(g->local.nRec, 1) * (wantCompact ? 16 : sizeof(halgpu_lift_rec)) + 255) & ~(size_t)255;
+            uint8_t *slotRecs = nullptr; // peer-memory path, 32-byte form: where a COPY of the records has to go (NULL: they are there)
             if (cm->pull) {
-                g->slot = acquireSlot(cm, recRegion + (myIdentity ? 0 : (size_t)(n + 1) * 4));
-                uint8_t *sb = cm->slots[(size_t)g->slot].buf;
-                if (wantCompact) g->sendWire = reinterpret_cast<unsigned long long *>(sb);
-                else slotRecs = sb;
-                if (!myIdentity) g->sendOff = reinterpret_cast<uint32_t *>(sb + recRegion);
+                if (wantCompact) {
+                    g->slot = acquireSlot(cm, recRegion + (myIdentity ? 0 : (size_t)(n + 1) * 4));
+                    g->sendWire = reinterpret_cast<unsigned long long *>(cm->slots[(size_t)g->slot].buf);
+                } else if (g->local.recsExternal) {
+                    recRegion = slotOffRegion; // (the records lie at the start of the slot already)
+                } else if (recRegion <= slotOffRegion) { // gathered by the engine into a cache buffer (complex intervals): copy
+                    recRegion = slotOffRegion;
+                    slotRecs = cm->slots[(size_t)g->slot].buf;
+                } else { // more records than the slot was sized for: take a larger one (nobody has been told about the first)
+                    cm->slots[(size_t)g->slot].busy = false;
+                    g->slot = acquireSlot(cm, recRegion + (size_t)(n + 1) * 4);
+                    slotRecs = cm->slots[(size_t)g->slot].buf;
+                }
+                if (!myIdentity) g->sendOff = reinterpret_cast<uint32_t *>(cm->slots[(size_t)g->slot].buf + recRegion);
             } else {
                 if (wantCompact) g->sendWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(g->local.nRec, 1) * 16));
                 if (!myIdentity) g->sendOff = static_cast<uint32_t *>(cache.take((size_t)(n + 1) * 4)); // (32-bit offsets on the wire)
@@ -458,17 +489,25 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                     }
                     return static_cast<const uint8_t *>(it->second);
                 };
+                const size_t nPull = cm->pullStreams.size();
+                for (size_t i = 0; i < nPull; ++i) g->ready->wait(cm->pullStreams[i]);
                 for (int k = 0; k < W; ++k) {
                     const int r = (me + 1 + k) % W; // (my own shard last: a local copy)
+                    const rt::Stream cs = (r == me || nPull == 0) ? cm->stream : cm->pullStreams[(size_t)k % nPull];
                     if (g->nRec[(size_t)r] > 0) {
                         const void *src = r == me ? sendRecs : (const void *)peerSlot(r);
-                        rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cm->stream);
+                        rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cs);
                     }
                     if (!g->identity && g->n[(size_t)r] > 0) {
                         const void *src = r == me ? (const void *)g->sendOff : (const void *)(peerSlot(r) + H[(size_t)r * H_WORDS + H_OFF_OFFS]);
                         const uint64_t at = uniform ? (uint64_t)r * g->n[0] : (uint64_t)r * (maxN + 1);
-                        rt::copyFromPeer(g->wireOff + at, src, (size_t)g->n[(size_t)r] * 4, cm->stream);
+                        rt::copyFromPeer(g->wireOff + at, src, (size_t)g->n[(size_t)r] * 4, cs);
                     }
+                }
+                for (size_t i = 0; i < nPull; ++i) { // the communicator's stream (and with it `done`) waits for every copy
+                    g->pullDone[i].reset(new rt::Event);
+                    g->pullDone[i]->record(cm->pullStreams[i]);
+                    g->pullDone[i]->wait(cm->stream);
                 }
             } else {
                 rt::commGroupStart();
@@ -485,7 +524,7 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             (void)me;
         } catch (...) {
             try { rt::sync(cm->stream); rt::sync(cm->hdrStream); } catch (...) {}
-            C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
+            C.release(g->local.offsets); if (!g->local.recsExternal) C.release(g->local.recs); C.release(g->local.psl);
             releaseSendSide(g.get());
             cache.give(g->wireOff); cache.give(g->offsets); cache.give(g->recs); cache.give(g->recvWire);
             throw;
@@ -547,7 +586,7 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
         *out = r;
     });
     if (rc != 0) { try { rt::sync(cm->stream); } catch (...) {} }
-    C.release(g->local.offsets); C.release(g->local.recs); C.release(g->local.psl);
+    C.release(g->local.offsets); if (!g->local.recsExternal) C.release(g->local.recs); C.release(g->local.psl);
     releaseSendSide(g);
     C.cache().give(g->wireOff); C.cache().give(g->offsets); C.cache().give(g->recs); C.cache().give(g->recvWire);
     delete g;
