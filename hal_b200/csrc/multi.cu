@@ -53,6 +53,7 @@ struct WireParams {
     unsigned long long *fitFlag;   // fits: cleared when a record does not fit
     int64_t n;
 };
+// (unpack: wire and out are advanced by the caller to the shard's first record)
 // pack + "does every record fit": one pass over this rank's records.  Runs BEFORE the header exchange (the header carries the
 // flag); when some rank's records do not fit the wire words are simply not used.
 __global__ void packRecKernel(const WireParams p) {
@@ -463,9 +464,30 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                 }
             }
             if (g->compact) g->recvWire = static_cast<unsigned long long *>(cache.take(std::max<uint64_t>(recTotal, 1) * 16));
-            // 3. the records (and offsets) of every rank, on the communicator's stream
+            // 3. the records (and offsets) of every rank, and their expansion into the result's form, all on the communicator's
+            //    streams: the engine's stream is free for the next batch's lift, end() only waits
             g->ready->wait(cm->stream);
             if (cm->timeline) { g->tl[1].reset(new rt::Event); g->tl[1]->record(cm->stream); }
+            UnpackOffParams up;
+            std::memset(&up, 0, sizeof(up));
+            up.off32 = g->wireOff; up.off64 = g->offsets; up.nranks = W;
+            for (int r = 0; r < W; ++r) {
+                up.ivBase[r + 1] = up.ivBase[r] + (int64_t)g->n[(size_t)r];
+                up.recBase[r + 1] = up.recBase[r] + g->nRec[(size_t)r];
+                up.wireBase[r] = uniform ? up.ivBase[r] : (int64_t)r * (int64_t)(maxN + 1);
+            }
+            if (g->identity) { // offsets[i] = i: nothing to wait for
+                IdentityOffParams ip;
+                ip.off64 = g->offsets; ip.n = up.ivBase[W];
+                rt::launch(identityOffKernel, gridOf(ip.n + 1, 256), 256, 0, cm->stream, ip);
+            }
+            auto unpackShard = [&](const unsigned long long *wire, uint64_t firstRec, uint64_t count, rt::Stream st) {
+                if (count == 0) return;
+                WireParams wp;
+                std::memset(&wp, 0, sizeof(wp));
+                wp.wire = const_cast<unsigned long long *>(wire); wp.out = g->recs + firstRec; wp.n = (int64_t)count;
+                rt::launch(unpackRecKernel, gridOf(wp.n, 256), 256, 0, st, wp);
+            };
             const void *sendRecs = g->compact ? (const void *)g->sendWire : (const void *)g->local.recs;
             uint8_t *recvRecs = g->compact ? reinterpret_cast<uint8_t *>(g->recvWire) : reinterpret_cast<uint8_t *>(g->recs);
             const size_t recBytes = g->compact ? 16 : sizeof(halgpu_lift_rec);
@@ -495,8 +517,14 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                     const int r = (me + 1 + k) % W; // (my own shard last: a local copy)
                     const rt::Stream cs = (r == me || nPull == 0) ? cm->stream : cm->pullStreams[(size_t)k % nPull];
                     if (g->nRec[(size_t)r] > 0) {
-                        const void *src = r == me ? sendRecs : (const void *)peerSlot(r);
-                        rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cs);
+                        if (r == me && g->compact) { // my own shard is expanded straight out of the send slot
+                            unpackShard(g->sendWire, recAt[r], g->nRec[(size_t)r], cs);
+                        } else {
+                            const void *src = r == me ? sendRecs : (const void *)peerSlot(r);
+                            rt::copyFromPeer(recvRecs + recAt[r] * recBytes, src, (size_t)g->nRec[(size_t)r] * recBytes, cs);
+                            // (each shard is expanded behind its own copy, while the next peer's copy is in flight)
+                            if (g->compact) unpackShard(g->recvWire + 2 * recAt[r], recAt[r], g->nRec[(size_t)r], cs);
+                        }
                     }
                     if (!g->identity && g->n[(size_t)r] > 0) {
                         const void *src = r == me ? (const void *)g->sendOff : (const void *)(peerSlot(r) + H[(size_t)r * H_WORDS + H_OFF_OFFS]);
@@ -519,7 +547,10 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
                     rt::commAllGatherV(cm->comm, sendRecs, recvRecs, g->nRec, recBytes, 0, cm->stream);
                 }
                 rt::commGroupEnd();
+                if (g->compact) unpackShard(g->recvWire, 0, recTotal, cm->stream);
             }
+            if (!g->identity) rt::launch(unpackOffKernel, gridOf(up.ivBase[W] + 1, 256), 256, 0, cm->stream, up);
+            if (cm->timeline) { g->tl[2].reset(new rt::Event); g->tl[2]->record(cm->stream); }
             g->done->record(cm->stream);
             (void)me;
         } catch (...) {
@@ -541,41 +572,17 @@ int halgpu_liftover_allgather_end(halgpu_gather *g, halgpu_lift_result **out, si
     const int rc = guardedCall(err, [&] {
         rt::setDevice(C.device());
         const int W = cm->comm->nranks;
-        UnpackOffParams up;
-        std::memset(&up, 0, sizeof(up));
-        up.off32 = g->wireOff; up.off64 = g->offsets; up.nranks = W;
-        uint64_t maxN = 0;
-        bool uniform = true;
-        for (int r = 0; r < W; ++r) { maxN = std::max(maxN, g->n[(size_t)r]); uniform = uniform && g->n[(size_t)r] == g->n[0] && g->nRec[(size_t)r] == g->nRec[0]; }
-        for (int r = 0; r < W; ++r) {
-            up.ivBase[r + 1] = up.ivBase[r] + (int64_t)g->n[(size_t)r];
-            up.recBase[r + 1] = up.recBase[r] + g->nRec[(size_t)r];
-            up.wireBase[r] = uniform ? up.ivBase[r] : (int64_t)r * (int64_t)(maxN + 1);
-        }
-        g->done->wait(C.stream()); // the engine's stream continues once the gather has landed
-        if (g->identity) {
-            IdentityOffParams ip;
-            ip.off64 = g->offsets; ip.n = up.ivBase[W];
-            rt::launch(identityOffKernel, gridOf(ip.n + 1, 256), 256, 0, C.stream(), ip);
-        } else {
-            rt::launch(unpackOffKernel, gridOf(up.ivBase[W] + 1, 256), 256, 0, C.stream(), up);
-        }
-        if (g->compact) {
-            WireParams wp;
-            std::memset(&wp, 0, sizeof(wp));
-            wp.wire = g->recvWire; wp.out = g->recs; wp.n = (int64_t)up.recBase[W];
-            if (wp.n > 0) rt::launch(unpackRecKernel, gridOf(wp.n, 256), 256, 0, C.stream(), wp);
-        }
-        if (cm->timeline) { g->tl[2].reset(new rt::Event); g->tl[2]->record(C.stream()); }
-        rt::sync(C.stream());
+        uint64_t nTotal = 0, recTotal = 0;
+        for (int r = 0; r < W; ++r) { nTotal += g->n[(size_t)r]; recTotal += g->nRec[(size_t)r]; }
+        g->done->hostWait(); // everything of this batch ran on the communicator's streams (begin)
         if (cm->timeline && g->tl[0] && g->tl[1] && g->tl[2]) {
             const rt::Event &o = *cm->origin;
-            fprintf(stderr, "[halgpu] gather timeline rank %d (ms since the communicator was made): lift done %.3f | gather %.3f .. %.3f | unpack done %.3f | lift kernels %.3f ms, compact %d\n",
-                    cm->comm->rank, rt::Event::elapsedMs(o, *g->tl[0]), rt::Event::elapsedMs(o, *g->tl[1]), rt::Event::elapsedMs(o, *g->done),
-                    rt::Event::elapsedMs(o, *g->tl[2]), g->kernelMs, (int)g->compact);
+            fprintf(stderr, "[halgpu] gather timeline rank %d (ms since the communicator was made): lift done %.3f | gather + expansion %.3f .. %.3f | lift kernels %.3f ms, compact %d, %s\n",
+                    cm->comm->rank, rt::Event::elapsedMs(o, *g->tl[0]), rt::Event::elapsedMs(o, *g->tl[1]), rt::Event::elapsedMs(o, *g->tl[2]),
+                    g->kernelMs, (int)g->compact, g->pulled ? "peer copies" : "NCCL");
         }
         halgpu_lift_result *r = static_cast<halgpu_lift_result *>(std::calloc(1, sizeof(halgpu_lift_result)));
-        r->n = (size_t)up.ivBase[W]; r->n_rec = (size_t)up.recBase[W]; r->offsets = g->offsets; r->recs = g->recs; r->on_device = 1;
+        r->n = (size_t)nTotal; r->n_rec = (size_t)recTotal; r->offsets = g->offsets; r->recs = g->recs; r->on_device = 1;
         r->kernel_ms = g->kernelMs; r->fast_ms = g->fastMs; r->n_complex = g->nComplex; r->n_retry = g->nRetry; r->launches = g->launches + 2;
         r->owner = cm->ctx;
         g->offsets = nullptr; g->recs = nullptr;

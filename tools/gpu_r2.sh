@@ -172,11 +172,17 @@ o)  # short multi-GPU run (gpurun --gpus N): NCCL tests + the peer-memory gather
     T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
     Q="--gpus $N --no-cpu-baseline --no-depth --no-c4 --steps 20 --warmup 5"
     if [ "$N" -le 2 ]; then timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu > gpurun_out/pytest_o.log 2>&1; tail -3 gpurun_out/pytest_o.log; fi
-    HALGPU_GATHER_PULL=1 HALGPU_GATHER_TIMELINE=1 timeout 600 $T --master-port 29612 bench.py $Q > gpurun_out/bench_o_n${N}_pull.json 2> gpurun_out/bench_o_n${N}_pull.err
-    grep "timeline rank 0" gpurun_out/bench_o_n${N}_pull.err | tail -3
-    HALGPU_GATHER_PULL=1 HALGPU_GATHER_WIRE16=1 timeout 600 $T --master-port 29613 bench.py $Q > gpurun_out/bench_o_n${N}_pull16.json 2> gpurun_out/bench_o_n${N}_pull16.err
+    if [ "$N" -le 2 ]; then
+        HALGPU_GATHER_PULL=1 HALGPU_GATHER_TIMELINE=1 timeout 600 $T --master-port 29612 bench.py $Q > gpurun_out/bench_o_n${N}_pull.json 2> gpurun_out/bench_o_n${N}_pull.err
+        grep "timeline rank 0" gpurun_out/bench_o_n${N}_pull.err | tail -3
+        V="_pull _pull16 _nccl"
+    else
+        V="_pull16 _nccl"
+    fi
+    HALGPU_GATHER_PULL=1 HALGPU_GATHER_WIRE16=1 HALGPU_GATHER_TIMELINE=1 timeout 600 $T --master-port 29613 bench.py $Q > gpurun_out/bench_o_n${N}_pull16.json 2> gpurun_out/bench_o_n${N}_pull16.err
+    grep "timeline rank 0" gpurun_out/bench_o_n${N}_pull16.err | tail -3
     HALGPU_GATHER_NCCL=1 timeout 600 $T --master-port 29614 bench.py $Q > gpurun_out/bench_o_n${N}_nccl.json 2> gpurun_out/bench_o_n${N}_nccl.err
-    for f in _pull _pull16 _nccl; do python -c "
+    for f in $V; do python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_o_n${N}$f.json').read().strip().splitlines()[-1])
 print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
