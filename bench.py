@@ -646,7 +646,7 @@ def main():
     # BASELINE.json configs[3] as a secondary of the 8-GPU run: its own file, staged after C2's context is gone
     c4 = None
     staged_bytes = a.staged_bytes
-    if dist and world == 8 and args.config == "C2" and not args.no_c4 and comm is not None:
+    if dist and (world == 8 or os.environ.get("HALGPU_BENCH_C4")) and args.config == "C2" and not args.no_c4 and comm is not None:
         comm.close()
         comm = None
         a.close()

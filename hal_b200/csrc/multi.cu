@@ -287,11 +287,9 @@ int halgpu_comm_init(halgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128
         rt::deviceUuid(ctx->impl->device(), me.uuid);
         if (nranks > 1) exchangeSmall(c.get(), &me, c->peers.data(), sizeof(PeerInfo));
         else c->peers[0] = me;
-        // Measured at 2 ranks (gpurun_out/bench_m_n2*.json): the copy-engine gather of 32-byte records 1.135 ms per step against
-        // 1.048 ms through ncclAllGather (one more copy of the shard into the send slot), so the peer-memory gather is the
-        // default from 4 ranks up, where the records travel in compact form and the pack pass writes the slot anyway;
-        // HALGPU_GATHER_PULL=1 / HALGPU_GATHER_NCCL=1 force either.
-        uint64_t capable = nranks >= 4 ? 1 : 0;
+        // Measured (profiles/r02_bench_n{2,4,8}_*.json): 2 ranks 1.04 ms per step either way, 4 ranks 1.44 ms against 1.56 ms through
+        // ncclAllGather, 8 ranks 2.84 against 2.97 ms (one copy stream, expansion still in end()).
+        uint64_t capable = 1;
         if (std::getenv("HALGPU_GATHER_PULL") != nullptr) capable = 1;
         if (std::getenv("HALGPU_GATHER_NCCL") != nullptr) capable = 0;
         for (int r = 0; r < nranks; ++r) {

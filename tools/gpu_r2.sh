@@ -188,5 +188,20 @@ d=json.loads(open('gpurun_out/bench_o_n${N}$f.json').read().strip().splitlines()
 print('n$N$f', 'value %.4g' % d['value'], 'ms_per_step %.4f' % d['ms_per_step'], 'kernels %.4f' % d['detail']['mapping_kernels_ms'], d['check'])
 "; done
     ;;
+p)  # 2 GPUs: the default bench line at N=2 with the C4 secondary forced (communicator closed and re-made on a second file)
+    N=$(nvidia-smi -L | wc -l)
+    T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+    HALGPU_BENCH_C4=1 timeout 500 $T --master-port 29612 bench.py --gpus $N --no-cpu-baseline --steps 20 --warmup 5 > gpurun_out/bench_p_n${N}.json 2> gpurun_out/bench_p_n${N}.err
+    tail -c 1800 gpurun_out/bench_p_n${N}.json; tail -3 gpurun_out/bench_p_n${N}.err
+    ;;
+q)  # final N=1 evidence: whole GPU tier (xdist), the default bench line, launch list, ncu --set full of the lane kernel
+    ( time timeout 330 python -m pytest tests -q -m gpu -n 6 --durations=12 ) > gpurun_out/pytest_q.log 2>&1; tail -22 gpurun_out/pytest_q.log
+    ( time timeout 400 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err
+    tail -c 300 gpurun_out/bench_q.json; tail -4 gpurun_out/bench_q.err
+    timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_q.csv \
+        python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/bench_ncu_q.err
+    timeout 200 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel' -s 1 -c 1 -o gpurun_out/prof_q_fast -f \
+        python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/prof_q.err
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
