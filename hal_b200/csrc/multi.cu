@@ -419,7 +419,7 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             g->ready.reset(new rt::Event);
             g->done.reset(new rt::Event);
             g->ready->record(C.stream());
-            // 2. every rank learns every shard's size (and buffers): one 256-byte header per rank over the header communicator
+            // 2. every rank learns every shard's size (and buffers): one 128-byte header per rank over the header communicator
             //    on its own stream -- the only host round trip of the gather, and not queued behind the previous batch's
             //    records.  With the peer-memory gather a rank's header also says "my buffers are complete": the engine's
             //    stream is drained first.

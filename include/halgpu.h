@@ -271,15 +271,17 @@ void halgpu_host_free(void *p);
 /* ---- multi-GPU liftover (the reference's only parallel driver partitions work the same way across
  *      processes: maf/hal2mafMP.py:63-79).  One process -- or host thread -- per GPU, each with its own context on the same
  *      HAL file (the staged index is replicated).  Every rank lifts its own shard of the interval batch; ONE all-gather of
- *      the output interval buffer over NCCL / NVLink then leaves the result of the WHOLE batch, shards in rank order, in the
- *      device memory of every rank.  The communicator is bootstrapped like NCCL's: rank 0 creates a 128-byte id
- *      (halgpu_comm_unique_id) and hands it to the other ranks by any out-of-band means (a file, MPI, torch.distributed);
- *      all ranks then call halgpu_comm_init.  NCCL is resolved at run time (libnccl.so.2); without it these calls fail and
- *      everything else works.
- *      begin() returns once this rank's shard is lifted and the collectives are enqueued on the communicator's own stream;
+ *      the output interval buffer over NVLink then leaves the result of the WHOLE batch, shards in rank order, in the
+ *      device memory of every rank: every rank copies the other ranks' shards out of their buffers (peer memory: CUDA IPC
+ *      between processes, peer access between threads of one process); NCCL carries the per-batch 128-byte headers and is
+ *      the fallback gather where peer access is not available.  The communicator is bootstrapped like NCCL's: rank 0
+ *      creates a 128-byte id (halgpu_comm_unique_id) and hands it to the other ranks by any out-of-band means (a file, MPI,
+ *      torch.distributed); all ranks then call halgpu_comm_init.  NCCL is resolved at run time (libnccl.so.2); without it
+ *      these calls fail and everything else works.
+ *      begin() returns once this rank's shard is lifted and the transfers are enqueued on the communicator's own streams;
  *      end() waits for them and hands out the gathered result (device memory of the context; halgpu_free_result).  A
- *      caller that begins batch k+1 before ending batch k overlaps the gather of k with the lift of k+1.  begin/end are
- *      collective: every rank must issue them in the same order. ---- */
+ *      caller that begins batch k+1 before ending batch k overlaps the gather of k with the lift of k+1.  begin / end /
+ *      halgpu_comm_free are collective: every rank must issue them in the same order. ---- */
 typedef struct halgpu_comm halgpu_comm;
 typedef struct halgpu_gather halgpu_gather;
 int halgpu_comm_unique_id(uint8_t id[128], char **err);
