@@ -677,12 +677,18 @@ def main():
     dom_ms = fast_ms if dom_fast else kmean
     # Algorithmic bytes per interval of the dominant kernel.  The warp-per-interval walk does the
     # reference walk piece by piece: SURVEY 8(d)'s figure with the oracle's visit counts.  The lane kernel maps a whole
-    # collinear run per hop, so ITS algorithm touches: the sorted work item (start + id|length, 16 B), one 32-byte FastRec
-    # per hop of the path, and the 32-byte output record -- the SURVEY figure over its time is kept as reference_walk.
+    # collinear run per hop: what it MUST move through the HBM is the sorted work item (start + id|length, 16 B) and the
+    # 32-byte output record of every interval, plus every FastRec of the path's transitions once (one 32-byte record per
+    # segment-sized position bucket; the sorted batch shares them through L1/L2) -- that is the roofline's numerator.  The
+    # bytes its loads and stores touch (16 + 32 per hop + 32 per interval, L1/L2-served) and the SURVEY figure of the
+    # reference walk over the same time are reported next to it.
     n_hops = sum(int(x.split()[0]) for x in W["hops"].split(","))
-    own_bytes = 16 + 32 * n_hops + 32 if dom_fast else per_interval
+    touched_bytes = 16 + 32 * n_hops + 32
+    index_bytes = min(n * n_hops * 32, n_hops * args.segs * 32)
+    own_bytes = (48 * n + index_bytes) / n if dom_fast else per_interval
     achieved = own_bytes * n / (dom_ms / 1e3) / 1e9
     ref_walk_gbs = per_interval * n / (dom_ms / 1e3) / 1e9
+    touched_gbs = touched_bytes * n / (dom_ms / 1e3) / 1e9
     traffic = {}
     if world == 1 and not args.no_traffic:
         if not args.no_divergent and args.config == "C2":
@@ -704,16 +710,20 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": tr, "kernel": dom_name, "kernel_ms": dom_ms,
                      "algorithmic_bytes_per_interval": own_bytes,
-                     "algorithmic_bytes_formula": ("16 B sorted work item + 32 B FastRec x %d hops + 32 B output record" % n_hops) if dom_fast
+                     "algorithmic_bytes_formula": ("compulsory HBM bytes: 16 B sorted work item + 32 B output record per interval + the FastRec tables of the "
+                                                   "%d transitions once (%d B: one 32-byte record per segment-sized bucket)" % (n_hops, index_bytes)) if dom_fast
                                                   else "SURVEY 8(d): 24 B in + search + visited records (oracle visit counts) + 40 B per output line",
+                     "touched": ({"bytes_per_interval": touched_bytes, "gbs": touched_gbs, "frac_of_hbm_peak": touched_gbs / peak,
+                                  "note": "bytes the kernel's loads and stores touch (16 + 32 per hop + 32), served by L1/L2 where neighbouring intervals share a FastRec"}
+                                 if dom_fast else None),
                      "reference_walk": {"bytes_per_interval": per_interval, "gbs": ref_walk_gbs, "frac": ref_walk_gbs / peak,
                                         "note": "SURVEY 8(d) bytes of the REFERENCE walk (one record per piece per hop, oracle visit counts) over this kernel's time"},
                      "peak_source": peak_src,
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, measured by a probe of this run" if tr else None,
                      "dram_gbs": (tr / (dom_ms / 1e3) / 1e9) if tr else None, "dram_frac": (tr / (dom_ms / 1e3) / 1e9 / peak) if tr else None,
-                     "note": "achieved/frac: the bytes this kernel's own algorithm touches per interval over its CUDA-event time (the sorted batch "
-                             "shares index sectors through L2, so DRAM moves less: traffic / dram_gbs / dram_frac are what the HBM delivered, "
-                             "measured by ncu in this run); reference_walk is the same time against the bytes the reference's piece-by-piece walk touches"},
+                     "note": "achieved/frac: the bytes this kernel must move through the HBM (algorithmic_bytes_formula) over its CUDA-event time; "
+                             "traffic / dram_gbs / dram_frac: what the HBM delivered, measured by ncu in this run; touched: the bytes its loads and "
+                             "stores address (L1/L2-served); reference_walk: the same time against the bytes the reference's piece-by-piece walk touches"},
         "check": check,
         "detail": {"output_lines_per_step": int(n_rec_last), "retry_intervals": int(last_info.get("n_retry") or 0), "wall_s_per_step": wall / args.steps,
                    "stage_seconds": stage_s, "staged_bytes": staged_bytes, "mapping_kernels_ms": kmean, "kernel_share_of_step": kmean / ms_step,

@@ -184,7 +184,7 @@ struct FastParams {
     int64_t srcLen;
     const int64_t *tgtSeqStart;
     int32_t tgtNumSeq;
-    int32_t tileGrab;                     // k > 0: a warp takes k tiles per atomicAdd on tileCursor; 0: tiles warp id, warp id + warps of the grid, ...
+    int32_t tileGrab;                     // a warp takes this many tiles per atomicAdd on tileCursor (>= 1)
     int64_t n;
     const int64_t *gs, *ge;               // input order
     const uint8_t *strand;                // may be NULL

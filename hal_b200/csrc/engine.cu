@@ -889,10 +889,10 @@ void Context::liftover(int src, int tgt, uint32_t flags, size_t n, const int64_t
             F.sortedGs = sortedGs; F.sortedVal = sortedVal; F.sortedKey = sortedKey;
             F.tileCursor = ctr + C_TILE; F.pool = pool;
             // tiles of 32 work items are handed out 4 at a time from an atomic cursor, so the resident warps sweep the sorted batch
-            // together.  Measured on 10 M intervals (gpurun_out/bench_k_*.json): 1 tile per atomicAdd 0.354 ms, 4 tiles 0.304 ms,
-            // fixed stride per warp (HALGPU_TILE_GRAB=0) 0.426 ms.
+            // together.  Measured on 10 M intervals (profiles/r02_bench_n1_tilegrab*.json): 1 tile per atomicAdd 0.354 ms, 4 tiles
+            // 0.302 ms, 16 tiles 0.411 ms, a fixed stride per warp (since removed) 0.426 ms.
             int tileGrab = 4;
-            if (const char *tg = std::getenv("HALGPU_TILE_GRAB")) tileGrab = std::max(0, std::min(64, std::atoi(tg))); // measurement switch
+            if (const char *tg = std::getenv("HALGPU_TILE_GRAB")) tileGrab = std::max(1, std::min(64, std::atoi(tg))); // measurement switch
             F.tileGrab = tileGrab;
             F.complexList = complexList; F.complexCount = ctr + C_COMPLEX;
             for (int c = 0; c < nSlices; ++c) {

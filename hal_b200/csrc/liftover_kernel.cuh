@@ -1064,21 +1064,22 @@ __global__ void __launch_bounds__(256) fastLiftKernel(const FastParams P) {
     for (int i = (int)threadIdx.x; i < P.P; i += (int)blockDim.x) sSteps[i] = P.steps[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t nTiles = (P.n + 31) >> 5;
-    const int64_t warpsInGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int64_t tile = P.tileGrab == 0 ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) - warpsInGrid : -1;
-    int64_t grabEnd = 0; // (atomic cursor: end of the tiles this warp holds)
+    // tiles of 32 work items, handed out P.tileGrab at a time by an atomic cursor (engine.cu: 4): the resident warps sweep the
+    // sorted batch together
+    const uint32_t nTiles = (uint32_t)((P.n + 31) >> 5);
+    uint32_t tile = 0, grabEnd = 0;
     while (true) {
-        if (P.tileGrab == 0) {
-            tile += warpsInGrid;
-        } else if (++tile >= grabEnd) {
+        if (tile >= grabEnd) {
             unsigned long long t0 = 0;
             if (lane == 0) t0 = atomicAdd(P.tileCursor, (unsigned long long)P.tileGrab);
-            tile = (int64_t)__shfl_sync(HG_FULL, t0, 0);
-            grabEnd = tile + P.tileGrab;
+            t0 = __shfl_sync(HG_FULL, t0, 0);
+            if (t0 >= (unsigned long long)nTiles) break;
+            tile = (uint32_t)t0;
+            grabEnd = tile + (uint32_t)P.tileGrab;
         }
         if (tile >= nTiles) break;
-        const int64_t w = tile * 32 + lane;
+        const int64_t w = (int64_t)tile * 32 + lane;
+        ++tile;
         const bool have = w < P.n;
         uint32_t item = 0;
         int64_t gs = 0, ge = -1;

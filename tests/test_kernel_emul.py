@@ -228,10 +228,9 @@ def test_emulated_fused_walk_equals_oracle(emul_lib, oracle_lib, monkeypatch, ha
     a.close()
 
 
-@pytest.mark.parametrize("env", [{"HALGPU_TILE_GRAB": "0"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "16"}, {"HALGPU_SORT_BITS": "8"}])
+@pytest.mark.parametrize("env", [{"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "16"}, {"HALGPU_SORT_BITS": "8"}])
 def test_emulated_order_switches_equal_default(emul_lib, oracle_lib, monkeypatch, env):
-    """the sort granularity and the way the lane kernel's warps take their tiles (4 per atomicAdd by default, fixed stride with
-    HALGPU_TILE_GRAB=0) never change a result"""
+    """the sort granularity and the way the lane kernel's warps take their tiles (4 per atomicAdd by default) never change a result"""
     import hal_b200
     path = os.path.join(GOLDEN, "varlen8.hal")
     o = oracle_lib.Oracle(path)

@@ -280,7 +280,7 @@ def test_cuda_fused_walk_equals_oracle(hb, oracle_lib, monkeypatch, hal, src, tg
             assert_same_as_oracle(off, recs, exp)
 
 
-@pytest.mark.parametrize("env", [{"HALGPU_TILE_GRAB": "0"}, {"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "16"}, {"HALGPU_SORT_BITS": "8"}])
+@pytest.mark.parametrize("env", [{"HALGPU_TILE_GRAB": "1"}, {"HALGPU_TILE_GRAB": "16"}, {"HALGPU_SORT_BITS": "8"}])
 def test_cuda_order_switches_equal_default(hb, oracle_lib, monkeypatch, env):
     """sort granularity and tile hand-out of the lane kernel (HALGPU_SORT_BITS, HALGPU_TILE_GRAB): identical results"""
     path = os.path.join(GOLDEN, "varlen8.hal")

@@ -49,8 +49,12 @@ def _run_ranks(emul_lib, hal, src, tgt, shards, flags=0, batches=1):
     return out
 
 
-@pytest.mark.parametrize("wire", ["default", "HALGPU_GATHER_WIRE16", "HALGPU_GATHER_PULL", "HALGPU_GATHER_NCCL"])
-@pytest.mark.parametrize("sizes,maxlen", [((120, 120), 12), ((150, 40), 200), ((0, 60), 100), ((70, 70, 70), 8), ((40, 50, 0, 60), 30)])
+@pytest.mark.parametrize("sizes,maxlen,wire", [
+    ((120, 120), 12, "default"), ((150, 40), 200, "default"), ((0, 60), 100, "default"), ((70, 70, 70), 8, "default"),
+    ((40, 50, 0, 60), 30, "default"),
+    ((150, 40), 200, "HALGPU_GATHER_WIRE16"), ((70, 70, 70), 8, "HALGPU_GATHER_WIRE16"),
+    ((150, 40), 200, "HALGPU_GATHER_NCCL"), ((40, 50, 0, 60), 30, "HALGPU_GATHER_NCCL"), ((0, 60), 100, "HALGPU_GATHER_NCCL"),
+])
 def test_emulated_allgather_equals_single_lift(emul_lib, monkeypatch, sizes, maxlen, wire):
     """(the records travel as they are below 4 ranks, in compact 16-byte form from 4 ranks up -- the first switch forces the latter; by default
     every rank copies the other ranks' shards out of their buffers, the last switch sends them through the all-gather collective)"""

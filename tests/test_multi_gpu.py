@@ -56,7 +56,7 @@ def _gather(world, shards, hal, src, tgt, batches=2):
     return out
 
 
-@pytest.mark.parametrize("wire", ["default", "HALGPU_GATHER_WIRE16", "HALGPU_GATHER_WIRE32", "HALGPU_GATHER_PULL", "HALGPU_GATHER_NCCL"])
+@pytest.mark.parametrize("wire", ["default", "HALGPU_GATHER_WIRE16", "HALGPU_GATHER_WIRE32", "HALGPU_GATHER_NCCL"])
 @pytest.mark.parametrize("ragged", [False, True])
 def test_nccl_allgather_equals_single_lift(monkeypatch, ragged, wire):
     import torch

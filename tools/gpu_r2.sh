@@ -203,5 +203,12 @@ q)  # final N=1 evidence: whole GPU tier (xdist), the default bench line, launch
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel' -s 1 -c 1 -o gpurun_out/prof_q_fast -f \
         python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/prof_q.err
     ;;
+r)  # last N=1 evidence of the round: liftover GPU tests, the default bench line, ncu --set full of the lane kernel (32 registers again)
+    timeout 200 python -m pytest tests/test_liftover_gpu.py -x -q -m gpu > gpurun_out/pytest_r.log 2>&1; tail -2 gpurun_out/pytest_r.log
+    ( time timeout 300 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_r.json 2> gpurun_out/bench_r.err
+    tail -c 200 gpurun_out/bench_r.json; tail -4 gpurun_out/bench_r.err
+    timeout 120 ncu --set full --clock-control none --import-source on -k regex:'fastLiftKernel' -s 1 -c 1 -o gpurun_out/prof_r_fast -f \
+        python bench.py --probe --no-divergent > /dev/null 2> gpurun_out/prof_r.err
+    ;;
 *)  echo "unknown stage $stage"; exit 2;;
 esac
