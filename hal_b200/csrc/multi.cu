@@ -365,8 +365,8 @@ int halgpu_liftover_allgather_begin(halgpu_comm *cm, int src, int tgt, int coale
             g->launches = g->local.launches;
             if (g->local.nRec >= 0xffffffffull) throw HalError("a shard produced 2^32 or more records; use smaller batches");
             // 1. this rank's records in compact wire form (packRecKernel also decides whether they all fit), on the engine's
-            //    stream.  The compact form halves the link bytes and costs one pack pass here and one unpack pass over ALL
-            //    ranks' records in end(): worth it from 4 ranks up (every rank receives (W - 1) / W of the result), while 2
+            //    stream.  The compact form halves the link bytes and costs one pack pass here and one expansion pass over ALL
+            //    ranks' records (step 3): worth it from 4 ranks up (every rank receives (W - 1) / W of the result), while 2
             //    ranks are faster with the 32-byte records moved as they are.  HALGPU_GATHER_WIRE32 / HALGPU_GATHER_WIRE16
             //    force either form (measurement switches).
             uint64_t *dHdr = static_cast<uint64_t *>(cache.take((size_t)(W + 1) * H_WORDS * 8));

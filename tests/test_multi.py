@@ -79,10 +79,10 @@ def test_emulated_allgather_equals_single_lift(emul_lib, monkeypatch, sizes, max
 
 @pytest.mark.parametrize("wire32", [False, True])
 def test_emulated_allgather_collinear_uniform_shards(emul_lib, tmp_path, monkeypatch, wire32):
-    monkeypatch.setenv("HALGPU_GATHER_WIRE32" if wire32 else "HALGPU_GATHER_WIRE16", "1")
     """equal shards of a collinear alignment: every interval ends in the one-lane-per-interval kernel, the offsets are the
     identity on every rank (not sent) and the records travel in compact 16-byte form -- or, with HALGPU_GATHER_WIRE32, as
     they are"""
+    monkeypatch.setenv("HALGPU_GATHER_WIRE32" if wire32 else "HALGPU_GATHER_WIRE16", "1")
     import subprocess
     import hal_b200
     from conftest import ROOT
@@ -101,3 +101,27 @@ def test_emulated_allgather_collinear_uniform_shards(emul_lib, tmp_path, monkeyp
     for r in range(2):
         goff, grecs, npr, nrr = out[r][0]
         assert np.array_equal(goff, off) and np.array_equal(grecs, recs)
+
+
+def test_emulated_allgather_compact_wanted_but_records_do_not_fit(emul_lib, tmp_path, monkeypatch):
+    """the compact wire form holds n_frag < 16: lines the warp-per-interval walk merges from more pieces do not fit, the ranks
+    learn that from the headers and the batch travels as 32-byte records (through the collective) -- same result"""
+    import subprocess
+    import hal_b200
+    from conftest import ROOT
+    from hal_b200 import build
+    build.build()
+    monkeypatch.setenv("HALGPU_GATHER_WIRE16", "1")
+    hal = str(tmp_path / "flat.hal")
+    subprocess.check_call([os.path.join(ROOT, "hal_b200", "bin", "halSynth"), "--newick", "((L0,L1)A0,(L2)A1)R;", "--segs", "3000", "--segLen", "16", hal])
+    a = hal_b200.Alignment(hal, lib_path=emul_lib)
+    s, t = a.genome_id("L0"), a.genome_id("L2")
+    shards = [random_intervals(a.genome_length(s) - 32, 60 + 20 * r, 600, seed=5 + r) for r in range(2)]
+    gs, ge, st = (np.concatenate([sh[k] for sh in shards]) for k in range(3))
+    off, recs, info = a.liftover(s, t, gs, ge, st, hal_b200.HALGPU_NO_FAST)
+    a.close()
+    assert recs["n_frag"].max() >= 16
+    out = _run_ranks(emul_lib, hal, "L0", "L2", shards, flags=hal_b200.HALGPU_NO_FAST, batches=2)
+    for r in range(2):
+        for goff, grecs, npr, nrr in out[r]:
+            assert np.array_equal(goff, off) and np.array_equal(grecs, recs)
