@@ -156,9 +156,10 @@ __device__ __forceinline__ void warpRankSort(const Frag *src, Frag *dst, int m, 
         int r = 0;
         for (int j = 0; j < m; ++j) {
             const int64_t ot = src[j].tLo;
-            if (ot < myT) {
-                ++r;
-            } else if (ot == myT) {
+            r += ot < myT ? 1 : 0;
+            // (j == i never counts, and testing for it keeps the element's comparison with ITSELF -- one lane of the warp in every
+            // iteration -- off the full-comparison path: round 2's profile had 27 % of the walk's instructions there)
+            if (ot == myT && j != i) {
                 const Frag o = src[j];
                 r += (fragLess(o, me) || (!fragLess(me, o) && j < i)) ? 1 : 0;
             }
