@@ -77,4 +77,4 @@ def test_blockviz_library_exports_every_declared_symbol(product_lib):
 def test_blockviz_cuda_matches_reference_answers():
     from hal_b200 import build
     build.build()
-    check_cases(os.path.join(ROOT, "hal_b200", "bin", "blockVizCli"), step=3)  # (every query is a process + CUDA context)
+    check_cases(os.path.join(ROOT, "hal_b200", "bin", "blockVizCli"), step=5)  # (every query is a process + CUDA context)

@@ -60,7 +60,11 @@ def test_cli_errors(emul_cli, tmp_path):
 def test_cli_cuda_matches_reference_outputs(golden_cases, tmp_path):
     from hal_b200 import build
     build.build()
-    check_all(os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), golden_cases, tmp_path, lambda c: True)
+    # every case except four of five of the 50 "all pairs" ones: each is a process with its own CUDA context (~1 s), and
+    # test_liftover_gpu.py::test_cuda_golden_text lifts ALL of them in-process through the same library
+    all_pairs = [c["name"] for c in golden_cases if "_all_" in c["name"]]
+    keep = set(all_pairs[::5])
+    check_all(os.path.join(ROOT, "hal_b200", "bin", "halLiftover"), golden_cases, tmp_path, lambda c: "_all_" not in c["name"] or c["name"] in keep)
 
 
 def check_depth(cli, tmp_path):
