@@ -9,7 +9,7 @@ A=${1:-/tmp/halgpu_asan}
 C=$R/hal_b200/csrc; H=$C/host
 F="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer"
 mkdir -p "$A"; cd "$A"
-g++ $F -DHALGPU_SIMT_EMUL -I$R/tests/simt -I$C -fPIC -shared -pthread -x c++ $C/capi.cu -x c++ $C/engine.cu -x c++ $C/halmmap.cpp -o libhalgpu_emul.so
+g++ $F -DHALGPU_SIMT_EMUL -I$R/tests/simt -I$C -fPIC -shared -pthread -x c++ $C/capi.cu -x c++ $C/engine.cu -x c++ $C/multi.cu -x c++ $C/halmmap.cpp -o libhalgpu_emul.so
 L="-L. -lhalgpu_emul -Wl,-rpath,\$ORIGIN -pthread"
 g++ $F -o halLiftover_emul $H/halLiftoverMain.cpp $H/gpu_liftover.cpp $H/bed.cpp $H/bed_fast.cpp $L
 g++ $F -o halWiggleLiftover_emul $H/halWiggleLiftoverMain.cpp $H/wiggle_liftover.cpp $L
